@@ -1,0 +1,127 @@
+/*
+ * pf_gpu.h -- C ABI of libpfgpu.so, the B200 (sm_100a) implementation of PloidyFrost's per-superbubble
+ * hot path.  Plain pointers and sizes only; no C++/torch/CUDA types cross this boundary.
+ *
+ * The reference has no FFI for this path: the seam is two C++ classes used by value,
+ *   CKMCFile  (KMC/kmc_api/kmc_file.h:105-167; member CDBG.hpp:13, vector<CKMCFile*> CCDBG.hpp:12)
+ *   SeqAlign  (src/SeqAlign.hpp:7-22; one stack object per bubble, CDBG.cpp:2036, :2265)
+ * so every entry point below names the reference member it stands in for.  Calls are *batched*
+ * (one k-mer or one bubble per call cannot feed a GPU); INTEGRATION.md shows the binding a maintainer
+ * of the reference would write (a CKMCFile / SeqAlign look-alike over these calls).
+ *
+ * Conventions: int return, 0 = PF_OK, negative = error class, text via pf_last_error() (thread-local).
+ * No exceptions or aborts cross the ABI.  Inputs are caller-owned.  Unless a function says otherwise,
+ * pointers are HOST pointers and the call includes the host<->device copies.  Functions ending in
+ * `_dev` take DEVICE pointers (inputs already resident in HBM) plus a CUDA stream handle (a
+ * cudaStream_t passed as void*, NULL = the context's own stream) and are asynchronous on that stream.
+ * A pf_ctx is bound to one GPU; one process per GPU is the intended deployment (bubbles shard
+ * across processes with no data-path collective).  A pf_ctx may be used from one host thread at a time.
+ */
+#ifndef PF_GPU_H
+#define PF_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "pf_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pf_ctx pf_ctx;
+typedef struct pf_kmc pf_kmc;
+
+enum {
+    PF_OK = 0,
+    PF_E_INVALID = -1, /* bad argument                                  */
+    PF_E_IO = -2,      /* file missing / malformed KMC database          */
+    PF_E_CUDA = -3,    /* CUDA runtime or kernel failure                 */
+    PF_E_NOMEM = -4,   /* host or device allocation failed               */
+    PF_E_UNSUPPORTED = -5 /* valid for the reference but outside this build (e.g. float counters, k>32) */
+};
+
+/* ---- context -------------------------------------------------------------------------------- */
+int pf_init(int device, pf_ctx **ctx);
+void pf_shutdown(pf_ctx *ctx);
+const char *pf_last_error(void);
+/* library + device description as a short static string ("libpfgpu <ver> sm_100a ...") */
+const char *pf_version(void);
+/* number of kernel launches issued by this context since creation (bench.py reports the delta) */
+uint64_t pf_launch_count(const pf_ctx *ctx);
+int pf_sync(pf_ctx *ctx);
+
+/* ---- KMC database: CKMCFile ------------------------------------------------------------------- */
+/* CKMCFile::OpenForRA (kmc_file.cpp:27): parse <prefix>.kmc_pre/.kmc_suf, build the HBM-resident index. */
+int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **db);
+/* CKMCFile::Close (kmc_file.cpp:631) */
+int pf_kmc_close(pf_kmc *db);
+/* CKMCFile::Info (kmc_file.cpp Info(CKMCFileInfo&)) */
+int pf_kmc_info(const pf_kmc *db, pf_kmc_info_t *info);
+/* CKMCFile::SetMinCount / SetMaxCount / ResetMinMaxCounts (kmc_file.h:118-128,157) */
+int pf_kmc_set_min_count(pf_kmc *db, uint32_t x);
+int pf_kmc_set_max_count(pf_kmc *db, uint32_t x);
+int pf_kmc_reset_min_max(pf_kmc *db);
+/* bytes of HBM held by the index */
+uint64_t pf_kmc_device_bytes(const pf_kmc *db);
+
+/*
+ * Batched CKMCFile::GetCountersForRead (kmc_file.cpp:904) / CheckKmer (:330) / IsKmer (:775).
+ * For every k-mer window of every sequence (len-k+1 windows, none when len < k), in sequence order:
+ *   counts[w] = counter if the key is present and min_count <= counter <= max_count, else 0
+ *   found[w]  = 1 / 0 likewise (may be NULL)
+ * `mode` is PF_LOOKUP_* (pf_types.h).  Windows containing a non-ACGT character are not found
+ * (kmc_file.cpp:1036-1047, kmer_api.h:502-509).  counts/found must hold sum(max(len-k+1,0)) entries.
+ */
+int pf_kmc_counts(pf_kmc *db, const char *bases, const uint64_t *seq_off, uint32_t n_seq, int mode,
+                  uint32_t *counts, uint8_t *found);
+
+/*
+ * Batched coverage reducers CDBG::readCov (CDBG.cpp:29, :66) / CCDBG::readCov, readCovUni
+ * (CCDBG.cpp:89, :123): one pf_cov_t per sequence.  The caller derives the reference's return values:
+ *   unitig form  : fatal if first_missing >= 0, else (sum / n_kmers, min)
+ *   string form  : scan order decides -- fatal if first_missing >= 0 and (first_outside < 0 or
+ *                  first_missing < first_outside); (0,false) if first_outside >= 0; else (sum/n_kmers, true)
+ */
+int pf_kmc_cov(pf_kmc *db, const char *bases, const uint64_t *seq_off, uint32_t n_seq, int mode,
+               uint32_t low, uint32_t up, pf_cov_t *out);
+
+/*
+ * Device-resident forms.  d_bases (n_bases chars), d_seq_off (n_seq+1 x u64) and d_win_off
+ * (n_seq+1 x u64, exclusive prefix sum of max(len-k+1,0); pf_window_offsets computes it on the host)
+ * are device pointers; d_seq_off[0] must be 0 and d_bases should be 16-byte aligned (it is staged with
+ * 128-bit loads; an unaligned pointer falls back to byte loads).  Outputs are device pointers; d_counts/d_found may be NULL when only d_cov is
+ * wanted and vice versa.  d_cov must be n_seq x pf_cov_t.
+ */
+int pf_kmc_lookup_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const void *d_seq_off,
+                      const void *d_win_off, uint32_t n_seq, uint64_t n_windows, int mode, uint32_t low,
+                      uint32_t up, void *d_counts, void *d_found, void *d_cov, void *cuda_stream);
+/* host helper: win_off[n_seq+1] from seq_off and k; returns the total number of windows */
+uint64_t pf_window_offsets(const uint64_t *seq_off, uint32_t n_seq, uint32_t k, uint64_t *win_off);
+
+/* ---- SeqAlign ------------------------------------------------------------------------------- */
+/*
+ * Batched SeqAlign::SequenceAlignment (SeqAlign.cpp:550) with scoring SeqAlign(M, D, G)
+ * (SeqAlign.hpp:10): for every bubble, aligns its sequences (already ordered by the caller) and calls
+ * sites exactly as needlemanWunch (:480) -> traceback (:306) -> variantAnalyze (:237) ->
+ * compareStrPair (:8) do.  `out` views context-owned pinned host memory, valid until the next
+ * pf_align* call on the same context.
+ */
+int pf_align(pf_ctx *ctx, double M, double D, double G, const char *bases, const uint64_t *seq_off,
+             const uint32_t *bubble_off, uint32_t n_bubbles, pf_msa_batch_t *out);
+
+/*
+ * Device-resident form: inputs are device pointers; results stay in context-owned device memory and
+ * `out_dev` receives DEVICE pointers (same layout).  Asynchronous on the stream except for one
+ * scalar read-back that sizes the compacted result.  `max_len` / `max_rows` are the longest sequence
+ * and the largest bubble in the batch (the host knows them from the offsets it built).
+ */
+int pf_align_dev(pf_ctx *ctx, double M, double D, double G, const void *d_bases, uint64_t n_bases,
+                 const void *d_seq_off, uint32_t n_seq, const void *d_bubble_off, uint32_t n_bubbles,
+                 uint32_t max_len, uint32_t max_rows, pf_msa_batch_t *out_dev, void *cuda_stream);
+/* diagnostics: bubbles of the last pf_align / pf_align_dev call that needed the large (tier-2) work area */
+uint32_t pf_align_last_retry_count(const pf_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PF_GPU_H */

@@ -1,0 +1,239 @@
+"""ctypes bindings of libpfgpu.so (include/pf_gpu.h).  Thin: numpy arrays in, numpy arrays out.
+
+There is deliberately no CPU path here: if the library is missing or no GPU is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libpfgpu.so")
+
+u8p = C.POINTER(C.c_uint8)
+u16p = C.POINTER(C.c_uint16)
+u32p = C.POINTER(C.c_uint32)
+i32p = C.POINTER(C.c_int32)
+u64p = C.POINTER(C.c_uint64)
+
+LOOKUP_CANONICAL, LOOKUP_FWD_THEN_RC, LOOKUP_FWD = 0, 1, 2
+
+# every symbol include/pf_gpu.h declares (tests check that the library exports all of them)
+EXPORTS = ["pf_init", "pf_shutdown", "pf_last_error", "pf_version", "pf_launch_count", "pf_sync", "pf_kmc_open",
+           "pf_kmc_close", "pf_kmc_info", "pf_kmc_set_min_count", "pf_kmc_set_max_count", "pf_kmc_reset_min_max",
+           "pf_kmc_device_bytes", "pf_kmc_counts", "pf_kmc_cov", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
+           "pf_align_dev", "pf_align_last_retry_count"]
+
+
+class KmcInfo(C.Structure):
+    _fields_ = [("kmer_length", C.c_uint32), ("mode", C.c_uint32), ("counter_size", C.c_uint32),
+                ("lut_prefix_length", C.c_uint32), ("signature_len", C.c_uint32), ("min_count", C.c_uint32),
+                ("max_count", C.c_uint64), ("total_kmers", C.c_uint64), ("both_strands", C.c_uint32),
+                ("kmc_version", C.c_uint32), ("n_bins", C.c_uint32), ("reserved", C.c_uint32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+COV_DTYPE = np.dtype([("sum", "<u8"), ("min", "<u4"), ("n_kmers", "<u4"), ("first_missing", "<i4"),
+                      ("first_outside", "<i4")])
+
+
+class MsaBatch(C.Structure):
+    _fields_ = [("n_bubbles", C.c_uint32), ("reserved", C.c_uint32), ("status", i32p), ("n_rows", u32p),
+                ("aln_len", u32p), ("rows_off", u64p), ("rows", C.POINTER(C.c_char)), ("var_off", u64p),
+                ("var_col", u32p), ("var_kind", u8p), ("cls_off", u64p), ("cls", u16p), ("ilen_off", u64p),
+                ("ilen", u32p)]
+
+
+class PfError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Loads libpfgpu.so (building it is __graft_entry__.build()'s / ploidyfrost_b200.build's job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PfError(f"{LIB_PATH} not built: run `python -m ploidyfrost_b200.build` (no CPU fallback exists)")
+    L = C.CDLL(LIB_PATH)
+    L.pf_last_error.restype = C.c_char_p
+    L.pf_version.restype = C.c_char_p
+    L.pf_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.pf_shutdown.argtypes = [C.c_void_p]
+    L.pf_shutdown.restype = None
+    L.pf_launch_count.argtypes = [C.c_void_p]
+    L.pf_launch_count.restype = C.c_uint64
+    L.pf_sync.argtypes = [C.c_void_p]
+    L.pf_kmc_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.pf_kmc_close.argtypes = [C.c_void_p]
+    L.pf_kmc_info.argtypes = [C.c_void_p, C.POINTER(KmcInfo)]
+    L.pf_kmc_set_min_count.argtypes = [C.c_void_p, C.c_uint32]
+    L.pf_kmc_set_max_count.argtypes = [C.c_void_p, C.c_uint32]
+    L.pf_kmc_reset_min_max.argtypes = [C.c_void_p]
+    L.pf_kmc_device_bytes.argtypes = [C.c_void_p]
+    L.pf_kmc_device_bytes.restype = C.c_uint64
+    L.pf_kmc_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+    L.pf_kmc_cov.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.pf_kmc_lookup_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,
+                                    C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pf_window_offsets.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.pf_window_offsets.restype = C.c_uint64
+    L.pf_align.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                           C.POINTER(MsaBatch)]
+    L.pf_align_dev.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_uint64, C.c_void_p,
+                               C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(MsaBatch), C.c_void_p]
+    L.pf_align_last_retry_count.argtypes = [C.c_void_p]
+    L.pf_align_last_retry_count.restype = C.c_uint32
+    _lib = L
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise PfError(f"{what} failed ({rc}): {load().pf_last_error().decode()}")
+
+
+def window_offsets(seq_off: np.ndarray, k: int) -> np.ndarray:
+    ln = (seq_off[1:] - seq_off[:-1]).astype(np.int64)
+    out = np.zeros(len(seq_off), dtype=np.uint64)
+    out[1:] = np.cumsum(np.maximum(ln - k + 1, 0)).astype(np.uint64)
+    return out
+
+
+def _np_from(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    nbytes = n * np.dtype(dtype).itemsize
+    return np.ctypeslib.as_array(C.cast(ptr, u8p), shape=(nbytes,)).view(dtype).copy()
+
+
+def msa_to_numpy(mb: MsaBatch) -> dict:
+    n = mb.n_bubbles
+    out = {"n_bubbles": n, "status": _np_from(mb.status, n, np.int32), "n_rows": _np_from(mb.n_rows, n, np.uint32),
+           "aln_len": _np_from(mb.aln_len, n, np.uint32)}
+    for name in ("rows", "var", "cls", "ilen"):
+        out[name + "_off"] = _np_from(getattr(mb, name + "_off"), n + 1, np.uint64) if n else np.zeros(1, np.uint64)
+    tr, tv, tc, ti = (int(out[k + "_off"][-1]) for k in ("rows", "var", "cls", "ilen"))
+    out["rows"] = _np_from(mb.rows, tr, np.uint8)
+    out["var_col"] = _np_from(mb.var_col, tv, np.uint32)
+    out["var_kind"] = _np_from(mb.var_kind, tv, np.uint8)
+    out["cls"] = _np_from(mb.cls, tc, np.uint16)
+    out["ilen"] = _np_from(mb.ilen, ti, np.uint32)
+    return out
+
+
+class Context:
+    """pf_ctx: one GPU.  Raises PfError when no CUDA device is available (there is no CPU path)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        _check(self.lib.pf_init(device, C.byref(h)), "pf_init")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.pf_shutdown(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.pf_launch_count(self.h))
+
+    def sync(self):
+        _check(self.lib.pf_sync(self.h), "pf_sync")
+
+    def align(self, bases, seq_off, bubble_off, M=2.0, D=-1.0, G=-3.0) -> dict:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        bubble_off = np.ascontiguousarray(bubble_off, dtype=np.uint32)
+        mb = MsaBatch()
+        _check(self.lib.pf_align(self.h, M, D, G, bases.ctypes.data, seq_off.ctypes.data, bubble_off.ctypes.data,
+                                 len(bubble_off) - 1, C.byref(mb)), "pf_align")
+        return msa_to_numpy(mb)
+
+    def align_dev(self, d_bases, n_bases, d_seq_off, n_seq, d_bubble_off, n_bubbles, max_len, max_rows, M=2.0, D=-1.0,
+                  G=-3.0, stream=None) -> MsaBatch:
+        mb = MsaBatch()
+        _check(self.lib.pf_align_dev(self.h, M, D, G, d_bases, n_bases, d_seq_off, n_seq, d_bubble_off, n_bubbles,
+                                     max_len, max_rows, C.byref(mb), stream), "pf_align_dev")
+        return mb
+
+    @property
+    def last_retry_count(self) -> int:
+        return int(self.lib.pf_align_last_retry_count(self.h))
+
+
+class KmcDb:
+    """pf_kmc: HBM-resident KMC index (CKMCFile opened for random access)."""
+
+    def __init__(self, ctx: Context, prefix: str):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        h = C.c_void_p()
+        _check(self.lib.pf_kmc_open(ctx.h, prefix.encode(), C.byref(h)), "pf_kmc_open")
+        self.h = h
+        self.refresh_info()
+        self.k = self.info["kmer_length"]
+
+    def close(self):
+        if self.h:
+            self.lib.pf_kmc_close(self.h)
+            self.h = None
+
+    def refresh_info(self):
+        i = KmcInfo()
+        _check(self.lib.pf_kmc_info(self.h, C.byref(i)), "pf_kmc_info")
+        self.info = i.as_dict()
+        return self.info
+
+    def set_min_count(self, x):
+        _check(self.lib.pf_kmc_set_min_count(self.h, x), "pf_kmc_set_min_count")
+
+    def set_max_count(self, x):
+        _check(self.lib.pf_kmc_set_max_count(self.h, x), "pf_kmc_set_max_count")
+
+    def reset_min_max(self):
+        _check(self.lib.pf_kmc_reset_min_max(self.h), "pf_kmc_reset_min_max")
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.pf_kmc_device_bytes(self.h))
+
+    def counts(self, bases, seq_off, mode=LOOKUP_CANONICAL):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        n = int(window_offsets(seq_off, self.k)[-1]) if len(seq_off) > 1 else 0
+        counts = np.zeros(max(n, 1), dtype=np.uint32)
+        found = np.zeros(max(n, 1), dtype=np.uint8)
+        _check(self.lib.pf_kmc_counts(self.h, bases.ctypes.data, seq_off.ctypes.data, len(seq_off) - 1, mode,
+                                      counts.ctypes.data, found.ctypes.data), "pf_kmc_counts")
+        return counts[:n], found[:n]
+
+    def cov(self, bases, seq_off, mode=LOOKUP_FWD_THEN_RC, low=0, up=0xFFFFFFFF):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        n = len(seq_off) - 1
+        out = np.zeros(max(n, 1), dtype=COV_DTYPE)
+        _check(self.lib.pf_kmc_cov(self.h, bases.ctypes.data, seq_off.ctypes.data, n, mode, low, up, out.ctypes.data),
+               "pf_kmc_cov")
+        return out[:n]
+
+    def lookup_dev(self, d_bases, n_bases, d_seq_off, d_win_off, n_seq, n_windows, mode=LOOKUP_CANONICAL, low=0,
+                   up=0xFFFFFFFF, d_counts=None, d_found=None, d_cov=None, stream=None):
+        _check(self.lib.pf_kmc_lookup_dev(self.h, d_bases, n_bases, d_seq_off, d_win_off, n_seq, n_windows, mode, low, up,
+                                          d_counts, d_found, d_cov, stream), "pf_kmc_lookup_dev")

@@ -1,0 +1,56 @@
+// pf_common.cuh -- shared host-side plumbing of libpfgpu.so: error channel, CUDA checks, the context.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../include/pf_gpu.h"
+
+namespace pf {
+
+void set_error(const char *fmt, ...);
+
+#define PF_CUDA_TRY(expr)                                                                     \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            pf::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PF_E_CUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+
+// Grow-only device / pinned-host buffers (work areas are reused across calls).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <class T> T *as() const { return (T *)p; }
+};
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <class T> T *as() const { return (T *)p; }
+};
+
+}  // namespace pf
+
+struct pf_align_state;  // defined in pf_align.cu
+
+struct pf_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    pf_align_state *align = nullptr;
+    // scratch shared by the host-pointer entry points
+    pf::DevBuf d_in[4];
+    pf::DevBuf d_out[4];
+    pf::PinnedBuf h_stage[2];
+};

@@ -1,0 +1,618 @@
+// pf_kmc.cu -- HBM-resident KMC index + batched k-mer lookup kernel for sm_100a.
+//
+// Stands in for CKMCFile's random-access path (KMC/kmc_api/kmc_file.cpp): OpenForRA :27,
+// ReadParamsFrom_prefix_file_buf :185, CheckKmer :330, BinarySearch :1383, GetCountersForRead :904,
+// and for the coverage reducers built on it (src/CDBG.cpp:29-120).  Semantics are the reference's;
+// the data layout and the execution are not:
+//
+//  * .kmc_pre  -> `lut`   : the prefix table verbatim (u32 entries when N+1 < 2^32, else u64), with the
+//                           N+1 end sentinel the reader plants (:233, :292); `sigmap` (KMC2) verbatim;
+//                           `norm` = the m-mer normalisation table of mmer.h:77-87, built on the host.
+//  * .kmc_suf  -> `rec`   : every R = S+C byte record re-packed on the GPU into one aligned u64
+//                           (suffix << 8C | counter) when R <= 8 -- one 8-byte load returns key and
+//                           counter, a 32-byte sector holds four records; otherwise split into
+//                           `suf` (u64 suffix) + `cnt` (u32 counter).  Order is unchanged, so the
+//                           reference's bucket ranges and search outcome are unchanged.
+//
+//  * lookup kernel: one CTA walks 2048-base tiles of the flat `bases` array.  The tile is staged into
+//    shared memory with 128-bit coalesced loads and turned into 2-bit codes; the m-mer normalisation
+//    is evaluated once per base position (not once per m-mer per window as get_signature does,
+//    kmer_api.h:653-672); window starts are compacted so that every thread of the search phase owns a
+//    live lookup; the search phase issues the dependent chain sigmap -> LUT pair -> records, and the
+//    readCov reductions are folded in with warp-aggregated atomics.  HBM-bound integer work: no
+//    tensor cores.
+#include "pf_common.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+
+namespace {
+
+struct KmcView {  // by-value kernel argument
+    uint32_t k, p, S, C, sig_len, is_kmc2, lut64, packed;
+    uint32_t min_count;
+    uint64_t max_count;
+    uint64_t N;
+    uint64_t single_lut;  // 4^p
+    uint64_t lut_n;       // entries including the sentinel
+    const void *lut;
+    const uint32_t *sigmap;
+    const uint32_t *norm;
+    const uint64_t *rec;  // packed layout
+    const uint64_t *suf;  // split layout
+    const uint32_t *cnt;
+};
+
+constexpr int LK_THREADS = 256;
+constexpr int LK_PPT = 8;                       // base positions per thread in the classification phase
+constexpr int LK_TILE = LK_THREADS * LK_PPT;    // 2048 base positions per tile
+constexpr int LK_HALO = 32;                     // >= k-1 for k <= 32
+
+__device__ __forceinline__ uint32_t base_code(uint32_t c) {  // kmer_api.h:264-275; 4 = not a symbol
+    c |= 0x20u;
+    return c == 'a' ? 0u : c == 'c' ? 1u : c == 'g' ? 2u : c == 't' ? 3u : 4u;
+}
+
+__device__ __forceinline__ uint64_t revcomp64(uint64_t v, uint32_t k) {
+    uint64_t x = __brevll(~v);  // reverses bit order; fix the order inside each 2-bit symbol
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+    return x >> (64 - 2 * k);
+}
+
+__device__ __forceinline__ uint64_t lut_at(const KmcView &db, uint64_t i) {
+    return db.lut64 ? __ldg((const unsigned long long *)db.lut + i) : (uint64_t)__ldg((const uint32_t *)db.lut + i);
+}
+
+// CheckKmer (:330-366) + BinarySearch (:1383-1462) for one key; `bin_base` = bin * 4^p (0 for KMC1).
+__device__ __forceinline__ bool kmc_search(const KmcView &db, uint64_t key, uint64_t bin_base, uint32_t &count) {
+    const uint32_t sbits = 2 * (db.k - db.p);
+    const uint64_t prefix = key >> sbits;  // sbits < 64 because p >= 1
+    const uint64_t suffix = key & ((1ull << sbits) - 1);
+    const uint64_t slot = bin_base + prefix;
+    if (slot + 1 >= db.lut_n) return false;
+    long long lo = (long long)lut_at(db, slot);
+    long long hi = (long long)lut_at(db, slot + 1) - 1;
+    if (lo >= (long long)db.N) return false;                 // :1385
+    if (hi > (long long)db.N - 1) hi = (long long)db.N - 1;  // the last bucket's stop is one past the end (:233,:292)
+    const uint32_t cbits = 8 * db.C;
+    while (lo <= hi) {
+        const long long mid = (lo + hi) >> 1;
+        uint64_t rs, c;
+        if (db.packed) {
+            const uint64_t r = __ldg((const unsigned long long *)db.rec + mid);
+            rs = r >> cbits;
+            c = r & ((1ull << cbits) - 1);
+        } else {
+            rs = __ldg((const unsigned long long *)db.suf + mid);
+            c = 0;
+        }
+        if (rs == suffix) {
+            if (!db.packed) c = __ldg(db.cnt + mid);
+            count = (uint32_t)c;
+            return c >= db.min_count && c <= db.max_count;  // :1459
+        }
+        if (rs < suffix) lo = mid + 1; else hi = mid - 1;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(LK_THREADS)
+kmc_lookup_kernel(const KmcView db, const uint8_t *__restrict__ bases, const uint64_t n_bases,
+                  const uint64_t *__restrict__ seq_off, const uint64_t *__restrict__ win_off, const uint32_t n_seq,
+                  const int mode, const uint32_t low, const uint32_t up, uint32_t *__restrict__ counts,
+                  uint8_t *__restrict__ found, pf_cov_t *__restrict__ cov, const uint64_t n_tiles) {
+    __shared__ __align__(16) uint8_t s_code[LK_TILE + LK_HALO];
+    __shared__ uint32_t s_nv[LK_TILE + LK_HALO];
+    __shared__ uint16_t s_q[LK_TILE];
+    __shared__ uint32_t s_wi[LK_TILE];
+    __shared__ uint32_t s_sq[LK_TILE];
+    __shared__ uint32_t s_warp_tot[LK_THREADS / 32];
+    __shared__ uint32_t s_total;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t k = db.k, m = db.sig_len;
+    const bool aligned16 = ((uintptr_t)bases & 15) == 0;
+
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t p0 = tile * LK_TILE;
+        // ---- phase A: stage bases -> 2-bit codes (128-bit coalesced loads for the tile body) ----
+        if (aligned16 && p0 + LK_TILE <= n_bases) {
+            if (tid < LK_TILE / 16) {
+                const uint4 v = __ldg((const uint4 *)(bases + p0) + tid);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    o[j] = base_code(w[j] & 0xff) | (base_code((w[j] >> 8) & 0xff) << 8) |
+                           (base_code((w[j] >> 16) & 0xff) << 16) | (base_code(w[j] >> 24) << 24);
+                *((uint4 *)s_code + tid) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            if (tid < LK_HALO) {
+                const uint64_t g = p0 + LK_TILE + tid;
+                s_code[LK_TILE + tid] = g < n_bases ? (uint8_t)base_code(__ldg(bases + g)) : (uint8_t)4;
+            }
+        } else {
+            for (uint32_t q = tid; q < LK_TILE + LK_HALO; q += LK_THREADS) {
+                const uint64_t g = p0 + q;
+                s_code[q] = g < n_bases ? (uint8_t)base_code(__ldg(bases + g)) : (uint8_t)4;
+            }
+        }
+        __syncthreads();
+        // ---- phase B (KMC2): normalised m-mer value once per base position (mmer.h:117-124) ----
+        if (db.is_kmc2) {
+            for (uint32_t q = tid; q + m <= LK_TILE + LK_HALO; q += LK_THREADS) {
+                uint32_t v = 0, bad = 0;
+                for (uint32_t j = 0; j < m; j++) {
+                    const uint32_t c = s_code[q + j];
+                    bad |= c >> 2;
+                    v = (v << 2) | (c & 3);
+                }
+                s_nv[q] = bad ? 0xFFFFFFFFu : __ldg(db.norm + v);
+            }
+        }
+        // ---- phase C: which positions start a window?  compact them ----
+        uint32_t my_wi[LK_PPT], my_sq[LK_PPT], my_mask = 0;  // statically indexed -> registers
+        const uint32_t q0 = tid * LK_PPT;
+        {
+            uint64_t g = p0 + q0;
+            if (g < n_bases) {
+                // sequence containing base g: last s with seq_off[s] <= g   (seq_off[0] == 0)
+                uint32_t lo = 0, hi = n_seq;  // invariant: seq_off[lo] <= g < seq_off[hi]
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg((const unsigned long long *)seq_off + mid) <= g) lo = mid; else hi = mid;
+                }
+                uint32_t s = lo;
+                uint64_t sb = __ldg((const unsigned long long *)seq_off + s);
+                uint64_t se = __ldg((const unsigned long long *)seq_off + s + 1);
+                uint64_t wo = __ldg((const unsigned long long *)win_off + s);
+                int last_bad = -1;  // largest tile-local index of a non-symbol among the codes scanned so far
+                for (uint32_t j = 0; j + 1 < k; j++)
+                    if (s_code[q0 + j] > 3) last_bad = (int)(q0 + j);
+#pragma unroll
+                for (uint32_t t = 0; t < LK_PPT; t++) {
+                    const uint32_t q = q0 + t;
+                    g = p0 + q;
+                    if (s_code[q + k - 1] > 3) last_bad = (int)(q + k - 1);
+                    if (g < n_bases) {
+                        while (g >= se) {  // next sequence (skips empty ones)
+                            s++;
+                            sb = se;
+                            se = __ldg((const unsigned long long *)seq_off + s + 1);
+                            wo = __ldg((const unsigned long long *)win_off + s);
+                        }
+                        if (g + k <= se) {
+                            const uint32_t wi = (uint32_t)(wo + (g - sb));
+                            if (last_bad >= (int)q) {  // window touches a non-ACGT character: not found
+                                if (counts) counts[wi] = 0;
+                                if (found) found[wi] = 0;
+                                if (cov) atomicMin((unsigned int *)&cov[s].first_missing, (unsigned int)(g - sb));
+                            } else {
+                                my_wi[t] = wi;
+                                my_sq[t] = s;
+                                my_mask |= 1u << t;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        const uint32_t my_n = __popc(my_mask);
+        uint32_t incl = my_n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += o;
+        }
+        if (lane == 31) s_warp_tot[wid] = incl;
+        __syncthreads();  // also publishes s_nv
+        if (tid == 0) {
+            uint32_t acc = 0;
+            for (int w = 0; w < LK_THREADS / 32; w++) {
+                const uint32_t t = s_warp_tot[w];
+                s_warp_tot[w] = acc;
+                acc += t;
+            }
+            s_total = acc;
+        }
+        __syncthreads();
+        {
+            uint32_t o = s_warp_tot[wid] + incl - my_n;
+#pragma unroll
+            for (uint32_t t = 0; t < LK_PPT; t++)
+                if (my_mask & (1u << t)) {
+                    s_q[o] = (uint16_t)(q0 + t);
+                    s_wi[o] = my_wi[t];
+                    s_sq[o] = my_sq[t];
+                    o++;
+                }
+        }
+        __syncthreads();
+        // ---- phase D: dense search phase ----
+        const uint32_t n_valid = s_total;
+        for (uint32_t base = 0; base < n_valid; base += LK_THREADS) {
+            const uint32_t idx = base + tid;
+            const bool live = idx < n_valid;
+            uint32_t cnt = 0, sq = 0xFFFFFFFFu;
+            bool ok = false;
+            if (live) {
+                const uint32_t q = s_q[idx];
+                sq = s_sq[idx];
+                uint64_t fwd = 0;
+                for (uint32_t j = 0; j < k; j++) fwd = (fwd << 2) | s_code[q + j];
+                uint64_t bin_base = 0;
+                if (db.is_kmc2) {  // signature = min over the window's m-mers (kmer_api.h:653-672); strand-symmetric
+                    uint32_t sig = 0xFFFFFFFFu;
+                    for (uint32_t j = 0; j + m <= k; j++) sig = min(sig, s_nv[q + j]);
+                    bin_base = (uint64_t)__ldg(db.sigmap + sig) * db.single_lut;  // kmc_file.cpp:349-351
+                }
+                if (mode == PF_LOOKUP_FWD) {
+                    ok = kmc_search(db, fwd, bin_base, cnt);
+                } else if (mode == PF_LOOKUP_FWD_THEN_RC) {  // CDBG.cpp:38-43
+                    ok = kmc_search(db, fwd, bin_base, cnt);
+                    if (!ok) ok = kmc_search(db, revcomp64(fwd, k), bin_base, cnt);
+                } else {  // canonical key, kmc_file.cpp:1060 / :1290
+                    const uint64_t rc = revcomp64(fwd, k);
+                    ok = kmc_search(db, fwd < rc ? fwd : rc, bin_base, cnt);
+                }
+                if (!ok) cnt = 0;
+                const uint32_t wi = s_wi[idx];
+                if (counts) counts[wi] = cnt;
+                if (found) found[wi] = ok ? 1 : 0;
+            }
+            if (cov) {  // readCov reductions (CDBG.cpp:29-120), aggregated per (warp, sequence) segment
+                const uint32_t grp = __match_any_sync(0xffffffffu, sq);
+                const uint32_t leader = __ffs(grp) - 1;
+                const uint32_t s_lo = __reduce_add_sync(grp, ok ? (cnt & 0xffffu) : 0u);
+                const uint32_t s_hi = __reduce_add_sync(grp, ok ? (cnt >> 16) : 0u);
+                const uint32_t mn = __reduce_min_sync(grp, ok ? cnt : 0xFFFFFFFFu);
+                uint32_t fm = 0xFFFFFFFFu, fo = 0xFFFFFFFFu;
+                if (live) {
+                    // window index inside its sequence = wi - win_off[sq]
+                    const uint32_t wloc = s_wi[idx] - (uint32_t)__ldg((const unsigned long long *)win_off + sq);
+                    if (!ok) fm = wloc;
+                    else if (!(cnt > low && cnt < up)) fo = wloc;
+                }
+                fm = __reduce_min_sync(grp, fm);
+                fo = __reduce_min_sync(grp, fo);
+                if (live && lane == leader) {
+                    const uint64_t sum = (uint64_t)s_lo + ((uint64_t)s_hi << 16);
+                    if (sum) atomicAdd((unsigned long long *)&cov[sq].sum, (unsigned long long)sum);
+                    if (mn != 0xFFFFFFFFu) atomicMin(&cov[sq].min, mn);
+                    if (fm != 0xFFFFFFFFu) atomicMin((unsigned int *)&cov[sq].first_missing, fm);
+                    if (fo != 0xFFFFFFFFu) atomicMin((unsigned int *)&cov[sq].first_outside, fo);
+                }
+            }
+        }
+        __syncthreads();  // smem is reused by the next tile
+    }
+}
+
+__global__ void cov_init_kernel(pf_cov_t *cov, const uint64_t *__restrict__ win_off, uint32_t n_seq) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seq) return;
+    pf_cov_t c;
+    c.sum = 0;
+    c.min = 10000;  // CDBG.cpp:71
+    c.n_kmers = (uint32_t)(win_off[s + 1] - win_off[s]);
+    c.first_missing = -1;
+    c.first_outside = -1;
+    cov[s] = c;
+}
+
+// .kmc_suf records (S suffix bytes MSB-first + C counter bytes little-endian, kmc_file.cpp:1405-1452)
+// -> one u64 per record, or suffix/counter arrays.
+__global__ void repack_records_kernel(const uint8_t *__restrict__ raw, uint64_t n, uint32_t S, uint32_t C, int packed,
+                                      uint64_t *__restrict__ rec, uint64_t *__restrict__ suf, uint32_t *__restrict__ cnt) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *r = raw + i * (S + C);
+    uint64_t s = 0, c = 0;
+    for (uint32_t a = 0; a < S; a++) s = (s << 8) | r[a];
+    for (uint32_t b = 0; b < C; b++) c |= (uint64_t)r[S + b] << (8 * b);
+    if (packed) rec[i] = (s << (8 * C)) | c;
+    else { suf[i] = s; cnt[i] = (uint32_t)c; }
+}
+
+bool slurp(const std::string &path, std::vector<unsigned char> &buf) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    if (fseek(f, 0, SEEK_END) != 0) { fclose(f); return false; }
+    const long long sz = ftell(f);
+    rewind(f);
+    if (sz < 0) { fclose(f); return false; }
+    buf.resize((size_t)sz);
+    const size_t got = sz ? fread(buf.data(), 1, (size_t)sz, f) : 0;
+    fclose(f);
+    return got == (size_t)sz;
+}
+
+inline uint32_t le32(const unsigned char *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline uint64_t le64(const unsigned char *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+// mmer.h:34-57
+bool sig_allowed(uint32_t mm, uint32_t len) {
+    if ((mm & 0x3f) == 0x3f || (mm & 0x3f) == 0x3b || (mm & 0x3c) == 0x3c) return false;
+    for (uint32_t j = 0; j + 3 < len; ++j) {
+        if ((mm & 0xf) == 0) return false;
+        mm >>= 2;
+    }
+    return !(mm == 0 || mm == 0x04 || (mm & 0xf) == 0);
+}
+
+}  // namespace
+
+struct pf_kmc {
+    pf_ctx *ctx = nullptr;
+    pf_kmc_info_t info{};
+    uint32_t orig_min = 0;
+    uint64_t orig_max = 0;
+    KmcView view{};
+    void *d_lut = nullptr, *d_sigmap = nullptr, *d_norm = nullptr, *d_rec = nullptr, *d_suf = nullptr, *d_cnt = nullptr;
+    uint64_t device_bytes = 0;
+};
+
+extern "C" {
+
+int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **out) {
+    if (!ctx || !prefix || !out) { pf::set_error("pf_kmc_open: null argument"); return PF_E_INVALID; }
+    *out = nullptr;
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    std::vector<unsigned char> pre;
+    const std::string base(prefix);
+    if (!slurp(base + ".kmc_pre", pre)) { pf::set_error("cannot read %s.kmc_pre", prefix); return PF_E_IO; }
+    const size_t fs = pre.size();
+    if (fs < 28 || memcmp(&pre[0], "KMCP", 4) || memcmp(&pre[fs - 4], "KMCP", 4)) {
+        pf::set_error("%s.kmc_pre: bad KMCP markers", prefix);
+        return PF_E_IO;
+    }
+    std::unique_ptr<pf_kmc> db(new pf_kmc());
+    db->ctx = ctx;
+    pf_kmc_info_t &I = db->info;
+    I.kmc_version = le32(&pre[fs - 12]);          // kmc_file.cpp:188-192
+    const uint64_t hoff = pre[fs - 8];            // one byte (:200, :257)
+    std::vector<uint64_t> lut;
+    std::vector<uint32_t> sigmap, norm;
+    if (I.kmc_version == 0x200) {                 // :196-245
+        if (fs < hoff + 12 || hoff < 37) { pf::set_error("%s.kmc_pre: truncated KMC2 header", prefix); return PF_E_IO; }
+        const unsigned char *h = &pre[fs - 8 - hoff];
+        I.kmer_length = le32(h); I.mode = le32(h + 4); I.counter_size = le32(h + 8);
+        I.lut_prefix_length = le32(h + 12); I.signature_len = le32(h + 16); I.min_count = le32(h + 20);
+        I.max_count = le32(h + 24); I.total_kmers = le64(h + 28); I.both_strands = h[36] ? 0 : 1;
+        if (I.signature_len < 5 || I.signature_len > 11) {
+            pf::set_error("%s.kmc_pre: signature length %u outside 5..11 (mmer.cpp:27-58)", prefix, I.signature_len);
+            return PF_E_UNSUPPORTED;
+        }
+        const uint64_t sig_n = (1ull << (2 * I.signature_len)) + 1;
+        const uint64_t body = fs - 12;
+        if (body < sig_n * 4 + hoff + 8 + 8) { pf::set_error("%s.kmc_pre: file too small", prefix); return PF_E_IO; }
+        const uint64_t lut_n = (body - (sig_n * 4 + hoff + 8)) / 8;  // index of the guard word (:224-233)
+        lut.resize(lut_n + 1);
+        memcpy(lut.data(), &pre[4], (lut_n + 1) * 8);
+        lut[lut_n] = I.total_kmers + 1;
+        sigmap.resize(sig_n);
+        memcpy(sigmap.data(), &pre[4 + (lut_n + 1) * 8], sig_n * 4);
+        const uint32_t special = 1u << (2 * I.signature_len);
+        norm.resize(special);
+        for (uint32_t x = 0; x < special; x++) {  // mmer.h:61-87
+            uint32_t rc = 0, t = x;
+            for (uint32_t i = 0; i < I.signature_len; i++) { rc = (rc << 2) | (3 - (t & 3)); t >>= 2; }
+            const uint32_t a = sig_allowed(x, I.signature_len) ? x : special;
+            const uint32_t b = sig_allowed(rc, I.signature_len) ? rc : special;
+            norm[x] = a < b ? a : b;
+        }
+    } else if (I.kmc_version == 0) {              // :246-300
+        const uint64_t body = fs - 12;
+        if (body < hoff || hoff < 40) { pf::set_error("%s.kmc_pre: truncated KMC1 header", prefix); return PF_E_IO; }
+        const uint64_t hi = (body - hoff) / 8;
+        const unsigned char *h = &pre[4 + hi * 8];
+        const uint64_t w0 = le64(h), w1 = le64(h + 8), w2 = le64(h + 16), w3 = le64(h + 24), w4 = le64(h + 32);
+        I.kmer_length = (uint32_t)w0; I.mode = (uint32_t)(w0 >> 32);
+        I.counter_size = (uint32_t)w1; I.lut_prefix_length = (uint32_t)(w1 >> 32);
+        I.min_count = (uint32_t)w2; I.max_count = (w2 >> 32) + (w4 & 0xFFFFFFFF00000000ull);
+        I.total_kmers = w3; I.both_strands = ((w4 & 0xF) == 1) ? 0 : 1;
+        I.signature_len = 0;
+        lut.resize(hi + 1);
+        memcpy(lut.data(), &pre[4], hi * 8);
+        lut[hi] = I.total_kmers + 1;              // sentinel over the first header word (:292)
+    } else {
+        pf::set_error("%s.kmc_pre: unsupported kmc_version 0x%x", prefix, I.kmc_version);
+        return PF_E_IO;
+    }
+    if (I.mode != 0) { pf::set_error("%s: quake-mode (float) counters are not supported", prefix); return PF_E_UNSUPPORTED; }
+    const uint32_t k = I.kmer_length, p = I.lut_prefix_length, C = I.counter_size;
+    if (k == 0 || k > 32) { pf::set_error("%s: k=%u outside 1..32 (reference build: MAX_KMER_SIZE=32)", prefix, k); return PF_E_UNSUPPORTED; }
+    if (p < 1 || p >= k || (k - p) % 4 != 0 || p > 15) { pf::set_error("%s: bad lut_prefix_length %u for k=%u", prefix, p, k); return PF_E_IO; }
+    if (C < 1 || C > 4) { pf::set_error("%s: counter_size %u outside 1..4", prefix, C); return PF_E_UNSUPPORTED; }
+    const uint32_t S = (k - p) / 4;
+    const uint64_t single = 1ull << (2 * p);
+    I.n_bins = I.kmc_version == 0x200 ? (uint32_t)((lut.size() - 1) / single) : 1;
+    if (I.kmc_version == 0 && lut.size() < single + 1) { pf::set_error("%s.kmc_pre: prefix table shorter than 4^p", prefix); return PF_E_IO; }
+    if (I.kmc_version == 0x200)
+        for (uint32_t v : sigmap)
+            if ((uint64_t)v >= I.n_bins) { pf::set_error("%s.kmc_pre: signature map points past the last bin", prefix); return PF_E_IO; }
+    pre.clear();
+    pre.shrink_to_fit();
+
+    std::vector<unsigned char> sufbuf;
+    if (!slurp(base + ".kmc_suf", sufbuf)) { pf::set_error("cannot read %s.kmc_suf", prefix); return PF_E_IO; }
+    if (sufbuf.size() < 8 || memcmp(&sufbuf[0], "KMCS", 4) || memcmp(&sufbuf[sufbuf.size() - 4], "KMCS", 4)) {
+        pf::set_error("%s.kmc_suf: bad KMCS markers", prefix);
+        return PF_E_IO;
+    }
+    const uint64_t N = I.total_kmers, R = S + C;
+    if (sufbuf.size() - 8 < N * R) { pf::set_error("%s.kmc_suf: %zu bytes, expected %llu records of %llu bytes", prefix, sufbuf.size(), (unsigned long long)N, (unsigned long long)R); return PF_E_IO; }
+
+    // ---- device image ----
+    KmcView &V = db->view;
+    V.k = k; V.p = p; V.S = S; V.C = C; V.sig_len = I.signature_len; V.is_kmc2 = I.kmc_version == 0x200;
+    V.min_count = I.min_count; V.max_count = I.max_count; V.N = N; V.single_lut = single; V.lut_n = lut.size();
+    V.lut64 = (N + 1 >= (1ull << 32)) ? 1 : 0;
+    V.packed = R <= 8 ? 1 : 0;
+    db->orig_min = I.min_count; db->orig_max = I.max_count;
+    cudaStream_t st = ctx->stream;
+    uint64_t bytes = 0;
+    if (V.lut64) {
+        PF_CUDA_TRY(cudaMalloc(&db->d_lut, lut.size() * 8));
+        PF_CUDA_TRY(cudaMemcpyAsync(db->d_lut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, st));
+        bytes += lut.size() * 8;
+    } else {
+        std::vector<uint32_t> l32(lut.size());
+        for (size_t i = 0; i < lut.size(); i++) l32[i] = (uint32_t)lut[i];
+        PF_CUDA_TRY(cudaMalloc(&db->d_lut, l32.size() * 4));
+        PF_CUDA_TRY(cudaMemcpyAsync(db->d_lut, l32.data(), l32.size() * 4, cudaMemcpyHostToDevice, st));
+        PF_CUDA_TRY(cudaStreamSynchronize(st));
+        bytes += l32.size() * 4;
+    }
+    V.lut = db->d_lut;
+    if (V.is_kmc2) {
+        PF_CUDA_TRY(cudaMalloc(&db->d_sigmap, sigmap.size() * 4));
+        PF_CUDA_TRY(cudaMemcpyAsync(db->d_sigmap, sigmap.data(), sigmap.size() * 4, cudaMemcpyHostToDevice, st));
+        PF_CUDA_TRY(cudaMalloc(&db->d_norm, norm.size() * 4));
+        PF_CUDA_TRY(cudaMemcpyAsync(db->d_norm, norm.data(), norm.size() * 4, cudaMemcpyHostToDevice, st));
+        bytes += (sigmap.size() + norm.size()) * 4;
+        V.sigmap = (const uint32_t *)db->d_sigmap;
+        V.norm = (const uint32_t *)db->d_norm;
+    }
+    if (N) {
+        void *d_raw = nullptr;
+        PF_CUDA_TRY(cudaMalloc(&d_raw, N * R));
+        PF_CUDA_TRY(cudaMemcpyAsync(d_raw, &sufbuf[4], N * R, cudaMemcpyHostToDevice, st));
+        if (V.packed) {
+            PF_CUDA_TRY(cudaMalloc(&db->d_rec, N * 8));
+            bytes += N * 8;
+        } else {
+            PF_CUDA_TRY(cudaMalloc(&db->d_suf, N * 8));
+            PF_CUDA_TRY(cudaMalloc(&db->d_cnt, N * 4));
+            bytes += N * 12;
+        }
+        const uint64_t nb = (N + 255) / 256;
+        repack_records_kernel<<<(unsigned)nb, 256, 0, st>>>((const uint8_t *)d_raw, N, S, C, (int)V.packed,
+                                                            (uint64_t *)db->d_rec, (uint64_t *)db->d_suf, (uint32_t *)db->d_cnt);
+        ctx->launches++;
+        PF_CUDA_TRY(cudaGetLastError());
+        PF_CUDA_TRY(cudaStreamSynchronize(st));
+        PF_CUDA_TRY(cudaFree(d_raw));
+    }
+    PF_CUDA_TRY(cudaStreamSynchronize(st));
+    V.rec = (const uint64_t *)db->d_rec; V.suf = (const uint64_t *)db->d_suf; V.cnt = (const uint32_t *)db->d_cnt;
+    db->device_bytes = bytes;
+    *out = db.release();
+    return PF_OK;
+}
+
+int pf_kmc_close(pf_kmc *db) {
+    if (!db) return PF_OK;
+    cudaSetDevice(db->ctx->device);
+    cudaFree(db->d_lut); cudaFree(db->d_sigmap); cudaFree(db->d_norm);
+    cudaFree(db->d_rec); cudaFree(db->d_suf); cudaFree(db->d_cnt);
+    delete db;
+    return PF_OK;
+}
+
+int pf_kmc_info(const pf_kmc *db, pf_kmc_info_t *info) {
+    if (!db || !info) { pf::set_error("pf_kmc_info: null argument"); return PF_E_INVALID; }
+    *info = db->info;
+    return PF_OK;
+}
+
+int pf_kmc_set_min_count(pf_kmc *db, uint32_t x) {
+    if (!db) return PF_E_INVALID;
+    db->info.min_count = x; db->view.min_count = x;
+    return PF_OK;
+}
+int pf_kmc_set_max_count(pf_kmc *db, uint32_t x) {
+    if (!db) return PF_E_INVALID;
+    db->info.max_count = x; db->view.max_count = x;
+    return PF_OK;
+}
+int pf_kmc_reset_min_max(pf_kmc *db) {
+    if (!db) return PF_E_INVALID;
+    db->info.min_count = db->view.min_count = db->orig_min;
+    db->info.max_count = db->view.max_count = db->orig_max;
+    return PF_OK;
+}
+uint64_t pf_kmc_device_bytes(const pf_kmc *db) { return db ? db->device_bytes : 0; }
+
+uint64_t pf_window_offsets(const uint64_t *seq_off, uint32_t n_seq, uint32_t k, uint64_t *win_off) {
+    uint64_t acc = 0;
+    for (uint32_t s = 0; s < n_seq; s++) {
+        win_off[s] = acc;
+        const uint64_t len = seq_off[s + 1] - seq_off[s];
+        if (len >= k) acc += len - k + 1;
+    }
+    win_off[n_seq] = acc;
+    return acc;
+}
+
+int pf_kmc_lookup_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const void *d_seq_off, const void *d_win_off,
+                      uint32_t n_seq, uint64_t n_windows, int mode, uint32_t low, uint32_t up, void *d_counts,
+                      void *d_found, void *d_cov, void *cuda_stream) {
+    if (!db) { pf::set_error("pf_kmc_lookup_dev: null database"); return PF_E_INVALID; }
+    if (mode < PF_LOOKUP_CANONICAL || mode > PF_LOOKUP_FWD) { pf::set_error("pf_kmc_lookup_dev: bad mode %d", mode); return PF_E_INVALID; }
+    if (n_windows >= (1ull << 32)) { pf::set_error("pf_kmc_lookup_dev: more than 2^32-1 windows in one call; split the batch"); return PF_E_INVALID; }
+    pf_ctx *ctx = db->ctx;
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    if (n_seq == 0) return PF_OK;
+    if (d_cov) {
+        cov_init_kernel<<<(n_seq + 255) / 256, 256, 0, st>>>((pf_cov_t *)d_cov, (const uint64_t *)d_win_off, n_seq);
+        ctx->launches++;
+    }
+    if (n_bases == 0 || n_windows == 0) { PF_CUDA_TRY(cudaGetLastError()); return PF_OK; }
+    const uint64_t n_tiles = (n_bases + LK_TILE - 1) / LK_TILE;
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 6);
+    kmc_lookup_kernel<<<grid, LK_THREADS, 0, st>>>(db->view, (const uint8_t *)d_bases, n_bases, (const uint64_t *)d_seq_off,
+                                                  (const uint64_t *)d_win_off, n_seq, mode, low, up, (uint32_t *)d_counts,
+                                                  (uint8_t *)d_found, (pf_cov_t *)d_cov, n_tiles);
+    ctx->launches++;
+    PF_CUDA_TRY(cudaGetLastError());
+    return PF_OK;
+}
+
+static int kmc_host_call(pf_kmc *db, const char *bases, const uint64_t *seq_off, uint32_t n_seq, int mode, uint32_t low,
+                         uint32_t up, uint32_t *counts, uint8_t *found, pf_cov_t *cov) {
+    if (!db || !seq_off || (!bases && n_seq && seq_off[n_seq] > 0)) { pf::set_error("pf_kmc: null argument"); return PF_E_INVALID; }
+    pf_ctx *ctx = db->ctx;
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n_seq == 0) return PF_OK;
+    const uint64_t n_bases = seq_off[n_seq] - seq_off[0];
+    std::vector<uint64_t> off(n_seq + 1), woff(n_seq + 1);
+    for (uint32_t s = 0; s <= n_seq; s++) off[s] = seq_off[s] - seq_off[0];
+    const uint64_t W = pf_window_offsets(off.data(), n_seq, db->info.kmer_length, woff.data());
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = ctx->d_in[0].reserve(n_bases + 16))) return rc;
+    if ((rc = ctx->d_in[1].reserve((n_seq + 1) * 8))) return rc;
+    if ((rc = ctx->d_in[2].reserve((n_seq + 1) * 8))) return rc;
+    if (counts && (rc = ctx->d_out[0].reserve(W * 4 + 4))) return rc;
+    if (found && (rc = ctx->d_out[1].reserve(W + 4))) return rc;
+    if (cov && (rc = ctx->d_out[2].reserve((uint64_t)n_seq * sizeof(pf_cov_t)))) return rc;
+    if (n_bases) PF_CUDA_TRY(cudaMemcpyAsync(ctx->d_in[0].p, bases + seq_off[0], n_bases, cudaMemcpyHostToDevice, st));
+    PF_CUDA_TRY(cudaMemcpyAsync(ctx->d_in[1].p, off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+    PF_CUDA_TRY(cudaMemcpyAsync(ctx->d_in[2].p, woff.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+    rc = pf_kmc_lookup_dev(db, ctx->d_in[0].p, n_bases, ctx->d_in[1].p, ctx->d_in[2].p, n_seq, W, mode, low, up,
+                           counts ? ctx->d_out[0].p : nullptr, found ? ctx->d_out[1].p : nullptr,
+                           cov ? ctx->d_out[2].p : nullptr, st);
+    if (rc) return rc;
+    if (counts && W) PF_CUDA_TRY(cudaMemcpyAsync(counts, ctx->d_out[0].p, W * 4, cudaMemcpyDeviceToHost, st));
+    if (found && W) PF_CUDA_TRY(cudaMemcpyAsync(found, ctx->d_out[1].p, W, cudaMemcpyDeviceToHost, st));
+    if (cov) PF_CUDA_TRY(cudaMemcpyAsync(cov, ctx->d_out[2].p, (uint64_t)n_seq * sizeof(pf_cov_t), cudaMemcpyDeviceToHost, st));
+    PF_CUDA_TRY(cudaStreamSynchronize(st));
+    return PF_OK;
+}
+
+int pf_kmc_counts(pf_kmc *db, const char *bases, const uint64_t *seq_off, uint32_t n_seq, int mode, uint32_t *counts,
+                  uint8_t *found) {
+    if (!counts && !found) { pf::set_error("pf_kmc_counts: no output requested"); return PF_E_INVALID; }
+    return kmc_host_call(db, bases, seq_off, n_seq, mode, 0, 0xFFFFFFFFu, counts, found, nullptr);
+}
+
+int pf_kmc_cov(pf_kmc *db, const char *bases, const uint64_t *seq_off, uint32_t n_seq, int mode, uint32_t low, uint32_t up,
+               pf_cov_t *out) {
+    if (!out) { pf::set_error("pf_kmc_cov: null output"); return PF_E_INVALID; }
+    return kmc_host_call(db, bases, seq_off, n_seq, mode, low, up, nullptr, nullptr, out);
+}
+
+}  // extern "C"

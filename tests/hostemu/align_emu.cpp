@@ -1,0 +1,117 @@
+// align_emu.cpp -- TEST INFRASTRUCTURE.  Runs the product's per-bubble alignment state machines
+// (ploidyfrost_b200/csrc/pf_align_core.cuh: traceback, progressive-MSA filter, site caller) on the CPU with a
+// trivial single-thread execution policy and a plain row-by-row fill, so the device logic can be
+// diffed against the oracle without a GPU.  Not part of libpfgpu.so and never used as a fallback.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <thread>
+#include <atomic>
+
+#include "../../ploidyfrost_b200/csrc/pf_align_core.cuh"
+#include "../../oracle/msa_pack.hpp"
+
+using namespace pfalign;
+
+namespace {
+
+struct HostExec {
+    std::vector<int> rowbuf;
+    bool leader() const { return true; }
+    uint32_t bcast(uint32_t v) const { return v; }
+    int bcast_i(int v) const { return v; }
+    uint32_t bcast_ld(const uint32_t *p) const { return *p; }
+    void sync() const {}
+    void fill(uint8_t *flags, const uint8_t *A, uint32_t m, const uint8_t *B, uint32_t n, const Scoring &sc, int32_t *) {
+        const uint32_t W = m + 1;
+        rowbuf.assign(2 * (size_t)(n + 1), 0);
+        int *prev = rowbuf.data(), *cur = rowbuf.data() + n + 1;
+        flags[0] = 0;
+        for (uint32_t j = 1; j <= n; j++) { prev[j] = pack_sf(border_score(sc, j), F_LEFT); flags[j * W] = F_LEFT * 0x11; }
+        prev[0] = pack_sf(0, 0);
+        for (uint32_t i = 1; i <= m; i++) {
+            cur[0] = pack_sf(border_score(sc, i), F_UP);
+            flags[i * W + i] = F_UP * 0x11;
+            const bool block_left = (i != m) && A[i] == '-';
+            for (uint32_t j = 1; j <= n; j++) {
+                cur[j] = nw_cell(sc, prev[j], prev[j - 1], cur[j - 1], A[i - 1], B[j - 1], block_left);
+                flags[(i + j) * W + i] = (uint8_t)(unpack_f(cur[j]) * 0x11);
+            }
+            std::swap(prev, cur);
+        }
+    }
+};
+
+Limits g_lim = {16, 0, 0, 16, 16, 0, 50000000ull};
+
+}  // namespace
+
+extern "C" {
+
+void pfemu_set_limits(uint32_t max_rows, uint32_t k_cand, uint32_t k_aln, uint32_t max_alen, uint32_t max_var) {
+    g_lim.max_rows = max_rows; g_lim.k_cand = k_cand; g_lim.k_aln = k_aln; g_lim.max_alen = max_alen; g_lim.max_var = max_var;
+}
+
+// stats[0] = max co-optimal alignments seen is not tracked here; kept simple.
+void *pfemu_align(double M, double D, double G, const char *bases, const uint64_t *seq_off, const uint32_t *bubble_off,
+                  uint32_t n_bubbles, int n_threads, pf_msa_batch_t *out) {
+    std::vector<pforacle::MsaResult> res(n_bubbles);
+    std::vector<int32_t> status(n_bubbles, 0);
+    const Scoring sc = make_scoring(M, D, G);
+    std::atomic<uint32_t> next(0);
+    auto worker = [&]() {
+        HostExec x;
+        std::vector<uint8_t> wbuf, slot;
+        for (;;) {
+            const uint32_t b = next.fetch_add(1);
+            if (b >= n_bubbles) return;
+            const uint32_t s0 = bubble_off[b], ns = bubble_off[b + 1] - s0;
+            Limits lim = g_lim;
+            uint64_t sum = 0, mx = 0;
+            for (uint32_t s = 0; s < ns; s++) {
+                const uint64_t l = seq_off[s0 + s + 1] - seq_off[s0 + s];
+                sum += l;
+                if (l > mx) mx = l;
+            }
+            if (lim.max_alen == 0) lim.max_alen = (uint32_t)sum;
+            lim.max_blen = (uint32_t)mx;
+            if (lim.max_var == 0) lim.max_var = lim.max_alen;
+            wbuf.assign(work_area_bytes(lim) + 64, 0);
+            const WorkArea ws = carve_work_area(wbuf.data(), lim);
+            const SlotLayout lay = slot_layout(ns, sum, lim);
+            slot.assign(lay.bytes + 64, 0);
+            msa_run(x, (const uint8_t *)bases, seq_off, s0, ns, ws, lim, sc, slot.data());
+            const SlotHdr *h = (const SlotHdr *)slot.data();
+            status[b] = h->status;
+            pforacle::MsaResult &r = res[b];
+            if (h->status == 0 && h->n_rows) {
+                for (uint32_t q = 0; q < h->n_rows; q++)
+                    r.rows.emplace_back((const char *)slot.data() + lay.off_rows + (size_t)q * h->alen, h->alen);
+                const uint32_t *vc = (const uint32_t *)(slot.data() + lay.off_varcol);
+                const uint8_t *vk = slot.data() + lay.off_kind;
+                const uint16_t *cl = (const uint16_t *)(slot.data() + lay.off_cls);
+                const uint32_t *il = (const uint32_t *)(slot.data() + lay.off_ilen);
+                r.partition.assign(h->alen, std::vector<unsigned short>(h->n_rows, 0));
+                for (uint32_t v = 0; v < h->n_var; v++) {
+                    if (vk[v] == 0) r.snp_pos.push_back(vc[v]);
+                    else if (vk[v] == 1) r.indel_pos.push_back(vc[v]);
+                    for (uint32_t q = 0; q < h->n_rows; q++) r.partition[vc[v]][q] = cl[(size_t)v * h->n_rows + q];
+                }
+                r.indel_len.assign(il, il + h->n_ilen);
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < (n_threads < 1 ? 1 : n_threads); t++) th.emplace_back(worker);
+    for (auto &t : th) t.join();
+    pforacle::MsaPacked *p = new pforacle::MsaPacked();
+    p->pack(res);
+    p->status = status;
+    p->view(out);
+    return p;
+}
+
+void pfemu_msa_free(void *h) { delete (pforacle::MsaPacked *)h; }
+
+}  // extern "C"

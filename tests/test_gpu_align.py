@@ -1,0 +1,105 @@
+"""-m gpu: the CUDA SeqAlign path (through the C ABI) against the oracle, bit-exact on every output field."""
+import numpy as np
+import pytest
+
+from oracle.bindings import flatten_bubbles, msa_bubble
+from tests import gen
+from tests.util import assert_msa_equal
+
+pytestmark = pytest.mark.gpu
+
+LITERALS = [  # SURVEY.md section 4, outputs of the unmodified SeqAlign
+    (["ACGTACGTAC", "ACGTTCGTAC"], ["ACGTACGTAC", "ACGTTCGTAC"], [4], [], [], {4: [1, 2]}),
+    (["ACGTACGGGTAC", "ACGTACGTAC"], ["ACGTACGGGTAC", "ACGTACG--TAC"], [], [7], [2], {7: [1, 2]}),
+    (["ACGTACGTAC", "ACGTACGGGTAC"], ["ACGTACG--TAC", "ACGTACGGGTAC"], [], [7], [2], {7: [1, 2]}),
+    (["AAAAAAAAAA", "AAAAAAAA"], ["AAAAAAAAAA", "AAAAAAAA--"], [], [8], [], {8: [1, 2]}),
+    (["ACGTAAAATTGCA", "ACGTAAATTGCA", "ACGTCAAATTGCA"], ["ACGTAAAATTGCA", "ACGTAAA-TTGCA", "ACGTCAAATTGCA"], [4], [7],
+     [1], {4: [1, 1, 2], 7: [1, 2, 1]}),
+    (["GATTACAGATTACA", "GATTACATTACA", "GATTACAGATTCCA", "GATTACATTCCA"],
+     ["GATTACAGATTACA", "GATTACA--TTACA", "GATTACAGATTCCA", "GATTACA--TTCCA"], [11], [7], [2],
+     {7: [1, 2, 1, 2], 11: [1, 1, 2, 2]}),
+]
+
+
+def test_literal_known_answers(gpu_ctx):
+    bubbles = [x[0] for x in LITERALS]
+    m = gpu_ctx.align(*flatten_bubbles(bubbles))
+    for i, (_, rows, snp, ind, ilen, part) in enumerate(LITERALS):
+        r = msa_bubble(m, i)
+        assert r["status"] == 0
+        assert r["rows"] == rows and r["snp_pos"] == snp and r["indel_pos"] == ind and r["indel_len"] == ilen
+        assert r["partition"] == part
+
+
+CASES = [
+    (1, {}, {}),
+    (2, dict(alphabet="AC"), {}),
+    (3, dict(alphabet="AC", len_range=(10, 40), max_indel=3), {}),
+    (4, dict(max_indel=4, max_snp=5), {}),
+    (5, {}, dict(M=2.5, D=-1.5, G=-3.5)),
+    (6, {}, dict(M=1.7, D=-0.3, G=-2.2)),
+    (7, dict(alphabet="AC"), dict(M=3, D=-2, G=-1.5)),
+    (8, dict(len_range=(100, 300), max_indel_len=40), {}),
+    (9, dict(alphabet="A", len_range=(5, 30)), {}),
+    (10, dict(alphabet="ACG", max_indel=5, max_indel_len=3), {}),
+    (11, dict(len_range=(49, 49), max_indel=0, max_snp=1, n_rows=2), {}),
+]
+
+
+@pytest.mark.parametrize("seed,kw,sc", CASES)
+def test_align_matches_oracle(gpu_ctx, oracle, seed, kw, sc):
+    bubbles = gen.random_bubbles(seed, 3000, **kw)
+    flat = flatten_bubbles(bubbles)
+    a = oracle.align(*flat, n_threads=8, **sc)
+    b = gpu_ctx.align(*flat, **sc)
+    assert_msa_equal(a, b, bubbles, f"seed {seed}")
+    assert (b["status"] == 0).all()
+
+
+def test_align_matches_reference_when_available(gpu_ctx, ref):
+    bubbles = gen.random_bubbles(99, 4000)
+    flat = flatten_bubbles(bubbles)
+    a = ref.align(*flat, n_threads=8)
+    b = gpu_ctx.align(*flat)
+    assert_msa_equal(a, b, bubbles, "vs reference")
+
+
+def test_empty_batch_and_bad_bubbles(gpu_ctx):
+    m = gpu_ctx.align(*flatten_bubbles([]))
+    assert m["n_bubbles"] == 0
+    m = gpu_ctx.align(*flatten_bubbles([["ACGT"], ["ACGT", "ACGA"]]))
+    assert m["status"][0] == 5 and m["n_rows"][0] == 0      # PF_BUBBLE_BAD_INPUT
+    assert m["status"][1] == 0 and m["n_rows"][1] == 2
+
+
+def test_long_pair_matches_oracle(gpu_ctx, oracle):
+    rng = np.random.default_rng(3)
+    bubbles = []
+    for L in (600, 1200, 2500):
+        a = gen.rand_seq(rng, L)
+        i = int(rng.integers(100, L - 200))
+        b = a[:i] + a[i + 90:]
+        b = gen.mutate(rng, b, 3, 0)
+        bubbles.append(gen.sort_branching([a, b]))
+    flat = flatten_bubbles(bubbles)
+    a = oracle.align(*flat, n_threads=4)
+    b = gpu_ctx.align(*flat)
+    assert_msa_equal(a, b, bubbles, "long pairs")
+
+
+def test_idempotence_and_permutation_properties(gpu_ctx):
+    """Size-independent properties: removing gaps from the aligned rows gives back the inputs, in order; all
+    rows of a bubble have the same length; the batch result does not depend on batch composition."""
+    bubbles = gen.random_bubbles(123, 20000, len_range=(40, 70))
+    flat = flatten_bubbles(bubbles)
+    m = gpu_ctx.align(*flat)
+    assert (m["status"] == 0).all()
+    for i in range(0, len(bubbles), 37):
+        r = msa_bubble(m, i)
+        if r["rows"]:
+            assert [x.replace("-", "") for x in r["rows"]] == bubbles[i]
+            assert len({len(x) for x in r["rows"]}) == 1
+    sub = bubbles[5000:5100]
+    m2 = gpu_ctx.align(*flatten_bubbles(sub))
+    for i in range(100):
+        assert msa_bubble(m2, i) == msa_bubble(m, 5000 + i)

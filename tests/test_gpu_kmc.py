@@ -1,0 +1,121 @@
+"""-m gpu: the CUDA KMC index + lookup kernel (through the C ABI) against the oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from oracle.bindings import flatten_seqs
+from tests import gen
+
+pytestmark = pytest.mark.gpu
+
+KMC_CASES = [(0, 5, 2, 25), (0x200, 5, 2, 25), (0x200, 9, 2, 25), (0, 9, 1, 25), (0x200, 9, 3, 25), (0, 1, 4, 25),
+             (0x200, 3, 2, 31), (0, 4, 2, 32), (0x200, 5, 2, 21), (0x200, 2, 2, 18), (0, 5, 4, 29)]
+
+
+@pytest.mark.parametrize("ver,p,C,k", KMC_CASES)
+def test_lookup_matches_oracle(gpu_ctx, oracle, tmp_path, ver, p, C, k):
+    from ploidyfrost_b200 import capi
+    rng = np.random.default_rng(200 + p + k)
+    sig = 9 if k >= 25 else 7
+    prefix, g, u, c = gen.make_genome_db(tmp_path, seed=ver + p + 1, k=k, version=ver, p=p, counter_size=C, sig_len=sig,
+                                         extra_copies=3)
+    ho = oracle.kmc_open(prefix)
+    db = capi.KmcDb(gpu_ctx, prefix)
+    try:
+        io = oracle.kmc_info(ho)
+        for f in ("kmer_length", "mode", "counter_size", "lut_prefix_length", "min_count", "max_count", "total_kmers",
+                  "both_strands", "kmc_version", "n_bins"):
+            assert db.info[f] == io[f], f
+        seqs = gen.query_sequences(rng, g, 3000, k=k) + ["", "A", g[:k], g[5:5 + k - 1], "N" * 40, g[:3000]]
+        bases, off = flatten_seqs(seqs)
+        for mode in (0, 1, 2):
+            co, fo = oracle.kmc_counts(ho, bases, off, k, mode=mode, n_threads=4)
+            cg, fg = db.counts(bases, off, mode=mode)
+            assert np.array_equal(co, cg), mode
+            assert np.array_equal(fo, fg), mode
+            assert fo.sum() > 0
+            a = oracle.kmc_cov(ho, bases, off, mode=mode, low=1, up=3, n_threads=4)
+            b = db.cov(bases, off, mode=mode, low=1, up=3)
+            assert np.array_equal(a, b), mode
+        oracle.kmc_set_min_count(ho, 2); oracle.kmc_set_max_count(ho, 3)
+        db.set_min_count(2); db.set_max_count(3)
+        co, fo = oracle.kmc_counts(ho, bases, off, k, mode=0)
+        cg, fg = db.counts(bases, off, mode=0)
+        assert np.array_equal(co, cg) and np.array_equal(fo, fg)
+        db.reset_min_max()
+        assert db.refresh_info()["min_count"] == io["min_count"]
+    finally:
+        oracle.kmc_close(ho)
+        db.close()
+
+
+def test_lookup_against_reference_when_available(gpu_ctx, ref, tmp_path):
+    from ploidyfrost_b200 import capi
+    rng = np.random.default_rng(5)
+    prefix, g, u, c = gen.make_genome_db(tmp_path, seed=77, k=25, version=0x200, p=9, genome_len=50000)
+    hr = ref.kmc_open(prefix)
+    db = capi.KmcDb(gpu_ctx, prefix)
+    try:
+        bases, off = flatten_seqs(gen.query_sequences(rng, g, 4000, k=25))
+        cr, fr = ref.kmc_counts(hr, bases, off, 25, mode=0, use_read_api=True, n_threads=4)   # GetCountersForRead
+        cg, fg = db.counts(bases, off, mode=0)
+        assert np.array_equal(cr, cg)
+        cr, fr = ref.kmc_counts(hr, bases, off, 25, mode=1, use_read_api=False, n_threads=4)  # readCov pattern
+        cg, fg = db.counts(bases, off, mode=1)
+        assert np.array_equal(cr, cg) and np.array_equal(fr, fg)
+    finally:
+        ref.kmc_close(hr)
+        db.close()
+
+
+def test_empty_and_degenerate_batches(gpu_ctx, tmp_path):
+    from ploidyfrost_b200 import capi
+    prefix, g, u, c = gen.make_genome_db(tmp_path, seed=3, k=25, version=0, p=5, genome_len=3000)
+    db = capi.KmcDb(gpu_ctx, prefix)
+    try:
+        bases, off = flatten_seqs([])
+        cg, fg = db.counts(bases, off)
+        assert len(cg) == 0
+        bases, off = flatten_seqs(["", "ACG", ""])
+        cg, fg = db.counts(bases, off)
+        assert len(cg) == 0
+        cov = db.cov(bases, off)
+        assert (cov["n_kmers"] == 0).all() and (cov["min"] == 10000).all() and (cov["first_missing"] == -1).all()
+    finally:
+        db.close()
+
+
+def test_open_errors_are_reported(gpu_ctx, tmp_path):
+    from ploidyfrost_b200 import capi
+    with pytest.raises(capi.PfError):
+        capi.KmcDb(gpu_ctx, str(tmp_path / "does_not_exist"))
+    bad = tmp_path / "bad"
+    (tmp_path / "bad.kmc_pre").write_bytes(b"XXXX" + b"\0" * 64 + b"XXXX")
+    (tmp_path / "bad.kmc_suf").write_bytes(b"KMCSKMCS")
+    with pytest.raises(capi.PfError):
+        capi.KmcDb(gpu_ctx, str(bad))
+
+
+def test_large_random_property(gpu_ctx, tmp_path):
+    """Size-independent properties on a bigger DB: every DB k-mer is found with its count (both strands),
+    and sum of counts over the genome's windows equals the sum computed from the writer's table."""
+    from ploidyfrost_b200 import capi
+    from ploidyfrost_b200.synth import kmcdb
+    k = 25
+    prefix, g, u, c = gen.make_genome_db(tmp_path, seed=11, k=k, version=0x200, p=9, genome_len=400000, n_bins=128)
+    db = capi.KmcDb(gpu_ctx, prefix)
+    try:
+        bases, off = flatten_seqs([g])
+        cg, fg = db.counts(bases, off, mode=0)
+        assert fg.all()
+        kv = kmcdb.canonical(kmcdb.kmers_of(kmcdb.encode_bases(g), k), k)
+        idx = np.searchsorted(u, kv)
+        assert np.array_equal(u[idx], kv)
+        assert np.array_equal(cg.astype(np.uint64), c[idx])
+        comp = str.maketrans("ACGT", "TGCA")
+        bases2, off2 = flatten_seqs([g.translate(comp)[::-1]])
+        cg2, _ = db.counts(bases2, off2, mode=0)
+        assert np.array_equal(cg2[::-1], cg)
+        cov = db.cov(bases, off, mode=1, low=0, up=100000)
+        assert int(cov["sum"][0]) == int(cg.sum()) and int(cov["min"][0]) == int(cg.min())
+    finally:
+        db.close()

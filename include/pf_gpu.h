@@ -120,6 +120,14 @@ int pf_align_dev(pf_ctx *ctx, double M, double D, double G, const void *d_bases,
                  uint32_t max_len, uint32_t max_rows, pf_msa_batch_t *out_dev, void *cuda_stream);
 /* diagnostics: bubbles of the last pf_align / pf_align_dev call that needed the large (tier-2) work area */
 uint32_t pf_align_last_retry_count(const pf_ctx *ctx);
+/* diagnostics: DP cells (m*n summed over every needlemanWunch fill) executed by the last pf_align* call */
+uint64_t pf_align_last_cells(const pf_ctx *ctx);
+
+/* ---- roofline denominators measured on this device (bench.py reports them next to the kernels) ------- */
+/* random 32-byte-sector gather rate over a `bytes`-sized table (GB/s of sectors touched) */
+int pf_bench_random_gather(pf_ctx *ctx, uint64_t bytes, double *gb_per_s);
+/* sustained INT32 ALU rate of an IADD3/VIMNMX/LOP3 mix (Gop/s, counting one op per lane-instruction) */
+int pf_bench_int32(pf_ctx *ctx, double *gop_per_s);
 
 #ifdef __cplusplus
 }

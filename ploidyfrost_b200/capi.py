@@ -24,7 +24,7 @@ LOOKUP_CANONICAL, LOOKUP_FWD_THEN_RC, LOOKUP_FWD = 0, 1, 2
 EXPORTS = ["pf_init", "pf_shutdown", "pf_last_error", "pf_version", "pf_launch_count", "pf_sync", "pf_kmc_open",
            "pf_kmc_close", "pf_kmc_info", "pf_kmc_set_min_count", "pf_kmc_set_max_count", "pf_kmc_reset_min_max",
            "pf_kmc_device_bytes", "pf_kmc_counts", "pf_kmc_cov", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
-           "pf_align_dev", "pf_align_last_retry_count"]
+           "pf_align_dev", "pf_align_last_retry_count", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32"]
 
 
 class KmcInfo(C.Structure):
@@ -91,6 +91,10 @@ def load():
                                C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(MsaBatch), C.c_void_p]
     L.pf_align_last_retry_count.argtypes = [C.c_void_p]
     L.pf_align_last_retry_count.restype = C.c_uint32
+    L.pf_align_last_cells.argtypes = [C.c_void_p]
+    L.pf_align_last_cells.restype = C.c_uint64
+    L.pf_bench_random_gather.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]
+    L.pf_bench_int32.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -176,6 +180,20 @@ class Context:
     @property
     def last_retry_count(self) -> int:
         return int(self.lib.pf_align_last_retry_count(self.h))
+
+    @property
+    def last_cells(self) -> int:
+        return int(self.lib.pf_align_last_cells(self.h))
+
+    def bench_random_gather(self, nbytes: int) -> float:
+        v = C.c_double()
+        _check(self.lib.pf_bench_random_gather(self.h, nbytes, C.byref(v)), "pf_bench_random_gather")
+        return v.value
+
+    def bench_int32(self) -> float:
+        v = C.c_double()
+        _check(self.lib.pf_bench_int32(self.h, C.byref(v)), "pf_bench_int32")
+        return v.value
 
 
 class KmcDb:

@@ -76,14 +76,16 @@ __device__ __forceinline__ void warp_fill(uint8_t *__restrict__ flags, const uin
 
 struct WarpExec {
     uint32_t lane;
+    unsigned long long cells;
     __device__ __forceinline__ bool leader() const { return lane == 0; }
     __device__ __forceinline__ uint32_t bcast(uint32_t v) const { return __shfl_sync(FULL, v, 0); }
     __device__ __forceinline__ int bcast_i(int v) const { return __shfl_sync(FULL, v, 0); }
     __device__ __forceinline__ uint32_t bcast_ld(const uint32_t *p) const { return *(const volatile uint32_t *)p; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     __device__ __forceinline__ void fill(uint8_t *flags, const uint8_t *A, uint32_t m, const uint8_t *B, uint32_t n,
-                                         const Scoring &sc, int32_t *brow) const {
+                                         const Scoring &sc, int32_t *brow) {
         warp_fill(flags, A, m, B, n, sc, brow, lane);
+        cells += (unsigned long long)m * n;
     }
 };
 
@@ -99,6 +101,7 @@ struct MsaArgs {
     uint8_t *ws_base;
     uint64_t ws_stride;
     uint32_t *counter;
+    unsigned long long *stat_cells;  // DP cells filled (m*n per needlemanWunch call), for the roofline figure
     Limits lim;
     Scoring sc;
 };
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(MSA_BLOCK) msa_kernel(const MsaArgs a) {
     const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim);
     WarpExec x;
     x.lane = lane;
+    x.cells = 0;
     for (;;) {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(a.counter, 1u);
@@ -120,6 +124,7 @@ __global__ void __launch_bounds__(MSA_BLOCK) msa_kernel(const MsaArgs a) {
         msa_run(x, a.bases, a.seq_off, s0, ns, ws, a.lim, a.sc, slot);
         if (lane == 0) a.slot_ptr[b] = (uint64_t)(uintptr_t)slot;
     }
+    if (lane == 0 && x.cells) atomicAdd(a.stat_cells, x.cells);
 }
 
 __global__ void slot_size_kernel(const uint64_t *__restrict__ seq_off, const uint32_t *__restrict__ bubble_off,
@@ -217,6 +222,7 @@ struct pf_align_state {
     pf::DevBuf in_bases, in_seq_off, in_bubble_off;
     pf::PinnedBuf h_scalars, h_out[12];
     uint32_t last_retry_count = 0;
+    uint64_t last_cells = 0;
 };
 
 void pf_align_state_free(pf_align_state *s) {
@@ -255,7 +261,7 @@ int run_tier(pf_ctx *ctx, pf_align_state *st, int tier, const Limits &lim, const
     int rc;
     if ((rc = st->slot_sizes.reserve((uint64_t)(n_items + 1) * 8))) return rc;
     if ((rc = st->slot_off.reserve((uint64_t)(n_items + 1) * 8))) return rc;
-    if ((rc = st->counter.reserve(64))) return rc;
+    if ((rc = st->counter.reserve(256))) return rc;
     if ((rc = st->h_scalars.reserve(256))) return rc;
     slot_size_kernel<<<(n_items + 1 + 255) / 256, 256, 0, s>>>(d_seq_off, d_bubble_off, d_order, n_items, lim,
                                                                st->slot_sizes.as<uint64_t>());
@@ -280,6 +286,7 @@ int run_tier(pf_ctx *ctx, pf_align_state *st, int tier, const Limits &lim, const
     a.slot_base = st->slots[tier].as<uint8_t>(); a.slot_off = st->slot_off.as<uint64_t>();
     a.slot_ptr = st->slot_ptr.as<uint64_t>(); a.ws_base = st->ws[tier].as<uint8_t>(); a.ws_stride = ws_bytes;
     a.counter = st->counter.as<uint32_t>(); a.lim = lim; a.sc = sc;
+    a.stat_cells = (unsigned long long *)(st->counter.as<uint8_t>() + 128);
     msa_kernel<<<blocks, MSA_BLOCK, 0, s>>>(a);
     fill_tier_kernel<<<(n_items + 255) / 256, 256, 0, s>>>(d_order, n_items, st->tier.as<uint8_t>(), (uint8_t)tier);
     ctx->launches += 2;
@@ -315,6 +322,8 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
     lim[1].k_cand = 64; lim[1].k_aln = 64; lim[1].max_var = lim[1].max_alen;
     lim[1].step_limit = 2000000000ull;
 
+    if ((rc = st->counter.reserve(256))) return rc;
+    PF_CUDA_TRY(cudaMemsetAsync(st->counter.as<uint8_t>() + 128, 0, 8, s));
     if ((rc = run_tier(ctx, st, 0, lim[0], sc, d_bases, d_seq_off, d_bubble_off, nullptr, n_bubbles, s))) return rc;
     // retry list
     uint32_t *d_retry_cnt = st->counter.as<uint32_t>() + 8;
@@ -348,7 +357,9 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         if ((rc = exclusive_scan_u64(ctx, st, st->sz[i].as<uint64_t>(), st->off[i].as<uint64_t>(), n1, s))) return rc;
         PF_CUDA_TRY(cudaMemcpyAsync(h_tot + i, st->off[i].as<uint64_t>() + n_bubbles, 8, cudaMemcpyDeviceToHost, s));
     }
+    PF_CUDA_TRY(cudaMemcpyAsync(h_tot + 4, st->counter.as<uint8_t>() + 128, 8, cudaMemcpyDeviceToHost, s));
     PF_CUDA_TRY(cudaStreamSynchronize(s));
+    st->last_cells = h_tot[4];
     res.tot_rows = h_tot[0]; res.tot_var = h_tot[1]; res.tot_cls = h_tot[2]; res.tot_ilen = h_tot[3];
     if ((rc = st->rows.reserve(res.tot_rows + 16))) return rc;
     if ((rc = st->var_col.reserve(res.tot_var * 4 + 16))) return rc;
@@ -449,5 +460,7 @@ int pf_align(pf_ctx *ctx, double M, double D, double G, const char *bases, const
 
 // diagnostics: how many bubbles of the last pf_align* call needed the large (tier-2) work area
 uint32_t pf_align_last_retry_count(const pf_ctx *ctx) { return (ctx && ctx->align) ? ctx->align->last_retry_count : 0; }
+// diagnostics: DP cells (m*n summed over every needlemanWunch fill) of the last pf_align* call
+uint64_t pf_align_last_cells(const pf_ctx *ctx) { return (ctx && ctx->align) ? ctx->align->last_cells : 0; }
 
 }  // extern "C"

@@ -112,3 +112,94 @@ int pf_sync(pf_ctx *ctx) {
 }
 
 }  // extern "C"
+
+// ---- roofline denominators ------------------------------------------------------------------------------
+namespace {
+
+// every thread chases independent pseudo-random 32-byte sectors of a big table (8 loads in flight)
+__global__ void gather_bench_kernel(const uint4 *__restrict__ table, uint64_t n_sectors, uint32_t iters, uint32_t *sink) {
+    uint64_t x = (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 12345;
+    uint32_t acc = 0;
+    for (uint32_t it = 0; it < iters; it++) {
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            v[u] = __ldg(&table[(x % n_sectors) * 2]).x;   // 2 x uint4 = one 32-byte sector
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc += v[u];
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+
+__global__ void int32_bench_kernel(uint32_t iters, int *sink) {
+    int a = threadIdx.x, b = blockIdx.x, c = 7, d = 3;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            a = max(a + b, c) ^ d;      // IADD + IMNMX + LOP: 3 ops
+            b = min(b + c, d) + a;      // 3 ops
+            c = (c + a) ^ b;            // 2 ops
+            d = max(d + b, a);          // 2 ops
+        }
+    }
+    if ((a ^ b ^ c ^ d) == 0x7fffffff) *sink = a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pf_bench_random_gather(pf_ctx *ctx, uint64_t bytes, double *gb_per_s) {
+    if (!ctx || !gb_per_s || bytes < (1u << 20)) { pf::set_error("pf_bench_random_gather: bad argument"); return PF_E_INVALID; }
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    void *tab = nullptr, *sink = nullptr;
+    PF_CUDA_TRY(cudaMalloc(&tab, bytes));
+    PF_CUDA_TRY(cudaMalloc(&sink, 4));
+    PF_CUDA_TRY(cudaMemsetAsync(tab, 1, bytes, ctx->stream));
+    const uint64_t n_sectors = bytes / 32;
+    const unsigned blocks = ctx->sm_count * 8, threads = 256;
+    const uint32_t iters = 64;
+    cudaEvent_t e0, e1;
+    PF_CUDA_TRY(cudaEventCreate(&e0));
+    PF_CUDA_TRY(cudaEventCreate(&e1));
+    gather_bench_kernel<<<blocks, threads, 0, ctx->stream>>>((const uint4 *)tab, n_sectors, 8, (uint32_t *)sink);
+    PF_CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+    gather_bench_kernel<<<blocks, threads, 0, ctx->stream>>>((const uint4 *)tab, n_sectors, iters, (uint32_t *)sink);
+    PF_CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+    PF_CUDA_TRY(cudaEventSynchronize(e1));
+    ctx->launches += 2;
+    float ms = 0;
+    PF_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    *gb_per_s = (double)blocks * threads * iters * 8 * 32.0 / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(tab); cudaFree(sink);
+    return PF_OK;
+}
+
+int pf_bench_int32(pf_ctx *ctx, double *gop_per_s) {
+    if (!ctx || !gop_per_s) { pf::set_error("pf_bench_int32: bad argument"); return PF_E_INVALID; }
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    void *sink = nullptr;
+    PF_CUDA_TRY(cudaMalloc(&sink, 4));
+    const unsigned blocks = ctx->sm_count * 8, threads = 256;
+    const uint32_t iters = 4096;
+    cudaEvent_t e0, e1;
+    PF_CUDA_TRY(cudaEventCreate(&e0));
+    PF_CUDA_TRY(cudaEventCreate(&e1));
+    int32_bench_kernel<<<blocks, threads, 0, ctx->stream>>>(64, (int *)sink);
+    PF_CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+    int32_bench_kernel<<<blocks, threads, 0, ctx->stream>>>(iters, (int *)sink);
+    PF_CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+    PF_CUDA_TRY(cudaEventSynchronize(e1));
+    ctx->launches += 2;
+    float ms = 0;
+    PF_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    *gop_per_s = (double)blocks * threads * iters * 16 * 10.0 / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(sink);
+    return PF_OK;
+}
+
+}  // extern "C"

@@ -217,8 +217,12 @@ def main():
     seq_len = np.diff(bb.seq_off)
     max_len, max_rows = int(seq_len.max()), int(np.diff(bb.bubble_off).max())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
+    # a side stream: the legacy default stream's handle is 0, which the C ABI reads as "use the context's own stream",
+    # and torch.cuda.Event only sees the stream it is recorded on -- so kernels and events share this explicit stream
+    stream = torch.cuda.Stream(dev)
     sptr = stream.cuda_stream
+    assert sptr != 0
+    torch.cuda.synchronize()
 
     def step_device(ev=None):
         if ev:
@@ -244,9 +248,10 @@ def main():
     torch.cuda.synchronize()
     launches0 = ctx.launches
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    for it in range(args.steps):
-        flush.fill_(it & 0xFF)
-        step_device(evs[it])
+    with torch.cuda.stream(stream):
+        for it in range(args.steps):
+            flush.fill_(it & 0xFF)
+            step_device(evs[it])
     torch.cuda.synchronize()
     barrier()
     launches = ctx.launches - launches0

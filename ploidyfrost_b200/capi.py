@@ -24,7 +24,7 @@ LOOKUP_CANONICAL, LOOKUP_FWD_THEN_RC, LOOKUP_FWD = 0, 1, 2
 EXPORTS = ["pf_init", "pf_shutdown", "pf_last_error", "pf_version", "pf_launch_count", "pf_sync", "pf_kmc_open",
            "pf_kmc_close", "pf_kmc_info", "pf_kmc_set_min_count", "pf_kmc_set_max_count", "pf_kmc_reset_min_max",
            "pf_kmc_device_bytes", "pf_kmc_counts", "pf_kmc_cov", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
-           "pf_align_dev", "pf_align_last_retry_count", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32"]
+           "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32"]
 
 
 class KmcInfo(C.Structure):
@@ -91,6 +91,7 @@ def load():
                                C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(MsaBatch), C.c_void_p]
     L.pf_align_last_retry_count.argtypes = [C.c_void_p]
     L.pf_align_last_retry_count.restype = C.c_uint32
+    L.pf_align_last_tier_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.pf_align_last_cells.argtypes = [C.c_void_p]
     L.pf_align_last_cells.restype = C.c_uint64
     L.pf_bench_random_gather.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]
@@ -180,6 +181,12 @@ class Context:
     @property
     def last_retry_count(self) -> int:
         return int(self.lib.pf_align_last_retry_count(self.h))
+
+    @property
+    def last_tier_counts(self) -> list:
+        a = (C.c_uint32 * 7)()
+        _check(self.lib.pf_align_last_tier_counts(self.h, a, 7), "pf_align_last_tier_counts")
+        return list(a)
 
     @property
     def last_cells(self) -> int:

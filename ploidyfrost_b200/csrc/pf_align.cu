@@ -1,21 +1,29 @@
 // pf_align.cu -- batched SeqAlign::SequenceAlignment (src/SeqAlign.cpp:550) on sm_100a.
 //
-// Execution model: persistent warps pull bubbles from an atomic queue; each warp owns a private work
-// area in HBM (DP flag bytes, DFS move string, co-optimal alignment store, two candidate-MSA buffers).
-//   * DP fill (needlemanWunch, SeqAlign.cpp:480-547): anti-diagonal wavefront inside the warp --
-//     lane = matrix row (32-row blocks), one column per step, neighbours exchanged by __shfl_up_sync,
-//     the block's bottom row carried to the next block through a small row buffer.  INT32 ALU only
-//     (FP64 add+truncate per term only when -M/-D/-G are not whole numbers).  Flag bytes are written
-//     diagonal-major so the 32 lanes of a step store 32 consecutive bytes.
-//   * traceback / progressive-MSA filter / site calling: leader lane, pf_align_core.cuh.
-//   * results land in per-bubble slots, then a size pass + CUB exclusive scans + a warp-per-bubble
-//     gather compact them into the flat pf_msa_batch_t arrays.
-//   * two capacity tiers: bubbles that overflow the small tier-1 work area (many co-optimal
-//     alignments, long insertions) are re-run with the large tier-2 limits; anything that still does
-//     not fit is reported per bubble in status[] -- never silently altered.
+// Two kernels run the same per-bubble state machines (pf_align_core.cuh) under two execution policies:
+//
+//   * msa_lane_kernel -- ONE THREAD PER BUBBLE, the path almost every superbubble takes (branches of 2k-1 ..
+//     a few hundred bases).  Bubbles are sorted on the device by (size class, #branches, longest branch) so
+//     that the 32 bubbles of a warp are alike and the lanes stay in lock-step.  Each lane fills its own DP
+//     matrix row by row (needlemanWunch, SeqAlign.cpp:480-547): the previous score row and the B
+//     characters live in shared memory, lane-interleaved ([j*32+lane], bank = lane, conflict free); flag
+//     bytes go to a lane-interleaved work area in HBM/L2, so the 32 lanes of a step write 32 consecutive
+//     bytes (one sector).  Traceback DFS, progressive-MSA filter and site calling then run on every lane
+//     at once instead of on one leader lane of a warp.  INT32 ALU only; the FP64 add+truncate variant is a
+//     separate template instantiation used only when -M/-D/-G are not whole numbers.
+//   * msa_warp_kernel -- one WARP per bubble for everything the lane kernel cannot hold (branches longer
+//     than 256 bases, more than 8 branches) and for its overflow cases: anti-diagonal wavefront inside the
+//     warp (lane = matrix row in 32-row blocks, neighbours exchanged by __shfl_up_sync), leader-lane
+//     traceback.  Work areas are sized from the batch, so 5 kbp branches fit.
+//
+// Results land in per-bubble slots; a size pass + CUB exclusive scans + a warp-per-bubble gather compact
+// them into the flat pf_msa_batch_t arrays.  A bubble that overflows its tier (too many co-optimal
+// alignments, long insertions, traceback step budget) is re-run with the large limits; anything that still
+// does not fit is reported per bubble in status[] -- never silently altered.
 #include "pf_common.cuh"
 #include "pf_align_core.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -25,13 +33,22 @@ using namespace pfalign;
 
 namespace {
 
-constexpr int MSA_BLOCK = 128;  // 4 warps per CTA
+constexpr int WARP_BLOCK = 128;  // msa_warp_kernel: 4 warps per CTA
+constexpr int LANE_BLOCK = 64;   // msa_lane_kernel: 2 warps per CTA (shared memory is per warp, small CTAs pack SMs tighter)
 constexpr uint32_t FULL = 0xffffffffu;
 
-// ---- warp-cooperative fill ---------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_fill(uint8_t *__restrict__ flags, const uint8_t *A, const uint32_t m,
-                                          const uint8_t *B, const uint32_t n, const Scoring &sc, int32_t *brow,
-                                          const uint32_t lane) {
+// size classes of the lane kernel: longest branch of the bubble <= LANE_NMAX[c]
+constexpr int N_LANE_CLASSES = 5;
+constexpr int CLS_BIG = N_LANE_CLASSES;        // first pass of the warp kernel
+constexpr int CLS_RETRY = N_LANE_CLASSES + 1;  // second pass (large limits)
+constexpr int N_TIERS = N_LANE_CLASSES + 2;
+__host__ __device__ constexpr uint32_t lane_nmax(int c) { return c == 0 ? 64u : c == 1 ? 96u : c == 2 ? 128u : c == 3 ? 192u : 256u; }
+constexpr uint32_t LANE_MAX_ROWS = 8;
+
+// ---- warp-cooperative fill (generic kernel) ----------------------------------------------------------------
+template <bool INTEGRAL>
+__device__ __forceinline__ void warp_fill(uint8_t *__restrict__ flags, const CBV A, const uint32_t m, const uint8_t *B,
+                                          const uint32_t n, const Scoring &sc, int32_t *brow, const uint32_t lane) {
     __syncwarp();
     const uint32_t W = m + 1;
     for (uint32_t i = lane; i <= m; i += 32) flags[i * W + i] = i ? (uint8_t)(F_UP * 0x11) : (uint8_t)0;   // column 0 (:486-491)
@@ -61,7 +78,7 @@ __device__ __forceinline__ void warp_fill(uint8_t *__restrict__ flags, const uin
             if (lane == 0) up = up0;                                        // row rb*32: carried row / top border
             const int j = (int)s - (int)lane + 1;
             if (active && j >= 1 && j <= (int)n) {
-                cur = nw_cell(sc, up, diag, cur, a, (uint8_t)b, block_left);
+                cur = nw_cell_t<INTEGRAL>(sc, up, diag, cur, a, (uint8_t)b, block_left);
                 flags[(i + (uint32_t)j) * W + i] = (uint8_t)(unpack_f(cur) * 0x11);
                 if (lane == 31) wr[j] = cur;
             }
@@ -74,7 +91,9 @@ __device__ __forceinline__ void warp_fill(uint8_t *__restrict__ flags, const uin
     __syncwarp();
 }
 
+template <bool INTEGRAL>
 struct WarpExec {
+    static constexpr bool kDiagFlags = true;
     uint32_t lane;
     unsigned long long cells;
     __device__ __forceinline__ bool leader() const { return lane == 0; }
@@ -82,9 +101,82 @@ struct WarpExec {
     __device__ __forceinline__ int bcast_i(int v) const { return __shfl_sync(FULL, v, 0); }
     __device__ __forceinline__ uint32_t bcast_ld(const uint32_t *p) const { return *(const volatile uint32_t *)p; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
-    __device__ __forceinline__ void fill(uint8_t *flags, const uint8_t *A, uint32_t m, const uint8_t *B, uint32_t n,
-                                         const Scoring &sc, int32_t *brow) {
-        warp_fill(flags, A, m, B, n, sc, brow, lane);
+    __device__ __forceinline__ void fill(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n, const Scoring &sc,
+                                         int32_t *brow) {
+        warp_fill<INTEGRAL>(flags.p, A, m, B.p, n, sc, brow, lane);
+        cells += (unsigned long long)m * n;
+    }
+};
+
+// ---- per-lane fill (lane kernel) ---------------------------------------------------------------------------
+// rowbuf / bs point at THIS lane's element 0 of the warp's lane-interleaved shared arrays (element j at [j*32]).
+// T is the storage type of the packed (score*8 + flags) row: int16_t when every score of the launch fits 13 bits.
+template <bool INTEGRAL, class T>
+struct LaneExec {
+    static constexpr bool kDiagFlags = false;
+    T *rowbuf;
+    uint8_t *bs;
+    unsigned long long cells;
+    __device__ __forceinline__ bool leader() const { return true; }
+    __device__ __forceinline__ uint32_t bcast(uint32_t v) const { return v; }
+    __device__ __forceinline__ int bcast_i(int v) const { return v; }
+    __device__ __forceinline__ uint32_t bcast_ld(const uint32_t *p) const { return *p; }
+    __device__ __forceinline__ void sync() const {}
+    __device__ __forceinline__ void fill(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n, const Scoring &sc,
+                                         int32_t *) {
+        for (uint32_t j = 0; j < n; j++) bs[j * 32] = B[j];
+        flags[0] = 0;
+        rowbuf[0] = (T)pack_sf(0, 0);
+        for (uint32_t j = 1; j <= n; j++) {                                  // row 0 (:492-496)
+            rowbuf[j * 32] = (T)pack_sf(border_score(sc, j), F_LEFT);
+            flags[j] = (uint8_t)(F_LEFT * 0x11);
+        }
+        const uint32_t W = n + 1;
+        uint8_t a_next = m ? A[0] : (uint8_t)0;
+        for (uint32_t i = 1; i <= m; i++) {
+            const uint8_t a = a_next;
+            a_next = i < m ? A[i] : (uint8_t)0;
+            const bool block_left = i != m && a_next == '-';
+            int dg = rowbuf[0];
+            const int c0 = pack_sf(border_score(sc, i), F_UP);               // column 0 (:486-491)
+            rowbuf[0] = (T)c0;
+            const BV frow = flags + (uint64_t)i * W;
+            frow[0] = (uint8_t)(F_UP * 0x11);
+            if (INTEGRAL) {
+                // Same cell as nw_cell_t (SeqAlign.cpp:512-545) with the loop-carried part cut to two operations:
+                // lf_t = score(i,j-1) + GAP + [Left flag of (i,j-1)] is carried ready-made, and a row whose Left move
+                // is blocked by the profile rule (:528-532) carries -2^28 instead, which can never win or tie.
+                const int G = sc.iG, Grow = block_left ? -(1 << 28) : sc.iG;
+                const int sub_ne = a == '-' ? sc.iG : sc.iD;
+                int lf_t = unpack_s(c0) + Grow;                              // (i,0) carries only Up
+#pragma unroll 4
+                for (uint32_t j = 1; j <= n; j++) {
+                    const int up = rowbuf[j * 32];
+                    const uint8_t b = bs[(j - 1) * 32];
+                    const int t_up = (up >> 3) + (up & 1) + G;
+                    const int sub = a == b ? sc.iM : (b == '-' ? sc.iG : sub_ne);
+                    const int t_dg = (dg >> 3) + ((dg >> 1) & 1) + sub;
+                    const int t = max(t_up, t_dg);
+                    const int best = max(t, lf_t);
+                    const int fl = lf_t >= t ? 1 : 0;
+                    const int f = (t_up == best ? F_UP : 0) | (t_dg == best ? F_DIAG : 0) | (fl ? F_LEFT : 0);
+                    lf_t = best + Grow + fl;
+                    rowbuf[j * 32] = (T)(best * 8 + f);
+                    frow[j] = (uint8_t)(f * 0x11);
+                    dg = up;
+                }
+            } else {
+                int lf = c0;
+                for (uint32_t j = 1; j <= n; j++) {
+                    const int up = rowbuf[j * 32];
+                    const int cur = nw_cell_t<false>(sc, up, dg, lf, a, bs[(j - 1) * 32], block_left);
+                    rowbuf[j * 32] = (T)cur;
+                    frow[j] = (uint8_t)(unpack_f(cur) * 0x11);
+                    dg = up;
+                    lf = cur;
+                }
+            }
+        }
         cells += (unsigned long long)m * n;
     }
 };
@@ -93,24 +185,28 @@ struct MsaArgs {
     const uint8_t *bases;
     const uint64_t *seq_off;
     const uint32_t *bubble_off;
-    const uint32_t *order;     // work item -> bubble id (nullptr = identity)
+    const uint32_t *order;     // work item -> bubble id
+    uint32_t first;            // first work item of this launch
     uint32_t n_items;
     uint8_t *slot_base;
     const uint64_t *slot_off;  // per work item
     uint64_t *slot_ptr;        // per bubble: address of its slot
+    uint8_t *tier;             // per bubble: tier whose Limits laid out its slot
+    uint8_t tier_id;
     uint8_t *ws_base;
-    uint64_t ws_stride;
+    uint64_t ws_stride;        // per warp
     uint32_t *counter;
     unsigned long long *stat_cells;  // DP cells filled (m*n per needlemanWunch call), for the roofline figure
     Limits lim;
     Scoring sc;
 };
 
-__global__ void __launch_bounds__(MSA_BLOCK) msa_kernel(const MsaArgs a) {
+template <bool INTEGRAL>
+__global__ void __launch_bounds__(WARP_BLOCK) msa_warp_kernel(const MsaArgs a) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim);
-    WarpExec x;
+    WarpExec<INTEGRAL> x;
     x.lane = lane;
     x.cells = 0;
     for (;;) {
@@ -118,35 +214,118 @@ __global__ void __launch_bounds__(MSA_BLOCK) msa_kernel(const MsaArgs a) {
         if (lane == 0) w = atomicAdd(a.counter, 1u);
         w = __shfl_sync(FULL, w, 0);
         if (w >= a.n_items) break;
-        const uint32_t b = a.order ? a.order[w] : w;
+        w += a.first;
+        const uint32_t b = a.order[w];
         const uint32_t s0 = a.bubble_off[b], ns = a.bubble_off[b + 1] - s0;
         uint8_t *slot = a.slot_base + a.slot_off[w];
         msa_run(x, a.bases, a.seq_off, s0, ns, ws, a.lim, a.sc, slot);
-        if (lane == 0) a.slot_ptr[b] = (uint64_t)(uintptr_t)slot;
+        if (lane == 0) { a.slot_ptr[b] = (uint64_t)(uintptr_t)slot; a.tier[b] = a.tier_id; }
     }
     if (lane == 0 && x.cells) atomicAdd(a.stat_cells, x.cells);
 }
 
+__host__ __device__ constexpr uint32_t lane_smem_per_warp(uint32_t nmax, uint32_t tsize) {
+    return 32 * tsize * (nmax + 1) + 32 * nmax;                               // score row + B characters; multiple of 32
+}
+
+template <bool INTEGRAL, class T>
+__global__ void __launch_bounds__(LANE_BLOCK) msa_lane_kernel(const MsaArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nmax = a.lim.max_blen;
+    const uint32_t per_warp = lane_smem_per_warp(nmax, sizeof(T));
+    LaneExec<INTEGRAL, T> x;
+    x.rowbuf = (T *)(smem + (size_t)wib * per_warp) + lane;
+    x.bs = smem + (size_t)wib * per_warp + 32 * sizeof(T) * (nmax + 1) + lane;
+    x.cells = 0;
+    const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim, 32, lane);
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(a.counter, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        const uint32_t n_groups = (a.n_items + 31) / 32;
+        if (g >= n_groups) break;
+        const uint32_t wi = (n_groups - 1 - g) * 32 + lane;                  // sorted ascending by size: biggest groups first
+        if (wi < a.n_items) {
+            const uint32_t w = a.first + wi;
+            const uint32_t b = a.order[w];
+            const uint32_t s0 = a.bubble_off[b], ns = a.bubble_off[b + 1] - s0;
+            uint8_t *slot = a.slot_base + a.slot_off[w];
+            msa_run(x, a.bases, a.seq_off, s0, ns, ws, a.lim, a.sc, slot);
+            a.slot_ptr[b] = (uint64_t)(uintptr_t)slot;
+            a.tier[b] = a.tier_id;
+        }
+        __syncwarp();
+    }
+    unsigned long long c = x.cells;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
+    if (lane == 0 && c) atomicAdd(a.stat_cells, c);
+}
+
+// ---- planning: size class per bubble, sort key -----------------------------------------------------------
+struct TierTable {
+    Limits lim[N_TIERS];
+};
+
+__global__ void plan_kernel(const uint64_t *__restrict__ seq_off, const uint32_t *__restrict__ bubble_off, uint32_t n,
+                            uint32_t *keys, uint32_t *ids) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const uint32_t s0 = bubble_off[b], ns = bubble_off[b + 1] - s0;
+    uint64_t mx = 0;
+    for (uint32_t s = 0; s < ns; s++) {
+        const uint64_t l = seq_off[s0 + s + 1] - seq_off[s0 + s];
+        mx = l > mx ? l : mx;
+    }
+    uint32_t cls = CLS_BIG;
+    if (ns <= LANE_MAX_ROWS) {
+#pragma unroll
+        for (int c = N_LANE_CLASSES - 1; c >= 0; c--)
+            if (mx <= lane_nmax(c)) cls = c;
+    }
+    // class | rows | longest branch: the 32 bubbles of a warp get alike shapes
+    keys[b] = (cls << 28) | (min(ns, 255u) << 20) | (uint32_t)min(mx, (uint64_t)0xFFFFF);
+    ids[b] = b;
+}
+
+// bounds[c] = first sorted work item of class c (c = 0 .. CLS_BIG), bounds[CLS_BIG + 1] = n
+__global__ void class_bounds_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t *bounds) {
+    const uint32_t c = threadIdx.x;
+    if (c > CLS_BIG + 1) return;
+    if (c == CLS_BIG + 1) { bounds[c] = n; return; }
+    uint32_t lo = 0, hi = n;
+    const uint32_t want = c << 28;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (keys[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    bounds[c] = lo;
+}
+
+// slot size of every work item; `keys` (sorted) gives the tier of first-pass items, `fixed_tier` >= 0 overrides
 __global__ void slot_size_kernel(const uint64_t *__restrict__ seq_off, const uint32_t *__restrict__ bubble_off,
-                                 const uint32_t *__restrict__ order, uint32_t n_items, Limits lim, uint64_t *sizes) {
+                                 const uint32_t *__restrict__ order, const uint32_t *__restrict__ keys, int fixed_tier,
+                                 uint32_t n_items, const TierTable tt, uint64_t *sizes) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w > n_items) return;
     if (w == n_items) { sizes[w] = 0; return; }
-    const uint32_t b = order ? order[w] : w;
+    const uint32_t b = order[w];
     const uint32_t s0 = bubble_off[b], ns = bubble_off[b + 1] - s0;
     const uint64_t sum = seq_off[s0 + ns] - seq_off[s0];
-    sizes[w] = slot_layout(ns, sum, lim).bytes;
+    const int t = fixed_tier >= 0 ? fixed_tier : (int)(keys[w] >> 28);
+    sizes[w] = slot_layout(ns, sum, tt.lim[t]).bytes;
 }
 
 __device__ __forceinline__ bool retryable(int st) {
-    return st == PF_BUBBLE_TOO_MANY_ROWS || st == PF_BUBBLE_TOO_LONG || st == PF_BUBBLE_CAND_OVERFLOW || st == PF_BUBBLE_OUT_OVERFLOW;
+    return st == PF_BUBBLE_TOO_MANY_ROWS || st == PF_BUBBLE_TOO_LONG || st == PF_BUBBLE_CAND_OVERFLOW ||
+           st == PF_BUBBLE_OUT_OVERFLOW || st == PF_BUBBLE_STEP_LIMIT;
 }
 
-__global__ void collect_retry_kernel(const uint32_t *__restrict__ order, uint32_t n_items, const uint64_t *__restrict__ slot_ptr,
-                                     uint32_t *retry_list, uint32_t *retry_count) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_items) return;
-    const uint32_t b = order ? order[w] : w;
+__global__ void collect_retry_kernel(uint32_t n, const uint64_t *__restrict__ slot_ptr, uint32_t *retry_list, uint32_t *retry_count) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
     const SlotHdr *h = (const SlotHdr *)(uintptr_t)slot_ptr[b];
     if (retryable(h->status)) retry_list[atomicAdd(retry_count, 1u)] = b;
 }
@@ -172,7 +351,7 @@ struct GatherArgs {
     const uint64_t *seq_off;
     const uint32_t *bubble_off;
     const uint8_t *tier;       // per bubble: which Limits its slot was laid out with
-    Limits lim[2];
+    TierTable tt;
     uint32_t n;
     const uint64_t *off_rows, *off_var, *off_cls, *off_ilen;
     uint8_t *rows;
@@ -190,7 +369,7 @@ __global__ void gather_kernel(const GatherArgs g) {
     const SlotHdr *h = (const SlotHdr *)slot;
     if (h->n_rows == 0) return;
     const uint32_t s0 = g.bubble_off[b], ns = g.bubble_off[b + 1] - s0;
-    const SlotLayout lay = slot_layout(ns, g.seq_off[s0 + ns] - g.seq_off[s0], g.lim[g.tier[b]]);
+    const SlotLayout lay = slot_layout(ns, g.seq_off[s0 + ns] - g.seq_off[s0], g.tt.lim[g.tier[b]]);
     const uint64_t nrow_bytes = (uint64_t)h->n_rows * h->alen;
     uint8_t *dr = g.rows + g.off_rows[b];
     for (uint64_t i = lane; i < nrow_bytes; i += 32) dr[i] = slot[lay.off_rows + i];
@@ -208,29 +387,34 @@ __global__ void gather_kernel(const GatherArgs g) {
     for (uint32_t i = lane; i < h->n_ilen; i += 32) g.ilen[g.off_ilen[b] + i] = il[i];
 }
 
-__global__ void fill_tier_kernel(const uint32_t *__restrict__ order, uint32_t n_items, uint8_t *tier, uint8_t value) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w < n_items) tier[order ? order[w] : w] = value;
-}
-
 }  // namespace
 
 struct pf_align_state {
-    pf::DevBuf ws[2], slots[2], slot_sizes, slot_off, slot_ptr, tier, counter, retry_list, cub_tmp;
+    pf::DevBuf ws_warp[2], slots[2], slot_sizes, slot_off, slot_ptr, tier, counter, retry_list, cub_tmp;
+    pf::DevBuf keys[2], ids[2];
     pf::DevBuf status, n_rows, aln_len, sz[4], off[4];
     pf::DevBuf rows, var_col, var_kind, cls, ilen;
     pf::DevBuf in_bases, in_seq_off, in_bubble_off;
     pf::PinnedBuf h_scalars, h_out[12];
     uint32_t last_retry_count = 0;
     uint64_t last_cells = 0;
+    uint32_t last_class_count[N_TIERS] = {0};
+    int lane_blocks_per_sm[3][N_LANE_CLASSES];   // [variant][class]; variants: 0 = FP64 scoring, 1 = int32 row, 2 = int16 row
+    bool lane_attr_done = false;
+    cudaStream_t aux[N_LANE_CLASSES + 1] = {nullptr};   // the size classes run concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join[N_LANE_CLASSES + 1] = {nullptr};
+    pf::DevBuf ws_cls[N_LANE_CLASSES];
 };
 
 void pf_align_state_free(pf_align_state *s) {
     if (!s) return;
-    for (auto &b : s->ws) b.release();
-    for (auto &b : s->slots) b.release();
-    pf::DevBuf *d[] = {&s->slot_sizes, &s->slot_off, &s->slot_ptr, &s->tier, &s->counter, &s->retry_list, &s->cub_tmp,
-                       &s->status, &s->n_rows, &s->aln_len, &s->rows, &s->var_col, &s->var_kind, &s->cls, &s->ilen,
+    for (auto &b : s->ws_cls) b.release();
+    for (auto &st : s->aux) if (st) cudaStreamDestroy(st);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    for (auto &e : s->ev_join) if (e) cudaEventDestroy(e);
+    pf::DevBuf *d[] = {&s->ws_warp[0], &s->ws_warp[1], &s->slots[0], &s->slots[1], &s->slot_sizes, &s->slot_off,
+                       &s->slot_ptr, &s->tier, &s->counter, &s->retry_list, &s->cub_tmp, &s->keys[0], &s->keys[1], &s->ids[0],
+                       &s->ids[1], &s->status, &s->n_rows, &s->aln_len, &s->rows, &s->var_col, &s->var_kind, &s->cls, &s->ilen,
                        &s->in_bases, &s->in_seq_off, &s->in_bubble_off};
     for (auto *b : d) b->release();
     for (auto &b : s->sz) b.release();
@@ -241,6 +425,32 @@ void pf_align_state_free(pf_align_state *s) {
 }
 
 namespace {
+
+constexpr uint64_t WS_BUDGET = 24ull << 30;  // cap on any one work-area pool
+
+size_t lane_smem_bytes(uint32_t nmax, int variant) { return (size_t)(LANE_BLOCK / 32) * lane_smem_per_warp(nmax, variant == 2 ? 2 : 4); }
+
+typedef void (*LaneKernel)(const MsaArgs);
+LaneKernel lane_kernel(int variant) {
+    return variant == 2 ? msa_lane_kernel<true, int16_t> : variant == 1 ? msa_lane_kernel<true, int32_t> : msa_lane_kernel<false, int32_t>;
+}
+// packed score*8+flags fits int16 when |score| < 4096 for every cell of the class (border, diagonal and bonus included)
+int lane_variant(const Scoring &sc, const Limits &l) {
+    if (!sc.integral) return 0;
+    const long long mag = std::max(std::max(std::llabs((long long)sc.iM), std::llabs((long long)sc.iD)), std::llabs((long long)sc.iG)) + 1;
+    return mag * (long long)(l.max_alen + l.max_blen + 2) < 4000 ? 2 : 1;
+}
+
+Limits lane_limits(int c) {
+    Limits l;
+    l.max_rows = LANE_MAX_ROWS;
+    l.max_blen = lane_nmax(c);
+    l.max_alen = l.max_blen + 32;
+    l.k_cand = 8; l.k_aln = 8; l.max_var = 48;
+    l.step_limit = 2000000ull;
+    l.diag_flags = 0; l.pad_ = 0;
+    return l;
+}
 
 int exclusive_scan_u64(pf_ctx *ctx, pf_align_state *st, const uint64_t *in, uint64_t *out, uint32_t n, cudaStream_t s) {
     size_t tmp = 0;
@@ -253,43 +463,34 @@ int exclusive_scan_u64(pf_ctx *ctx, pf_align_state *st, const uint64_t *in, uint
     return PF_OK;
 }
 
-// One tier: lay out slots for the work items, run the MSA kernel.  `order` is a device list of bubble ids
-// (nullptr = all bubbles 0..n_items-1).
-int run_tier(pf_ctx *ctx, pf_align_state *st, int tier, const Limits &lim, const Scoring &sc, const uint8_t *d_bases,
-             const uint64_t *d_seq_off, const uint32_t *d_bubble_off, const uint32_t *d_order, uint32_t n_items,
-             cudaStream_t s) {
-    int rc;
-    if ((rc = st->slot_sizes.reserve((uint64_t)(n_items + 1) * 8))) return rc;
-    if ((rc = st->slot_off.reserve((uint64_t)(n_items + 1) * 8))) return rc;
-    if ((rc = st->counter.reserve(256))) return rc;
-    if ((rc = st->h_scalars.reserve(256))) return rc;
-    slot_size_kernel<<<(n_items + 1 + 255) / 256, 256, 0, s>>>(d_seq_off, d_bubble_off, d_order, n_items, lim,
-                                                               st->slot_sizes.as<uint64_t>());
-    ctx->launches++;
-    if ((rc = exclusive_scan_u64(ctx, st, st->slot_sizes.as<uint64_t>(), st->slot_off.as<uint64_t>(), n_items + 1, s))) return rc;
-    uint64_t *h_total = st->h_scalars.as<uint64_t>();
-    PF_CUDA_TRY(cudaMemcpyAsync(h_total, st->slot_off.as<uint64_t>() + n_items, 8, cudaMemcpyDeviceToHost, s));
-    PF_CUDA_TRY(cudaMemsetAsync(st->counter.p, 0, 64, s));
-    PF_CUDA_TRY(cudaStreamSynchronize(s));
-    if ((rc = st->slots[tier].reserve(*h_total + 64))) return rc;
-    // warps: as many as the SMs can hold, bounded by a work-area budget
-    const uint64_t ws_bytes = align_up(work_area_bytes(lim), 256);
-    const uint64_t budget = 24ull << 30;
-    uint64_t warps = (uint64_t)ctx->sm_count * 16;
-    warps = std::min<uint64_t>(warps, std::max<uint64_t>(1, budget / ws_bytes));
-    warps = std::min<uint64_t>(warps, (uint64_t)n_items);
-    const uint32_t wpb = MSA_BLOCK / 32;
-    const uint32_t blocks = (uint32_t)((warps + wpb - 1) / wpb);
-    if ((rc = st->ws[tier].reserve((uint64_t)blocks * wpb * ws_bytes))) return rc;
-    MsaArgs a;
-    a.bases = d_bases; a.seq_off = d_seq_off; a.bubble_off = d_bubble_off; a.order = d_order; a.n_items = n_items;
-    a.slot_base = st->slots[tier].as<uint8_t>(); a.slot_off = st->slot_off.as<uint64_t>();
-    a.slot_ptr = st->slot_ptr.as<uint64_t>(); a.ws_base = st->ws[tier].as<uint8_t>(); a.ws_stride = ws_bytes;
-    a.counter = st->counter.as<uint32_t>(); a.lim = lim; a.sc = sc;
+void fill_args(MsaArgs &a, pf_align_state *st, int slot_pool, const Limits &lim, const Scoring &sc, const uint8_t *d_bases,
+               const uint64_t *d_seq_off, const uint32_t *d_bubble_off, const uint32_t *d_order, uint32_t first, uint32_t n_items,
+               int tier_id, uint32_t *counter) {
+    a.bases = d_bases; a.seq_off = d_seq_off; a.bubble_off = d_bubble_off; a.order = d_order; a.first = first; a.n_items = n_items;
+    a.slot_base = st->slots[slot_pool].as<uint8_t>(); a.slot_off = st->slot_off.as<uint64_t>();
+    a.slot_ptr = st->slot_ptr.as<uint64_t>(); a.tier = st->tier.as<uint8_t>(); a.tier_id = (uint8_t)tier_id;
+    a.counter = counter; a.lim = lim; a.sc = sc;
     a.stat_cells = (unsigned long long *)(st->counter.as<uint8_t>() + 128);
-    msa_kernel<<<blocks, MSA_BLOCK, 0, s>>>(a);
-    fill_tier_kernel<<<(n_items + 255) / 256, 256, 0, s>>>(d_order, n_items, st->tier.as<uint8_t>(), (uint8_t)tier);
-    ctx->launches += 2;
+}
+
+// one launch of the warp-per-bubble kernel over work items [first, first + n_items) of `d_order`
+int launch_warp_tier(pf_ctx *ctx, pf_align_state *st, int pool, const Limits &lim, const Scoring &sc, const uint8_t *d_bases,
+                     const uint64_t *d_seq_off, const uint32_t *d_bubble_off, const uint32_t *d_order, uint32_t first,
+                     uint32_t n_items, int tier_id, uint32_t *counter, cudaStream_t s) {
+    const uint64_t ws_bytes = align_up(work_area_bytes(lim), 256);
+    uint64_t warps = (uint64_t)ctx->sm_count * 16;
+    warps = std::min<uint64_t>(warps, std::max<uint64_t>(1, WS_BUDGET / ws_bytes));
+    warps = std::min<uint64_t>(warps, (uint64_t)n_items);
+    const uint32_t wpb = WARP_BLOCK / 32;
+    const uint32_t blocks = (uint32_t)((warps + wpb - 1) / wpb);
+    int rc;
+    if ((rc = st->ws_warp[pool].reserve((uint64_t)blocks * wpb * ws_bytes))) return rc;
+    MsaArgs a;
+    fill_args(a, st, pool, lim, sc, d_bases, d_seq_off, d_bubble_off, d_order, first, n_items, tier_id, counter);
+    a.ws_base = st->ws_warp[pool].as<uint8_t>(); a.ws_stride = ws_bytes;
+    if (sc.integral) msa_warp_kernel<true><<<blocks, WARP_BLOCK, 0, s>>>(a);
+    else msa_warp_kernel<false><<<blocks, WARP_BLOCK, 0, s>>>(a);
+    ctx->launches++;
     PF_CUDA_TRY(cudaGetLastError());
     return PF_OK;
 }
@@ -304,42 +505,135 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
                  DevResult &res) {
     if (!ctx->align) ctx->align = new pf_align_state();
     pf_align_state *st = ctx->align;
+    const uint32_t n = n_bubbles;
     int rc;
-    if ((rc = st->slot_ptr.reserve((uint64_t)n_bubbles * 8 + 8))) return rc;
-    if ((rc = st->tier.reserve((uint64_t)n_bubbles + 8))) return rc;
-    if ((rc = st->retry_list.reserve((uint64_t)n_bubbles * 4 + 64))) return rc;
-    Limits lim[2];
-    // tier 1: small per-warp work area (keeps more of it L2-resident)
-    lim[0].max_rows = std::min<uint32_t>(std::max<uint32_t>(max_rows, 2), 8);
-    lim[0].max_blen = std::max<uint32_t>(max_len, 1);
-    lim[0].max_alen = lim[0].max_blen + std::min<uint32_t>(64, lim[0].max_blen);
-    lim[0].k_cand = 8; lim[0].k_aln = 8; lim[0].max_var = 48;
-    lim[0].step_limit = 200000000ull;
-    // tier 2: generous
-    lim[1].max_rows = std::min<uint32_t>(std::max<uint32_t>(max_rows, 2), 64);
-    lim[1].max_blen = lim[0].max_blen;
-    lim[1].max_alen = (uint32_t)std::min<uint64_t>((uint64_t)lim[1].max_blen * std::min<uint32_t>(lim[1].max_rows, 4) + 64, 1u << 20);
-    lim[1].k_cand = 64; lim[1].k_aln = 64; lim[1].max_var = lim[1].max_alen;
-    lim[1].step_limit = 2000000000ull;
+    if ((rc = st->slot_ptr.reserve((uint64_t)n * 8 + 8))) return rc;
+    if ((rc = st->tier.reserve((uint64_t)n + 8))) return rc;
+    if ((rc = st->retry_list.reserve((uint64_t)n * 4 + 64))) return rc;
+    if ((rc = st->counter.reserve(1024))) return rc;
+    if ((rc = st->h_scalars.reserve(1024))) return rc;
+    for (int i = 0; i < 2; i++) {
+        if ((rc = st->keys[i].reserve((uint64_t)n * 4 + 16))) return rc;
+        if ((rc = st->ids[i].reserve((uint64_t)n * 4 + 16))) return rc;
+    }
+    if ((rc = st->slot_sizes.reserve((uint64_t)(n + 1) * 8))) return rc;
+    if ((rc = st->slot_off.reserve((uint64_t)(n + 1) * 8))) return rc;
 
-    if ((rc = st->counter.reserve(256))) return rc;
-    PF_CUDA_TRY(cudaMemsetAsync(st->counter.as<uint8_t>() + 128, 0, 8, s));
-    if ((rc = run_tier(ctx, st, 0, lim[0], sc, d_bases, d_seq_off, d_bubble_off, nullptr, n_bubbles, s))) return rc;
-    // retry list
-    uint32_t *d_retry_cnt = st->counter.as<uint32_t>() + 8;
-    PF_CUDA_TRY(cudaMemsetAsync(d_retry_cnt, 0, 4, s));
-    collect_retry_kernel<<<(n_bubbles + 255) / 256, 256, 0, s>>>(nullptr, n_bubbles, st->slot_ptr.as<uint64_t>(),
-                                                                 st->retry_list.as<uint32_t>(), d_retry_cnt);
+    if (!st->lane_attr_done) {
+        for (int v = 0; v < 3; v++) {
+            PF_CUDA_TRY(cudaFuncSetAttribute(lane_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)lane_smem_bytes(lane_nmax(N_LANE_CLASSES - 1), v)));
+            for (int c = 0; c < N_LANE_CLASSES; c++)
+                PF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st->lane_blocks_per_sm[v][c], lane_kernel(v), LANE_BLOCK,
+                                                                          lane_smem_bytes(lane_nmax(c), v)));
+        }
+        for (auto &a : st->aux) PF_CUDA_TRY(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+        PF_CUDA_TRY(cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming));
+        for (auto &e : st->ev_join) PF_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        st->lane_attr_done = true;
+    }
+
+    TierTable tt;
+    for (int c = 0; c < N_LANE_CLASSES; c++) tt.lim[c] = lane_limits(c);
+    Limits &big = tt.lim[CLS_BIG];        // warp kernel, first pass: work area sized from the batch's longest branch
+    big.max_rows = std::min<uint32_t>(std::max<uint32_t>(max_rows, 2), 8);
+    big.max_blen = std::max<uint32_t>(max_len, 1);
+    big.max_alen = big.max_blen + std::min<uint32_t>(64, big.max_blen);
+    big.k_cand = 8; big.k_aln = 8; big.max_var = 48;
+    big.step_limit = 200000000ull; big.diag_flags = 1; big.pad_ = 0;
+    Limits &huge = tt.lim[CLS_RETRY];     // warp kernel, second pass: generous
+    huge.max_rows = std::min<uint32_t>(std::max<uint32_t>(max_rows, 2), 64);
+    huge.max_blen = big.max_blen;
+    huge.max_alen = (uint32_t)std::min<uint64_t>((uint64_t)huge.max_blen * std::min<uint32_t>(huge.max_rows, 4) + 64, 1u << 20);
+    huge.k_cand = 64; huge.k_aln = 64; huge.max_var = huge.max_alen;
+    huge.step_limit = 2000000000ull; huge.diag_flags = 1; huge.pad_ = 0;
+
+    // ---- plan: class + sort ----
+    uint32_t *k0 = st->keys[0].as<uint32_t>(), *k1 = st->keys[1].as<uint32_t>();
+    uint32_t *i0 = st->ids[0].as<uint32_t>(), *i1 = st->ids[1].as<uint32_t>();
+    plan_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_seq_off, d_bubble_off, n, k0, i0);
+    {
+        size_t tmp = 0;
+        PF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k0, k1, i0, i1, (int)n, 0, 32, s));
+        if ((rc = st->cub_tmp.reserve(tmp + 16))) return rc;
+        tmp = st->cub_tmp.cap;
+        PF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(st->cub_tmp.p, tmp, k0, k1, i0, i1, (int)n, 0, 32, s));
+    }
+    const uint32_t *d_keys = k1, *d_order = i1;
+    uint32_t *d_bounds = st->counter.as<uint32_t>() + 64;   // byte offset 256
+    class_bounds_kernel<<<1, 32, 0, s>>>(d_keys, n, d_bounds);
+    slot_size_kernel<<<(n + 1 + 255) / 256, 256, 0, s>>>(d_seq_off, d_bubble_off, d_order, d_keys, -1, n, tt, st->slot_sizes.as<uint64_t>());
+    ctx->launches += 5;  // plan, sort (2 passes counted as 2), bounds, sizes
+    if ((rc = exclusive_scan_u64(ctx, st, st->slot_sizes.as<uint64_t>(), st->slot_off.as<uint64_t>(), n + 1, s))) return rc;
+    uint64_t *h_total = st->h_scalars.as<uint64_t>();
+    uint32_t *h_bounds = (uint32_t *)(st->h_scalars.as<uint8_t>() + 256);
+    PF_CUDA_TRY(cudaMemcpyAsync(h_total, st->slot_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));
+    PF_CUDA_TRY(cudaMemcpyAsync(h_bounds, d_bounds, (CLS_BIG + 2) * 4, cudaMemcpyDeviceToHost, s));
+    PF_CUDA_TRY(cudaMemsetAsync(st->counter.p, 0, 256, s));   // work queues [0..15], stat_cells at byte 128
+    PF_CUDA_TRY(cudaStreamSynchronize(s));
+    if ((rc = st->slots[0].reserve(*h_total + 64))) return rc;
+
+    // ---- first pass: every non-empty size class on its own stream (they overlap; heaviest first) ----
+    PF_CUDA_TRY(cudaEventRecord(st->ev_fork, s));
+    {
+        const uint32_t cnt = h_bounds[CLS_BIG + 1] - h_bounds[CLS_BIG];
+        st->last_class_count[CLS_BIG] = cnt;
+        if (cnt) {
+            cudaStream_t as = st->aux[N_LANE_CLASSES];
+            PF_CUDA_TRY(cudaStreamWaitEvent(as, st->ev_fork, 0));
+            if ((rc = launch_warp_tier(ctx, st, 0, big, sc, d_bases, d_seq_off, d_bubble_off, d_order, h_bounds[CLS_BIG], cnt, CLS_BIG,
+                                       st->counter.as<uint32_t>() + CLS_BIG, as))) return rc;
+            PF_CUDA_TRY(cudaEventRecord(st->ev_join[N_LANE_CLASSES], as));
+            PF_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_join[N_LANE_CLASSES], 0));
+        }
+    }
+    for (int c = N_LANE_CLASSES - 1; c >= 0; c--) {
+        const uint32_t cnt = h_bounds[c + 1] - h_bounds[c];
+        st->last_class_count[c] = cnt;
+        if (!cnt) continue;
+        const int v = lane_variant(sc, tt.lim[c]);
+        const uint64_t ws_bytes = align_up(work_area_bytes(tt.lim[c], 32), 256);
+        const uint32_t wpb = LANE_BLOCK / 32;
+        uint64_t warps = (uint64_t)ctx->sm_count * std::max(1, st->lane_blocks_per_sm[v][c]) * wpb;
+        warps = std::min<uint64_t>(warps, std::max<uint64_t>(1, WS_BUDGET / ws_bytes));
+        warps = std::min<uint64_t>(warps, ((uint64_t)cnt + 31) / 32);
+        const uint32_t grid = (uint32_t)((warps + wpb - 1) / wpb);
+        if ((rc = st->ws_cls[c].reserve((uint64_t)grid * wpb * ws_bytes))) return rc;
+        MsaArgs a;
+        fill_args(a, st, 0, tt.lim[c], sc, d_bases, d_seq_off, d_bubble_off, d_order, h_bounds[c], cnt, c, st->counter.as<uint32_t>() + c);
+        a.ws_base = st->ws_cls[c].as<uint8_t>();
+        a.ws_stride = ws_bytes;
+        cudaStream_t as = st->aux[c];
+        PF_CUDA_TRY(cudaStreamWaitEvent(as, st->ev_fork, 0));
+        lane_kernel(v)<<<grid, LANE_BLOCK, lane_smem_bytes(lane_nmax(c), v), as>>>(a);
+        ctx->launches++;
+        PF_CUDA_TRY(cudaGetLastError());
+        PF_CUDA_TRY(cudaEventRecord(st->ev_join[c], as));
+        PF_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_join[c], 0));
+    }
+    // ---- retry list -> second pass of the warp kernel with the large limits ----
+    uint32_t *d_retry_cnt = st->counter.as<uint32_t>() + 16;
+    collect_retry_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, st->slot_ptr.as<uint64_t>(), st->retry_list.as<uint32_t>(), d_retry_cnt);
     ctx->launches++;
     uint32_t *h_cnt = (uint32_t *)(st->h_scalars.as<uint8_t>() + 64);
     PF_CUDA_TRY(cudaMemcpyAsync(h_cnt, d_retry_cnt, 4, cudaMemcpyDeviceToHost, s));
     PF_CUDA_TRY(cudaStreamSynchronize(s));
     st->last_retry_count = *h_cnt;
+    st->last_class_count[CLS_RETRY] = *h_cnt;
     if (*h_cnt) {
-        if ((rc = run_tier(ctx, st, 1, lim[1], sc, d_bases, d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), *h_cnt, s))) return rc;
+        const uint32_t nr = *h_cnt;
+        slot_size_kernel<<<(nr + 1 + 255) / 256, 256, 0, s>>>(d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), nullptr, CLS_RETRY, nr,
+                                                              tt, st->slot_sizes.as<uint64_t>());
+        ctx->launches++;
+        if ((rc = exclusive_scan_u64(ctx, st, st->slot_sizes.as<uint64_t>(), st->slot_off.as<uint64_t>(), nr + 1, s))) return rc;
+        PF_CUDA_TRY(cudaMemcpyAsync(h_total, st->slot_off.as<uint64_t>() + nr, 8, cudaMemcpyDeviceToHost, s));
+        PF_CUDA_TRY(cudaStreamSynchronize(s));
+        if ((rc = st->slots[1].reserve(*h_total + 64))) return rc;
+        if ((rc = launch_warp_tier(ctx, st, 1, huge, sc, d_bases, d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), 0, nr, CLS_RETRY,
+                                   st->counter.as<uint32_t>() + CLS_RETRY, s))) return rc;
     }
-    // sizes -> offsets
-    const uint32_t n1 = n_bubbles + 1;
+    // ---- sizes -> offsets ----
+    const uint32_t n1 = n + 1;
     if ((rc = st->status.reserve((uint64_t)n1 * 4))) return rc;
     if ((rc = st->n_rows.reserve((uint64_t)n1 * 4))) return rc;
     if ((rc = st->aln_len.reserve((uint64_t)n1 * 4))) return rc;
@@ -347,7 +641,7 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         if ((rc = st->sz[i].reserve((uint64_t)n1 * 8))) return rc;
         if ((rc = st->off[i].reserve((uint64_t)n1 * 8))) return rc;
     }
-    result_size_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(st->slot_ptr.as<uint64_t>(), n_bubbles, st->status.as<int32_t>(),
+    result_size_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(st->slot_ptr.as<uint64_t>(), n, st->status.as<int32_t>(),
                                                         st->n_rows.as<uint32_t>(), st->aln_len.as<uint32_t>(),
                                                         st->sz[0].as<uint64_t>(), st->sz[1].as<uint64_t>(),
                                                         st->sz[2].as<uint64_t>(), st->sz[3].as<uint64_t>());
@@ -355,7 +649,7 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
     uint64_t *h_tot = st->h_scalars.as<uint64_t>() + 16;
     for (int i = 0; i < 4; i++) {
         if ((rc = exclusive_scan_u64(ctx, st, st->sz[i].as<uint64_t>(), st->off[i].as<uint64_t>(), n1, s))) return rc;
-        PF_CUDA_TRY(cudaMemcpyAsync(h_tot + i, st->off[i].as<uint64_t>() + n_bubbles, 8, cudaMemcpyDeviceToHost, s));
+        PF_CUDA_TRY(cudaMemcpyAsync(h_tot + i, st->off[i].as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));
     }
     PF_CUDA_TRY(cudaMemcpyAsync(h_tot + 4, st->counter.as<uint8_t>() + 128, 8, cudaMemcpyDeviceToHost, s));
     PF_CUDA_TRY(cudaStreamSynchronize(s));
@@ -368,12 +662,12 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
     if ((rc = st->ilen.reserve(res.tot_ilen * 4 + 16))) return rc;
     GatherArgs g;
     g.slot_ptr = st->slot_ptr.as<uint64_t>(); g.seq_off = d_seq_off; g.bubble_off = d_bubble_off;
-    g.tier = st->tier.as<uint8_t>(); g.lim[0] = lim[0]; g.lim[1] = lim[1]; g.n = n_bubbles;
+    g.tier = st->tier.as<uint8_t>(); g.tt = tt; g.n = n;
     g.off_rows = st->off[0].as<uint64_t>(); g.off_var = st->off[1].as<uint64_t>();
     g.off_cls = st->off[2].as<uint64_t>(); g.off_ilen = st->off[3].as<uint64_t>();
     g.rows = st->rows.as<uint8_t>(); g.var_col = st->var_col.as<uint32_t>(); g.var_kind = st->var_kind.as<uint8_t>();
     g.cls = st->cls.as<uint16_t>(); g.ilen = st->ilen.as<uint32_t>();
-    const uint64_t threads = (uint64_t)n_bubbles * 32;
+    const uint64_t threads = (uint64_t)n * 32;
     gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g);
     ctx->launches++;
     PF_CUDA_TRY(cudaGetLastError());
@@ -458,9 +752,15 @@ int pf_align(pf_ctx *ctx, double M, double D, double G, const char *bases, const
     return PF_OK;
 }
 
-// diagnostics: how many bubbles of the last pf_align* call needed the large (tier-2) work area
+// diagnostics: how many bubbles of the last pf_align* call needed the second (large-limit) pass
 uint32_t pf_align_last_retry_count(const pf_ctx *ctx) { return (ctx && ctx->align) ? ctx->align->last_retry_count : 0; }
 // diagnostics: DP cells (m*n summed over every needlemanWunch fill) of the last pf_align* call
 uint64_t pf_align_last_cells(const pf_ctx *ctx) { return (ctx && ctx->align) ? ctx->align->last_cells : 0; }
+// diagnostics: bubbles per tier of the last call: [0..4] lane-kernel size classes (<=64/96/128/192/256), [5] warp kernel, [6] retries
+int pf_align_last_tier_counts(const pf_ctx *ctx, uint32_t *out, int n) {
+    if (!ctx || !out) return PF_E_INVALID;
+    for (int i = 0; i < n; i++) out[i] = (ctx->align && i < N_TIERS) ? ctx->align->last_class_count[i] : 0;
+    return PF_OK;
+}
 
 }  // extern "C"

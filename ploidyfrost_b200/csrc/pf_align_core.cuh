@@ -39,6 +39,38 @@ enum { F_UP = 1, F_DIAG = 2, F_LEFT = 4 };
 enum { MV_L = 0, MV_U = 1, MV_D = 2, MV_NONE = 0xFF };
 enum { PF_BUBBLE_OUT_OVERFLOW = 6 };  // more variable columns than the output slot holds
 
+// Strided views.  Every per-bubble array of the work area is addressed through a view so that the same
+// state machines run (a) on one warp's private, contiguous area (stride 1: the generic kernel, the host
+// emulation) and (b) one bubble per LANE with the 32 lanes' arrays interleaved element by element
+// (stride 32: lanes that advance in lock-step touch 32 consecutive bytes = one sector).
+struct BV {
+    uint8_t *p;
+    uint32_t s;
+    PF_HD uint8_t &operator[](uint64_t i) const { return p[i * s]; }
+    PF_HD BV operator+(uint64_t o) const { BV r; r.p = p + o * s; r.s = s; return r; }
+};
+struct CBV {
+    const uint8_t *p;
+    uint32_t s;
+    PF_HD uint8_t operator[](uint64_t i) const { return p[i * s]; }
+    PF_HD CBV operator+(uint64_t o) const { CBV r; r.p = p + o * s; r.s = s; return r; }
+};
+struct WV {   // uint32 elements, stride in elements
+    uint32_t *p;
+    uint32_t s;
+    PF_HD uint32_t &operator[](uint64_t i) const { return p[i * s]; }
+};
+PF_HD BV bv(uint8_t *p, uint32_t s = 1) { BV r; r.p = p; r.s = s; return r; }
+PF_HD CBV cbv(const uint8_t *p, uint32_t s = 1) { CBV r; r.p = p; r.s = s; return r; }
+PF_HD CBV cbv(const BV &v) { CBV r; r.p = v.p; r.s = v.s; return r; }
+PF_HD WV wv(uint32_t *p, uint32_t s = 1) { WV r; r.p = p; r.s = s; return r; }
+
+// Flag-byte address of cell (i,j) of an (m+1) x (n+1) matrix
+template <bool DIAG>
+PF_HD uint32_t flag_index(uint32_t i, uint32_t j, uint32_t m, uint32_t n) {
+    return DIAG ? (i + j) * (m + 1) + i : i * (n + 1) + j;
+}
+
 struct Scoring {   // SeqAlign(double&,double&,double&), SeqAlign.hpp:10
     double M, D, G;
     int iM, iD, iG;
@@ -54,9 +86,11 @@ PF_HD Scoring make_scoring(double M, double D, double G) {
     return s;
 }
 
-// `int x = long + double` (SeqAlign.cpp:512, :517, :522)
+// `int x = long + double` (SeqAlign.cpp:512, :517, :522).  INTEGRAL is a compile-time switch so that the
+// integer kernels carry no FP64 instructions at all.
+template <bool INTEGRAL>
 PF_HD int add_trunc(const Scoring &sc, int s, int iv, double dv) {
-    return sc.integral ? s + iv : (int)((double)s + dv);
+    return INTEGRAL ? s + iv : (int)((double)s + dv);
 }
 // border scores `long = GAP * i` (SeqAlign.cpp:489, :494)
 PF_HD int border_score(const Scoring &sc, uint32_t i) {
@@ -69,14 +103,15 @@ PF_HD int unpack_f(int p) { return p & 7; }
 
 // One DP cell (SeqAlign.cpp:512-545).  up/dg/lf are the packed (score,flags) of the three neighbours;
 // block_left is `i != m && A[i] == '-'` (the profile rule, :528-532).
-PF_HD int nw_cell(const Scoring &sc, int up, int dg, int lf, uint8_t a, uint8_t b, bool block_left) {
-    int s_up = add_trunc(sc, unpack_s(up), sc.iG, sc.G) + ((unpack_f(up) & F_UP) ? 1 : 0);
+template <bool INTEGRAL>
+PF_HD int nw_cell_t(const Scoring &sc, int up, int dg, int lf, uint8_t a, uint8_t b, bool block_left) {
+    int s_up = add_trunc<INTEGRAL>(sc, unpack_s(up), sc.iG, sc.G) + ((unpack_f(up) & F_UP) ? 1 : 0);
     int s_dg;
-    if (a == b) s_dg = add_trunc(sc, unpack_s(dg), sc.iM, sc.M);                    // :498-506, equality first
-    else if (a == '-' || b == '-') s_dg = add_trunc(sc, unpack_s(dg), sc.iG, sc.G);
-    else s_dg = add_trunc(sc, unpack_s(dg), sc.iD, sc.D);
+    if (a == b) s_dg = add_trunc<INTEGRAL>(sc, unpack_s(dg), sc.iM, sc.M);                    // :498-506, equality first
+    else if (a == '-' || b == '-') s_dg = add_trunc<INTEGRAL>(sc, unpack_s(dg), sc.iG, sc.G);
+    else s_dg = add_trunc<INTEGRAL>(sc, unpack_s(dg), sc.iD, sc.D);
     s_dg += (unpack_f(dg) & F_DIAG) ? 1 : 0;
-    int s_lf = add_trunc(sc, unpack_s(lf), sc.iG, sc.G) + ((unpack_f(lf) & F_LEFT) ? 1 : 0);
+    int s_lf = add_trunc<INTEGRAL>(sc, unpack_s(lf), sc.iG, sc.G) + ((unpack_f(lf) & F_LEFT) ? 1 : 0);
     int best = s_up > s_dg ? s_up : s_dg;
     if (s_lf > best) best = s_lf;
     if (best == s_lf && block_left) {
@@ -85,6 +120,9 @@ PF_HD int nw_cell(const Scoring &sc, int up, int dg, int lf, uint8_t a, uint8_t 
     }
     int f = (s_up == best ? F_UP : 0) | (s_dg == best ? F_DIAG : 0) | (s_lf == best ? F_LEFT : 0);
     return pack_sf(best, f);
+}
+PF_HD int nw_cell(const Scoring &sc, int up, int dg, int lf, uint8_t a, uint8_t b, bool block_left) {
+    return sc.integral ? nw_cell_t<true>(sc, up, dg, lf, a, b, block_left) : nw_cell_t<false>(sc, up, dg, lf, a, b, block_left);
 }
 
 // AlignUnit::operator- (SeqAlign.hpp:43-67) truncated to int like its call sites (SeqAlign.cpp:334, :599).
@@ -104,7 +142,7 @@ struct PairKey {
 // characters consumed by Up/Diag moves (row 0 of the profile for the pair itself, an earlier MSA row for
 // the projection of :583-598); Left moves put a gap into it.  Moves are stored in DFS order, i.e. the
 // alignment reads from mv[depth-1] down to mv[0].
-PF_HD PairKey analyze_moves(const Scoring &sc, const uint8_t *row, const uint8_t *B, const uint8_t *mv, uint32_t depth) {
+PF_HD PairKey analyze_moves(const Scoring &sc, const CBV row, const CBV B, const CBV mv, uint32_t depth) {
     PairKey k;
     k.score = 0; k.n_pos = 0; k.n_indel = 0;
     uint32_t ia = 0, jb = 0;
@@ -132,21 +170,21 @@ struct TbResult {
 
 // traceback (SeqAlign.cpp:306-478).  flags: diagonal-major bytes written by the fill.
 // Kept alignments go to ext_mv[a*mv_stride ..] with lengths ext_len[a].
-PF_HDN inline TbResult traceback(uint8_t *flags, const uint8_t *A, uint32_t m, const uint8_t *B, uint32_t n,
-                                 const Scoring &sc, uint8_t *mv, uint8_t *ext_mv, uint32_t *ext_len,
+template <bool DIAG>
+PF_HDN inline TbResult traceback(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n,
+                                 const Scoring &sc, const BV mv, const BV ext_mv, const WV ext_len,
                                  uint32_t mv_stride, uint32_t k_aln, uint64_t step_limit) {
     TbResult r;
     r.n_aln = 0; r.status = PF_BUBBLE_OK; r.steps = 0;
-    const uint32_t W = m + 1;
     uint32_t i = m, j = n, depth = 0;
     uint64_t open_a = 0, open_b = 0, cap_a = 5, cap_b = 5;  // indel1, indel2, indel1_max, indel2_max (:312-315)
     PairKey last;
     last.score = 0; last.n_pos = 0; last.n_indel = 0;
     for (;;) {
         if (++r.steps > step_limit) { r.status = PF_BUBBLE_STEP_LIMIT; return r; }
-        const uint32_t cell = (i + j) * W + i;
+        const uint32_t cell = flag_index<DIAG>(i, j, m, n);
         if (i == 0 && j == 0 && open_a <= cap_a && open_b <= cap_b) {   // :322-355
-            const PairKey cand = analyze_moves(sc, A, B, mv, depth);
+            const PairKey cand = analyze_moves(sc, A, B, cbv(mv), depth);
             bool keep = true;
             if (r.n_aln > 0) {
                 const int d = rank_diff(last.score, last.n_pos, last.n_indel, cand.score, cand.n_pos, cand.n_indel);
@@ -155,7 +193,7 @@ PF_HDN inline TbResult traceback(uint8_t *flags, const uint8_t *A, uint32_t m, c
             }
             if (keep) {
                 if (r.n_aln == k_aln) { r.status = PF_BUBBLE_CAND_OVERFLOW; return r; }
-                uint8_t *dst = ext_mv + (uint64_t)r.n_aln * mv_stride;
+                const BV dst = ext_mv + (uint64_t)r.n_aln * mv_stride;
                 for (uint32_t t = 0; t < depth; t++) dst[t] = mv[t];
                 ext_len[r.n_aln] = depth;
                 r.n_aln++;
@@ -205,12 +243,12 @@ PF_HDN inline TbResult traceback(uint8_t *flags, const uint8_t *A, uint32_t m, c
 }
 
 // Writes one aligned row: `src` stretched by the gaps of a move string (Left moves insert '-').
-PF_HD void project_row(const uint8_t *src, const uint8_t *mv, uint32_t depth, uint8_t *dst) {
+PF_HD void project_row(const CBV src, const CBV mv, uint32_t depth, const BV dst) {
     uint32_t ia = 0;
     for (uint32_t c = 0, t = depth; t-- > 0; c++) dst[c] = (mv[t] == MV_L) ? (uint8_t)'-' : src[ia++];
 }
 // The new sequence's row: Up moves insert '-'.
-PF_HD void project_new(const uint8_t *B, const uint8_t *mv, uint32_t depth, uint8_t *dst) {
+PF_HD void project_new(const CBV B, const CBV mv, uint32_t depth, const BV dst) {
     uint32_t jb = 0;
     for (uint32_t c = 0, t = depth; t-- > 0; c++) dst[c] = (mv[t] == MV_U) ? (uint8_t)'-' : B[jb++];
 }
@@ -257,7 +295,7 @@ struct SlotView {   // where the winner is written (one bubble's output slot in 
 
 // One pass over a candidate MSA (rows r at cand + r*stride, L columns).  Fills `key`; when `emit` also
 // writes var columns / classes / indel lengths into `out` and returns their counts.
-PF_HDN inline int scan_candidate(const uint8_t *cand, uint32_t stride, uint32_t nr, uint32_t L, uint64_t Llast,
+PF_HDN inline int scan_candidate(const CBV cand, uint32_t stride, uint32_t nr, uint32_t L, uint64_t Llast,
                                  MsaKey &key, bool emit, SlotView *out, uint32_t *n_var_out, uint32_t *n_ilen_out) {
     PosStats snp, ind, all;
     snp.init(); ind.init(); all.init();
@@ -289,7 +327,7 @@ PF_HDN inline int scan_candidate(const uint8_t *cand, uint32_t stride, uint32_t 
                 bool continues = true;
                 if (open) {
                     for (uint32_t r = 0; r < nr; r++) {
-                        const uint8_t *row = cand + (uint64_t)r * stride;
+                        const CBV row = cand + (uint64_t)r * stride;
                         if ((row[j] == '-') != (row[j - 1] == '-')) { continues = false; break; }
                     }
                     if (!continues) {
@@ -355,7 +393,7 @@ PF_HDN inline int scan_candidate(const uint8_t *cand, uint32_t stride, uint32_t 
 }
 
 // strcmp(a, b) > 0 for two rows of possibly different length (no NUL inside rows).
-PF_HD bool row_greater(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb) {
+PF_HD bool row_greater(const CBV a, uint32_t la, const CBV b, uint32_t lb) {
     const uint32_t n = la < lb ? la : lb;
     for (uint32_t i = 0; i < n; i++)
         if (a[i] != b[i]) return a[i] > b[i];
@@ -412,41 +450,51 @@ struct Limits {          // uniform for one launch
     uint32_t k_aln;      // co-optimal pairwise alignments kept by one traceback (<= 64)
     uint32_t max_var;    // variable columns per output slot
     uint64_t step_limit; // traceback iterations per pair
+    uint32_t diag_flags; // 1: flag bytes stored diagonal-major (generic warp kernel), 0: row-major (lane kernel, host)
+    uint32_t pad_;
 };
 
+PF_HD uint64_t flag_area_cells(const Limits &l) {
+    return l.diag_flags ? (uint64_t)(l.max_alen + l.max_blen + 1) * (l.max_alen + 1) : (uint64_t)(l.max_alen + 1) * (l.max_blen + 1);
+}
+
+
 struct WorkArea {
-    uint8_t *flags;      // (max_alen + max_blen + 1) * (max_alen + 1)
-    uint8_t *mv;         // max_alen + max_blen
-    uint8_t *ext_mv;     // k_aln * (max_alen + max_blen)
-    uint32_t *ext_len;   // k_aln
-    uint8_t *cand[2];    // k_cand * max_rows * max_alen each
-    uint32_t *cand_len[2];  // k_cand each
-    int32_t *brow;       // 2 * (max_blen + 1)
+    BV flags;            // flag_area_cells() bytes, see flag_index()
+    BV mv;               // max_alen + max_blen
+    BV ext_mv;           // k_aln * (max_alen + max_blen)
+    WV ext_len;          // k_aln
+    BV cand[2];          // k_cand * max_rows * max_alen each
+    WV cand_len[2];      // k_cand each
+    int32_t *brow;       // 2 * (max_blen + 1)   (generic kernel only: carried row of the 32-row blocks)
 };
 
 PF_HD uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
-PF_HD uint64_t work_area_bytes(const Limits &l) {
+// Bytes of ONE bubble's work area (`lanes` = 1) or of a lane-interleaved group (`lanes` = 32).
+PF_HD uint64_t work_area_bytes(const Limits &l, uint32_t lanes = 1) {
     uint64_t b = 0;
-    b += align_up((uint64_t)(l.max_alen + l.max_blen + 1) * (l.max_alen + 1), 16);
+    b += align_up(flag_area_cells(l), 16);
     b += align_up(l.max_alen + l.max_blen, 16);
     b += align_up((uint64_t)l.k_aln * (l.max_alen + l.max_blen), 16);
     b += align_up((uint64_t)l.k_aln * 4, 16);
     b += 2 * align_up((uint64_t)l.k_cand * l.max_rows * l.max_alen, 16);
     b += 2 * align_up((uint64_t)l.k_cand * 4, 16);
-    b += align_up((uint64_t)2 * (l.max_blen + 1) * 4, 16);
+    b *= lanes;
+    if (lanes == 1) b += align_up((uint64_t)2 * (l.max_blen + 1) * 4, 16);
     return b;
 }
 
-PF_HD WorkArea carve_work_area(uint8_t *base, const Limits &l) {
+// lanes == 1: contiguous private area.  lanes == 32: element t of lane L's array sits at array_base + t*32 + L.
+PF_HD WorkArea carve_work_area(uint8_t *base, const Limits &l, uint32_t lanes = 1, uint32_t lane = 0) {
     WorkArea w;
     uint8_t *p = base;
-    w.flags = p; p += align_up((uint64_t)(l.max_alen + l.max_blen + 1) * (l.max_alen + 1), 16);
-    w.mv = p; p += align_up(l.max_alen + l.max_blen, 16);
-    w.ext_mv = p; p += align_up((uint64_t)l.k_aln * (l.max_alen + l.max_blen), 16);
-    w.ext_len = (uint32_t *)p; p += align_up((uint64_t)l.k_aln * 4, 16);
-    for (int i = 0; i < 2; i++) { w.cand[i] = p; p += align_up((uint64_t)l.k_cand * l.max_rows * l.max_alen, 16); }
-    for (int i = 0; i < 2; i++) { w.cand_len[i] = (uint32_t *)p; p += align_up((uint64_t)l.k_cand * 4, 16); }
+    w.flags = bv(p + lane, lanes); p += lanes * align_up(flag_area_cells(l), 16);
+    w.mv = bv(p + lane, lanes); p += lanes * align_up(l.max_alen + l.max_blen, 16);
+    w.ext_mv = bv(p + lane, lanes); p += lanes * align_up((uint64_t)l.k_aln * (l.max_alen + l.max_blen), 16);
+    w.ext_len = wv((uint32_t *)p + lane, lanes); p += lanes * align_up((uint64_t)l.k_aln * 4, 16);
+    for (int i = 0; i < 2; i++) { w.cand[i] = bv(p + lane, lanes); p += lanes * align_up((uint64_t)l.k_cand * l.max_rows * l.max_alen, 16); }
+    for (int i = 0; i < 2; i++) { w.cand_len[i] = wv((uint32_t *)p + lane, lanes); p += lanes * align_up((uint64_t)l.k_cand * 4, 16); }
     w.brow = (int32_t *)p;
     return w;
 }
@@ -479,15 +527,18 @@ PF_HD SlotLayout slot_layout(uint32_t n_seq, uint64_t sum_len, const Limits &l) 
 
 // ---- the per-bubble driver: SequenceAlignment (SeqAlign.cpp:550-640) --------------------------------------
 //
-// X is the execution policy: on the GPU a warp (leader = lane 0, fill = wavefront kernel, bcast = shuffle);
-// in tests/hostemu a single thread.
+// X is the execution policy:
+//   * generic kernel: a warp (leader = lane 0, fill = wavefront by shuffle, bcast = shuffle), contiguous work area;
+//   * lane kernel: ONE THREAD per bubble (every lane is its own leader, fill = row-by-row with the score row
+//     in shared memory), lane-interleaved work area;
+//   * tests/hostemu: a single CPU thread.
+// X::kDiagFlags selects the flag-byte layout the policy's fill writes.
 template <class X>
 PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, uint32_t s0, uint32_t ns,
                            const WorkArea &ws, const Limits &lim, const Scoring &sc, uint8_t *slot) {
     const uint32_t mv_stride = lim.max_alen + lim.max_blen;
     const uint64_t cand_stride = (uint64_t)lim.max_rows * lim.max_alen;
-    uint64_t sum_len = 0;
-    for (uint32_t s = 0; s < ns; s++) sum_len += seq_off[s0 + s + 1] - seq_off[s0 + s];
+    const uint64_t sum_len = seq_off[s0 + ns] - seq_off[s0];
     const SlotLayout lay = slot_layout(ns, sum_len, lim);
     SlotHdr *hdr = (SlotHdr *)slot;
     int status = PF_BUBBLE_OK;
@@ -496,22 +547,22 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
     uint32_t ncand = 0;   // leader-owned; other lanes learn it through bcast
     int cur = 0;
     for (uint32_t i = 1; i < ns && status == PF_BUBBLE_OK; i++) {
-        const uint8_t *B = bases + seq_off[s0 + i];
+        const CBV B = cbv(bases + seq_off[s0 + i]);
         const uint32_t n = (uint32_t)(seq_off[s0 + i + 1] - seq_off[s0 + i]);
         if (n > lim.max_blen) { status = PF_BUBBLE_TOO_LONG; break; }
         const uint32_t nk = (i == 1) ? 1u : x.bcast(ncand);
         uint32_t nnext = 0;
         int best_total = INT_MIN;
         for (uint32_t k = 0; k < nk && status == PF_BUBBLE_OK; k++) {
-            const uint8_t *A;
+            CBV A;
             uint32_t m;
-            if (i == 1) { A = bases + seq_off[s0]; m = (uint32_t)(seq_off[s0 + 1] - seq_off[s0]); }
-            else { A = ws.cand[cur] + k * cand_stride; m = x.bcast_ld(ws.cand_len[cur] + k); }
+            if (i == 1) { A = cbv(bases + seq_off[s0]); m = (uint32_t)(seq_off[s0 + 1] - seq_off[s0]); }
+            else { A = cbv(ws.cand[cur] + k * cand_stride); m = x.bcast_ld(&ws.cand_len[cur][k]); }
             if (m > lim.max_alen) { status = PF_BUBBLE_TOO_LONG; break; }
             x.fill(ws.flags, A, m, B, n, sc, ws.brow);
             if (x.leader()) {
-                const TbResult tb = traceback(ws.flags, A, m, B, n, sc, ws.mv, ws.ext_mv, ws.ext_len, mv_stride,
-                                              lim.k_aln, lim.step_limit);
+                const TbResult tb = traceback<X::kDiagFlags>(ws.flags, A, m, B, n, sc, ws.mv, ws.ext_mv, ws.ext_len, mv_stride,
+                                                             lim.k_aln, lim.step_limit);
                 status = tb.status;
                 if (status == PF_BUBBLE_OK) {
                     uint64_t alive = tb.n_aln >= 64 ? ~0ull : ((1ull << tb.n_aln) - 1);
@@ -521,10 +572,10 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
                         inc.score = INT_MIN; inc.n_pos = 0; inc.n_indel = 0;
                         int best_j = INT_MIN;
                         uint64_t alive_j = 0;
-                        const uint8_t *rowj = A + (uint64_t)j * lim.max_alen;
+                        const CBV rowj = A + (uint64_t)j * lim.max_alen;
                         for (uint32_t v = 0; v < tb.n_aln; v++) {
                             if (!((alive >> v) & 1)) continue;
-                            const PairKey pk = analyze_moves(sc, rowj, B, ws.ext_mv + (uint64_t)v * mv_stride, ws.ext_len[v]);
+                            const PairKey pk = analyze_moves(sc, rowj, B, cbv(ws.ext_mv + (uint64_t)v * mv_stride), ws.ext_len[v]);
                             const int d = rank_diff(pk.score, pk.n_pos, pk.n_indel, inc.score, inc.n_pos, inc.n_indel);
                             if (d > 0) { inc = pk; best_j = (int)inc.score; alive_j = 1ull << v; }
                             else if (d == 0) { best_j = (int)inc.score; alive_j |= 1ull << v; }
@@ -539,8 +590,8 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
                             const uint32_t depth = ws.ext_len[v];
                             if (nnext == lim.k_cand) { status = PF_BUBBLE_CAND_OVERFLOW; break; }
                             if (depth > lim.max_alen) { status = PF_BUBBLE_TOO_LONG; break; }
-                            const uint8_t *mvv = ws.ext_mv + (uint64_t)v * mv_stride;
-                            uint8_t *dst = ws.cand[cur ^ 1] + nnext * cand_stride;
+                            const CBV mvv = cbv(ws.ext_mv + (uint64_t)v * mv_stride);
+                            const BV dst = ws.cand[cur ^ 1] + nnext * cand_stride;
                             for (uint32_t r = 0; r < i; r++)
                                 project_row(A + (uint64_t)r * lim.max_alen, mvv, depth, dst + (uint64_t)r * lim.max_alen);
                             project_new(B, mvv, depth, dst + (uint64_t)i * lim.max_alen);
@@ -561,8 +612,8 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
         hdr->n_rows = 0; hdr->alen = 0; hdr->n_var = 0; hdr->n_ilen = 0;
         hdr->pad[0] = hdr->pad[1] = hdr->pad[2] = 0;
         if (status == PF_BUBBLE_OK && ncand > 0) {
-            const uint8_t *cbase = ws.cand[cur];
-            const uint32_t *clen = ws.cand_len[cur];
+            const CBV cbase = cbv(ws.cand[cur]);
+            const WV clen = ws.cand_len[cur];
             const uint64_t Llast = clen[ncand - 1];
             Incumbent inc;
             inc.init();
@@ -572,16 +623,16 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
                 int p = prefer(key, inc);
                 if (p == 2) {   // :190-211: replace as soon as any row compares greater than the incumbent's
                     p = 0;
-                    const uint8_t *ib = cbase + (uint64_t)inc.index * cand_stride;
+                    const CBV ib = cbase + (uint64_t)inc.index * cand_stride;
                     for (uint32_t r = 0; r < ns; r++)
-                        if (row_greater(cbase + c * cand_stride + (uint64_t)r * lim.max_alen, clen[c],
+                        if (row_greater(cbase + (c * cand_stride + (uint64_t)r * lim.max_alen), clen[c],
                                         ib + (uint64_t)r * lim.max_alen, clen[inc.index])) { p = 1; break; }
                 }
                 if (p == 1) adopt(inc, key, (int)c);
             }
             if (inc.index >= 0) {
                 const uint32_t L = clen[inc.index];
-                const uint8_t *win = cbase + (uint64_t)inc.index * cand_stride;
+                const CBV win = cbase + (uint64_t)inc.index * cand_stride;
                 if (L > lay.alen_cap) status = PF_BUBBLE_TOO_LONG;
                 else {
                     SlotView sv;

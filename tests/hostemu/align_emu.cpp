@@ -16,38 +16,44 @@ using namespace pfalign;
 
 namespace {
 
+template <bool DIAG>
 struct HostExec {
+    static constexpr bool kDiagFlags = DIAG;
     std::vector<int> rowbuf;
     bool leader() const { return true; }
     uint32_t bcast(uint32_t v) const { return v; }
     int bcast_i(int v) const { return v; }
     uint32_t bcast_ld(const uint32_t *p) const { return *p; }
     void sync() const {}
-    void fill(uint8_t *flags, const uint8_t *A, uint32_t m, const uint8_t *B, uint32_t n, const Scoring &sc, int32_t *) {
-        const uint32_t W = m + 1;
+    void fill(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n, const Scoring &sc, int32_t *) {
         rowbuf.assign(2 * (size_t)(n + 1), 0);
         int *prev = rowbuf.data(), *cur = rowbuf.data() + n + 1;
         flags[0] = 0;
-        for (uint32_t j = 1; j <= n; j++) { prev[j] = pack_sf(border_score(sc, j), F_LEFT); flags[j * W] = F_LEFT * 0x11; }
+        for (uint32_t j = 1; j <= n; j++) { prev[j] = pack_sf(border_score(sc, j), F_LEFT); flags[flag_index<DIAG>(0, j, m, n)] = F_LEFT * 0x11; }
         prev[0] = pack_sf(0, 0);
         for (uint32_t i = 1; i <= m; i++) {
             cur[0] = pack_sf(border_score(sc, i), F_UP);
-            flags[i * W + i] = F_UP * 0x11;
+            flags[flag_index<DIAG>(i, 0, m, n)] = F_UP * 0x11;
             const bool block_left = (i != m) && A[i] == '-';
             for (uint32_t j = 1; j <= n; j++) {
                 cur[j] = nw_cell(sc, prev[j], prev[j - 1], cur[j - 1], A[i - 1], B[j - 1], block_left);
-                flags[(i + j) * W + i] = (uint8_t)(unpack_f(cur[j]) * 0x11);
+                flags[flag_index<DIAG>(i, j, m, n)] = (uint8_t)(unpack_f(cur[j]) * 0x11);
             }
             std::swap(prev, cur);
         }
     }
 };
 
-Limits g_lim = {16, 0, 0, 16, 16, 0, 50000000ull};
+Limits g_lim = {16, 0, 0, 16, 16, 0, 50000000ull, 0, 0};
+uint32_t g_lanes = 1;   // 32: lay the work area out lane-interleaved like msa_lane_kernel and use slot `g_lane`
+uint32_t g_lane = 0;
 
 }  // namespace
 
 extern "C" {
+
+// diag = 1: diagonal-major flag bytes (msa_warp_kernel); lanes = 32: lane-interleaved work area (msa_lane_kernel)
+void pfemu_set_layout(uint32_t diag, uint32_t lanes, uint32_t lane) { g_lim.diag_flags = diag; g_lanes = lanes; g_lane = lane; }
 
 void pfemu_set_limits(uint32_t max_rows, uint32_t k_cand, uint32_t k_aln, uint32_t max_alen, uint32_t max_var) {
     g_lim.max_rows = max_rows; g_lim.k_cand = k_cand; g_lim.k_aln = k_aln; g_lim.max_alen = max_alen; g_lim.max_var = max_var;
@@ -61,7 +67,8 @@ void *pfemu_align(double M, double D, double G, const char *bases, const uint64_
     const Scoring sc = make_scoring(M, D, G);
     std::atomic<uint32_t> next(0);
     auto worker = [&]() {
-        HostExec x;
+        HostExec<true> xd;
+        HostExec<false> xr;
         std::vector<uint8_t> wbuf, slot;
         for (;;) {
             const uint32_t b = next.fetch_add(1);
@@ -77,11 +84,12 @@ void *pfemu_align(double M, double D, double G, const char *bases, const uint64_
             if (lim.max_alen == 0) lim.max_alen = (uint32_t)sum;
             lim.max_blen = (uint32_t)mx;
             if (lim.max_var == 0) lim.max_var = lim.max_alen;
-            wbuf.assign(work_area_bytes(lim) + 64, 0);
-            const WorkArea ws = carve_work_area(wbuf.data(), lim);
+            wbuf.assign(work_area_bytes(lim, g_lanes) + 64, 0);
+            const WorkArea ws = carve_work_area(wbuf.data(), lim, g_lanes, g_lanes > 1 ? (b + g_lane) % g_lanes : 0);
             const SlotLayout lay = slot_layout(ns, sum, lim);
             slot.assign(lay.bytes + 64, 0);
-            msa_run(x, (const uint8_t *)bases, seq_off, s0, ns, ws, lim, sc, slot.data());
+            if (lim.diag_flags) msa_run(xd, (const uint8_t *)bases, seq_off, s0, ns, ws, lim, sc, slot.data());
+            else msa_run(xr, (const uint8_t *)bases, seq_off, s0, ns, ws, lim, sc, slot.data());
             const SlotHdr *h = (const SlotHdr *)slot.data();
             status[b] = h->status;
             pforacle::MsaResult &r = res[b];

@@ -56,11 +56,18 @@ def _emu_align(emu, bubbles, M=2.0, D=-1.0, G=-3.0):
 ])
 def test_device_state_machines_on_host_match_oracle(oracle, hostemu, seed, kw, sc):
     hostemu.pfemu_set_limits.argtypes = [C.c_uint32] * 5
+    hostemu.pfemu_set_layout.argtypes = [C.c_uint32] * 3
     hostemu.pfemu_set_limits(16, 64, 64, 0, 0)
     bubbles = gen.random_bubbles(seed, 1500, **kw)
     a = oracle.align_bubbles(bubbles, n_threads=8, **sc)
-    b = _emu_align(hostemu, bubbles, **sc)
-    assert_msa_equal(a, b, bubbles, f"seed {seed}")
+    try:
+        # (diagonal-major flags, contiguous area) = msa_warp_kernel; (row-major, lane-interleaved) = msa_lane_kernel
+        for diag, lanes in ((1, 1), (0, 1), (0, 32)):
+            hostemu.pfemu_set_layout(diag, lanes, seed)
+            b = _emu_align(hostemu, bubbles, **sc)
+            assert_msa_equal(a, b, bubbles, f"seed {seed} diag={diag} lanes={lanes}")
+    finally:
+        hostemu.pfemu_set_layout(0, 1, 0)
 
 
 def test_small_capacity_reports_overflow_not_wrong_answers(oracle, hostemu):

@@ -112,25 +112,29 @@ def window_offsets(seq_off: np.ndarray, k: int) -> np.ndarray:
     return out
 
 
-def _np_from(ptr, n, dtype):
+def _np_from(ptr, n, dtype, copy=True):
     if n == 0:
         return np.zeros(0, dtype=dtype)
     nbytes = n * np.dtype(dtype).itemsize
-    return np.ctypeslib.as_array(C.cast(ptr, u8p), shape=(nbytes,)).view(dtype).copy()
+    a = np.ctypeslib.as_array(C.cast(ptr, u8p), shape=(nbytes,)).view(dtype)
+    return a.copy() if copy else a
 
 
-def msa_to_numpy(mb: MsaBatch) -> dict:
+def msa_to_numpy(mb: MsaBatch, copy=True) -> dict:
+    """pf_msa_batch_t -> dict of numpy arrays.  copy=False returns views of the context-owned pinned result
+    buffers (valid until the next pf_align* call on the same context, exactly as the C ABI states)."""
     n = mb.n_bubbles
-    out = {"n_bubbles": n, "status": _np_from(mb.status, n, np.int32), "n_rows": _np_from(mb.n_rows, n, np.uint32),
-           "aln_len": _np_from(mb.aln_len, n, np.uint32)}
+    get = lambda ptr, cnt, dt: _np_from(ptr, cnt, dt, copy)
+    out = {"n_bubbles": n, "status": get(mb.status, n, np.int32), "n_rows": get(mb.n_rows, n, np.uint32),
+           "aln_len": get(mb.aln_len, n, np.uint32)}
     for name in ("rows", "var", "cls", "ilen"):
-        out[name + "_off"] = _np_from(getattr(mb, name + "_off"), n + 1, np.uint64) if n else np.zeros(1, np.uint64)
+        out[name + "_off"] = get(getattr(mb, name + "_off"), n + 1, np.uint64) if n else np.zeros(1, np.uint64)
     tr, tv, tc, ti = (int(out[k + "_off"][-1]) for k in ("rows", "var", "cls", "ilen"))
-    out["rows"] = _np_from(mb.rows, tr, np.uint8)
-    out["var_col"] = _np_from(mb.var_col, tv, np.uint32)
-    out["var_kind"] = _np_from(mb.var_kind, tv, np.uint8)
-    out["cls"] = _np_from(mb.cls, tc, np.uint16)
-    out["ilen"] = _np_from(mb.ilen, ti, np.uint32)
+    out["rows"] = get(mb.rows, tr, np.uint8)
+    out["var_col"] = get(mb.var_col, tv, np.uint32)
+    out["var_kind"] = get(mb.var_kind, tv, np.uint8)
+    out["cls"] = get(mb.cls, tc, np.uint16)
+    out["ilen"] = get(mb.ilen, ti, np.uint32)
     return out
 
 
@@ -162,14 +166,16 @@ class Context:
     def sync(self):
         _check(self.lib.pf_sync(self.h), "pf_sync")
 
-    def align(self, bases, seq_off, bubble_off, M=2.0, D=-1.0, G=-3.0) -> dict:
+    def align(self, bases, seq_off, bubble_off, M=2.0, D=-1.0, G=-3.0, copy=True) -> dict:
+        """SeqAlign::SequenceAlignment over a bubble batch (pf_align).  copy=False: zero-copy views of the result
+        arena, valid until the next align call on this context."""
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
         bubble_off = np.ascontiguousarray(bubble_off, dtype=np.uint32)
         mb = MsaBatch()
         _check(self.lib.pf_align(self.h, M, D, G, bases.ctypes.data, seq_off.ctypes.data, bubble_off.ctypes.data,
                                  len(bubble_off) - 1, C.byref(mb)), "pf_align")
-        return msa_to_numpy(mb)
+        return msa_to_numpy(mb, copy=copy)
 
     def align_dev(self, d_bases, n_bases, d_seq_off, n_seq, d_bubble_off, n_bubbles, max_len, max_rows, M=2.0, D=-1.0,
                   G=-3.0, stream=None) -> MsaBatch:
@@ -249,11 +255,15 @@ class KmcDb:
                                       counts.ctypes.data, found.ctypes.data), "pf_kmc_counts")
         return counts[:n], found[:n]
 
-    def cov(self, bases, seq_off, mode=LOOKUP_FWD_THEN_RC, low=0, up=0xFFFFFFFF):
+    def cov(self, bases, seq_off, mode=LOOKUP_FWD_THEN_RC, low=0, up=0xFFFFFFFF, out=None):
+        """readCov reductions, one record per sequence (pf_kmc_cov).  `out`: optional preallocated COV_DTYPE array
+        (e.g. over pinned memory, which makes the device->host copy a direct DMA)."""
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
         n = len(seq_off) - 1
-        out = np.zeros(max(n, 1), dtype=COV_DTYPE)
+        if out is None:
+            out = np.zeros(max(n, 1), dtype=COV_DTYPE)
+        assert out.dtype == COV_DTYPE and len(out) >= n and out.flags.c_contiguous
         _check(self.lib.pf_kmc_cov(self.h, bases.ctypes.data, seq_off.ctypes.data, n, mode, low, up, out.ctypes.data),
                "pf_kmc_cov")
         return out[:n]

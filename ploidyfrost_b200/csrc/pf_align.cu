@@ -229,7 +229,7 @@ __host__ __device__ constexpr uint32_t lane_smem_per_warp(uint32_t nmax, uint32_
 }
 
 template <bool INTEGRAL, class T>
-__global__ void __launch_bounds__(LANE_BLOCK) msa_lane_kernel(const MsaArgs a) {
+__global__ void __launch_bounds__(LANE_BLOCK, 12) msa_lane_kernel(const MsaArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -715,18 +715,19 @@ int pf_align(pf_ctx *ctx, double M, double D, double G, const char *bases, const
     const uint32_t n_seq = bubble_off[n_bubbles];
     if (bubble_off[0] != 0) { pf::set_error("pf_align: bubble_off[0] must be 0"); return PF_E_INVALID; }
     const uint64_t base0 = seq_off[0], n_bases = seq_off[n_seq] - base0;
-    std::vector<uint64_t> off(n_seq + 1);
     uint32_t max_len = 0, max_rows = 0;
+    int rc;
+    if ((rc = ctx->h_stage[0].reserve((uint64_t)(n_seq + 1) * 8))) return rc;   // rebased offsets, pinned
+    uint64_t *off = ctx->h_stage[0].as<uint64_t>();
     for (uint32_t s = 0; s <= n_seq; s++) off[s] = seq_off[s] - base0;
     for (uint32_t s = 0; s < n_seq; s++) max_len = std::max<uint32_t>(max_len, (uint32_t)(off[s + 1] - off[s]));
     for (uint32_t b = 0; b < n_bubbles; b++) max_rows = std::max(max_rows, bubble_off[b + 1] - bubble_off[b]);
     cudaStream_t s = ctx->stream;
-    int rc;
     if ((rc = st->in_bases.reserve(n_bases + 16))) return rc;
     if ((rc = st->in_seq_off.reserve((uint64_t)(n_seq + 1) * 8))) return rc;
     if ((rc = st->in_bubble_off.reserve((uint64_t)(n_bubbles + 1) * 4))) return rc;
     if (n_bases) PF_CUDA_TRY(cudaMemcpyAsync(st->in_bases.p, bases + base0, n_bases, cudaMemcpyHostToDevice, s));
-    PF_CUDA_TRY(cudaMemcpyAsync(st->in_seq_off.p, off.data(), (uint64_t)(n_seq + 1) * 8, cudaMemcpyHostToDevice, s));
+    PF_CUDA_TRY(cudaMemcpyAsync(st->in_seq_off.p, off, (uint64_t)(n_seq + 1) * 8, cudaMemcpyHostToDevice, s));
     PF_CUDA_TRY(cudaMemcpyAsync(st->in_bubble_off.p, bubble_off, (uint64_t)(n_bubbles + 1) * 4, cudaMemcpyHostToDevice, s));
     DevResult res;
     const Scoring sc = make_scoring(M, D, G);

@@ -578,11 +578,13 @@ static int kmc_host_call(pf_kmc *db, const char *bases, const uint64_t *seq_off,
     PF_CUDA_TRY(cudaSetDevice(ctx->device));
     if (n_seq == 0) return PF_OK;
     const uint64_t n_bases = seq_off[n_seq] - seq_off[0];
-    std::vector<uint64_t> off(n_seq + 1), woff(n_seq + 1);
-    for (uint32_t s = 0; s <= n_seq; s++) off[s] = seq_off[s] - seq_off[0];
-    const uint64_t W = pf_window_offsets(off.data(), n_seq, db->info.kmer_length, woff.data());
-    cudaStream_t st = ctx->stream;
     int rc;
+    // rebased offsets + window offsets are built straight into pinned staging (one async copy each, no bounce buffer)
+    if ((rc = ctx->h_stage[0].reserve((uint64_t)(n_seq + 1) * 16))) return rc;
+    uint64_t *off = ctx->h_stage[0].as<uint64_t>(), *woff = off + (n_seq + 1);
+    for (uint32_t s = 0; s <= n_seq; s++) off[s] = seq_off[s] - seq_off[0];
+    const uint64_t W = pf_window_offsets(off, n_seq, db->info.kmer_length, woff);
+    cudaStream_t st = ctx->stream;
     if ((rc = ctx->d_in[0].reserve(n_bases + 16))) return rc;
     if ((rc = ctx->d_in[1].reserve((n_seq + 1) * 8))) return rc;
     if ((rc = ctx->d_in[2].reserve((n_seq + 1) * 8))) return rc;
@@ -590,8 +592,8 @@ static int kmc_host_call(pf_kmc *db, const char *bases, const uint64_t *seq_off,
     if (found && (rc = ctx->d_out[1].reserve(W + 4))) return rc;
     if (cov && (rc = ctx->d_out[2].reserve((uint64_t)n_seq * sizeof(pf_cov_t)))) return rc;
     if (n_bases) PF_CUDA_TRY(cudaMemcpyAsync(ctx->d_in[0].p, bases + seq_off[0], n_bases, cudaMemcpyHostToDevice, st));
-    PF_CUDA_TRY(cudaMemcpyAsync(ctx->d_in[1].p, off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
-    PF_CUDA_TRY(cudaMemcpyAsync(ctx->d_in[2].p, woff.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+    PF_CUDA_TRY(cudaMemcpyAsync(ctx->d_in[1].p, off, (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+    PF_CUDA_TRY(cudaMemcpyAsync(ctx->d_in[2].p, woff, (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
     rc = pf_kmc_lookup_dev(db, ctx->d_in[0].p, n_bases, ctx->d_in[1].p, ctx->d_in[2].p, n_seq, W, mode, low, up,
                            counts ? ctx->d_out[0].p : nullptr, found ? ctx->d_out[1].p : nullptr,
                            cov ? ctx->d_out[2].p : nullptr, st);

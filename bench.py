@@ -293,13 +293,9 @@ def main():
     n_ok = int((msa["status"] == 0).sum())
 
     # ---- reduce over ranks (max time, summed work) ----
-    stats = torch.tensor([ms_step, ms_e2e, sum(t_lookup) / len(t_lookup), sum(t_align) / len(t_align)], dtype=torch.float64, device=dev)
-    work = torch.tensor([bb.n_bubbles, n_win, cells], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    ms_step, ms_e2e, ms_lookup, ms_align = [float(x) for x in stats.tolist()]
-    tot_bubbles, tot_win, tot_cells = [float(x) for x in work.tolist()]
+    from ploidyfrost_b200 import shard
+    (ms_step, ms_e2e, ms_lookup, ms_align), (tot_bubbles, tot_win, tot_cells) = shard.reduce_step(
+        [ms_step, ms_e2e, sum(t_lookup) / len(t_lookup), sum(t_align) / len(t_align)], [bb.n_bubbles, n_win, cells], device=dev)
 
     if rank == 0:
         peaks = {}

@@ -103,3 +103,9 @@ def test_idempotence_and_permutation_properties(gpu_ctx):
     m2 = gpu_ctx.align(*flatten_bubbles(sub))
     for i in range(100):
         assert msa_bubble(m2, i) == msa_bubble(m, 5000 + i)
+
+
+def test_align_matches_golden_reference_vectors(gpu_ctx):
+    """Committed outputs of the unmodified reference (tests/golden, no /root/reference needed on this box)."""
+    from tests.test_cpu_golden import check_align
+    check_align(lambda b, M, D, G: gpu_ctx.align(*flatten_bubbles(b), M=M, D=D, G=G))

@@ -119,3 +119,12 @@ def test_large_random_property(gpu_ctx, tmp_path):
         assert int(cov["sum"][0]) == int(cg.sum()) and int(cov["min"][0]) == int(cg.min())
     finally:
         db.close()
+
+
+def test_lookup_matches_golden_reference_vectors(gpu_ctx):
+    """Committed outputs of the unmodified CKMCFile (tests/golden), both on-disk layouts, three lookup dialects."""
+    from ploidyfrost_b200 import capi
+    from tests.test_cpu_golden import check_kmc
+    check_kmc(lambda prefix: capi.KmcDb(gpu_ctx, prefix), lambda db: db.close(),
+              lambda db, b, o, k, mode: db.counts(b, o, mode=mode),
+              lambda db, b, o, mode, low, up: db.cov(b, o, mode=mode, low=low, up=up))

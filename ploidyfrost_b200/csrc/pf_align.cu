@@ -51,8 +51,8 @@ __device__ __forceinline__ void warp_fill(uint8_t *__restrict__ flags, const CBV
                                           const uint32_t n, const Scoring &sc, int32_t *brow, const uint32_t lane) {
     __syncwarp();
     const uint32_t W = m + 1;
-    for (uint32_t i = lane; i <= m; i += 32) flags[i * W + i] = i ? (uint8_t)(F_UP * 0x11) : (uint8_t)0;   // column 0 (:486-491)
-    for (uint32_t j = 1 + lane; j <= n; j += 32) flags[j * W] = (uint8_t)(F_LEFT * 0x11);                  // row 0 (:492-496)
+    for (uint32_t i = lane; i <= m; i += 32) flags[i * W + i] = i ? (uint8_t)F_UP : (uint8_t)0;   // column 0 (:486-491)
+    for (uint32_t j = 1 + lane; j <= n; j += 32) flags[j * W] = (uint8_t)F_LEFT;                  // row 0 (:492-496)
     int32_t *rd = brow, *wr = brow + (n + 1);
     for (uint32_t rb = 0; rb * 32 < m; rb++) {
         const uint32_t i = rb * 32 + lane + 1;
@@ -79,7 +79,7 @@ __device__ __forceinline__ void warp_fill(uint8_t *__restrict__ flags, const CBV
             const int j = (int)s - (int)lane + 1;
             if (active && j >= 1 && j <= (int)n) {
                 cur = nw_cell_t<INTEGRAL>(sc, up, diag, cur, a, (uint8_t)b, block_left);
-                flags[(i + (uint32_t)j) * W + i] = (uint8_t)(unpack_f(cur) * 0x11);
+                flags[(i + (uint32_t)j) * W + i] = (uint8_t)unpack_f(cur);
                 if (lane == 31) wr[j] = cur;
             }
             diag = up;
@@ -110,11 +110,47 @@ struct WarpExec {
 
 // ---- per-lane fill (lane kernel) ---------------------------------------------------------------------------
 // rowbuf / bs point at THIS lane's element 0 of the warp's lane-interleaved shared arrays (element j at [j*32]).
-// T is the storage type of the packed (score*8 + flags) row: int16_t when every score of the launch fits 13 bits.
-template <bool INTEGRAL, class T>
+// VARIANT 0: FP64 add+truncate scoring (-M/-D/-G not whole numbers), 1: INT32, 2: two DP rows per step as s16x2.
+constexpr int LANE_FP64 = 0, LANE_I32 = 1, LANE_S16X2 = 2;
+constexpr int S16_BLOCK = -16000;   // "Left is blocked" addend of the s16x2 fill: below every reachable score, no int16 wrap
+
+__device__ __forceinline__ uint32_t pack2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+
+// One step of the two-row fill.  Halves: lo = cell (i, s) of row i, hi = cell (i+1, s-1) of row i+1.
+// Carried per half: U = S + [Up flag], D = S + [Diag flag], L = S + [Left flag] of the previous cell of the row
+// (what the cell below / diagonally below / to the right adds its own term to, SeqAlign.cpp:512-526).
+// `best + flag` is max(best, t + 1) because t <= best: one VIADDMNMX per carried value, no compare/select.
+struct S16Step {
+    uint32_t curU, curD, curL, upD_prev, b2;
+    template <bool LO, bool HI>
+    __device__ __forceinline__ void step(uint32_t w, uint32_t b, uint32_t a2, uint32_t M2, uint32_t NE2, uint32_t G2,
+                                         uint32_t Grow2, uint8_t *f_lo, uint8_t *f_hi, uint32_t *row_out) {
+        const uint32_t ONE2 = 0x00010001u;
+        const uint32_t upU = __byte_perm(w, curU, 0x5410);          // lo: U(i-1,s) from the row buffer, hi: U(i,s-1)
+        const uint32_t upD = __byte_perm(w, curD, 0x5432);          // lo: D(i-1,s),                     hi: D(i,s-1)
+        b2 = __byte_perm(b, b2, 0x5410);                            // lo: B[s-1] (column s), hi: previous column's
+        const uint32_t mask = __vminu2(a2 ^ b2, ONE2) * 0xFFFFu;    // per half: 0xFFFF where the characters differ
+        const uint32_t sub2 = (mask & NE2) | (~mask & M2);          // :498-506 (B holds no '-', checked by the caller)
+        const uint32_t t_up = __vadd2(upU, G2);
+        const uint32_t t_dg = __vadd2(upD_prev, sub2);
+        const uint32_t t_lf = __vadd2(curL, Grow2);
+        const uint32_t best = __vimax3_s16x2(t_up, t_dg, t_lf);
+        const uint32_t nU = __viaddmax_s16x2(t_up, ONE2, best);
+        const uint32_t nD = __viaddmax_s16x2(t_dg, ONE2, best);
+        const uint32_t nL = __viaddmax_s16x2(t_lf, ONE2, best);
+        const uint32_t f2 = ((nU ^ best) & ONE2) + (((nD ^ best) & ONE2) << 1) + (((nL ^ best) & ONE2) << 2);
+        if (LO) *f_lo = (uint8_t)f2;
+        if (HI) { *f_hi = (uint8_t)(f2 >> 16); *row_out = __byte_perm(nU, nD, 0x7632); }
+        upD_prev = upD;
+        curU = nU; curD = nD; curL = nL;
+    }
+};
+
+template <int VARIANT>
 struct LaneExec {
     static constexpr bool kDiagFlags = false;
-    T *rowbuf;
+    static constexpr bool INTEGRAL = VARIANT != LANE_FP64;
+    int32_t *rowbuf;     // 4 bytes per column: packed score*8+flags (scalar fills) or (U, D) as two int16 (s16x2 fill)
     uint8_t *bs;
     unsigned long long cells;
     __device__ __forceinline__ bool leader() const { return true; }
@@ -122,14 +158,14 @@ struct LaneExec {
     __device__ __forceinline__ int bcast_i(int v) const { return v; }
     __device__ __forceinline__ uint32_t bcast_ld(const uint32_t *p) const { return *p; }
     __device__ __forceinline__ void sync() const {}
-    __device__ __forceinline__ void fill(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n, const Scoring &sc,
-                                         int32_t *) {
-        for (uint32_t j = 0; j < n; j++) bs[j * 32] = B[j];
+
+    // rows i = 1..m one at a time
+    __device__ __forceinline__ void fill_scalar(const BV flags, const CBV A, uint32_t m, uint32_t n, const Scoring &sc) {
         flags[0] = 0;
-        rowbuf[0] = (T)pack_sf(0, 0);
+        rowbuf[0] = pack_sf(0, 0);
         for (uint32_t j = 1; j <= n; j++) {                                  // row 0 (:492-496)
-            rowbuf[j * 32] = (T)pack_sf(border_score(sc, j), F_LEFT);
-            flags[j] = (uint8_t)(F_LEFT * 0x11);
+            rowbuf[j * 32] = pack_sf(border_score(sc, j), F_LEFT);
+            flags[j] = (uint8_t)F_LEFT;
         }
         const uint32_t W = n + 1;
         uint8_t a_next = m ? A[0] : (uint8_t)0;
@@ -139,9 +175,9 @@ struct LaneExec {
             const bool block_left = i != m && a_next == '-';
             int dg = rowbuf[0];
             const int c0 = pack_sf(border_score(sc, i), F_UP);               // column 0 (:486-491)
-            rowbuf[0] = (T)c0;
+            rowbuf[0] = c0;
             const BV frow = flags + (uint64_t)i * W;
-            frow[0] = (uint8_t)(F_UP * 0x11);
+            frow[0] = (uint8_t)F_UP;
             if (INTEGRAL) {
                 // Same cell as nw_cell_t (SeqAlign.cpp:512-545) with the loop-carried part cut to two operations:
                 // lf_t = score(i,j-1) + GAP + [Left flag of (i,j-1)] is carried ready-made, and a row whose Left move
@@ -161,8 +197,8 @@ struct LaneExec {
                     const int fl = lf_t >= t ? 1 : 0;
                     const int f = (t_up == best ? F_UP : 0) | (t_dg == best ? F_DIAG : 0) | (fl ? F_LEFT : 0);
                     lf_t = best + Grow + fl;
-                    rowbuf[j * 32] = (T)(best * 8 + f);
-                    frow[j] = (uint8_t)(f * 0x11);
+                    rowbuf[j * 32] = best * 8 + f;
+                    frow[j] = (uint8_t)f;
                     dg = up;
                 }
             } else {
@@ -170,13 +206,76 @@ struct LaneExec {
                 for (uint32_t j = 1; j <= n; j++) {
                     const int up = rowbuf[j * 32];
                     const int cur = nw_cell_t<false>(sc, up, dg, lf, a, bs[(j - 1) * 32], block_left);
-                    rowbuf[j * 32] = (T)cur;
-                    frow[j] = (uint8_t)(unpack_f(cur) * 0x11);
+                    rowbuf[j * 32] = cur;
+                    frow[j] = (uint8_t)unpack_f(cur);
                     dg = up;
                     lf = cur;
                 }
             }
         }
+    }
+
+    // rows (i, i+1) together, row i+1 one column behind: s16x2 arithmetic (VIMNMX3.S16x2 / VIADDMNMX.S16x2 / VIADD.16x2).
+    // Needs n >= 1, integral scoring, every |score| + 1 < 16000 and no '-' in B (the launcher / caller check).
+    __device__ __forceinline__ void fill_s16x2(const BV flags, const CBV A, uint32_t m, uint32_t n, const Scoring &sc) {
+        uint32_t *rb = (uint32_t *)rowbuf;
+        const uint32_t W = n + 1;
+        const int G = sc.iG;
+        flags[0] = 0;
+        rb[0] = pack2(0, 0);                                                 // (0,0): no flags
+        for (uint32_t j = 1; j <= n; j++) {                                  // row 0 carries only Left (:492-496)
+            rb[j * 32] = pack2(G * (int)j, G * (int)j);
+            flags[j] = (uint8_t)F_LEFT;
+        }
+        const uint32_t M2 = pack2(sc.iM, sc.iM), G2 = pack2(G, G);
+        for (uint32_t i = 1; i <= m; i += 2) {
+            const bool two = i < m;                                          // is row i+1 real?
+            const uint8_t a_lo = A[i - 1], a_hi = two ? A[i] : (uint8_t)0;
+            const uint8_t a_after = i + 1 < m ? A[i + 1] : (uint8_t)0;
+            const bool blk_lo = two && a_hi == '-';                          // i != m && A[i] == '-'      (:528)
+            const bool blk_hi = i + 1 < m && a_after == '-';
+            const uint32_t a2 = (uint32_t)a_lo | ((uint32_t)a_hi << 16);
+            const uint32_t NE2 = pack2(a_lo == '-' ? G : sc.iD, a_hi == '-' ? G : sc.iD);
+            const uint32_t Grow2 = pack2(blk_lo ? S16_BLOCK : G, blk_hi ? S16_BLOCK : G);
+            const int b_lo = G * (int)i, b_hi = G * (int)(i + 1);            // border scores (:489)
+            S16Step st;
+            st.curU = pack2(b_lo + 1, 0); st.curD = pack2(b_lo, 0); st.curL = pack2(b_lo, 0);   // cell (i,0): Up only
+            st.upD_prev = rb[0] >> 16;                                       // D(i-1, 0)
+            st.b2 = 0;
+            uint8_t *f0 = &flags[(uint64_t)i * W], *f1 = &flags[(uint64_t)(i + 1) * W];         // stride-32 rows
+            f0[0] = (uint8_t)F_UP;
+            uint32_t dummy;
+            // step 1: only row i has a cell
+            st.step<true, false>(rb[32], bs[0], a2, M2, NE2, G2, Grow2, f0 + 32, nullptr, &dummy);
+            if (two) {
+                f1[0] = (uint8_t)F_UP;
+                rb[0] = pack2(b_hi + 1, b_hi);                               // (i+1,0) for the next pair
+                st.curU = (st.curU & 0xFFFFu) | ((uint32_t)(b_hi + 1) << 16);
+                st.curD = (st.curD & 0xFFFFu) | ((uint32_t)b_hi << 16);
+                st.curL = (st.curL & 0xFFFFu) | ((uint32_t)b_hi << 16);
+#pragma unroll 2
+                for (uint32_t s = 2; s <= n; s++)
+                    st.step<true, true>(rb[s * 32], bs[(s - 1) * 32], a2, M2, NE2, G2, Grow2, f0 + (uint64_t)s * 32,
+                                        f1 + (uint64_t)(s - 1) * 32, rb + (s - 1) * 32);
+                // step n+1: only row i+1 has a cell
+                st.step<false, true>(0, 0, a2, M2, NE2, G2, Grow2, nullptr, f1 + (uint64_t)n * 32, rb + n * 32);
+            } else {
+                for (uint32_t s = 2; s <= n; s++)
+                    st.step<true, false>(rb[s * 32], bs[(s - 1) * 32], a2, M2, NE2, G2, Grow2, f0 + (uint64_t)s * 32, nullptr, &dummy);
+            }
+        }
+    }
+
+    __device__ __forceinline__ void fill(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n, const Scoring &sc,
+                                         int32_t *) {
+        bool dash = false;
+        for (uint32_t j = 0; j < n; j++) {
+            const uint8_t b = B[j];
+            bs[j * 32] = b;
+            dash |= b == '-';
+        }
+        if (VARIANT == LANE_S16X2 && !dash && n >= 1) fill_s16x2(flags, A, m, n, sc);
+        else fill_scalar(flags, A, m, n, sc);
         cells += (unsigned long long)m * n;
     }
 };
@@ -228,16 +327,16 @@ __host__ __device__ constexpr uint32_t lane_smem_per_warp(uint32_t nmax, uint32_
     return 32 * tsize * (nmax + 1) + 32 * nmax;                               // score row + B characters; multiple of 32
 }
 
-template <bool INTEGRAL, class T>
+template <int VARIANT>
 __global__ void __launch_bounds__(LANE_BLOCK, 12) msa_lane_kernel(const MsaArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nmax = a.lim.max_blen;
-    const uint32_t per_warp = lane_smem_per_warp(nmax, sizeof(T));
-    LaneExec<INTEGRAL, T> x;
-    x.rowbuf = (T *)(smem + (size_t)wib * per_warp) + lane;
-    x.bs = smem + (size_t)wib * per_warp + 32 * sizeof(T) * (nmax + 1) + lane;
+    const uint32_t per_warp = lane_smem_per_warp(nmax, 4);
+    LaneExec<VARIANT> x;
+    x.rowbuf = (int32_t *)(smem + (size_t)wib * per_warp) + lane;
+    x.bs = smem + (size_t)wib * per_warp + 32 * 4 * (nmax + 1) + lane;
     x.cells = 0;
     const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim, 32, lane);
     for (;;) {
@@ -399,7 +498,7 @@ struct pf_align_state {
     uint32_t last_retry_count = 0;
     uint64_t last_cells = 0;
     uint32_t last_class_count[N_TIERS] = {0};
-    int lane_blocks_per_sm[3][N_LANE_CLASSES];   // [variant][class]; variants: 0 = FP64 scoring, 1 = int32 row, 2 = int16 row
+    int lane_blocks_per_sm[3][N_LANE_CLASSES];   // [variant][class]; variants: LANE_FP64, LANE_I32, LANE_S16X2
     bool lane_attr_done = false;
     cudaStream_t aux[N_LANE_CLASSES + 1] = {nullptr};   // the size classes run concurrently
     cudaEvent_t ev_fork = nullptr, ev_join[N_LANE_CLASSES + 1] = {nullptr};
@@ -428,17 +527,17 @@ namespace {
 
 constexpr uint64_t WS_BUDGET = 24ull << 30;  // cap on any one work-area pool
 
-size_t lane_smem_bytes(uint32_t nmax, int variant) { return (size_t)(LANE_BLOCK / 32) * lane_smem_per_warp(nmax, variant == 2 ? 2 : 4); }
+size_t lane_smem_bytes(uint32_t nmax, int) { return (size_t)(LANE_BLOCK / 32) * lane_smem_per_warp(nmax, 4); }
 
 typedef void (*LaneKernel)(const MsaArgs);
 LaneKernel lane_kernel(int variant) {
-    return variant == 2 ? msa_lane_kernel<true, int16_t> : variant == 1 ? msa_lane_kernel<true, int32_t> : msa_lane_kernel<false, int32_t>;
+    return variant == LANE_S16X2 ? msa_lane_kernel<LANE_S16X2> : variant == LANE_I32 ? msa_lane_kernel<LANE_I32> : msa_lane_kernel<LANE_FP64>;
 }
-// packed score*8+flags fits int16 when |score| < 4096 for every cell of the class (border, diagonal and bonus included)
+// the s16x2 fill needs every score (border, diagonal, +1 bonuses) to stay well inside int16 even after S16_BLOCK is added
 int lane_variant(const Scoring &sc, const Limits &l) {
-    if (!sc.integral) return 0;
+    if (!sc.integral) return LANE_FP64;
     const long long mag = std::max(std::max(std::llabs((long long)sc.iM), std::llabs((long long)sc.iD)), std::llabs((long long)sc.iG)) + 1;
-    return mag * (long long)(l.max_alen + l.max_blen + 2) < 4000 ? 2 : 1;
+    return mag * (long long)(l.max_alen + l.max_blen + 2) < 15000 ? LANE_S16X2 : LANE_I32;
 }
 
 Limits lane_limits(int c) {

@@ -8,7 +8,7 @@
 //
 // Design notes (what differs from the reference, results identical):
 //   * cell flags are one byte: base flags in bits 0-2 (the by-value `matrix`, permanently pruned) and
-//     work flags in bits 4-6 (`matrix_temp`), stored diagonal-major so the wavefront writes coalesce:
+//     "already tried" marks in bits 4-6 (`matrix_temp` = base & ~tried; the fill writes the 3 base bits only), stored diagonal-major so the wavefront writes coalesce:
 //     byte (i,j) lives at (i+j)*(m+1)+i.  1 byte/cell instead of the reference's 16-byte MatrixUnit x 3 copies.
 //   * the DFS keeps a move string (L/U/D per step) instead of the prepend-built resA/resB/gap_pos and the
 //     (i,j) stack; every test the reference makes on resA[0]/resA[1]/resB[0]/resB[1] is a test on the last
@@ -203,15 +203,15 @@ PF_HDN inline TbResult traceback(const BV flags, const CBV A, uint32_t m, const 
             }
         }
         const uint8_t c = flags[cell];
-        const uint8_t w = c >> 4;
+        const uint8_t w = (uint8_t)(c & 7 & ~(c >> 4));                   // still-untried directions of this cell
         const uint8_t lastmv = depth ? mv[depth - 1] : (uint8_t)MV_NONE;
         if (w & F_LEFT) {                                               // :356-392
             bool take;
             if (open_a < cap_a) { if (lastmv != MV_L) ++open_a; take = true; }
             else if (open_a == cap_a) take = (lastmv == MV_L);
             else take = false;
-            if (!take) { flags[cell] = c & (uint8_t)~(F_LEFT | (F_LEFT << 4)); continue; }
-            flags[cell] = c & (uint8_t)~(F_LEFT << 4);
+            if (!take) { flags[cell] = c & (uint8_t)~F_LEFT; continue; }          // permanent prune of the base matrix
+            flags[cell] = c | (uint8_t)(F_LEFT << 4);
             mv[depth++] = MV_L;
             j--;
         } else if (w & F_UP) {                                          // :393-424
@@ -219,17 +219,17 @@ PF_HDN inline TbResult traceback(const BV flags, const CBV A, uint32_t m, const 
             if (open_b < cap_b) { if (depth == 0 || lastmv == MV_U) ++open_b; take = true; }  // sic (:397)
             else if (open_b == cap_b) take = (lastmv == MV_U);
             else take = false;
-            if (!take) { flags[cell] = c & (uint8_t)~(F_UP | (F_UP << 4)); continue; }
-            flags[cell] = c & (uint8_t)~(F_UP << 4);
+            if (!take) { flags[cell] = c & (uint8_t)~F_UP; continue; }
+            flags[cell] = c | (uint8_t)(F_UP << 4);
             mv[depth++] = MV_U;
             i--;
         } else if (w & F_DIAG) {                                        // :425-431
-            flags[cell] = c & (uint8_t)~(F_DIAG << 4);
+            flags[cell] = c | (uint8_t)(F_DIAG << 4);
             mv[depth++] = MV_D;
             i--; j--;
         } else {                                                        // :432-474
             if (depth == 0) break;
-            flags[cell] = (uint8_t)((c & 7) * 0x11);                    // matrix_temp[p] = matrix[p]
+            flags[cell] = (uint8_t)(c & 7);                             // matrix_temp[p] = matrix[p]
             const uint8_t prev = depth >= 2 ? mv[depth - 2] : (uint8_t)MV_NONE;
             if (lastmv == MV_L && prev != MV_L) --open_a;
             if (lastmv == MV_U && prev != MV_U) --open_b;               // may wrap below zero, as in the reference

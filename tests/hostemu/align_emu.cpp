@@ -29,15 +29,15 @@ struct HostExec {
         rowbuf.assign(2 * (size_t)(n + 1), 0);
         int *prev = rowbuf.data(), *cur = rowbuf.data() + n + 1;
         flags[0] = 0;
-        for (uint32_t j = 1; j <= n; j++) { prev[j] = pack_sf(border_score(sc, j), F_LEFT); flags[flag_index<DIAG>(0, j, m, n)] = F_LEFT * 0x11; }
+        for (uint32_t j = 1; j <= n; j++) { prev[j] = pack_sf(border_score(sc, j), F_LEFT); flags[flag_index<DIAG>(0, j, m, n)] = F_LEFT; }
         prev[0] = pack_sf(0, 0);
         for (uint32_t i = 1; i <= m; i++) {
             cur[0] = pack_sf(border_score(sc, i), F_UP);
-            flags[flag_index<DIAG>(i, 0, m, n)] = F_UP * 0x11;
+            flags[flag_index<DIAG>(i, 0, m, n)] = F_UP;
             const bool block_left = (i != m) && A[i] == '-';
             for (uint32_t j = 1; j <= n; j++) {
                 cur[j] = nw_cell(sc, prev[j], prev[j - 1], cur[j - 1], A[i - 1], B[j - 1], block_left);
-                flags[flag_index<DIAG>(i, j, m, n)] = (uint8_t)(unpack_f(cur[j]) * 0x11);
+                flags[flag_index<DIAG>(i, j, m, n)] = (uint8_t)unpack_f(cur[j]);
             }
             std::swap(prev, cur);
         }

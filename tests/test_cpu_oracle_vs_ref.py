@@ -21,6 +21,8 @@ ALIGN_CASES = [
     (8, dict(len_range=(100, 300), max_indel_len=40), {}),
     (9, dict(alphabet="A", len_range=(5, 30)), {}),
     (10, dict(alphabet="ACG", max_indel=5, max_indel_len=3), {}),
+    (12, {}, dict(M=200, D=-100, G=-300)),
+    (13, dict(alphabet="AC", len_range=(20, 60)), dict(M=1, D=-1, G=-1)),
 ]
 
 

@@ -43,6 +43,9 @@ CASES = [
     (9, dict(alphabet="A", len_range=(5, 30)), {}),
     (10, dict(alphabet="ACG", max_indel=5, max_indel_len=3), {}),
     (11, dict(len_range=(49, 49), max_indel=0, max_snp=1, n_rows=2), {}),
+    (12, {}, dict(M=200, D=-100, G=-300)),          # integral but too large for the s16x2 fill -> INT32 variant
+    (13, dict(alphabet="AC", len_range=(20, 60)), dict(M=1, D=-1, G=-1)),
+    (14, dict(len_range=(150, 250), max_indel_len=20, max_indel=3), {}),   # the 192/256 size classes
 ]
 
 

@@ -147,7 +147,9 @@ def workload_config(args, n_bubbles, info):
                         f"60x-equivalent KMC2 db (k=25, p=9, sig 9, 512 bins), -z 8, M/D/G = 2/-1/-3",
             "batch_bubbles": int(n_bubbles), "db_kmers": (info or {}).get("N"),
             "step": "lookup-A (readCov of entrance + branch unitigs) + SequenceAlignment per bubble",
-            "l2": "flushed between timed steps (256 MiB memset); KMC index (>2 GB) exceeds L2"}
+            "l2": "flushed between timed steps (256 MiB memset); KMC index (>2 GB) exceeds L2",
+            "kmc_index": "partitioned by bin % n_gpus, queries routed by NCCL all-to-all" if getattr(args, "sharded_db", False)
+                         else "replicated on every GPU"}
 
 
 def main():
@@ -163,6 +165,9 @@ def main():
     ap.add_argument("--low", type=int, default=2)
     ap.add_argument("--up", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded-db", action="store_true",
+                    help="partition the KMC index across the ranks (bin % world) and route queries with an NCCL all-to-all "
+                         "instead of replicating it (BASELINE config 3 variant)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -197,7 +202,12 @@ def main():
     barrier()
     torch.cuda.empty_cache()
     ctx = capi.Context(local_rank)
-    db = capi.KmcDb(ctx, prefix)
+    if args.sharded_db:
+        from ploidyfrost_b200 import sharded
+        db = capi.KmcDb(ctx, prefix, part=rank, n_parts=world)
+        sh = sharded.ShardedKmcDb(db)
+    else:
+        db = capi.KmcDb(ctx, prefix)
     barrier()
     t_setup = time.perf_counter() - t_setup
 
@@ -227,8 +237,11 @@ def main():
     def step_device(ev=None):
         if ev:
             ev[0].record(stream)
-        db.lookup_dev(d_lb.data_ptr(), len(lb), d_lo.data_ptr(), d_wo.data_ptr(), n_lseq, n_win, capi.LOOKUP_CANONICAL, args.low,
-                      args.up, None, None, d_cov.data_ptr(), sptr)
+        if args.sharded_db:
+            sh.lookup(d_lb, d_lo, d_wo, n_win, mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up, stream=stream)
+        else:
+            db.lookup_dev(d_lb.data_ptr(), len(lb), d_lo.data_ptr(), d_wo.data_ptr(), n_lseq, n_win, capi.LOOKUP_CANONICAL, args.low,
+                          args.up, None, None, d_cov.data_ptr(), sptr)
         if ev:
             ev[1].record(stream)
         ctx.align_dev(d_ab.data_ptr(), len(bb.bases), d_ao.data_ptr(), bb.n_seq, d_bo.data_ptr(), bb.n_bubbles, max_len, max_rows,
@@ -236,8 +249,9 @@ def main():
         if ev:
             ev[2].record(stream)
 
-    for _ in range(max(args.warmup, 1)):
-        step_device()
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 1)):
+            step_device()
     torch.cuda.synchronize()
     cells = ctx.last_cells
     retry = ctx.last_retry_count
@@ -266,8 +280,8 @@ def main():
         return t, t.numpy()
 
     keep = []
-    h_lb, h_lo, h_ab, h_ao, h_bo = [pinned(x) for x in (lb, lo, bb.bases, bb.seq_off, bb.bubble_off)]
-    keep += [h_lb, h_lo, h_ab, h_ao, h_bo]
+    h_lb, h_lo, h_ab, h_ao, h_bo, h_wo = [pinned(x) for x in (lb, lo, bb.bases, bb.seq_off, bb.bubble_off, wo)]
+    keep += [h_lb, h_lo, h_ab, h_ao, h_bo, h_wo]
     e2e_times = []
     e2e_cov_times = []
     cov_pinned = torch.empty(n_lseq * 24, dtype=torch.uint8).pin_memory()
@@ -277,7 +291,17 @@ def main():
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        cov = db.cov(h_lb[1], h_lo[1], mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up, out=cov_out)
+        if args.sharded_db:   # no host-pointer form of the partitioned lookup: copy in, route/exchange/lookup, copy the cov records out
+            with torch.cuda.stream(stream):
+                e_lb = h_lb[0].to(dev, non_blocking=True)
+                e_lo = h_lo[0].to(dev, non_blocking=True).view(torch.int64)
+                e_wo = h_wo[0].to(dev, non_blocking=True).view(torch.int64)
+                _, _, e_cov = sh.lookup(e_lb, e_lo, e_wo, n_win, mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up, stream=stream)
+                cov_pinned.copy_(e_cov[:n_lseq * 24], non_blocking=True)
+            stream.synchronize()
+            cov = cov_out
+        else:
+            cov = db.cov(h_lb[1], h_lo[1], mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up, out=cov_out)
         t1 = time.perf_counter()
         msa = ctx.align(h_ab[1], h_ao[1], h_bo[1], copy=False)   # views of the pinned result arena (C-ABI ownership rule)
         torch.cuda.synchronize()

@@ -98,6 +98,36 @@ int pf_kmc_lookup_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const v
 /* host helper: win_off[n_seq+1] from seq_off and k; returns the total number of windows */
 uint64_t pf_window_offsets(const uint64_t *seq_off, uint32_t n_seq, uint32_t k, uint64_t *win_off);
 
+/* ---- partitioned database (BASELINE config 3) --------------------------------------------------------
+ * When the index does not fit one GPU it is partitioned -- KMC2: bins with bin % n_parts == part (a k-mer's bin is
+ * signature_map[signature], kmc_file.cpp:349-351); KMC1: the part-th range of ceil(4^p / n_parts) prefixes -- and every
+ * query is answered by the rank that owns its bin.  Per batch, on every rank:
+ *   pf_kmc_route_dev        keys of all live windows, bucketed by owner      (kernel + sort)
+ *   [all-to-all of keys]    8 bytes per query; the caller's transport (NCCL via torch.distributed in sharded.py)
+ *   pf_kmc_lookup_keys_dev  CheckKmer of the received keys against the local partition
+ *   [all-to-all of replies] 4-byte counter + 1-byte found per query
+ *   pf_kmc_scatter_dev      replies back into window order + the readCov reductions
+ * Results equal the unpartitioned calls (PF_LOOKUP_FWD_THEN_RC is routed as the canonical key, which is the same
+ * lookup on a both-strands database and refused otherwise). */
+int pf_kmc_open_part(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, pf_kmc **db);
+/* records held by this index (== total_kmers unless partitioned) */
+uint64_t pf_kmc_local_kmers(const pf_kmc *db);
+/* d_send_keys: u64[n_windows], d_send_idx: u32[n_windows] (device, caller-allocated).  On return h_send_off[0..n_parts]
+ * (host) holds the bucket boundaries: keys for partition o are d_send_keys[h_send_off[o] .. h_send_off[o+1]), and
+ * d_send_idx[t] is the window each sent key came from.  Windows that are not looked up (non-ACGT) are not sent.
+ * Synchronises the stream once (the boundaries are needed to size the exchange). */
+int pf_kmc_route_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const void *d_seq_off, const void *d_win_off,
+                     uint32_t n_seq, uint64_t n_windows, int mode, void *d_send_keys, void *d_send_idx, uint64_t *h_send_off,
+                     void *cuda_stream);
+/* d_keys: u64[n] right-aligned 2-bit k-mers -> d_counts u32[n], d_found u8[n] (0 / 0 when absent, out of
+ * [min_count,max_count] or not owned by this partition) */
+int pf_kmc_lookup_keys_dev(pf_kmc *db, const void *d_keys, uint64_t n, void *d_counts, void *d_found, void *cuda_stream);
+/* replies in send order -> d_counts u32[n_windows], d_found u8[n_windows] (both required) and, when d_cov != NULL,
+ * one pf_cov_t per sequence */
+int pf_kmc_scatter_dev(pf_kmc *db, const void *d_send_idx, uint64_t n_sent, const void *d_reply_counts, const void *d_reply_found,
+                       const void *d_win_off, uint32_t n_seq, uint64_t n_windows, uint32_t low, uint32_t up, void *d_counts,
+                       void *d_found, void *d_cov, void *cuda_stream);
+
 /* ---- SeqAlign ------------------------------------------------------------------------------- */
 /*
  * Batched SeqAlign::SequenceAlignment (SeqAlign.cpp:550) with scoring SeqAlign(M, D, G)

@@ -23,7 +23,8 @@ LOOKUP_CANONICAL, LOOKUP_FWD_THEN_RC, LOOKUP_FWD = 0, 1, 2
 # every symbol include/pf_gpu.h declares (tests check that the library exports all of them)
 EXPORTS = ["pf_init", "pf_shutdown", "pf_last_error", "pf_version", "pf_launch_count", "pf_sync", "pf_kmc_open",
            "pf_kmc_close", "pf_kmc_info", "pf_kmc_set_min_count", "pf_kmc_set_max_count", "pf_kmc_reset_min_max",
-           "pf_kmc_device_bytes", "pf_kmc_counts", "pf_kmc_cov", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
+           "pf_kmc_device_bytes", "pf_kmc_open_part", "pf_kmc_local_kmers", "pf_kmc_route_dev", "pf_kmc_lookup_keys_dev",
+           "pf_kmc_scatter_dev", "pf_kmc_counts", "pf_kmc_cov", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
            "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32"]
 
 
@@ -72,6 +73,14 @@ def load():
     L.pf_launch_count.restype = C.c_uint64
     L.pf_sync.argtypes = [C.c_void_p]
     L.pf_kmc_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.pf_kmc_open_part.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.pf_kmc_local_kmers.argtypes = [C.c_void_p]
+    L.pf_kmc_local_kmers.restype = C.c_uint64
+    L.pf_kmc_route_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pf_kmc_lookup_keys_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pf_kmc_scatter_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,
+                                     C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pf_kmc_close.argtypes = [C.c_void_p]
     L.pf_kmc_info.argtypes = [C.c_void_p, C.POINTER(KmcInfo)]
     L.pf_kmc_set_min_count.argtypes = [C.c_void_p, C.c_uint32]
@@ -212,11 +221,17 @@ class Context:
 class KmcDb:
     """pf_kmc: HBM-resident KMC index (CKMCFile opened for random access)."""
 
-    def __init__(self, ctx: Context, prefix: str):
+    def __init__(self, ctx: Context, prefix: str, part: int = 0, n_parts: int = 1):
+        """n_parts > 1: load only partition `part` of the database (pf_kmc_open_part); such an index answers
+        route_dev / lookup_keys_dev / scatter_dev, not counts / cov."""
         self.ctx = ctx
         self.lib = ctx.lib
+        self.part, self.n_parts = part, n_parts
         h = C.c_void_p()
-        _check(self.lib.pf_kmc_open(ctx.h, prefix.encode(), C.byref(h)), "pf_kmc_open")
+        if n_parts == 1:
+            _check(self.lib.pf_kmc_open(ctx.h, prefix.encode(), C.byref(h)), "pf_kmc_open")
+        else:
+            _check(self.lib.pf_kmc_open_part(ctx.h, prefix.encode(), part, n_parts, C.byref(h)), "pf_kmc_open_part")
         self.h = h
         self.refresh_info()
         self.k = self.info["kmer_length"]
@@ -244,6 +259,25 @@ class KmcDb:
     @property
     def device_bytes(self) -> int:
         return int(self.lib.pf_kmc_device_bytes(self.h))
+
+    @property
+    def local_kmers(self) -> int:
+        return int(self.lib.pf_kmc_local_kmers(self.h))
+
+    def route_dev(self, d_bases, n_bases, d_seq_off, d_win_off, n_seq, n_windows, mode, d_send_keys, d_send_idx, stream=None):
+        """-> send_off[n_parts + 1] (numpy uint64): bucket boundaries of the routed keys."""
+        off = np.zeros(self.n_parts + 1, dtype=np.uint64)
+        _check(self.lib.pf_kmc_route_dev(self.h, d_bases, n_bases, d_seq_off, d_win_off, n_seq, n_windows, mode, d_send_keys,
+                                         d_send_idx, off.ctypes.data, stream), "pf_kmc_route_dev")
+        return off
+
+    def lookup_keys_dev(self, d_keys, n, d_counts, d_found, stream=None):
+        _check(self.lib.pf_kmc_lookup_keys_dev(self.h, d_keys, n, d_counts, d_found, stream), "pf_kmc_lookup_keys_dev")
+
+    def scatter_dev(self, d_send_idx, n_sent, d_reply_counts, d_reply_found, d_win_off, n_seq, n_windows, low, up, d_counts,
+                    d_found, d_cov=None, stream=None):
+        _check(self.lib.pf_kmc_scatter_dev(self.h, d_send_idx, n_sent, d_reply_counts, d_reply_found, d_win_off, n_seq, n_windows,
+                                           low, up, d_counts, d_found, d_cov, stream), "pf_kmc_scatter_dev")
 
     def counts(self, bases, seq_off, mode=LOOKUP_CANONICAL):
         bases = np.ascontiguousarray(bases, dtype=np.uint8)

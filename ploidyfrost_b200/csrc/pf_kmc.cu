@@ -23,9 +23,16 @@
 //    tensor cores.
 #include "pf_common.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <cstring>
 #include <memory>
+
+__global__ void pf_iota_u32(uint32_t *p, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
 
 namespace {
 
@@ -33,9 +40,12 @@ struct KmcView {  // by-value kernel argument
     uint32_t k, p, S, C, sig_len, is_kmc2, lut64, packed;
     uint32_t min_count;
     uint64_t max_count;
-    uint64_t N;
+    uint64_t N;           // records held by THIS index (all of the database, or one partition of it)
     uint64_t single_lut;  // 4^p
     uint64_t lut_n;       // entries including the sentinel
+    uint32_t n_parts, part;   // partitioned index: KMC2 bins with bin % n_parts == part, KMC1 prefixes of one range
+    uint64_t prefix_lo, prefix_cnt;   // KMC1 partition: owned prefixes [prefix_lo, prefix_lo + prefix_cnt)
+    uint64_t prefix_per_part;         // KMC1: ceil(4^p / n_parts)
     const void *lut;
     const uint32_t *sigmap;
     const uint32_t *norm;
@@ -64,12 +74,30 @@ __device__ __forceinline__ uint64_t lut_at(const KmcView &db, uint64_t i) {
     return db.lut64 ? __ldg((const unsigned long long *)db.lut + i) : (uint64_t)__ldg((const uint32_t *)db.lut + i);
 }
 
-// CheckKmer (:330-366) + BinarySearch (:1383-1462) for one key; `bin_base` = bin * 4^p (0 for KMC1).
-__device__ __forceinline__ bool kmc_search(const KmcView &db, uint64_t key, uint64_t bin_base, uint32_t &count) {
+// Which partition owns a key (KMC2: by bin, KMC1: by prefix range); 0 for an unpartitioned index.
+__device__ __forceinline__ uint32_t kmc_owner(const KmcView &db, uint64_t key, uint32_t bin) {
+    if (db.n_parts <= 1) return 0;
+    if (db.is_kmc2) return bin % db.n_parts;
+    return (uint32_t)((key >> (2 * (db.k - db.p))) / db.prefix_per_part);
+}
+
+// CheckKmer (:330-366) + BinarySearch (:1383-1462) for one key; `bin` = signature_map[signature] (0 for KMC1).
+// A key whose bin / prefix is not held by this (partitioned) index is reported absent.
+__device__ __forceinline__ bool kmc_search(const KmcView &db, uint64_t key, uint32_t bin, uint32_t &count) {
     const uint32_t sbits = 2 * (db.k - db.p);
     const uint64_t prefix = key >> sbits;  // sbits < 64 because p >= 1
     const uint64_t suffix = key & ((1ull << sbits) - 1);
-    const uint64_t slot = bin_base + prefix;
+    uint64_t slot;
+    if (db.is_kmc2) {
+        if (db.n_parts > 1) {
+            if (bin % db.n_parts != db.part) return false;
+            bin /= db.n_parts;
+        }
+        slot = (uint64_t)bin * db.single_lut + prefix;
+    } else {
+        if (prefix < db.prefix_lo || prefix - db.prefix_lo >= db.prefix_cnt) return false;
+        slot = prefix - db.prefix_lo;
+    }
     if (slot + 1 >= db.lut_n) return false;
     long long lo = (long long)lut_at(db, slot);
     long long hi = (long long)lut_at(db, slot + 1) - 1;
@@ -97,11 +125,16 @@ __device__ __forceinline__ bool kmc_search(const KmcView &db, uint64_t key, uint
     return false;
 }
 
+// ROUTE = false: look every window up (this index holds the whole database).
+// ROUTE = true : partitioned database -- emit the key of every live window and the partition that owns it
+//                (route_keys[wi], route_owner[wi]; 0xFF = window is not looked up) instead of searching.
+template <bool ROUTE>
 __global__ void __launch_bounds__(LK_THREADS)
 kmc_lookup_kernel(const KmcView db, const uint8_t *__restrict__ bases, const uint64_t n_bases,
                   const uint64_t *__restrict__ seq_off, const uint64_t *__restrict__ win_off, const uint32_t n_seq,
                   const int mode, const uint32_t low, const uint32_t up, uint32_t *__restrict__ counts,
-                  uint8_t *__restrict__ found, pf_cov_t *__restrict__ cov, const uint64_t n_tiles) {
+                  uint8_t *__restrict__ found, pf_cov_t *__restrict__ cov, const uint64_t n_tiles,
+                  unsigned long long *__restrict__ route_keys, uint8_t *__restrict__ route_owner) {
     __shared__ __align__(16) uint8_t s_code[LK_TILE + LK_HALO];
     __shared__ uint32_t s_nv[LK_TILE + LK_HALO];
     __shared__ uint16_t s_q[LK_TILE];
@@ -185,9 +218,12 @@ kmc_lookup_kernel(const KmcView db, const uint8_t *__restrict__ bases, const uin
                         if (g + k <= se) {
                             const uint32_t wi = (uint32_t)(wo + (g - sb));
                             if (last_bad >= (int)q) {  // window touches a non-ACGT character: not found
-                                if (counts) counts[wi] = 0;
-                                if (found) found[wi] = 0;
-                                if (cov) atomicMin((unsigned int *)&cov[s].first_missing, (unsigned int)(g - sb));
+                                if (ROUTE) route_owner[wi] = 0xFF;
+                                else {
+                                    if (counts) counts[wi] = 0;
+                                    if (found) found[wi] = 0;
+                                    if (cov) atomicMin((unsigned int *)&cov[s].first_missing, (unsigned int)(g - sb));
+                                }
                             } else {
                                 my_wi[t] = wi;
                                 my_sq[t] = s;
@@ -241,27 +277,35 @@ kmc_lookup_kernel(const KmcView db, const uint8_t *__restrict__ bases, const uin
                 sq = s_sq[idx];
                 uint64_t fwd = 0;
                 for (uint32_t j = 0; j < k; j++) fwd = (fwd << 2) | s_code[q + j];
-                uint64_t bin_base = 0;
+                uint32_t bin = 0;
                 if (db.is_kmc2) {  // signature = min over the window's m-mers (kmer_api.h:653-672); strand-symmetric
                     uint32_t sig = 0xFFFFFFFFu;
                     for (uint32_t j = 0; j + m <= k; j++) sig = min(sig, s_nv[q + j]);
-                    bin_base = (uint64_t)__ldg(db.sigmap + sig) * db.single_lut;  // kmc_file.cpp:349-351
+                    bin = __ldg(db.sigmap + sig);  // kmc_file.cpp:349-351
+                }
+                if (ROUTE) {  // the owner searches; FWD_THEN_RC is routed as the canonical key (equal on a both-strands DB)
+                    const uint64_t rc = revcomp64(fwd, k);
+                    const uint64_t key = mode == PF_LOOKUP_FWD ? fwd : (fwd < rc ? fwd : rc);
+                    const uint32_t wi = s_wi[idx];
+                    route_keys[wi] = key;
+                    route_owner[wi] = (uint8_t)kmc_owner(db, key, bin);
+                    continue;
                 }
                 if (mode == PF_LOOKUP_FWD) {
-                    ok = kmc_search(db, fwd, bin_base, cnt);
+                    ok = kmc_search(db, fwd, bin, cnt);
                 } else if (mode == PF_LOOKUP_FWD_THEN_RC) {  // CDBG.cpp:38-43
-                    ok = kmc_search(db, fwd, bin_base, cnt);
-                    if (!ok) ok = kmc_search(db, revcomp64(fwd, k), bin_base, cnt);
+                    ok = kmc_search(db, fwd, bin, cnt);
+                    if (!ok) ok = kmc_search(db, revcomp64(fwd, k), bin, cnt);
                 } else {  // canonical key, kmc_file.cpp:1060 / :1290
                     const uint64_t rc = revcomp64(fwd, k);
-                    ok = kmc_search(db, fwd < rc ? fwd : rc, bin_base, cnt);
+                    ok = kmc_search(db, fwd < rc ? fwd : rc, bin, cnt);
                 }
                 if (!ok) cnt = 0;
                 const uint32_t wi = s_wi[idx];
                 if (counts) counts[wi] = cnt;
                 if (found) found[wi] = ok ? 1 : 0;
             }
-            if (cov) {  // readCov reductions (CDBG.cpp:29-120), aggregated per (warp, sequence) segment
+            if (!ROUTE && cov) {  // readCov reductions (CDBG.cpp:29-120), aggregated per (warp, sequence) segment
                 const uint32_t grp = __match_any_sync(0xffffffffu, sq);
                 const uint32_t leader = __ffs(grp) - 1;
                 const uint32_t s_lo = __reduce_add_sync(grp, ok ? (cnt & 0xffffu) : 0u);
@@ -315,6 +359,74 @@ __global__ void repack_records_kernel(const uint8_t *__restrict__ raw, uint64_t 
     else { suf[i] = s; cnt[i] = (uint32_t)c; }
 }
 
+// ---- partitioned database: the owner's side and the way back ---------------------------------------------------
+// One thread per routed key: signature -> bin (KMC2) -> local LUT -> search.
+__global__ void kmc_lookup_keys_kernel(const KmcView db, const unsigned long long *__restrict__ keys, const uint64_t n,
+                                       uint32_t *__restrict__ counts, uint8_t *__restrict__ found) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = keys[i];
+    uint32_t bin = 0;
+    if (db.is_kmc2) {  // kmer_api.h:653-672 on the packed key
+        const uint32_t m = db.sig_len;
+        const uint64_t mask = (1ull << (2 * m)) - 1;
+        uint32_t sig = 0xFFFFFFFFu;
+        for (uint32_t j = 0; j + m <= db.k; j++) sig = min(sig, __ldg(db.norm + ((key >> (2 * (db.k - m - j))) & mask)));
+        bin = __ldg(db.sigmap + sig);
+    }
+    uint32_t c = 0;
+    const bool ok = kmc_search(db, key, bin, c);
+    counts[i] = ok ? c : 0;
+    found[i] = ok ? 1 : 0;
+}
+
+// send_keys[t] = keys[idx[t]] for the t-th window in owner order
+__global__ void kmc_gather_keys_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ idx, uint64_t n,
+                                       unsigned long long *__restrict__ out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = keys[idx[t]];
+}
+
+// bounds[o] = first position of owner o in the sorted owner list, o = 0 .. n_parts (0xFF entries sort last)
+__global__ void kmc_owner_bounds_kernel(const uint8_t *__restrict__ owners, uint64_t n, uint32_t n_parts, uint64_t *bounds) {
+    const uint32_t o = threadIdx.x;
+    if (o > n_parts) return;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (owners[mid] < o) lo = mid + 1; else hi = mid;
+    }
+    bounds[o] = lo;
+}
+
+// replies (in send order) -> per-window outputs
+__global__ void kmc_scatter_kernel(const uint32_t *__restrict__ idx, uint64_t n, const uint32_t *__restrict__ r_counts,
+                                   const uint8_t *__restrict__ r_found, uint32_t *__restrict__ counts, uint8_t *__restrict__ found) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t wi = idx[t];
+    counts[wi] = r_counts[t];
+    found[wi] = r_found[t];
+}
+
+// readCov reductions (CDBG.cpp:29-120) from per-window results, one thread per sequence
+__global__ void kmc_cov_from_counts_kernel(const uint64_t *__restrict__ win_off, uint32_t n_seq, const uint32_t *__restrict__ counts,
+                                           const uint8_t *__restrict__ found, uint32_t low, uint32_t up, pf_cov_t *__restrict__ cov) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seq) return;
+    const uint64_t w0 = win_off[s], w1 = win_off[s + 1];
+    pf_cov_t c;
+    c.sum = 0; c.min = 10000; c.n_kmers = (uint32_t)(w1 - w0); c.first_missing = -1; c.first_outside = -1;
+    for (uint64_t w = w0; w < w1; w++) {
+        if (!found[w]) { if (c.first_missing < 0) c.first_missing = (int32_t)(w - w0); continue; }
+        const uint32_t v = counts[w];
+        c.sum += v;
+        if (v < c.min) c.min = v;
+        if (!(v > low && v < up) && c.first_outside < 0) c.first_outside = (int32_t)(w - w0);
+    }
+    cov[s] = c;
+}
+
 bool slurp(const std::string &path, std::vector<unsigned char> &buf) {
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) return false;
@@ -351,13 +463,23 @@ struct pf_kmc {
     KmcView view{};
     void *d_lut = nullptr, *d_sigmap = nullptr, *d_norm = nullptr, *d_rec = nullptr, *d_suf = nullptr, *d_cnt = nullptr;
     uint64_t device_bytes = 0;
+    uint64_t local_kmers = 0;
+    struct pf_kmc_route_state *route = nullptr;
 };
 
-extern "C" {
+struct pf_kmc_route_state {   // scratch of pf_kmc_route_dev (grow-only)
+    pf::DevBuf keys, owner, owner_sorted, idx, idx_sorted, bounds, cub_tmp;
+    pf::PinnedBuf h_bounds;
+};
 
-int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **out) {
+namespace {
+
+// part / n_parts: n_parts == 1 loads the whole database; otherwise only the partition `part`
+// (KMC2: bins with bin % n_parts == part; KMC1: the part-th range of ceil(4^p / n_parts) prefixes).
+int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, pf_kmc **out) {
     if (!ctx || !prefix || !out) { pf::set_error("pf_kmc_open: null argument"); return PF_E_INVALID; }
     *out = nullptr;
+    if (n_parts == 0 || part >= n_parts || n_parts > 254) { pf::set_error("pf_kmc_open: bad partition %u of %u", part, n_parts); return PF_E_INVALID; }
     PF_CUDA_TRY(cudaSetDevice(ctx->device));
     std::vector<unsigned char> pre;
     const std::string base(prefix);
@@ -441,11 +563,44 @@ int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **out) {
         pf::set_error("%s.kmc_suf: bad KMCS markers", prefix);
         return PF_E_IO;
     }
-    const uint64_t N = I.total_kmers, R = S + C;
-    if (sufbuf.size() - 8 < N * R) { pf::set_error("%s.kmc_suf: %zu bytes, expected %llu records of %llu bytes", prefix, sufbuf.size(), (unsigned long long)N, (unsigned long long)R); return PF_E_IO; }
+    const uint64_t Nall = I.total_kmers, R = S + C;
+    if (sufbuf.size() - 8 < Nall * R) { pf::set_error("%s.kmc_suf: %zu bytes, expected %llu records of %llu bytes", prefix, sufbuf.size(), (unsigned long long)Nall, (unsigned long long)R); return PF_E_IO; }
+    for (size_t i = 0; i + 1 < lut.size(); i++)
+        if (lut[i] > lut[i + 1] || lut[i] > Nall) { pf::set_error("%s.kmc_pre: prefix table is not monotone", prefix); return PF_E_IO; }
+
+    // ---- partition: local prefix table (rebased record indices) + the byte ranges of the owned records ----
+    KmcView &V = db->view;
+    V.n_parts = n_parts; V.part = part; V.prefix_lo = 0; V.prefix_cnt = single;
+    V.prefix_per_part = (single + n_parts - 1) / n_parts;
+    std::vector<std::pair<uint64_t, uint64_t>> ranges;   // [first, last) global record indices, in local order
+    uint64_t N = Nall;
+    if (n_parts > 1) {
+        std::vector<uint64_t> loc;
+        uint64_t acc = 0;
+        auto rec_end = [&](uint64_t slot) { return std::min<uint64_t>(lut[slot], Nall); };
+        if (I.kmc_version == 0x200) {
+            for (uint32_t b = part; b < I.n_bins; b += n_parts) {
+                const uint64_t s0 = (uint64_t)b * single, g0 = rec_end(s0), g1 = rec_end(s0 + single);
+                for (uint64_t x = 0; x < single; x++) loc.push_back(rec_end(s0 + x) - g0 + acc);
+                ranges.emplace_back(g0, g1);
+                acc += g1 - g0;
+            }
+        } else {
+            V.prefix_lo = std::min<uint64_t>((uint64_t)part * V.prefix_per_part, single);
+            V.prefix_cnt = std::min<uint64_t>(V.prefix_per_part, single - V.prefix_lo);
+            const uint64_t g0 = rec_end(V.prefix_lo), g1 = rec_end(V.prefix_lo + V.prefix_cnt);
+            for (uint64_t x = 0; x < V.prefix_cnt; x++) loc.push_back(rec_end(V.prefix_lo + x) - g0);
+            ranges.emplace_back(g0, g1);
+            acc = g1 - g0;
+        }
+        loc.push_back(acc + 1);   // same N+1 end sentinel convention as the reader (:233, :292)
+        lut.swap(loc);
+        N = acc;
+    } else {
+        ranges.emplace_back(0, Nall);
+    }
 
     // ---- device image ----
-    KmcView &V = db->view;
     V.k = k; V.p = p; V.S = S; V.C = C; V.sig_len = I.signature_len; V.is_kmc2 = I.kmc_version == 0x200;
     V.min_count = I.min_count; V.max_count = I.max_count; V.N = N; V.single_lut = single; V.lut_n = lut.size();
     V.lut64 = (N + 1 >= (1ull << 32)) ? 1 : 0;
@@ -456,6 +611,7 @@ int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **out) {
     if (V.lut64) {
         PF_CUDA_TRY(cudaMalloc(&db->d_lut, lut.size() * 8));
         PF_CUDA_TRY(cudaMemcpyAsync(db->d_lut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, st));
+        PF_CUDA_TRY(cudaStreamSynchronize(st));
         bytes += lut.size() * 8;
     } else {
         std::vector<uint32_t> l32(lut.size());
@@ -471,6 +627,7 @@ int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **out) {
         PF_CUDA_TRY(cudaMemcpyAsync(db->d_sigmap, sigmap.data(), sigmap.size() * 4, cudaMemcpyHostToDevice, st));
         PF_CUDA_TRY(cudaMalloc(&db->d_norm, norm.size() * 4));
         PF_CUDA_TRY(cudaMemcpyAsync(db->d_norm, norm.data(), norm.size() * 4, cudaMemcpyHostToDevice, st));
+        PF_CUDA_TRY(cudaStreamSynchronize(st));
         bytes += (sigmap.size() + norm.size()) * 4;
         V.sigmap = (const uint32_t *)db->d_sigmap;
         V.norm = (const uint32_t *)db->d_norm;
@@ -478,7 +635,12 @@ int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **out) {
     if (N) {
         void *d_raw = nullptr;
         PF_CUDA_TRY(cudaMalloc(&d_raw, N * R));
-        PF_CUDA_TRY(cudaMemcpyAsync(d_raw, &sufbuf[4], N * R, cudaMemcpyHostToDevice, st));
+        uint64_t at = 0;
+        for (auto &r : ranges) {
+            const uint64_t nb = (r.second - r.first) * R;
+            if (nb) PF_CUDA_TRY(cudaMemcpyAsync((uint8_t *)d_raw + at, &sufbuf[4 + r.first * R], nb, cudaMemcpyHostToDevice, st));
+            at += nb;
+        }
         if (V.packed) {
             PF_CUDA_TRY(cudaMalloc(&db->d_rec, N * 8));
             bytes += N * 8;
@@ -498,13 +660,33 @@ int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **out) {
     PF_CUDA_TRY(cudaStreamSynchronize(st));
     V.rec = (const uint64_t *)db->d_rec; V.suf = (const uint64_t *)db->d_suf; V.cnt = (const uint32_t *)db->d_cnt;
     db->device_bytes = bytes;
+    db->local_kmers = N;
     *out = db.release();
     return PF_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
+int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **out) { return kmc_open_impl(ctx, prefix, 0, 1, out); }
+
+int pf_kmc_open_part(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, pf_kmc **out) {
+    return kmc_open_impl(ctx, prefix, part, n_parts, out);
+}
+
+uint64_t pf_kmc_local_kmers(const pf_kmc *db) { return db ? db->local_kmers : 0; }
+
 int pf_kmc_close(pf_kmc *db) {
     if (!db) return PF_OK;
     cudaSetDevice(db->ctx->device);
+    if (db->route) {
+        pf::DevBuf *d[] = {&db->route->keys, &db->route->owner, &db->route->owner_sorted, &db->route->idx, &db->route->idx_sorted,
+                           &db->route->bounds, &db->route->cub_tmp};
+        for (auto *b : d) b->release();
+        db->route->h_bounds.release();
+        delete db->route;
+    }
     cudaFree(db->d_lut); cudaFree(db->d_sigmap); cudaFree(db->d_norm);
     cudaFree(db->d_rec); cudaFree(db->d_suf); cudaFree(db->d_cnt);
     delete db;
@@ -552,6 +734,7 @@ int pf_kmc_lookup_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const v
     if (!db) { pf::set_error("pf_kmc_lookup_dev: null database"); return PF_E_INVALID; }
     if (mode < PF_LOOKUP_CANONICAL || mode > PF_LOOKUP_FWD) { pf::set_error("pf_kmc_lookup_dev: bad mode %d", mode); return PF_E_INVALID; }
     if (n_windows >= (1ull << 32)) { pf::set_error("pf_kmc_lookup_dev: more than 2^32-1 windows in one call; split the batch"); return PF_E_INVALID; }
+    if (db->view.n_parts > 1) { pf::set_error("pf_kmc_lookup_dev: this index holds one partition of the database; use pf_kmc_route_dev / pf_kmc_lookup_keys_dev"); return PF_E_INVALID; }
     pf_ctx *ctx = db->ctx;
     PF_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
@@ -563,10 +746,104 @@ int pf_kmc_lookup_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const v
     if (n_bases == 0 || n_windows == 0) { PF_CUDA_TRY(cudaGetLastError()); return PF_OK; }
     const uint64_t n_tiles = (n_bases + LK_TILE - 1) / LK_TILE;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 6);
-    kmc_lookup_kernel<<<grid, LK_THREADS, 0, st>>>(db->view, (const uint8_t *)d_bases, n_bases, (const uint64_t *)d_seq_off,
-                                                  (const uint64_t *)d_win_off, n_seq, mode, low, up, (uint32_t *)d_counts,
-                                                  (uint8_t *)d_found, (pf_cov_t *)d_cov, n_tiles);
+    kmc_lookup_kernel<false><<<grid, LK_THREADS, 0, st>>>(db->view, (const uint8_t *)d_bases, n_bases, (const uint64_t *)d_seq_off,
+                                                         (const uint64_t *)d_win_off, n_seq, mode, low, up, (uint32_t *)d_counts,
+                                                         (uint8_t *)d_found, (pf_cov_t *)d_cov, n_tiles, nullptr, nullptr);
     ctx->launches++;
+    PF_CUDA_TRY(cudaGetLastError());
+    return PF_OK;
+}
+
+// ---- partitioned database: route -> [all-to-all] -> lookup at the owner -> [all-to-all] -> scatter ----
+int pf_kmc_route_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const void *d_seq_off, const void *d_win_off,
+                     uint32_t n_seq, uint64_t n_windows, int mode, void *d_send_keys, void *d_send_idx, uint64_t *h_send_off,
+                     void *cuda_stream) {
+    if (!db || !h_send_off) { pf::set_error("pf_kmc_route_dev: null argument"); return PF_E_INVALID; }
+    if (mode < PF_LOOKUP_CANONICAL || mode > PF_LOOKUP_FWD) { pf::set_error("pf_kmc_route_dev: bad mode %d", mode); return PF_E_INVALID; }
+    if (mode == PF_LOOKUP_FWD_THEN_RC && !db->info.both_strands) {
+        pf::set_error("pf_kmc_route_dev: FWD_THEN_RC is routed as the canonical key, which needs a both-strands database");
+        return PF_E_UNSUPPORTED;
+    }
+    if (n_windows >= (1ull << 32)) { pf::set_error("pf_kmc_route_dev: more than 2^32-1 windows in one call; split the batch"); return PF_E_INVALID; }
+    pf_ctx *ctx = db->ctx;
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const uint32_t P = db->view.n_parts;
+    for (uint32_t o = 0; o <= P; o++) h_send_off[o] = 0;
+    if (n_seq == 0 || n_windows == 0 || n_bases == 0) return PF_OK;
+    if (!db->route) db->route = new pf_kmc_route_state();
+    pf_kmc_route_state *R = db->route;
+    int rc;
+    if ((rc = R->keys.reserve(n_windows * 8))) return rc;
+    if ((rc = R->owner.reserve(n_windows + 16))) return rc;
+    if ((rc = R->owner_sorted.reserve(n_windows + 16))) return rc;
+    if ((rc = R->idx.reserve(n_windows * 4))) return rc;
+    if ((rc = R->bounds.reserve((P + 2) * 8))) return rc;
+    if ((rc = R->h_bounds.reserve((P + 2) * 8))) return rc;
+    // windows shorter sequences never produce stay 0xFF (not sent)
+    PF_CUDA_TRY(cudaMemsetAsync(R->owner.p, 0xFF, n_windows, st));
+    const uint64_t n_tiles = (n_bases + LK_TILE - 1) / LK_TILE;
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 6);
+    kmc_lookup_kernel<true><<<grid, LK_THREADS, 0, st>>>(db->view, (const uint8_t *)d_bases, n_bases, (const uint64_t *)d_seq_off,
+                                                        (const uint64_t *)d_win_off, n_seq, mode, 0, 0, nullptr, nullptr, nullptr, n_tiles,
+                                                        R->keys.as<unsigned long long>(), R->owner.as<uint8_t>());
+    // bucket by owner: stable radix sort of (owner, window index) on the 8 owner bits
+    {
+        uint32_t *idx = R->idx.as<uint32_t>();   // window indices 0..n-1 as the sort's value array
+        pf_iota_u32<<<(unsigned)((n_windows + 255) / 256), 256, 0, st>>>(idx, n_windows);
+        size_t tmp = 0;
+        PF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp, R->owner.as<uint8_t>(), R->owner_sorted.as<uint8_t>(), idx,
+                                                    (uint32_t *)d_send_idx, (int)n_windows, 0, 8, st));
+        if ((rc = R->cub_tmp.reserve(tmp + 16))) return rc;
+        tmp = R->cub_tmp.cap;
+        PF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(R->cub_tmp.p, tmp, R->owner.as<uint8_t>(), R->owner_sorted.as<uint8_t>(), idx,
+                                                    (uint32_t *)d_send_idx, (int)n_windows, 0, 8, st));
+    }
+    kmc_owner_bounds_kernel<<<1, 256, 0, st>>>(R->owner_sorted.as<uint8_t>(), n_windows, P, R->bounds.as<uint64_t>());
+    kmc_gather_keys_kernel<<<(unsigned)((n_windows + 255) / 256), 256, 0, st>>>(R->keys.as<unsigned long long>(), (const uint32_t *)d_send_idx,
+                                                                               n_windows, (unsigned long long *)d_send_keys);
+    ctx->launches += 6;
+    PF_CUDA_TRY(cudaGetLastError());
+    PF_CUDA_TRY(cudaMemcpyAsync(R->h_bounds.p, R->bounds.p, (P + 1) * 8, cudaMemcpyDeviceToHost, st));
+    PF_CUDA_TRY(cudaStreamSynchronize(st));
+    for (uint32_t o = 0; o <= P; o++) h_send_off[o] = R->h_bounds.as<uint64_t>()[o];
+    return PF_OK;
+}
+
+int pf_kmc_lookup_keys_dev(pf_kmc *db, const void *d_keys, uint64_t n, void *d_counts, void *d_found, void *cuda_stream) {
+    if (!db || (n && (!d_keys || !d_counts || !d_found))) { pf::set_error("pf_kmc_lookup_keys_dev: null argument"); return PF_E_INVALID; }
+    pf_ctx *ctx = db->ctx;
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    if (!n) return PF_OK;
+    kmc_lookup_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(db->view, (const unsigned long long *)d_keys, n, (uint32_t *)d_counts,
+                                                                       (uint8_t *)d_found);
+    ctx->launches++;
+    PF_CUDA_TRY(cudaGetLastError());
+    return PF_OK;
+}
+
+int pf_kmc_scatter_dev(pf_kmc *db, const void *d_send_idx, uint64_t n_sent, const void *d_reply_counts, const void *d_reply_found,
+                       const void *d_win_off, uint32_t n_seq, uint64_t n_windows, uint32_t low, uint32_t up, void *d_counts,
+                       void *d_found, void *d_cov, void *cuda_stream) {
+    if (!db || !d_counts || !d_found) { pf::set_error("pf_kmc_scatter_dev: null argument (d_counts and d_found are required)"); return PF_E_INVALID; }
+    pf_ctx *ctx = db->ctx;
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    if (n_windows) {
+        PF_CUDA_TRY(cudaMemsetAsync(d_counts, 0, n_windows * 4, st));   // windows that were not routed are "not found"
+        PF_CUDA_TRY(cudaMemsetAsync(d_found, 0, n_windows, st));
+    }
+    if (n_sent) {
+        kmc_scatter_kernel<<<(unsigned)((n_sent + 255) / 256), 256, 0, st>>>((const uint32_t *)d_send_idx, n_sent, (const uint32_t *)d_reply_counts,
+                                                                            (const uint8_t *)d_reply_found, (uint32_t *)d_counts, (uint8_t *)d_found);
+        ctx->launches++;
+    }
+    if (d_cov && n_seq) {
+        kmc_cov_from_counts_kernel<<<(n_seq + 255) / 256, 256, 0, st>>>((const uint64_t *)d_win_off, n_seq, (const uint32_t *)d_counts,
+                                                                       (const uint8_t *)d_found, low, up, (pf_cov_t *)d_cov);
+        ctx->launches++;
+    }
     PF_CUDA_TRY(cudaGetLastError());
     return PF_OK;
 }
@@ -577,6 +854,7 @@ static int kmc_host_call(pf_kmc *db, const char *bases, const uint64_t *seq_off,
     pf_ctx *ctx = db->ctx;
     PF_CUDA_TRY(cudaSetDevice(ctx->device));
     if (n_seq == 0) return PF_OK;
+    if (db->view.n_parts > 1) { pf::set_error("pf_kmc_counts/cov: this index holds one partition of the database; use the route / lookup_keys / scatter calls"); return PF_E_INVALID; }
     const uint64_t n_bases = seq_off[n_seq] - seq_off[0];
     int rc;
     // rebased offsets + window offsets are built straight into pinned staging (one async copy each, no bounce buffer)

@@ -39,34 +39,49 @@ def env_int(name, default):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons of one GPU during the timed region, through NVML in-process (an `nvidia-smi`
+    subprocess per sample initialises NVML for every GPU of the box each time and perturbs a multi-rank run)."""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []       # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
         self.stop_flag = False
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
+        while not self.stop_flag and self.h is not None:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                mhz = int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, rs))
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for n, bit in self.REASONS.items() if any(s[1] & bit for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples),
+                "source": "NVML (nvmlDeviceGetClockInfo / CurrentClocksEventReasons), 50 ms period, timed region + e2e loop"}
 
 
 def make_workload(args, rank, world, need_db_files, db_dir, device=None):
@@ -317,6 +332,8 @@ def main():
     n_ok = int((msa["status"] == 0).sum())
 
     # ---- reduce over ranks (max time, summed work) ----
+    sys.stderr.write(f"[rank {rank}] step {ms_step:.2f} ms (lookup {sum(t_lookup) / len(t_lookup):.2f}, align {sum(t_align) / len(t_align):.2f}), "
+                     f"e2e {ms_e2e:.2f} ms; tiers {ctx.last_tier_counts}; batch {bb.stats()}\n")
     from ploidyfrost_b200 import shard
     (ms_step, ms_e2e, ms_lookup, ms_align), (tot_bubbles, tot_win, tot_cells) = shard.reduce_step(
         [ms_step, ms_e2e, sum(t_lookup) / len(t_lookup), sum(t_align) / len(t_align)], [bb.n_bubbles, n_win, cells], device=dev)

@@ -130,7 +130,7 @@ __device__ __forceinline__ bool kmc_search(const KmcView &db, uint64_t key, uint
 //                (route_keys[wi], route_owner[wi]; 0xFF = window is not looked up) instead of searching.
 template <bool ROUTE>
 __global__ void __launch_bounds__(LK_THREADS)
-kmc_lookup_kernel(const KmcView db, const uint8_t *__restrict__ bases, const uint64_t n_bases,
+kmc_lookup_kernel(const KmcView db, const uint8_t *__restrict__ bases, const uint64_t n_bases_arg,
                   const uint64_t *__restrict__ seq_off, const uint64_t *__restrict__ win_off, const uint32_t n_seq,
                   const int mode, const uint32_t low, const uint32_t up, uint32_t *__restrict__ counts,
                   uint8_t *__restrict__ found, pf_cov_t *__restrict__ cov, const uint64_t n_tiles,
@@ -146,6 +146,8 @@ kmc_lookup_kernel(const KmcView db, const uint8_t *__restrict__ bases, const uin
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t k = db.k, m = db.sig_len;
     const bool aligned16 = ((uintptr_t)bases & 15) == 0;
+    // a caller may hand over a padded buffer: bases past the last sequence belong to no window
+    const uint64_t n_bases = min(n_bases_arg, (uint64_t)__ldg((const unsigned long long *)seq_off + n_seq));
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t p0 = tile * LK_TILE;

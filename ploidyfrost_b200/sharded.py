@@ -59,7 +59,8 @@ class ShardedKmcDb:
 
     def lookup(self, d_bases: torch.Tensor, d_seq_off: torch.Tensor, d_win_off: torch.Tensor, n_windows: int, mode=0, low=0,
                up=0xFFFFFFFF, want_cov=True, stream=None):
-        """Device tensors in (uint8 bases, int64 offsets), device tensors out: (counts int32-as-u32, found uint8, cov bytes)."""
+        """Device tensors in (uint8 bases -- may be padded past the last sequence --, int64 offsets), device tensors
+        out: (counts int32-as-u32, found uint8, cov bytes)."""
         dev = d_bases.device
         n_seq = d_seq_off.numel() - 1
         sptr = stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream

@@ -47,7 +47,7 @@ def test_partitioned_lookup_equals_replicated(gpu_ctx, tmp_path, ver, p, n_parts
             exp_cov = full.cov(bases, off, mode=mode, low=1, up=3)
             keys = torch.empty(nw, dtype=torch.int64, device=dev)
             idx = torch.empty(nw, dtype=torch.int32, device=dev)
-            soff = parts[0].route_dev(d_b.data_ptr(), len(bases), d_o.data_ptr(), d_w.data_ptr(), ns, nw, mode, keys.data_ptr(), idx.data_ptr())
+            soff = parts[0].route_dev(d_b.data_ptr(), d_b.numel(), d_o.data_ptr(), d_w.data_ptr(), ns, nw, mode, keys.data_ptr(), idx.data_ptr())
             n_sent = int(soff[-1])
             assert n_sent <= nw and (np.diff(soff.astype(np.int64)) >= 0).all()
             rc = torch.zeros(max(n_sent, 1), dtype=torch.int32, device=dev)

@@ -149,7 +149,8 @@ int pf_align_dev(pf_ctx *ctx, double M, double D, double G, const void *d_bases,
                  const void *d_seq_off, uint32_t n_seq, const void *d_bubble_off, uint32_t n_bubbles,
                  uint32_t max_len, uint32_t max_rows, pf_msa_batch_t *out_dev, void *cuda_stream);
 /* diagnostics: bubbles per execution tier of the last pf_align* call: out[0..4] = thread-per-bubble kernel, size classes
- * (longest branch <= 64/96/128/192/256); out[5] = warp-per-bubble kernel; out[6] = re-runs with the large limits */
+ * (longest branch <= 64/96/128/192/256); out[5] = warp-per-bubble kernel; out[6] = re-runs with the flag matrix in shared
+ * memory (long co-optimal searches); out[7] = re-runs with the large limits */
 int pf_align_last_tier_counts(const pf_ctx *ctx, uint32_t *out, int n);
 /* diagnostics: bubbles of the last pf_align / pf_align_dev call that needed the large (tier-2) work area */
 uint32_t pf_align_last_retry_count(const pf_ctx *ctx);

@@ -199,8 +199,8 @@ class Context:
 
     @property
     def last_tier_counts(self) -> list:
-        a = (C.c_uint32 * 7)()
-        _check(self.lib.pf_align_last_tier_counts(self.h, a, 7), "pf_align_last_tier_counts")
+        a = (C.c_uint32 * 8)()
+        _check(self.lib.pf_align_last_tier_counts(self.h, a, 8), "pf_align_last_tier_counts")
         return list(a)
 
     @property

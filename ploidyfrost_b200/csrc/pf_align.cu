@@ -40,8 +40,10 @@ constexpr uint32_t FULL = 0xffffffffu;
 // size classes of the lane kernel: longest branch of the bubble <= LANE_NMAX[c]
 constexpr int N_LANE_CLASSES = 5;
 constexpr int CLS_BIG = N_LANE_CLASSES;        // first pass of the warp kernel
-constexpr int CLS_RETRY = N_LANE_CLASSES + 1;  // second pass (large limits)
-constexpr int N_TIERS = N_LANE_CLASSES + 2;
+constexpr int CLS_RETRY_SMEM = N_LANE_CLASSES + 1;  // re-run, warp kernel with the flag bytes in shared memory (long DFS searches)
+constexpr int CLS_RETRY = N_LANE_CLASSES + 2;       // re-run, warp kernel with the large limits
+constexpr int N_TIERS = N_LANE_CLASSES + 3;
+constexpr uint32_t LANE_STEP_LIMIT = 6144;          // traceback iterations a lane may spend on one bubble (typical: ~300, p99.9 ~1500)
 __host__ __device__ constexpr uint32_t lane_nmax(int c) { return c == 0 ? 64u : c == 1 ? 96u : c == 2 ? 128u : c == 3 ? 192u : 256u; }
 constexpr uint32_t LANE_MAX_ROWS = 8;
 
@@ -101,6 +103,7 @@ struct WarpExec {
     __device__ __forceinline__ int bcast_i(int v) const { return __shfl_sync(FULL, v, 0); }
     __device__ __forceinline__ uint32_t bcast_ld(const uint32_t *p) const { return *(const volatile uint32_t *)p; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ void note_steps(uint64_t) const {}
     __device__ __forceinline__ void fill(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n, const Scoring &sc,
                                          int32_t *brow) {
         warp_fill<INTEGRAL>(flags.p, A, m, B.p, n, sc, brow, lane);
@@ -158,6 +161,7 @@ struct LaneExec {
     __device__ __forceinline__ int bcast_i(int v) const { return v; }
     __device__ __forceinline__ uint32_t bcast_ld(const uint32_t *p) const { return *p; }
     __device__ __forceinline__ void sync() const {}
+    __device__ __forceinline__ void note_steps(uint64_t) const {}
 
     // rows i = 1..m one at a time
     __device__ __forceinline__ void fill_scalar(const BV flags, const CBV A, uint32_t m, uint32_t n, const Scoring &sc) {
@@ -300,11 +304,15 @@ struct MsaArgs {
     Scoring sc;
 };
 
-template <bool INTEGRAL>
+// SMEM_FLAGS: one warp per CTA with the flag matrix in dynamic shared memory -- the tier for bubbles whose co-optimal
+// DFS is long (tens of thousands of dependent flag reads: ~30 cycles each from shared memory instead of an L2/HBM trip).
+template <bool INTEGRAL, bool SMEM_FLAGS>
 __global__ void __launch_bounds__(WARP_BLOCK) msa_warp_kernel(const MsaArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_flags[];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim);
+    WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim);
+    if (SMEM_FLAGS) ws.flags = bv(smem_flags);
     WarpExec<INTEGRAL> x;
     x.lane = lane;
     x.cells = 0;
@@ -489,7 +497,7 @@ __global__ void gather_kernel(const GatherArgs g) {
 }  // namespace
 
 struct pf_align_state {
-    pf::DevBuf ws_warp[2], slots[2], slot_sizes, slot_off, slot_ptr, tier, counter, retry_list, cub_tmp;
+    pf::DevBuf ws_warp[3], slots[3], slot_sizes, slot_off, slot_ptr, tier, counter, retry_list, cub_tmp;
     pf::DevBuf keys[2], ids[2];
     pf::DevBuf status, n_rows, aln_len, sz[4], off[4];
     pf::DevBuf rows, var_col, var_kind, cls, ilen;
@@ -511,7 +519,7 @@ void pf_align_state_free(pf_align_state *s) {
     for (auto &st : s->aux) if (st) cudaStreamDestroy(st);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     for (auto &e : s->ev_join) if (e) cudaEventDestroy(e);
-    pf::DevBuf *d[] = {&s->ws_warp[0], &s->ws_warp[1], &s->slots[0], &s->slots[1], &s->slot_sizes, &s->slot_off,
+    pf::DevBuf *d[] = {&s->ws_warp[0], &s->ws_warp[1], &s->ws_warp[2], &s->slots[0], &s->slots[1], &s->slots[2], &s->slot_sizes, &s->slot_off,
                        &s->slot_ptr, &s->tier, &s->counter, &s->retry_list, &s->cub_tmp, &s->keys[0], &s->keys[1], &s->ids[0],
                        &s->ids[1], &s->status, &s->n_rows, &s->aln_len, &s->rows, &s->var_col, &s->var_kind, &s->cls, &s->ilen,
                        &s->in_bases, &s->in_seq_off, &s->in_bubble_off};
@@ -546,7 +554,7 @@ Limits lane_limits(int c) {
     l.max_blen = lane_nmax(c);
     l.max_alen = l.max_blen + 32;
     l.k_cand = 8; l.k_aln = 8; l.max_var = 48;
-    l.step_limit = 2000000ull;
+    l.step_limit = LANE_STEP_LIMIT;
     l.diag_flags = 0; l.pad_ = 0;
     return l;
 }
@@ -587,8 +595,33 @@ int launch_warp_tier(pf_ctx *ctx, pf_align_state *st, int pool, const Limits &li
     MsaArgs a;
     fill_args(a, st, pool, lim, sc, d_bases, d_seq_off, d_bubble_off, d_order, first, n_items, tier_id, counter);
     a.ws_base = st->ws_warp[pool].as<uint8_t>(); a.ws_stride = ws_bytes;
-    if (sc.integral) msa_warp_kernel<true><<<blocks, WARP_BLOCK, 0, s>>>(a);
-    else msa_warp_kernel<false><<<blocks, WARP_BLOCK, 0, s>>>(a);
+    if (sc.integral) msa_warp_kernel<true, false><<<blocks, WARP_BLOCK, 0, s>>>(a);
+    else msa_warp_kernel<false, false><<<blocks, WARP_BLOCK, 0, s>>>(a);
+    ctx->launches++;
+    PF_CUDA_TRY(cudaGetLastError());
+    return PF_OK;
+}
+
+// the shared-memory-flags variant: one warp per CTA, dynamic smem = the flag matrix of `lim`
+int launch_warp_smem_tier(pf_ctx *ctx, pf_align_state *st, int pool, const Limits &lim, const Scoring &sc, const uint8_t *d_bases,
+                          const uint64_t *d_seq_off, const uint32_t *d_bubble_off, const uint32_t *d_order, uint32_t n_items,
+                          int tier_id, uint32_t *counter, cudaStream_t s) {
+    const size_t smem = (size_t)align_up(flag_area_cells(lim), 16);
+    static bool attr_done = false;
+    if (!attr_done) {
+        PF_CUDA_TRY(cudaFuncSetAttribute(msa_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PF_CUDA_TRY(cudaFuncSetAttribute(msa_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const uint64_t ws_bytes = align_up(work_area_bytes(lim), 256);
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((uint64_t)n_items, (uint64_t)ctx->sm_count);
+    int rc;
+    if ((rc = st->ws_warp[pool].reserve((uint64_t)blocks * ws_bytes))) return rc;
+    MsaArgs a;
+    fill_args(a, st, pool, lim, sc, d_bases, d_seq_off, d_bubble_off, d_order, 0, n_items, tier_id, counter);
+    a.ws_base = st->ws_warp[pool].as<uint8_t>(); a.ws_stride = ws_bytes;
+    if (sc.integral) msa_warp_kernel<true, true><<<blocks, 32, smem, s>>>(a);
+    else msa_warp_kernel<false, true><<<blocks, 32, smem, s>>>(a);
     ctx->launches++;
     PF_CUDA_TRY(cudaGetLastError());
     return PF_OK;
@@ -640,6 +673,12 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
     big.max_alen = big.max_blen + std::min<uint32_t>(64, big.max_blen);
     big.k_cand = 8; big.k_aln = 8; big.max_var = 48;
     big.step_limit = 200000000ull; big.diag_flags = 1; big.pad_ = 0;
+    Limits &heavy = tt.lim[CLS_RETRY_SMEM];   // warp kernel, flag bytes in shared memory: (320+256+1)*321 = 185 KB per CTA
+    heavy.max_rows = std::min<uint32_t>(std::max<uint32_t>(max_rows, 2), 64);
+    heavy.max_blen = lane_nmax(N_LANE_CLASSES - 1);
+    heavy.max_alen = heavy.max_blen + 64;
+    heavy.k_cand = 64; heavy.k_aln = 64; heavy.max_var = heavy.max_alen;
+    heavy.step_limit = 2000000000ull; heavy.diag_flags = 1; heavy.pad_ = 0;
     Limits &huge = tt.lim[CLS_RETRY];     // warp kernel, second pass: generous
     huge.max_rows = std::min<uint32_t>(std::max<uint32_t>(max_rows, 2), 64);
     huge.max_blen = big.max_blen;
@@ -710,26 +749,33 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         PF_CUDA_TRY(cudaEventRecord(st->ev_join[c], as));
         PF_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_join[c], 0));
     }
-    // ---- retry list -> second pass of the warp kernel with the large limits ----
-    uint32_t *d_retry_cnt = st->counter.as<uint32_t>() + 16;
-    collect_retry_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, st->slot_ptr.as<uint64_t>(), st->retry_list.as<uint32_t>(), d_retry_cnt);
-    ctx->launches++;
-    uint32_t *h_cnt = (uint32_t *)(st->h_scalars.as<uint8_t>() + 64);
-    PF_CUDA_TRY(cudaMemcpyAsync(h_cnt, d_retry_cnt, 4, cudaMemcpyDeviceToHost, s));
-    PF_CUDA_TRY(cudaStreamSynchronize(s));
-    st->last_retry_count = *h_cnt;
-    st->last_class_count[CLS_RETRY] = *h_cnt;
-    if (*h_cnt) {
+    // ---- re-runs: whatever overflowed its tier goes to the shared-memory-flags warp kernel (branches <= 256), and what
+    //      still does not fit to the warp kernel with the large limits ----
+    st->last_retry_count = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        const int tier = pass == 0 ? CLS_RETRY_SMEM : CLS_RETRY;
+        uint32_t *d_retry_cnt = st->counter.as<uint32_t>() + 16 + pass;
+        collect_retry_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, st->slot_ptr.as<uint64_t>(), st->retry_list.as<uint32_t>(), d_retry_cnt);
+        ctx->launches++;
+        uint32_t *h_cnt = (uint32_t *)(st->h_scalars.as<uint8_t>() + 64);
+        PF_CUDA_TRY(cudaMemcpyAsync(h_cnt, d_retry_cnt, 4, cudaMemcpyDeviceToHost, s));
+        PF_CUDA_TRY(cudaStreamSynchronize(s));
         const uint32_t nr = *h_cnt;
-        slot_size_kernel<<<(nr + 1 + 255) / 256, 256, 0, s>>>(d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), nullptr, CLS_RETRY, nr,
-                                                              tt, st->slot_sizes.as<uint64_t>());
+        st->last_class_count[tier] = nr;
+        if (pass == 0) st->last_retry_count = nr;
+        if (!nr) break;
+        slot_size_kernel<<<(nr + 1 + 255) / 256, 256, 0, s>>>(d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), nullptr, tier, nr, tt,
+                                                              st->slot_sizes.as<uint64_t>());
         ctx->launches++;
         if ((rc = exclusive_scan_u64(ctx, st, st->slot_sizes.as<uint64_t>(), st->slot_off.as<uint64_t>(), nr + 1, s))) return rc;
         PF_CUDA_TRY(cudaMemcpyAsync(h_total, st->slot_off.as<uint64_t>() + nr, 8, cudaMemcpyDeviceToHost, s));
         PF_CUDA_TRY(cudaStreamSynchronize(s));
-        if ((rc = st->slots[1].reserve(*h_total + 64))) return rc;
-        if ((rc = launch_warp_tier(ctx, st, 1, huge, sc, d_bases, d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), 0, nr, CLS_RETRY,
-                                   st->counter.as<uint32_t>() + CLS_RETRY, s))) return rc;
+        if ((rc = st->slots[1 + pass].reserve(*h_total + 64))) return rc;
+        if (pass == 0) rc = launch_warp_smem_tier(ctx, st, 1, heavy, sc, d_bases, d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), nr, tier,
+                                                  st->counter.as<uint32_t>() + tier, s);
+        else rc = launch_warp_tier(ctx, st, 2, huge, sc, d_bases, d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), 0, nr, tier,
+                                   st->counter.as<uint32_t>() + tier, s);
+        if (rc) return rc;
     }
     // ---- sizes -> offsets ----
     const uint32_t n1 = n + 1;
@@ -856,7 +902,8 @@ int pf_align(pf_ctx *ctx, double M, double D, double G, const char *bases, const
 uint32_t pf_align_last_retry_count(const pf_ctx *ctx) { return (ctx && ctx->align) ? ctx->align->last_retry_count : 0; }
 // diagnostics: DP cells (m*n summed over every needlemanWunch fill) of the last pf_align* call
 uint64_t pf_align_last_cells(const pf_ctx *ctx) { return (ctx && ctx->align) ? ctx->align->last_cells : 0; }
-// diagnostics: bubbles per tier of the last call: [0..4] lane-kernel size classes (<=64/96/128/192/256), [5] warp kernel, [6] retries
+// diagnostics: bubbles per tier of the last call: [0..4] lane-kernel size classes (<=64/96/128/192/256), [5] warp kernel,
+// [6] re-runs in the shared-memory-flags warp kernel, [7] re-runs with the large limits
 int pf_align_last_tier_counts(const pf_ctx *ctx, uint32_t *out, int n) {
     if (!ctx || !out) return PF_E_INVALID;
     for (int i = 0; i < n; i++) out[i] = (ctx->align && i < N_TIERS) ? ctx->align->last_class_count[i] : 0;

@@ -449,7 +449,7 @@ struct Limits {          // uniform for one launch
     uint32_t k_cand;     // candidate MSAs carried between rounds (<= 64)
     uint32_t k_aln;      // co-optimal pairwise alignments kept by one traceback (<= 64)
     uint32_t max_var;    // variable columns per output slot
-    uint64_t step_limit; // traceback iterations per pair
+    uint64_t step_limit; // traceback iterations per bubble (summed over its pairwise alignments)
     uint32_t diag_flags; // 1: flag bytes stored diagonal-major (generic warp kernel), 0: row-major (lane kernel, host)
     uint32_t pad_;
 };
@@ -545,6 +545,7 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
     if (ns < 2) status = PF_BUBBLE_BAD_INPUT;
     else if (ns > lim.max_rows) status = PF_BUBBLE_TOO_MANY_ROWS;
     uint32_t ncand = 0;   // leader-owned; other lanes learn it through bcast
+    uint64_t steps_left = lim.step_limit;   // traceback budget of the whole bubble (all its pairwise alignments)
     int cur = 0;
     for (uint32_t i = 1; i < ns && status == PF_BUBBLE_OK; i++) {
         const CBV B = cbv(bases + seq_off[s0 + i]);
@@ -562,7 +563,9 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
             x.fill(ws.flags, A, m, B, n, sc, ws.brow);
             if (x.leader()) {
                 const TbResult tb = traceback<X::kDiagFlags>(ws.flags, A, m, B, n, sc, ws.mv, ws.ext_mv, ws.ext_len, mv_stride,
-                                                             lim.k_aln, lim.step_limit);
+                                                             lim.k_aln, steps_left);
+                steps_left -= tb.steps < steps_left ? tb.steps : steps_left;
+                x.note_steps(tb.steps);
                 status = tb.status;
                 if (status == PF_BUBBLE_OK) {
                     uint64_t alive = tb.n_aln >= 64 ? ~0ull : ((1ull << tb.n_aln) - 1);

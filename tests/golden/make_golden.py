@@ -38,6 +38,9 @@ LITERALS = [
     (["ACGTAAAATTGCA", "ACGTAAATTGCA", "ACGTCAAATTGCA"], (2, -1, -3)),
     (["GATTACAGATTACA", "GATTACATTACA", "GATTACAGATTCCA", "GATTACATTCCA"], (2, -1, -3)),
     (["ACGTACGTAC", "ACGTTCGTAC"], (2.5, -1.5, -3.5)),
+    # a real bubble of the config-2 workload whose co-optimal traceback takes ~32 000 DFS steps (100x the typical 2 x length):
+    # it overflows the thread-per-bubble tier's step budget and is re-run with the flag matrix in shared memory
+    (["CTAACGATAACACCGGACGTGATTACGTATTACCTGAAGCTACCGGGGCGCCTGTTGCCAAGCGTTACGTCGATCAAGCTAGCCTTACGACCGTCTTATCGTTAACCACCGCAGCTTCGCTAGTGTGTGTATCTATGTTTTATCCTCGCCCGCCCGAGCTATCTCCACAAGACACA", "CTAACGATAACACCGGACGTGATTACGTATTACCTGAAGCTACCGGGGCGCCTGTTGCCAAGCGTTCCGGCGATCCAGCTAGCCTTACGACCGTCTTATCGTTAACCACCGCAGCGAGTGTGTATCTATGGTTTATCCTCGCCGGCCCGAGCTATCTCCACAAGACACA", "CTAACGATAACACCGGACGTGATTACGTATTACCTGAAGCTACCGGGGCGCCTGTTGCCAAGCGTTCCGGCGATCAAGCTAGCCTTACGACCGTCTTATCATTAACCACCGCAGCGAGTGTGTATCTATGTTTTATCCTCGCCCGCCCGAGCTATCTCCACAAGACACA", "CTAACGATAACACCGGACGTGATTAAGTATTACGTGAAGCTACCGTGGCGCCTGTTGCCAAGCGTTCCGGCGATCAAGCTAGCCTTACGACCGTCTTATCGTTAACCACCGCAGCGAGTGTGTATCTATGTTATATCCTCGCCCGCCCGAGCTATCTCCACAAGACACA"], (2, -1, -3)),
 ]
 
 RANDOM_GROUPS = [

@@ -25,6 +25,8 @@ struct HostExec {
     int bcast_i(int v) const { return v; }
     uint32_t bcast_ld(const uint32_t *p) const { return *p; }
     void sync() const {}
+    uint64_t steps = 0;
+    void note_steps(uint64_t n) { steps += n; }
     void fill(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n, const Scoring &sc, int32_t *) {
         rowbuf.assign(2 * (size_t)(n + 1), 0);
         int *prev = rowbuf.data(), *cur = rowbuf.data() + n + 1;
@@ -47,6 +49,7 @@ struct HostExec {
 Limits g_lim = {16, 0, 0, 16, 16, 0, 50000000ull, 0, 0};
 uint32_t g_lanes = 1;   // 32: lay the work area out lane-interleaved like msa_lane_kernel and use slot `g_lane`
 uint32_t g_lane = 0;
+std::vector<uint64_t> g_steps;   // traceback iterations per bubble of the last pfemu_align call
 
 }  // namespace
 
@@ -64,6 +67,7 @@ void *pfemu_align(double M, double D, double G, const char *bases, const uint64_
                   uint32_t n_bubbles, int n_threads, pf_msa_batch_t *out) {
     std::vector<pforacle::MsaResult> res(n_bubbles);
     std::vector<int32_t> status(n_bubbles, 0);
+    g_steps.assign(n_bubbles, 0);
     const Scoring sc = make_scoring(M, D, G);
     std::atomic<uint32_t> next(0);
     auto worker = [&]() {
@@ -88,8 +92,10 @@ void *pfemu_align(double M, double D, double G, const char *bases, const uint64_
             const WorkArea ws = carve_work_area(wbuf.data(), lim, g_lanes, g_lanes > 1 ? (b + g_lane) % g_lanes : 0);
             const SlotLayout lay = slot_layout(ns, sum, lim);
             slot.assign(lay.bytes + 64, 0);
+            xd.steps = xr.steps = 0;
             if (lim.diag_flags) msa_run(xd, (const uint8_t *)bases, seq_off, s0, ns, ws, lim, sc, slot.data());
             else msa_run(xr, (const uint8_t *)bases, seq_off, s0, ns, ws, lim, sc, slot.data());
+            g_steps[b] = xd.steps + xr.steps;
             const SlotHdr *h = (const SlotHdr *)slot.data();
             status[b] = h->status;
             pforacle::MsaResult &r = res[b];
@@ -119,6 +125,8 @@ void *pfemu_align(double M, double D, double G, const char *bases, const uint64_
     p->view(out);
     return p;
 }
+
+const uint64_t *pfemu_last_steps() { return g_steps.data(); }
 
 void pfemu_msa_free(void *h) { delete (pforacle::MsaPacked *)h; }
 

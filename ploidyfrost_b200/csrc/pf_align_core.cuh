@@ -142,22 +142,51 @@ struct PairKey {
 // characters consumed by Up/Diag moves (row 0 of the profile for the pair itself, an earlier MSA row for
 // the projection of :583-598); Left moves put a gap into it.  Moves are stored in DFS order, i.e. the
 // alignment reads from mv[depth-1] down to mv[0].
+// The loops below are latency bound on the GPU (one thread, dependent global loads), so they work in chunks
+// of PF_CH elements: all loads of a chunk are issued before any of them is used.
+#define PF_CH 8
+// dst[0..n) = src[0..n), chunked
+PF_HD void copy_bytes(const CBV src, const BV dst, uint32_t n) {
+    for (uint32_t c0 = 0; c0 < n; c0 += PF_CH) {
+        uint8_t v[PF_CH];
+#pragma unroll
+        for (uint32_t q = 0; q < PF_CH; q++) v[q] = c0 + q < n ? src[c0 + q] : (uint8_t)0;
+#pragma unroll
+        for (uint32_t q = 0; q < PF_CH; q++) if (c0 + q < n) dst[c0 + q] = v[q];
+    }
+}
+
 PF_HD PairKey analyze_moves(const Scoring &sc, const CBV row, const CBV B, const CBV mv, uint32_t depth) {
     PairKey k;
     k.score = 0; k.n_pos = 0; k.n_indel = 0;
     uint32_t ia = 0, jb = 0;
     int run = 0;
-    for (uint32_t t = depth; t-- > 0;) {
-        const uint8_t m = mv[t];
-        const uint8_t a = (m == MV_L) ? (uint8_t)'-' : row[ia++];
-        const uint8_t b = (m == MV_U) ? (uint8_t)'-' : B[jb++];
-        if (sc.integral) k.score += (a == '-' || b == '-') ? sc.iG : (a == b ? sc.iM : sc.iD);      // :241-246, gap first
-        else k.score = (long long)((double)k.score + ((a == '-' || b == '-') ? sc.G : (a == b ? sc.M : sc.D)));  // long += double
-        if (a != b) {
-            if (a == '-') { if (run != 1) { run = 1; k.n_indel++; k.n_pos++; } }
-            else if (b == '-') { if (run != 2) { run = 2; k.n_indel++; k.n_pos++; } }
-            else { run = 0; k.n_pos++; }
-        } else run = 0;
+    for (uint32_t t0 = depth; t0 > 0;) {
+        const uint32_t cnt = t0 < PF_CH ? t0 : PF_CH;
+        uint8_t m[PF_CH], a[PF_CH], b[PF_CH];
+#pragma unroll
+        for (uint32_t q = 0; q < PF_CH; q++) m[q] = q < cnt ? mv[t0 - 1 - q] : (uint8_t)MV_NONE;
+        uint32_t ia_q = ia, jb_q = jb;
+#pragma unroll
+        for (uint32_t q = 0; q < PF_CH; q++) {
+            const bool use_a = q < cnt && m[q] != MV_L, use_b = q < cnt && m[q] != MV_U;
+            a[q] = use_a ? row[ia_q] : (uint8_t)'-';
+            b[q] = use_b ? B[jb_q] : (uint8_t)'-';
+            ia_q += use_a; jb_q += use_b;
+        }
+        ia = ia_q; jb = jb_q;
+#pragma unroll
+        for (uint32_t q = 0; q < PF_CH; q++) {
+            if (q >= cnt) break;
+            if (sc.integral) k.score += (a[q] == '-' || b[q] == '-') ? sc.iG : (a[q] == b[q] ? sc.iM : sc.iD);      // :241-246, gap first
+            else k.score = (long long)((double)k.score + ((a[q] == '-' || b[q] == '-') ? sc.G : (a[q] == b[q] ? sc.M : sc.D)));  // long += double
+            if (a[q] != b[q]) {
+                if (a[q] == '-') { if (run != 1) { run = 1; k.n_indel++; k.n_pos++; } }
+                else if (b[q] == '-') { if (run != 2) { run = 2; k.n_indel++; k.n_pos++; } }
+                else { run = 0; k.n_pos++; }
+            } else run = 0;
+        }
+        t0 -= cnt;
     }
     return k;
 }
@@ -193,8 +222,7 @@ PF_HDN inline TbResult traceback(const BV flags, const CBV A, uint32_t m, const 
             }
             if (keep) {
                 if (r.n_aln == k_aln) { r.status = PF_BUBBLE_CAND_OVERFLOW; return r; }
-                const BV dst = ext_mv + (uint64_t)r.n_aln * mv_stride;
-                for (uint32_t t = 0; t < depth; t++) dst[t] = mv[t];
+                copy_bytes(cbv(mv), ext_mv + (uint64_t)r.n_aln * mv_stride, depth);
                 ext_len[r.n_aln] = depth;
                 r.n_aln++;
                 last = cand;
@@ -242,16 +270,31 @@ PF_HDN inline TbResult traceback(const BV flags, const CBV A, uint32_t m, const 
     return r;
 }
 
-// Writes one aligned row: `src` stretched by the gaps of a move string (Left moves insert '-').
-PF_HD void project_row(const CBV src, const CBV mv, uint32_t depth, const BV dst) {
-    uint32_t ia = 0;
-    for (uint32_t c = 0, t = depth; t-- > 0; c++) dst[c] = (mv[t] == MV_L) ? (uint8_t)'-' : src[ia++];
+// Writes one aligned row: `src` stretched by the gaps of a move string (`gap_move` = MV_L for the rows of the profile,
+// MV_U for the new sequence: that move inserts '-').
+PF_HD void project_moves(const CBV src, const CBV mv, uint32_t depth, const BV dst, const uint8_t gap_move) {
+    uint32_t ia = 0, c = 0;
+    for (uint32_t t0 = depth; t0 > 0;) {
+        const uint32_t cnt = t0 < PF_CH ? t0 : PF_CH;
+        uint8_t m[PF_CH], v[PF_CH];
+#pragma unroll
+        for (uint32_t q = 0; q < PF_CH; q++) m[q] = q < cnt ? mv[t0 - 1 - q] : gap_move;
+        uint32_t ia_q = ia;
+#pragma unroll
+        for (uint32_t q = 0; q < PF_CH; q++) {
+            const bool use = m[q] != gap_move;
+            v[q] = use ? src[ia_q] : (uint8_t)'-';
+            ia_q += use;
+        }
+        ia = ia_q;
+#pragma unroll
+        for (uint32_t q = 0; q < PF_CH; q++) if (q < cnt) dst[c + q] = v[q];
+        c += cnt;
+        t0 -= cnt;
+    }
 }
-// The new sequence's row: Up moves insert '-'.
-PF_HD void project_new(const CBV B, const CBV mv, uint32_t depth, const BV dst) {
-    uint32_t jb = 0;
-    for (uint32_t c = 0, t = depth; t-- > 0; c++) dst[c] = (mv[t] == MV_U) ? (uint8_t)'-' : B[jb++];
-}
+PF_HD void project_row(const CBV src, const CBV mv, uint32_t depth, const BV dst) { project_moves(src, mv, depth, dst, MV_L); }
+PF_HD void project_new(const CBV B, const CBV mv, uint32_t depth, const BV dst) { project_moves(B, mv, depth, dst, MV_U); }
 
 // ---- site calling: compareStrPair (SeqAlign.cpp:8-236) ------------------------------------------------
 
@@ -649,8 +692,7 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
                     uint32_t nv = 0, nil = 0;
                     status = scan_candidate(win, lim.max_alen, ns, L, Llast, key, true, &sv, &nv, &nil);
                     if (status == PF_BUBBLE_OK) {
-                        for (uint32_t r = 0; r < ns; r++)
-                            for (uint32_t c = 0; c < L; c++) sv.rows[(uint64_t)r * L + c] = win[(uint64_t)r * lim.max_alen + c];
+                        for (uint32_t r = 0; r < ns; r++) copy_bytes(win + (uint64_t)r * lim.max_alen, bv(sv.rows + (uint64_t)r * L), L);
                         hdr->n_rows = ns; hdr->alen = L; hdr->n_var = nv; hdr->n_ilen = nil;
                     }
                 }

@@ -257,10 +257,15 @@ struct LaneExec {
                 st.curU = (st.curU & 0xFFFFu) | ((uint32_t)(b_hi + 1) << 16);
                 st.curD = (st.curD & 0xFFFFu) | ((uint32_t)b_hi << 16);
                 st.curL = (st.curL & 0xFFFFu) | ((uint32_t)b_hi << 16);
+                // the row-buffer word and the B character of step s+1 are fetched before step s stores (the compiler cannot
+                // hoist them itself: the byte loads may alias the row-buffer stores)
+                uint32_t w_next = n >= 2 ? rb[2 * 32] : 0u, b_next = n >= 2 ? (uint32_t)bs[32] : 0u;
 #pragma unroll 2
-                for (uint32_t s = 2; s <= n; s++)
-                    st.step<true, true>(rb[s * 32], bs[(s - 1) * 32], a2, M2, NE2, G2, Grow2, f0 + (uint64_t)s * 32,
-                                        f1 + (uint64_t)(s - 1) * 32, rb + (s - 1) * 32);
+                for (uint32_t s = 2; s <= n; s++) {
+                    const uint32_t w = w_next, b = b_next;
+                    if (s < n) { w_next = rb[(s + 1) * 32]; b_next = bs[s * 32]; }
+                    st.step<true, true>(w, b, a2, M2, NE2, G2, Grow2, f0 + (uint64_t)s * 32, f1 + (uint64_t)(s - 1) * 32, rb + (s - 1) * 32);
+                }
                 // step n+1: only row i+1 has a cell
                 st.step<false, true>(0, 0, a2, M2, NE2, G2, Grow2, nullptr, f1 + (uint64_t)n * 32, rb + n * 32);
             } else {
@@ -336,7 +341,7 @@ __host__ __device__ constexpr uint32_t lane_smem_per_warp(uint32_t nmax, uint32_
 }
 
 template <int VARIANT>
-__global__ void __launch_bounds__(LANE_BLOCK, 12) msa_lane_kernel(const MsaArgs a) {
+__global__ void __launch_bounds__(LANE_BLOCK, 8) msa_lane_kernel(const MsaArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -353,7 +353,8 @@ def main():
         roof_lookup = {"kernel": "kmc_lookup_kernel", "bound": "hbm", "achieved": lookups_s * 64 / 1e9, "peak": hbm_peak,
                        "unit": "GB/s", "frac": lookups_s * 64 / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
                        "algorithmic_bytes_per_lookup": 64, "lookups_per_launch": tot_win / world, "ms": ms_lookup,
-                       "random_sector_gather_gbs": gather_gbs, "frac_of_random_gather": lookups_s * 64 / 1e9 / gather_gbs}
+                       "random_sector_gather_gbs": gather_gbs, "index": db.index_kind,
+                       "index_bytes": db.device_bytes, "frac_of_random_gather": lookups_s * 64 / 1e9 / gather_gbs}
         roof_align = {"kernel": "msa_lane_kernel (+ msa_warp_kernel for branches > 256 bases), whole alignment pipeline", "bound": "int32", "achieved": cells_s * 18 / 1e9, "peak": int32_gops,
                       "unit": "Gop/s", "frac": cells_s * 18 / 1e9 / int32_gops, "traffic": None,
                       "peak_source": "measured in this run (pf_bench_int32: IADD/IMNMX/LOP mix)", "int32_ops_per_cell": 18,

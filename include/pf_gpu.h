@@ -53,6 +53,19 @@ int pf_sync(pf_ctx *ctx);
 /* ---- KMC database: CKMCFile ------------------------------------------------------------------- */
 /* CKMCFile::OpenForRA (kmc_file.cpp:27): parse <prefix>.kmc_pre/.kmc_suf, build the HBM-resident index. */
 int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **db);
+/*
+ * Index layout held in HBM.  By default (PF_KMC_INDEX_AUTO) the records are re-hashed at open time into one-sector
+ * buckets (one 32-byte load per lookup instead of the reference's signature -> prefix table -> binary search chain;
+ * ploidyfrost_b200/csrc/pf_kmc_hash.cuh) after every record has been verified to be where the reference's own search
+ * (CheckKmer kmc_file.cpp:330, BinarySearch :1383) would find it; a database that fails the verification, and every
+ * partitioned index, keeps the verbatim image (prefix table + sorted records) and the reference's chain.  Results are
+ * the same either way.  PF_KMC_INDEX_VERBATIM as `flags` (or PF_KMC_INDEX=verbatim in the environment of pf_kmc_open)
+ * forces the verbatim image.
+ */
+enum { PF_KMC_INDEX_AUTO = 0, PF_KMC_INDEX_VERBATIM = 1, PF_KMC_INDEX_HASH = 2 };
+int pf_kmc_open_ex(pf_ctx *ctx, const char *prefix, uint32_t flags, pf_kmc **db);
+/* PF_KMC_INDEX_VERBATIM or PF_KMC_INDEX_HASH: the layout this handle ended up with */
+int pf_kmc_index_kind(const pf_kmc *db);
 /* CKMCFile::Close (kmc_file.cpp:631) */
 int pf_kmc_close(pf_kmc *db);
 /* CKMCFile::Info (kmc_file.cpp Info(CKMCFileInfo&)) */

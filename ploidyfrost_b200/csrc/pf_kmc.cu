@@ -22,6 +22,7 @@
 //    readCov reductions are folded in with warp-aggregated atomics.  HBM-bound integer work: no
 //    tensor cores.
 #include "pf_common.cuh"
+#include "pf_kmc_hash.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -361,6 +362,54 @@ __global__ void repack_records_kernel(const uint8_t *__restrict__ raw, uint64_t 
     else { suf[i] = s; cnt[i] = (uint32_t)c; }
 }
 
+// ---- one-sector hash index (pf_kmc_hash.cuh): build + verification, one thread per record ------------------------------
+// Every record is re-keyed (prefix from its position in the prefix table, suffix from the record) and inserted; on the
+// way the kernel checks that the reference's own search (BinarySearch, kmc_file.cpp:1383) would find this record:
+//   bit 0  suffixes not strictly ascending inside a prefix bucket      -> binary search outcome undefined
+//   bit 1  KMC2: the record is not in the bin its signature maps to     -> CheckKmer (:349-354) looks elsewhere
+//   bit 3  a key would sit more than H_MAX_DIST buckets from home       -> table too dense
+// (any of these keeps the verbatim index) and whether every key is the canonical form of its k-mer:
+//   bit 2  key > reverse complement                                      -> FWD_THEN_RC stays a two-probe lookup
+enum { HB_UNSORTED = 1, HB_WRONG_BIN = 2, HB_NOT_CANONICAL = 4, HB_OVERFLOW = 8 };
+__global__ void kmc_hash_build_kernel(const KmcView db, const pfkmc::HashView hv, uint32_t *__restrict__ status) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= db.N) return;
+    if (lut_at(db, 0) > i) return;                     // before the first bucket: no prefix reaches it
+    uint64_t lo = 0, hi = db.lut_n - 1;               // lut[lut_n-1] = N+1 > i
+    while (hi - lo > 1) {                              // last slot with lut[slot] <= i  (empty slots share a value)
+        const uint64_t mid = (lo + hi) >> 1;
+        if (lut_at(db, mid) <= i) lo = mid; else hi = mid;
+    }
+    const uint64_t slot = lo;
+    if (!db.is_kmc2 && slot >= db.single_lut) return;  // KMC1: entries past 4^p are never indexed (:353)
+    const uint64_t prefix = db.is_kmc2 ? slot % db.single_lut : slot;
+    const uint32_t bin = db.is_kmc2 ? (uint32_t)(slot / db.single_lut) : 0u;
+    const uint32_t cbits = 8 * db.C, sbits = 2 * (db.k - db.p);
+    uint64_t rs, c, prev = 0;
+    const bool has_prev = i > lut_at(db, slot);
+    if (db.packed) {
+        const uint64_t r = db.rec[i];
+        rs = r >> cbits; c = r & ((1ull << cbits) - 1);
+        if (has_prev) prev = db.rec[i - 1] >> cbits;
+    } else {
+        rs = db.suf[i]; c = db.cnt[i];
+        if (has_prev) prev = db.suf[i - 1];
+    }
+    uint32_t st = 0;
+    if (has_prev && !(prev < rs)) st |= HB_UNSORTED;
+    const uint64_t key = (prefix << sbits) | rs;
+    if (db.is_kmc2) {                                  // kmer_api.h:653-672 on the packed key
+        const uint32_t m = db.sig_len;
+        const uint64_t mask = (1ull << (2 * m)) - 1;
+        uint32_t sig = 0xFFFFFFFFu;
+        for (uint32_t j = 0; j + m <= db.k; j++) sig = min(sig, __ldg(db.norm + ((key >> (2 * (db.k - m - j))) & mask)));
+        if (__ldg(db.sigmap + sig) != bin) st |= HB_WRONG_BIN;
+    }
+    if (key > revcomp64(key, db.k)) st |= HB_NOT_CANONICAL;
+    if (!pfkmc::hash_insert(hv, key, c)) st |= HB_OVERFLOW;
+    if (st) atomicOr(status, st);
+}
+
 // ---- partitioned database: the owner's side and the way back ---------------------------------------------------
 // One thread per routed key: signature -> bin (KMC2) -> local LUT -> search.
 __global__ void kmc_lookup_keys_kernel(const KmcView db, const unsigned long long *__restrict__ keys, const uint64_t n,
@@ -467,6 +516,11 @@ struct pf_kmc {
     uint64_t device_bytes = 0;
     uint64_t local_kmers = 0;
     struct pf_kmc_route_state *route = nullptr;
+    // one-sector hash index (pf_kmc_hash.cuh); when active it replaces lut/rec/suf/cnt
+    bool hash_on = false, canonical_ok = false;
+    pfkmc::HashView hview{};
+    void *d_hash = nullptr;
+    uint32_t build_status = 0;
 };
 
 struct pf_kmc_route_state {   // scratch of pf_kmc_route_dev (grow-only)
@@ -478,7 +532,55 @@ namespace {
 
 // part / n_parts: n_parts == 1 loads the whole database; otherwise only the partition `part`
 // (KMC2: bins with bin % n_parts == part; KMC1: the part-th range of ceil(4^p / n_parts) prefixes).
-int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, pf_kmc **out) {
+// Re-hash the verbatim image into the one-sector index; on success the prefix table and the record arrays are released.
+// Returns PF_OK also when the hash index is not used (database fails the verification, or the slot does not fit).
+int kmc_build_hash(pf_kmc *db) {
+    pf_ctx *ctx = db->ctx;
+    const KmcView &V = db->view;
+    const uint64_t N = V.N;
+    if (!N) return PF_OK;
+    uint32_t b = 4;
+    while (b < 40 && (2ull << b) < N) b++;                                  // <= 2 keys per 4-slot bucket on average
+    const int need = (int)(2 * V.k + 8 * V.C + pfkmc::H_DIST_BITS) - 63;    // dist + rem + counter must leave the all-ones slot free
+    if (need > (int)b) {
+        if (need > 23 || need > 2 * (int)V.k) return PF_OK;                 // would inflate a small table past 256 MB: keep the verbatim index
+        b = (uint32_t)need;
+    }
+    if (b > 2 * V.k) b = 2 * V.k;
+    if ((2 * V.k - b) + 8 * V.C + pfkmc::H_DIST_BITS > 63) return PF_OK;
+    pfkmc::HashView hv;
+    hv.bucket_bits = b; hv.rem_bits = 2 * V.k - b; hv.cbits = 8 * V.C; hv.kbits = 2 * V.k;
+    const uint64_t bytes = 32ull << b;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < bytes + (256ull << 20)) { cudaGetLastError(); return PF_OK; }
+    void *tab = nullptr, *d_status = nullptr;
+    if (cudaMalloc(&tab, bytes) != cudaSuccess) { cudaGetLastError(); return PF_OK; }
+    hv.tab = (unsigned long long *)tab;
+    cudaStream_t st = ctx->stream;
+    uint32_t status = 0;
+    PF_CUDA_TRY(cudaMalloc(&d_status, 4));
+    PF_CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, st));
+    PF_CUDA_TRY(cudaMemsetAsync(tab, 0xFF, bytes, st));
+    kmc_hash_build_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(V, hv, (uint32_t *)d_status);
+    ctx->launches++;
+    PF_CUDA_TRY(cudaGetLastError());
+    PF_CUDA_TRY(cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, st));
+    PF_CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_status);
+    db->build_status = status;
+    if (status & (HB_UNSORTED | HB_WRONG_BIN | HB_OVERFLOW)) { cudaFree(tab); return PF_OK; }
+    db->hash_on = true;
+    db->canonical_ok = !(status & HB_NOT_CANONICAL);
+    db->hview = hv;
+    db->d_hash = tab;
+    cudaFree(db->d_lut); cudaFree(db->d_rec); cudaFree(db->d_suf); cudaFree(db->d_cnt);
+    db->d_lut = db->d_rec = db->d_suf = db->d_cnt = nullptr;
+    db->view.lut = nullptr; db->view.rec = nullptr; db->view.suf = nullptr; db->view.cnt = nullptr;
+    db->device_bytes = bytes + (V.is_kmc2 ? ((1ull << (2 * V.sig_len)) * 8 + 4) : 0);
+    return PF_OK;
+}
+
+int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, uint32_t flags, pf_kmc **out) {
     if (!ctx || !prefix || !out) { pf::set_error("pf_kmc_open: null argument"); return PF_E_INVALID; }
     *out = nullptr;
     if (n_parts == 0 || part >= n_parts || n_parts > 254) { pf::set_error("pf_kmc_open: bad partition %u of %u", part, n_parts); return PF_E_INVALID; }
@@ -663,6 +765,10 @@ int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_par
     V.rec = (const uint64_t *)db->d_rec; V.suf = (const uint64_t *)db->d_suf; V.cnt = (const uint32_t *)db->d_cnt;
     db->device_bytes = bytes;
     db->local_kmers = N;
+    if (n_parts == 1 && !(flags & PF_KMC_INDEX_VERBATIM)) {
+        const int rc = kmc_build_hash(db.get());
+        if (rc) { pf_kmc_close(db.release()); return rc; }
+    }
     *out = db.release();
     return PF_OK;
 }
@@ -671,10 +777,19 @@ int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_par
 
 extern "C" {
 
-int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **out) { return kmc_open_impl(ctx, prefix, 0, 1, out); }
+static uint32_t env_open_flags() {   // PF_KMC_INDEX=verbatim keeps the prefix-table + sorted-record image (diagnostics, A/B runs)
+    const char *e = getenv("PF_KMC_INDEX");
+    return (e && (!strcmp(e, "verbatim") || !strcmp(e, "sorted"))) ? (uint32_t)PF_KMC_INDEX_VERBATIM : 0u;
+}
+
+int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **out) { return kmc_open_impl(ctx, prefix, 0, 1, env_open_flags(), out); }
+
+int pf_kmc_open_ex(pf_ctx *ctx, const char *prefix, uint32_t flags, pf_kmc **out) { return kmc_open_impl(ctx, prefix, 0, 1, flags, out); }
+
+int pf_kmc_index_kind(const pf_kmc *db) { return db ? (db->hash_on ? PF_KMC_INDEX_HASH : PF_KMC_INDEX_VERBATIM) : PF_E_INVALID; }
 
 int pf_kmc_open_part(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, pf_kmc **out) {
-    return kmc_open_impl(ctx, prefix, part, n_parts, out);
+    return kmc_open_impl(ctx, prefix, part, n_parts, PF_KMC_INDEX_VERBATIM, out);
 }
 
 uint64_t pf_kmc_local_kmers(const pf_kmc *db) { return db ? db->local_kmers : 0; }
@@ -690,7 +805,7 @@ int pf_kmc_close(pf_kmc *db) {
         delete db->route;
     }
     cudaFree(db->d_lut); cudaFree(db->d_sigmap); cudaFree(db->d_norm);
-    cudaFree(db->d_rec); cudaFree(db->d_suf); cudaFree(db->d_cnt);
+    cudaFree(db->d_rec); cudaFree(db->d_suf); cudaFree(db->d_cnt); cudaFree(db->d_hash);
     delete db;
     return PF_OK;
 }
@@ -746,6 +861,26 @@ int pf_kmc_lookup_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const v
         ctx->launches++;
     }
     if (n_bases == 0 || n_windows == 0) { PF_CUDA_TRY(cudaGetLastError()); return PF_OK; }
+    if (db->hash_on) {
+        pfkmc::HashLookupArgs a;
+        a.hv = db->hview; a.k = db->view.k; a.min_count = db->view.min_count; a.max_count = db->view.max_count;
+        // on a verified canonical both-strands database "as written, else reverse complement" IS the canonical lookup
+        a.mode = (mode == PF_LOOKUP_FWD_THEN_RC && db->info.both_strands && db->canonical_ok) ? (int)PF_LOOKUP_CANONICAL : mode;
+        a.bases = (const uint8_t *)d_bases; a.n_bases = n_bases; a.seq_off = (const uint64_t *)d_seq_off;
+        a.win_off = (const uint64_t *)d_win_off; a.n_seq = n_seq; a.low = low; a.up = up;
+        a.counts = (uint32_t *)d_counts; a.found = (uint8_t *)d_found; a.cov = (pf_cov_t *)d_cov;
+        a.n_tiles = (n_bases + pfkmc::HL_TILE - 1) / pfkmc::HL_TILE;
+        static int per_sm = 0;
+        if (!per_sm) {
+            PF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pfkmc::kmc_hash_lookup_kernel, pfkmc::HL_THREADS, 0));
+            if (per_sm < 1) per_sm = 1;
+        }
+        const unsigned hgrid = (unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)ctx->sm_count * per_sm);
+        pfkmc::kmc_hash_lookup_kernel<<<hgrid, pfkmc::HL_THREADS, 0, st>>>(a);
+        ctx->launches++;
+        PF_CUDA_TRY(cudaGetLastError());
+        return PF_OK;
+    }
     const uint64_t n_tiles = (n_bases + LK_TILE - 1) / LK_TILE;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 6);
     kmc_lookup_kernel<false><<<grid, LK_THREADS, 0, st>>>(db->view, (const uint8_t *)d_bases, n_bases, (const uint64_t *)d_seq_off,
@@ -818,6 +953,14 @@ int pf_kmc_lookup_keys_dev(pf_kmc *db, const void *d_keys, uint64_t n, void *d_c
     PF_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     if (!n) return PF_OK;
+    if (db->hash_on) {
+        pfkmc::kmc_hash_lookup_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(db->hview, db->view.min_count, db->view.max_count,
+                                                                                       (const unsigned long long *)d_keys, n,
+                                                                                       (uint32_t *)d_counts, (uint8_t *)d_found);
+        ctx->launches++;
+        PF_CUDA_TRY(cudaGetLastError());
+        return PF_OK;
+    }
     kmc_lookup_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(db->view, (const unsigned long long *)d_keys, n, (uint32_t *)d_counts,
                                                                        (uint8_t *)d_found);
     ctx->launches++;

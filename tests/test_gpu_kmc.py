@@ -11,16 +11,23 @@ KMC_CASES = [(0, 5, 2, 25), (0x200, 5, 2, 25), (0x200, 9, 2, 25), (0, 9, 1, 25),
              (0x200, 3, 2, 31), (0, 4, 2, 32), (0x200, 5, 2, 21), (0x200, 2, 2, 18), (0, 5, 4, 29)]
 
 
+def expect_hash(k, C):
+    """pf_kmc_hash.cuh: the slot (3 distance bits + remainder + counter) must fit 63 bits with a table <= 256 MB."""
+    return 2 * k + 8 * C + 3 - 63 <= 23
+
+
+@pytest.mark.parametrize("index", ["auto", "verbatim"])
 @pytest.mark.parametrize("ver,p,C,k", KMC_CASES)
-def test_lookup_matches_oracle(gpu_ctx, oracle, tmp_path, ver, p, C, k):
+def test_lookup_matches_oracle(gpu_ctx, oracle, tmp_path, ver, p, C, k, index):
     from ploidyfrost_b200 import capi
     rng = np.random.default_rng(200 + p + k)
     sig = 9 if k >= 25 else 7
     prefix, g, u, c = gen.make_genome_db(tmp_path, seed=ver + p + 1, k=k, version=ver, p=p, counter_size=C, sig_len=sig,
                                          extra_copies=3)
     ho = oracle.kmc_open(prefix)
-    db = capi.KmcDb(gpu_ctx, prefix)
+    db = capi.KmcDb(gpu_ctx, prefix, index=index)
     try:
+        assert db.index_kind == ("hash" if index == "auto" and expect_hash(k, C) else "verbatim")
         io = oracle.kmc_info(ho)
         for f in ("kmer_length", "mode", "counter_size", "lut_prefix_length", "min_count", "max_count", "total_kmers",
                   "both_strands", "kmc_version", "n_bins"):
@@ -128,3 +135,93 @@ def test_lookup_matches_golden_reference_vectors(gpu_ctx):
     check_kmc(lambda prefix: capi.KmcDb(gpu_ctx, prefix), lambda db: db.close(),
               lambda db, b, o, k, mode: db.counts(b, o, mode=mode),
               lambda db, b, o, mode, low, up: db.cov(b, o, mode=mode, low=low, up=up))
+
+
+def _swap_two_records(prefix, k, p, C, first_bucket_of=2):
+    """Swap the first two records of the first prefix bucket that holds >= `first_bucket_of` records (KMC1 layout)."""
+    S = (k - p) // 4
+    R = S + C
+    pre = open(prefix + ".kmc_pre", "rb").read()
+    lut = np.frombuffer(pre[4:4 + 8 * (4 ** p)], dtype=np.uint64)
+    sizes = np.diff(np.concatenate([lut, [lut[-1]]]).astype(np.int64))
+    b = int(np.argmax(sizes >= first_bucket_of))
+    assert sizes[b] >= first_bucket_of
+    suf = bytearray(open(prefix + ".kmc_suf", "rb").read())
+    a = 4 + int(lut[b]) * R
+    suf[a:a + R], suf[a + R:a + 2 * R] = suf[a + R:a + 2 * R], suf[a:a + R]
+    open(prefix + ".kmc_suf", "wb").write(bytes(suf))
+
+
+def test_database_the_reference_cannot_search_keeps_the_verbatim_index(gpu_ctx, oracle, tmp_path):
+    """A bucket whose suffixes are not ascending makes BinarySearch's outcome order-dependent: the hash index must
+    refuse it, and the verbatim image must still reproduce whatever the reference's search returns."""
+    from ploidyfrost_b200 import capi
+    k, p, C = 25, 5, 2
+    prefix, g, u, c = gen.make_genome_db(tmp_path, seed=21, k=k, version=0, p=p, counter_size=C, genome_len=30000)
+    _swap_two_records(prefix, k, p, C, first_bucket_of=3)
+    ho = oracle.kmc_open(prefix)
+    db = capi.KmcDb(gpu_ctx, prefix)
+    try:
+        assert db.index_kind == "verbatim"
+        bases, off = flatten_seqs([g, g[100:5000]])
+        for mode in (0, 1, 2):
+            co, fo = oracle.kmc_counts(ho, bases, off, k, mode=mode, n_threads=4)
+            cg, fg = db.counts(bases, off, mode=mode)
+            assert np.array_equal(co, cg) and np.array_equal(fo, fg), mode
+        assert not fo.all()   # the swap did hide records from the binary search
+    finally:
+        oracle.kmc_close(ho)
+        db.close()
+
+
+@pytest.mark.parametrize("ver", [0, 0x200])
+def test_strand_specific_database(gpu_ctx, oracle, tmp_path, ver):
+    """both_strands == false: keys are stored as written, so 'as written, else reverse complement' stays two probes
+    (CDBG.cpp:38-43) and the canonical shortcut must not be taken."""
+    from ploidyfrost_b200 import capi
+    from ploidyfrost_b200.synth import kmcdb
+    k = 25
+    rng = np.random.default_rng(9)
+    g = gen.rand_seq(rng, 20000)
+    kv = kmcdb.kmers_of(kmcdb.encode_bases(g), k)                      # forward k-mers, NOT canonicalised
+    u, c = np.unique(kv, return_counts=True)
+    prefix = str(tmp_path / f"fwd_{ver}")
+    kmcdb.write_kmc_db(prefix, u, c.astype(np.uint64), k, version=ver, lut_prefix_len=5, counter_size=2, n_bins=32, sig_len=9,
+                       both_strands=False)
+    ho = oracle.kmc_open(prefix)
+    db = capi.KmcDb(gpu_ctx, prefix)
+    try:
+        assert db.info["both_strands"] == 0 and db.index_kind == "hash"
+        bases, off = flatten_seqs(gen.query_sequences(rng, g, 2000, k=k))
+        for mode in (0, 1, 2):
+            co, fo = oracle.kmc_counts(ho, bases, off, k, mode=mode, n_threads=4)
+            cg, fg = db.counts(bases, off, mode=mode)
+            assert np.array_equal(co, cg) and np.array_equal(fo, fg), mode
+            a = oracle.kmc_cov(ho, bases, off, mode=mode, low=0, up=3, n_threads=4)
+            b = db.cov(bases, off, mode=mode, low=0, up=3)
+            assert np.array_equal(a, b), mode
+    finally:
+        oracle.kmc_close(ho)
+        db.close()
+
+
+def test_dense_buckets_and_tiny_tables(gpu_ctx, oracle, tmp_path):
+    """Few k-mers (table of a handful of buckets, chains across buckets) and min/max gates on the hash path."""
+    from ploidyfrost_b200 import capi
+    k = 25
+    for n, seed in ((40, 1), (300, 2), (5000, 3)):
+        prefix, g, u, c = gen.make_genome_db(tmp_path, seed=seed, k=k, version=0x200, p=5, genome_len=n + k - 1, extra_copies=0,
+                                             name=f"tiny{n}", n_bins=8)
+        ho = oracle.kmc_open(prefix)
+        db = capi.KmcDb(gpu_ctx, prefix)
+        try:
+            assert db.index_kind == "hash"
+            rng = np.random.default_rng(seed)
+            bases, off = flatten_seqs([g, gen.rand_seq(rng, 500)] + gen.query_sequences(rng, g, 50, k=k, len_range=(25, min(60, len(g) - 1))))
+            for mode in (0, 1, 2):
+                co, fo = oracle.kmc_counts(ho, bases, off, k, mode=mode)
+                cg, fg = db.counts(bases, off, mode=mode)
+                assert np.array_equal(co, cg) and np.array_equal(fo, fg), (n, mode)
+        finally:
+            oracle.kmc_close(ho)
+            db.close()

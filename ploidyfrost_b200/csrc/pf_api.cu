@@ -86,6 +86,11 @@ int pf_init(int device, pf_ctx **out) {
     PF_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     PF_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    if (const char *e = getenv("PF_L2_FETCH_GRANULARITY")) {   // 32 / 64 / 128: a hint to the L2 (random-sector workloads)
+        const int g = atoi(e);
+        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+        cudaGetLastError();
+    }
     *out = ctx;
     return PF_OK;
 }

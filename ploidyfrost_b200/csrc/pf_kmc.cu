@@ -521,6 +521,7 @@ struct pf_kmc {
     pfkmc::HashView hview{};
     void *d_hash = nullptr;
     uint32_t build_status = 0;
+    pf::DevBuf tile_seq;   // per-call scratch of the hash lookup (grow-only)
 };
 
 struct pf_kmc_route_state {   // scratch of pf_kmc_route_dev (grow-only)
@@ -806,6 +807,7 @@ int pf_kmc_close(pf_kmc *db) {
     }
     cudaFree(db->d_lut); cudaFree(db->d_sigmap); cudaFree(db->d_norm);
     cudaFree(db->d_rec); cudaFree(db->d_suf); cudaFree(db->d_cnt); cudaFree(db->d_hash);
+    db->tile_seq.release();
     delete db;
     return PF_OK;
 }
@@ -870,6 +872,10 @@ int pf_kmc_lookup_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const v
         a.win_off = (const uint64_t *)d_win_off; a.n_seq = n_seq; a.low = low; a.up = up;
         a.counts = (uint32_t *)d_counts; a.found = (uint8_t *)d_found; a.cov = (pf_cov_t *)d_cov;
         a.n_tiles = (n_bases + pfkmc::HL_TILE - 1) / pfkmc::HL_TILE;
+        if (int rc = db->tile_seq.reserve((a.n_tiles + 1) * 4)) return rc;
+        a.tile_seq = db->tile_seq.as<uint32_t>();
+        pfkmc::tile_seq_kernel<<<(unsigned)((a.n_tiles + 1 + 255) / 256), 256, 0, st>>>(a.seq_off, n_seq, a.n_tiles, db->tile_seq.as<uint32_t>());
+        ctx->launches++;
         static int per_sm = 0;
         if (!per_sm) {
             PF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pfkmc::kmc_hash_lookup_kernel, pfkmc::HL_THREADS, 0));

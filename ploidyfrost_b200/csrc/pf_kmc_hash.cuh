@@ -110,6 +110,7 @@ constexpr int HL_THREADS = 256;
 constexpr int HL_PPT = 8;                          // window starts per thread
 constexpr int HL_TILE = HL_THREADS * HL_PPT;       // 2048 base positions per tile
 constexpr int HL_WORDS = HL_TILE / 16 + 3;         // 16 bases per packed word + 48 bases of halo (k-1+7 <= 38)
+constexpr int HL_NSEQ = 512;                       // sequence ends staged per tile (more than that: per-thread search)
 
 struct HashLookupArgs {
     HashView hv;
@@ -127,7 +128,21 @@ struct HashLookupArgs {
     uint8_t *found;
     pf_cov_t *cov;
     uint64_t n_tiles;
+    const uint32_t *tile_seq;   // [n_tiles + 1] sequence containing the first base of each tile (tile_seq_kernel)
 };
+
+// tile_seq[t] = last s with seq_off[s] <= t * HL_TILE (clamped to the last sequence); one thread per tile
+__global__ void tile_seq_kernel(const uint64_t *__restrict__ seq_off, uint32_t n_seq, uint64_t n_tiles, uint32_t *__restrict__ tile_seq) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    const uint64_t g = t * HL_TILE;
+    uint32_t lo = 0, hi = n_seq;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (seq_off[mid] <= g) lo = mid; else hi = mid;
+    }
+    tile_seq[t] = lo;
+}
 
 struct CovRun {   // readCov partials of one (thread, sequence) run  (CDBG.cpp:29-120)
     uint32_t s;
@@ -148,9 +163,10 @@ struct CovRun {   // readCov partials of one (thread, sequence) run  (CDBG.cpp:2
 // window starts, takes its first k-mer from three packed words, rolls the forward and reverse-complement values from
 // base to base in registers, and keeps four bucket loads in flight at a time.  The readCov reductions are accumulated
 // per (thread, sequence) run and leave the warp as one set of atomics per (warp, sequence).
-__global__ void __launch_bounds__(HL_THREADS) kmc_hash_lookup_kernel(const HashLookupArgs a) {
+__global__ void __launch_bounds__(HL_THREADS, 3) kmc_hash_lookup_kernel(const HashLookupArgs a) {
     __shared__ uint32_t s_pk[HL_WORDS];
     __shared__ uint32_t s_bad[HL_WORDS];
+    __shared__ uint32_t s_end[HL_NSEQ];   // end of the tile's sequences relative to the tile start (saturated)
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t k = a.k;
     const uint64_t kmask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
@@ -195,6 +211,15 @@ __global__ void __launch_bounds__(HL_THREADS) kmc_hash_lookup_kernel(const HashL
             s_pk[tid] = pk;
             s_bad[tid] = bad;
         }
+        // the sequences this tile touches: [s_lo, s_hi]; their ends, relative to p0, go to shared memory
+        const uint32_t s_lo = __ldg(a.tile_seq + tile), s_hi = __ldg(a.tile_seq + tile + 1);
+        const uint32_t ns = s_hi - s_lo + 1;
+        const bool staged = ns <= (uint32_t)HL_NSEQ;
+        if (staged)
+            for (uint32_t i = tid; i < ns; i += HL_THREADS) {
+                const uint64_t e = __ldg((const unsigned long long *)a.seq_off + s_lo + i + 1);
+                s_end[i] = e - p0 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)(e - p0);   // e > p0 except for empty leading sequences
+            }
         __syncthreads();
 
         CovRun run;
@@ -203,12 +228,22 @@ __global__ void __launch_bounds__(HL_THREADS) kmc_hash_lookup_kernel(const HashL
         uint64_t g = p0 + q0;
         if (g < n_bases) {
             // sequence containing base g: last s with seq_off[s] <= g   (seq_off[0] == 0)
-            uint32_t lo = 0, hi = n_seq;
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (__ldg((const unsigned long long *)a.seq_off + mid) <= g) lo = mid; else hi = mid;
+            uint32_t s;
+            if (staged) {                                                    // first staged sequence that ends after q0
+                uint32_t lo = 0, hi = ns - 1;                                // the last one ends after every base of the tile
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (s_end[mid] > q0) hi = mid; else lo = mid + 1;
+                }
+                s = s_lo + lo;
+            } else {
+                uint32_t lo = s_lo, hi = n_seq;
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg((const unsigned long long *)a.seq_off + mid) <= g) lo = mid; else hi = mid;
+                }
+                s = lo;
             }
-            uint32_t s = lo;
             uint64_t sb = __ldg((const unsigned long long *)a.seq_off + s);
             uint64_t se = __ldg((const unsigned long long *)a.seq_off + s + 1);
             uint64_t wo = __ldg((const unsigned long long *)a.win_off + s);

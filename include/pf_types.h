@@ -89,7 +89,7 @@ enum {
     PF_BUBBLE_TOO_LONG = 2,       /* DP matrix does not fit the device work area                      */
     PF_BUBBLE_CAND_OVERFLOW = 3,  /* more co-optimal alignments than the device arena can hold        */
     PF_BUBBLE_STEP_LIMIT = 4,     /* traceback exceeded the step budget (combinatorial explosion)     */
-    PF_BUBBLE_BAD_INPUT = 5       /* fewer than 2 sequences / empty sequence                          */
+    PF_BUBBLE_BAD_INPUT = 5       /* fewer than 2 sequences, or a sequence contains a literal '-'     */
 };
 
 #ifdef __cplusplus

@@ -43,7 +43,10 @@ constexpr int CLS_BIG = N_LANE_CLASSES;        // first pass of the warp kernel
 constexpr int CLS_RETRY_SMEM = N_LANE_CLASSES + 1;  // re-run, warp kernel with the flag bytes in shared memory (long DFS searches)
 constexpr int CLS_RETRY = N_LANE_CLASSES + 2;       // re-run, warp kernel with the large limits
 constexpr int N_TIERS = N_LANE_CLASSES + 3;
-constexpr uint32_t LANE_STEP_LIMIT = 6144;          // traceback iterations a lane may spend on one bubble (typical: ~300, p99.9 ~1500)
+// traceback iterations a lane / group may spend on one bubble before it is handed to the shared-memory-flags tier (typical: ~300,
+// p99.9 ~1500).  Generous on purpose: a 30k-step co-optimal search costs its lane ~2 ms INSIDE the first pass, where other warps
+// hide it; handing it over costs a 3 ms serial re-run after the pass (measured on B200, profiles/r01_summary.md).
+constexpr uint32_t LANE_STEP_LIMIT = 65536;
 __host__ __device__ constexpr uint32_t lane_nmax(int c) { return c == 0 ? 64u : c == 1 ? 96u : c == 2 ? 128u : c == 3 ? 192u : 256u; }
 constexpr uint32_t LANE_MAX_ROWS = 8;
 
@@ -104,6 +107,7 @@ struct WarpExec {
     __device__ __forceinline__ uint32_t bcast_ld(const uint32_t *p) const { return *(const volatile uint32_t *)p; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     __device__ __forceinline__ void note_steps(uint64_t) const {}
+    __device__ __forceinline__ uint32_t pitch_n(uint32_t n) const { return n; }
     __device__ __forceinline__ void fill(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n, const Scoring &sc,
                                          int32_t *brow) {
         warp_fill<INTEGRAL>(flags.p, A, m, B.p, n, sc, brow, lane);
@@ -162,6 +166,7 @@ struct LaneExec {
     __device__ __forceinline__ uint32_t bcast_ld(const uint32_t *p) const { return *p; }
     __device__ __forceinline__ void sync() const {}
     __device__ __forceinline__ void note_steps(uint64_t) const {}
+    __device__ __forceinline__ uint32_t pitch_n(uint32_t n) const { return n; }
 
     // rows i = 1..m one at a time
     __device__ __forceinline__ void fill_scalar(const BV flags, const CBV A, uint32_t m, uint32_t n, const Scoring &sc) {
@@ -289,6 +294,163 @@ struct LaneExec {
     }
 };
 
+// ---- G lanes per bubble (group kernel) -------------------------------------------------------------------------
+// The thread-per-bubble kernel is throughput-efficient but one long bubble is a long serial job (a bubble with 250-base
+// branches is ~3 M dependent instructions on its lane), and a batch holds too few long bubbles to hide that behind other
+// warps.  For the long size classes a bubble therefore gets G = 2..32 adjacent lanes.  The fill splits every DP row into G
+// column strips; lane g fills strip g of row pair (T - g) at time step T (a software pipeline across the lanes, the same
+// two-rows-per-step s16x2 arithmetic as the lane kernel), and hands the last column of its strip -- (U, D, L) of both
+// rows -- to lane g+1 with one shuffle per value per time step.  Each lane owns its strip's slice of the bubble's
+// shared-memory score row, so the fill needs no barrier at all.  Everything after the fill (traceback DFS, MSA filter,
+// site calling) runs on the group's first lane, exactly as in the warp kernel.
+//
+// Layouts: the NB = 32 / G bubbles of a warp interleave their work-area arrays element by element (stride NB), flag rows
+// are row-major with the same pitch for every bubble of the launch (lanes of different bubbles at the same cell share a
+// sector), the score row of bubble b sits at rb[j * NB + b] and strips are an odd number of columns wide, which makes
+// the G x NB lanes of a step hit 32 different banks.
+template <int G>
+struct GroupExec {
+    static constexpr bool kDiagFlags = false;
+    static constexpr uint32_t NB = 32 / G;
+    uint32_t g;          // lane within the group
+    uint32_t gmask;      // the group's lanes
+    uint32_t *rb;        // this bubble's score row: element j at rb[j * NB]
+    uint8_t *bs;         // this bubble's B characters: element j at bs[j * NB]
+    uint32_t pn;         // flag row pitch - 1
+    unsigned long long cells;
+    __device__ __forceinline__ bool leader() const { return g == 0; }
+    __device__ __forceinline__ uint32_t bcast(uint32_t v) const { return __shfl_sync(gmask, v, 0, G); }
+    __device__ __forceinline__ int bcast_i(int v) const { return __shfl_sync(gmask, v, 0, G); }
+    __device__ __forceinline__ uint32_t bcast_ld(const uint32_t *p) const { return *(const volatile uint32_t *)p; }
+    __device__ __forceinline__ void sync() const { __syncwarp(gmask); }
+    __device__ __forceinline__ void note_steps(uint64_t) const {}
+    __device__ __forceinline__ uint32_t pitch_n(uint32_t) const { return pn; }
+
+    // leader only: the one-row-at-a-time fill (B contains '-': the s16x2 substitution select does not apply)
+    __device__ __forceinline__ void fill_scalar(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n, const Scoring &sc) {
+        int32_t *row = (int32_t *)rb;
+        const uint32_t W = pn + 1;
+        flags[0] = 0;
+        row[0] = pack_sf(0, 0);
+        for (uint32_t j = 1; j <= n; j++) {
+            row[j * NB] = pack_sf(border_score(sc, j), F_LEFT);
+            flags[j] = (uint8_t)F_LEFT;
+        }
+        for (uint32_t i = 1; i <= m; i++) {
+            const bool block_left = i != m && A[i] == '-';
+            const uint8_t a = A[i - 1];
+            int dg = row[0];
+            int lf = pack_sf(border_score(sc, i), F_UP);
+            row[0] = lf;
+            const BV frow = flags + (uint64_t)i * W;
+            frow[0] = (uint8_t)F_UP;
+            for (uint32_t j = 1; j <= n; j++) {
+                const int up = row[j * NB];
+                const int cur = nw_cell_t<true>(sc, up, dg, lf, a, B[j - 1], block_left);
+                row[j * NB] = cur;
+                frow[j] = (uint8_t)unpack_f(cur);
+                dg = up;
+                lf = cur;
+            }
+        }
+    }
+
+    __device__ __forceinline__ void fill(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n, const Scoring &sc,
+                                         int32_t *) {
+        __syncwarp(gmask);                                                   // the leader is done reading the previous matrix
+        if (g == 0) cells += (unsigned long long)m * n;
+        const uint32_t w = ((n + G - 1) / G) | 1u;                           // strip width, odd
+        const uint32_t a = g * w + 1;                                        // my strip: columns a .. b (empty when a > n)
+        const uint32_t b = min(a + w - 1, n);
+        const bool have = a <= n;
+        bool dash = false;
+        if (have)
+            for (uint32_t j0 = a; j0 <= b; j0 += PF_CH) {                    // my B characters, chunked loads
+                uint8_t v[PF_CH];
+#pragma unroll
+                for (uint32_t q = 0; q < PF_CH; q++) v[q] = j0 + q <= b ? B[j0 + q - 1] : (uint8_t)0;
+#pragma unroll
+                for (uint32_t q = 0; q < PF_CH; q++) if (j0 + q <= b) { bs[(j0 + q) * NB] = v[q]; dash |= v[q] == '-'; }
+            }
+        if (__any_sync(gmask, dash) || n == 0) {
+            if (g == 0) fill_scalar(flags, A, m, B, n, sc);
+            __syncwarp(gmask);
+            return;
+        }
+        const uint32_t W = pn + 1;
+        const int Gp = sc.iG;
+        const uint32_t M2 = pack2(sc.iM, sc.iM), G2 = pack2(Gp, Gp);
+        if (g == 0) flags[0] = 0;
+        if (have)
+            for (uint32_t j = a; j <= b; j++) {                              // row 0 carries only Left (:492-496)
+                rb[j * NB] = pack2(Gp * (int)j, Gp * (int)j);
+                flags[j] = (uint8_t)F_LEFT;
+            }
+        const uint32_t R = (m + 1) / 2;                                      // row pairs
+        uint32_t inU = 0, inD = 0, inL = 0;                                  // column a-1 of the pair I fill next (from lane g-1)
+        uint32_t prev_hi_d = (uint32_t)(Gp * (int)(a - 1)) & 0xFFFFu;        // D(i-1, a-1); row 0: its score
+        for (uint32_t T = 0; T < R + G - 1; T++) {
+            uint32_t outU = 0, outD = 0, outL = 0;
+            const uint32_t r = T - g;
+            if (have && T >= g && r < R) {
+                const uint32_t i = 2 * r + 1;
+                const bool two = i < m;                                      // is row i+1 real?
+                const uint8_t a_lo = A[i - 1], a_hi = two ? A[i] : (uint8_t)0;
+                const uint8_t a_after = i + 1 < m ? A[i + 1] : (uint8_t)0;
+                const bool blk_lo = two && a_hi == '-';                      // i != m && A[i] == '-'      (:528)
+                const bool blk_hi = i + 1 < m && a_after == '-';
+                const uint32_t a2 = (uint32_t)a_lo | ((uint32_t)a_hi << 16);
+                const uint32_t NE2 = pack2(a_lo == '-' ? Gp : sc.iD, a_hi == '-' ? Gp : sc.iD);
+                const uint32_t Grow2 = pack2(blk_lo ? S16_BLOCK : Gp, blk_hi ? S16_BLOCK : Gp);
+                uint32_t cU, cD, cL;                                         // the column left of my strip
+                if (g == 0) {                                                // the border (:486-491): Up only
+                    const int b_lo = Gp * (int)i, b_hi = Gp * (int)(i + 1);
+                    cU = pack2(b_lo + 1, b_hi + 1); cD = pack2(b_lo, b_hi); cL = pack2(b_lo, b_hi);
+                } else { cU = inU; cD = inD; cL = inL; }
+                S16Step st;
+                st.curU = cU & 0xFFFFu; st.curD = cD & 0xFFFFu; st.curL = cL & 0xFFFFu;
+                st.upD_prev = prev_hi_d;
+                st.b2 = 0;
+                prev_hi_d = cD >> 16;                                        // D(i+1, a-1): the next pair's diagonal
+                uint8_t *f0 = &flags[(uint64_t)i * W], *f1 = &flags[(uint64_t)(i + 1) * W];
+                if (g == 0) f0[0] = (uint8_t)F_UP;
+                uint32_t dummy;
+                // step a: only row i has a cell in my strip
+                st.step<true, false>(rb[a * NB], bs[a * NB], a2, M2, NE2, G2, Grow2, f0 + (uint64_t)a * NB, nullptr, &dummy);
+                uint32_t loU, loD, loL;                                      // (i, b) once row i is through
+                if (two) {
+                    if (g == 0) f1[0] = (uint8_t)F_UP;
+                    st.curU = (st.curU & 0xFFFFu) | (cU & 0xFFFF0000u);
+                    st.curD = (st.curD & 0xFFFFu) | (cD & 0xFFFF0000u);
+                    st.curL = (st.curL & 0xFFFFu) | (cL & 0xFFFF0000u);
+                    uint32_t w_next = b > a ? rb[(a + 1) * NB] : 0u, b_next = b > a ? (uint32_t)bs[(a + 1) * NB] : 0u;
+#pragma unroll 2
+                    for (uint32_t s = a + 1; s <= b; s++) {
+                        const uint32_t wv_ = w_next, bc = b_next;
+                        if (s < b) { w_next = rb[(s + 1) * NB]; b_next = bs[(s + 1) * NB]; }
+                        st.step<true, true>(wv_, bc, a2, M2, NE2, G2, Grow2, f0 + (uint64_t)s * NB, f1 + (uint64_t)(s - 1) * NB, rb + (s - 1) * NB);
+                    }
+                    loU = st.curU; loD = st.curD; loL = st.curL;
+                    // step b+1: only row i+1 has a cell
+                    st.step<false, true>(0, 0, a2, M2, NE2, G2, Grow2, nullptr, f1 + (uint64_t)b * NB, rb + b * NB);
+                } else {
+                    for (uint32_t s = a + 1; s <= b; s++)
+                        st.step<true, false>(rb[s * NB], bs[s * NB], a2, M2, NE2, G2, Grow2, f0 + (uint64_t)s * NB, nullptr, &dummy);
+                    loU = st.curU; loD = st.curD; loL = st.curL;
+                }
+                outU = __byte_perm(loU, st.curU, 0x7610);
+                outD = __byte_perm(loD, st.curD, 0x7610);
+                outL = __byte_perm(loL, st.curL, 0x7610);
+            }
+            // my last column becomes the right neighbour's left column for the same row pair, one time step later
+            inU = __shfl_up_sync(gmask, outU, 1, G);
+            inD = __shfl_up_sync(gmask, outD, 1, G);
+            inL = __shfl_up_sync(gmask, outL, 1, G);
+        }
+        __syncwarp(gmask);                                                   // flags visible to the leader's traceback
+    }
+};
+
 struct MsaArgs {
     const uint8_t *bases;
     const uint64_t *seq_off;
@@ -376,6 +538,43 @@ __global__ void __launch_bounds__(LANE_BLOCK, 8) msa_lane_kernel(const MsaArgs a
     if (lane == 0 && c) atomicAdd(a.stat_cells, c);
 }
 
+constexpr int GROUP_BLOCK = 64;
+__host__ __device__ constexpr uint32_t group_smem_per_warp(uint32_t nmax, uint32_t nb) {
+    return (nb * 4 * (nmax + 2) + nb * (nmax + 2) + 15) / 16 * 16;           // score rows + B characters (index 1..nmax)
+}
+
+template <int G>
+__global__ void __launch_bounds__(GROUP_BLOCK) msa_group_kernel(const MsaArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr uint32_t NB = 32 / G;
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nmax = a.lim.max_blen;
+    const uint32_t per_warp = group_smem_per_warp(nmax, NB);
+    GroupExec<G> x;
+    x.g = lane % G;
+    const uint32_t bi = lane / G;
+    x.gmask = G == 32 ? FULL : (((1u << G) - 1u) << (bi * G));
+    x.rb = (uint32_t *)(smem + (size_t)wib * per_warp) + bi;
+    x.bs = smem + (size_t)wib * per_warp + NB * 4 * (nmax + 2) + bi;
+    x.pn = nmax;
+    x.cells = 0;
+    const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim, NB, bi);
+    for (;;) {   // every group pulls its own bubbles: biggest first
+        uint32_t q = 0;
+        if (x.g == 0) q = atomicAdd(a.counter, 1u);
+        q = __shfl_sync(x.gmask, q, 0, G);
+        if (q >= a.n_items) break;
+        const uint32_t w = a.first + (a.n_items - 1 - q);
+        const uint32_t b = a.order[w];
+        const uint32_t s0 = a.bubble_off[b], ns = a.bubble_off[b + 1] - s0;
+        uint8_t *slot = a.slot_base + a.slot_off[w];
+        msa_run(x, a.bases, a.seq_off, s0, ns, ws, a.lim, a.sc, slot);
+        if (x.g == 0) { a.slot_ptr[b] = (uint64_t)(uintptr_t)slot; a.tier[b] = a.tier_id; }
+    }
+    if (x.g == 0 && x.cells) atomicAdd(a.stat_cells, x.cells);
+}
+
 // ---- planning: size class per bubble, sort key -----------------------------------------------------------
 struct TierTable {
     Limits lim[N_TIERS];
@@ -440,6 +639,30 @@ __global__ void collect_retry_kernel(uint32_t n, const uint64_t *__restrict__ sl
     if (b >= n) return;
     const SlotHdr *h = (const SlotHdr *)(uintptr_t)slot_ptr[b];
     if (retryable(h->status)) retry_list[atomicAdd(retry_count, 1u)] = b;
+}
+
+// A literal '-' in an input sequence is outside the contract: SeqAlign's traceback tells "gap I just opened" from the
+// characters of the strings it builds (resB[0] == '-', SeqAlign.cpp:397), so an input dash changes its control flow in a
+// way the move-string state machines here do not mirror.  No caller produces one (branch strings are unitig sequences),
+// so such a bubble is reported, not guessed at: status PF_BUBBLE_BAD_INPUT, no rows.
+__global__ void reject_dash_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ seq_off,
+                                   const uint32_t *__restrict__ bubble_off, uint32_t n, const uint64_t *__restrict__ slot_ptr) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const uint32_t s0 = bubble_off[b], s1 = bubble_off[b + 1];
+    const uint64_t p0 = seq_off[s0], p1 = seq_off[s1];
+    bool dash = false;
+    uint64_t p = p0;
+    for (; p < p1 && ((uintptr_t)(bases + p) & 7); p++) dash |= bases[p] == '-';
+    for (; p + 8 <= p1; p += 8) {
+        const uint64_t v = *(const uint64_t *)(bases + p) ^ 0x2D2D2D2D2D2D2D2Dull;             // a zero byte where a '-' was
+        dash |= ((v - 0x0101010101010101ull) & ~v & 0x8080808080808080ull) != 0;
+    }
+    for (; p < p1; p++) dash |= bases[p] == '-';
+    if (!dash) return;
+    SlotHdr *h = (SlotHdr *)(uintptr_t)slot_ptr[b];
+    h->status = PF_BUBBLE_BAD_INPUT;
+    h->n_rows = 0; h->alen = 0; h->n_var = 0; h->n_ilen = 0;
 }
 
 // per bubble: sizes of its four variable-length outputs (+ the scalar outputs)
@@ -516,6 +739,8 @@ struct pf_align_state {
     cudaStream_t aux[N_LANE_CLASSES + 1] = {nullptr};   // the size classes run concurrently
     cudaEvent_t ev_fork = nullptr, ev_join[N_LANE_CLASSES + 1] = {nullptr};
     pf::DevBuf ws_cls[N_LANE_CLASSES];
+    int group_lanes[N_LANE_CLASSES] = {1, 1, 2, 2, 4};   // lanes per bubble of each size class (1 = thread-per-bubble kernel)
+    bool group_env_done = false;
 };
 
 void pf_align_state_free(pf_align_state *s) {
@@ -546,6 +771,16 @@ typedef void (*LaneKernel)(const MsaArgs);
 LaneKernel lane_kernel(int variant) {
     return variant == LANE_S16X2 ? msa_lane_kernel<LANE_S16X2> : variant == LANE_I32 ? msa_lane_kernel<LANE_I32> : msa_lane_kernel<LANE_FP64>;
 }
+typedef void (*GroupKernel)(const MsaArgs);
+GroupKernel group_kernel(int G) {
+    switch (G) {
+        case 2: return msa_group_kernel<2>;
+        case 4: return msa_group_kernel<4>;
+        case 8: return msa_group_kernel<8>;
+        case 16: return msa_group_kernel<16>;
+        default: return msa_group_kernel<32>;
+    }
+}
 // the s16x2 fill needs every score (border, diagonal, +1 bonuses) to stay well inside int16 even after S16_BLOCK is added
 int lane_variant(const Scoring &sc, const Limits &l) {
     if (!sc.integral) return LANE_FP64;
@@ -559,7 +794,8 @@ Limits lane_limits(int c) {
     l.max_blen = lane_nmax(c);
     l.max_alen = l.max_blen + 32;
     l.k_cand = 8; l.k_aln = 8; l.max_var = 48;
-    l.step_limit = LANE_STEP_LIMIT;
+    static const uint64_t step_env = getenv("PF_LANE_STEP_LIMIT") ? strtoull(getenv("PF_LANE_STEP_LIMIT"), nullptr, 10) : 0;
+    l.step_limit = step_env ? step_env : LANE_STEP_LIMIT;
     l.diag_flags = 0; l.pad_ = 0;
     return l;
 }
@@ -632,6 +868,33 @@ int launch_warp_smem_tier(pf_ctx *ctx, pf_align_state *st, int pool, const Limit
     return PF_OK;
 }
 
+// one launch of the G-lanes-per-bubble kernel over work items [first, first + n_items) of `d_order`
+int launch_group_tier(pf_ctx *ctx, pf_align_state *st, pf::DevBuf &pool, const Limits &lim, int GL, const Scoring &sc,
+                      const uint8_t *d_bases, const uint64_t *d_seq_off, const uint32_t *d_bubble_off, const uint32_t *d_order,
+                      uint32_t first, uint32_t n_items, int tier_id, uint32_t *counter, cudaStream_t s) {
+    const uint32_t NB = 32 / GL, wpb = GROUP_BLOCK / 32;
+    const uint64_t ws_bytes = align_up(work_area_bytes(lim, NB), 256);
+    const size_t smem = (size_t)wpb * group_smem_per_warp(lim.max_blen, NB);
+    if (smem > 200 * 1024) { pf::set_error("group kernel: %u-base branches do not fit shared memory", lim.max_blen); return PF_E_INVALID; }
+    int per_sm = 0;
+    PF_CUDA_TRY(cudaFuncSetAttribute(group_kernel(GL), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, group_kernel(GL), GROUP_BLOCK, smem));
+    uint64_t warps = (uint64_t)ctx->sm_count * std::max(1, per_sm) * wpb;
+    warps = std::min<uint64_t>(warps, std::max<uint64_t>(1, WS_BUDGET / ws_bytes));
+    warps = std::min<uint64_t>(warps, ((uint64_t)n_items + NB - 1) / NB);
+    const uint32_t grid = (uint32_t)((warps + wpb - 1) / wpb);
+    int rc;
+    if ((rc = pool.reserve((uint64_t)grid * wpb * ws_bytes))) return rc;
+    MsaArgs a;
+    fill_args(a, st, 0, lim, sc, d_bases, d_seq_off, d_bubble_off, d_order, first, n_items, tier_id, counter);
+    a.ws_base = pool.as<uint8_t>();
+    a.ws_stride = ws_bytes;
+    group_kernel(GL)<<<grid, GROUP_BLOCK, smem, s>>>(a);
+    ctx->launches++;
+    PF_CUDA_TRY(cudaGetLastError());
+    return PF_OK;
+}
+
 struct DevResult {
     uint64_t tot_rows, tot_var, tot_cls, tot_ilen;
 };
@@ -670,6 +933,15 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         st->lane_attr_done = true;
     }
 
+    if (!st->group_env_done) {   // PF_GROUP_LANES="1,1,4,4,8": lanes per bubble of the five size classes (tuning / A-B runs)
+        if (const char *e = getenv("PF_GROUP_LANES")) {
+            int v[N_LANE_CLASSES];
+            if (sscanf(e, "%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4]) == N_LANE_CLASSES)
+                for (int c = 0; c < N_LANE_CLASSES; c++)
+                    if (v[c] == 1 || v[c] == 2 || v[c] == 4 || v[c] == 8 || v[c] == 16 || v[c] == 32) st->group_lanes[c] = v[c];
+        }
+        st->group_env_done = true;
+    }
     TierTable tt;
     for (int c = 0; c < N_LANE_CLASSES; c++) tt.lim[c] = lane_limits(c);
     Limits &big = tt.lim[CLS_BIG];        // warp kernel, first pass: work area sized from the batch's longest branch
@@ -678,6 +950,11 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
     big.max_alen = big.max_blen + std::min<uint32_t>(64, big.max_blen);
     big.k_cand = 8; big.k_aln = 8; big.max_var = 48;
     big.step_limit = 200000000ull; big.diag_flags = 1; big.pad_ = 0;
+    // a warp per bubble either way: the strip-pipelined s16x2 fill (group kernel, G = 32, row-major flags) when every score
+    // fits int16 and the score row fits shared memory, else the INT32 / FP64 wavefront of the warp kernel
+    const bool big_group = lane_variant(sc, big) == LANE_S16X2 && group_smem_per_warp(big.max_blen, 1) * (GROUP_BLOCK / 32) <= 160 * 1024 &&
+                           !getenv("PF_BIG_WARP_KERNEL");
+    if (big_group) big.diag_flags = 0;
     Limits &heavy = tt.lim[CLS_RETRY_SMEM];   // warp kernel, flag bytes in shared memory: (320+256+1)*321 = 185 KB per CTA
     heavy.max_rows = std::min<uint32_t>(std::max<uint32_t>(max_rows, 2), 64);
     heavy.max_blen = lane_nmax(N_LANE_CLASSES - 1);
@@ -724,8 +1001,11 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         if (cnt) {
             cudaStream_t as = st->aux[N_LANE_CLASSES];
             PF_CUDA_TRY(cudaStreamWaitEvent(as, st->ev_fork, 0));
-            if ((rc = launch_warp_tier(ctx, st, 0, big, sc, d_bases, d_seq_off, d_bubble_off, d_order, h_bounds[CLS_BIG], cnt, CLS_BIG,
-                                       st->counter.as<uint32_t>() + CLS_BIG, as))) return rc;
+            if (big_group) rc = launch_group_tier(ctx, st, st->ws_warp[0], big, 32, sc, d_bases, d_seq_off, d_bubble_off, d_order, h_bounds[CLS_BIG], cnt,
+                                                  CLS_BIG, st->counter.as<uint32_t>() + CLS_BIG, as);
+            else rc = launch_warp_tier(ctx, st, 0, big, sc, d_bases, d_seq_off, d_bubble_off, d_order, h_bounds[CLS_BIG], cnt, CLS_BIG,
+                                       st->counter.as<uint32_t>() + CLS_BIG, as);
+            if (rc) return rc;
             PF_CUDA_TRY(cudaEventRecord(st->ev_join[N_LANE_CLASSES], as));
             PF_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_join[N_LANE_CLASSES], 0));
         }
@@ -735,20 +1015,27 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         st->last_class_count[c] = cnt;
         if (!cnt) continue;
         const int v = lane_variant(sc, tt.lim[c]);
-        const uint64_t ws_bytes = align_up(work_area_bytes(tt.lim[c], 32), 256);
-        const uint32_t wpb = LANE_BLOCK / 32;
-        uint64_t warps = (uint64_t)ctx->sm_count * std::max(1, st->lane_blocks_per_sm[v][c]) * wpb;
-        warps = std::min<uint64_t>(warps, std::max<uint64_t>(1, WS_BUDGET / ws_bytes));
-        warps = std::min<uint64_t>(warps, ((uint64_t)cnt + 31) / 32);
-        const uint32_t grid = (uint32_t)((warps + wpb - 1) / wpb);
-        if ((rc = st->ws_cls[c].reserve((uint64_t)grid * wpb * ws_bytes))) return rc;
-        MsaArgs a;
-        fill_args(a, st, 0, tt.lim[c], sc, d_bases, d_seq_off, d_bubble_off, d_order, h_bounds[c], cnt, c, st->counter.as<uint32_t>() + c);
-        a.ws_base = st->ws_cls[c].as<uint8_t>();
-        a.ws_stride = ws_bytes;
+        const int GL = v == LANE_S16X2 ? st->group_lanes[c] : 1;
         cudaStream_t as = st->aux[c];
         PF_CUDA_TRY(cudaStreamWaitEvent(as, st->ev_fork, 0));
-        lane_kernel(v)<<<grid, LANE_BLOCK, lane_smem_bytes(lane_nmax(c), v), as>>>(a);
+        MsaArgs a;
+        fill_args(a, st, 0, tt.lim[c], sc, d_bases, d_seq_off, d_bubble_off, d_order, h_bounds[c], cnt, c, st->counter.as<uint32_t>() + c);
+        if (GL > 1) {   // G lanes per bubble
+            if ((rc = launch_group_tier(ctx, st, st->ws_cls[c], tt.lim[c], GL, sc, d_bases, d_seq_off, d_bubble_off, d_order, h_bounds[c], cnt, c,
+                                        st->counter.as<uint32_t>() + c, as))) return rc;
+            ctx->launches--;   // counted once below
+        } else {
+            const uint64_t ws_bytes = align_up(work_area_bytes(tt.lim[c], 32), 256);
+            const uint32_t wpb = LANE_BLOCK / 32;
+            uint64_t warps = (uint64_t)ctx->sm_count * std::max(1, st->lane_blocks_per_sm[v][c]) * wpb;
+            warps = std::min<uint64_t>(warps, std::max<uint64_t>(1, WS_BUDGET / ws_bytes));
+            warps = std::min<uint64_t>(warps, ((uint64_t)cnt + 31) / 32);
+            const uint32_t grid = (uint32_t)((warps + wpb - 1) / wpb);
+            if ((rc = st->ws_cls[c].reserve((uint64_t)grid * wpb * ws_bytes))) return rc;
+            a.ws_base = st->ws_cls[c].as<uint8_t>();
+            a.ws_stride = ws_bytes;
+            lane_kernel(v)<<<grid, LANE_BLOCK, lane_smem_bytes(lane_nmax(c), v), as>>>(a);
+        }
         ctx->launches++;
         PF_CUDA_TRY(cudaGetLastError());
         PF_CUDA_TRY(cudaEventRecord(st->ev_join[c], as));
@@ -791,6 +1078,8 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         if ((rc = st->sz[i].reserve((uint64_t)n1 * 8))) return rc;
         if ((rc = st->off[i].reserve((uint64_t)n1 * 8))) return rc;
     }
+    reject_dash_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_bases, d_seq_off, d_bubble_off, n, st->slot_ptr.as<uint64_t>());
+    ctx->launches++;
     result_size_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(st->slot_ptr.as<uint64_t>(), n, st->status.as<int32_t>(),
                                                         st->n_rows.as<uint32_t>(), st->aln_len.as<uint32_t>(),
                                                         st->sz[0].as<uint64_t>(), st->sz[1].as<uint64_t>(),

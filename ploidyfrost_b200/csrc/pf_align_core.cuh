@@ -65,7 +65,8 @@ PF_HD CBV cbv(const uint8_t *p, uint32_t s = 1) { CBV r; r.p = p; r.s = s; retur
 PF_HD CBV cbv(const BV &v) { CBV r; r.p = v.p; r.s = v.s; return r; }
 PF_HD WV wv(uint32_t *p, uint32_t s = 1) { WV r; r.p = p; r.s = s; return r; }
 
-// Flag-byte address of cell (i,j) of an (m+1) x (n+1) matrix
+// Flag-byte address of cell (i,j) of an (m+1) x (n+1) matrix.  Row-major storage may use a row pitch wider than the
+// matrix (pass n = pitch - 1): the group kernel gives every bubble of a launch the same pitch (X::pitch_n).
 template <bool DIAG>
 PF_HD uint32_t flag_index(uint32_t i, uint32_t j, uint32_t m, uint32_t n) {
     return DIAG ? (i + j) * (m + 1) + i : i * (n + 1) + j;
@@ -202,7 +203,7 @@ struct TbResult {
 template <bool DIAG>
 PF_HDN inline TbResult traceback(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n,
                                  const Scoring &sc, const BV mv, const BV ext_mv, const WV ext_len,
-                                 uint32_t mv_stride, uint32_t k_aln, uint64_t step_limit) {
+                                 uint32_t mv_stride, uint32_t k_aln, uint64_t step_limit, uint32_t pitch_n) {
     TbResult r;
     r.n_aln = 0; r.status = PF_BUBBLE_OK; r.steps = 0;
     uint32_t i = m, j = n, depth = 0;
@@ -211,7 +212,7 @@ PF_HDN inline TbResult traceback(const BV flags, const CBV A, uint32_t m, const 
     last.score = 0; last.n_pos = 0; last.n_indel = 0;
     for (;;) {
         if (++r.steps > step_limit) { r.status = PF_BUBBLE_STEP_LIMIT; return r; }
-        const uint32_t cell = flag_index<DIAG>(i, j, m, n);
+        const uint32_t cell = flag_index<DIAG>(i, j, m, pitch_n);
         if (i == 0 && j == 0 && open_a <= cap_a && open_b <= cap_b) {   // :322-355
             const PairKey cand = analyze_moves(sc, A, B, cbv(mv), depth);
             bool keep = true;
@@ -606,7 +607,7 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
             x.fill(ws.flags, A, m, B, n, sc, ws.brow);
             if (x.leader()) {
                 const TbResult tb = traceback<X::kDiagFlags>(ws.flags, A, m, B, n, sc, ws.mv, ws.ext_mv, ws.ext_len, mv_stride,
-                                                             lim.k_aln, steps_left);
+                                                             lim.k_aln, steps_left, x.pitch_n(n));
                 steps_left -= tb.steps < steps_left ? tb.steps : steps_left;
                 x.note_steps(tb.steps);
                 status = tb.status;

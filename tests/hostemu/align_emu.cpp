@@ -27,6 +27,7 @@ struct HostExec {
     void sync() const {}
     uint64_t steps = 0;
     void note_steps(uint64_t n) { steps += n; }
+    uint32_t pitch_n(uint32_t n) const { return n; }
     void fill(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n, const Scoring &sc, int32_t *) {
         rowbuf.assign(2 * (size_t)(n + 1), 0);
         int *prev = rowbuf.data(), *cur = rowbuf.data() + n + 1;

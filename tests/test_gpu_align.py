@@ -59,6 +59,26 @@ def test_align_matches_oracle(gpu_ctx, oracle, seed, kw, sc):
     assert (b["status"] == 0).all()
 
 
+@pytest.mark.parametrize("lanes", ["2,4,8,16,32", "32,16,8,4,2", "1,1,1,1,1", "4,4,4,4,4"])
+def test_lanes_per_bubble_configurations(oracle, lanes, monkeypatch):
+    """The group kernel (G lanes per bubble, strip-pipelined fill) at every G, on every size class, against the oracle.
+    PF_GROUP_LANES is read once per context, so each configuration gets its own."""
+    from ploidyfrost_b200 import capi
+    monkeypatch.setenv("PF_GROUP_LANES", lanes)
+    ctx = capi.Context(0)
+    try:
+        for seed, kw in ((1, {}), (2, dict(alphabet="AC")), (8, dict(len_range=(100, 300), max_indel_len=40)),
+                         (14, dict(len_range=(150, 250), max_indel_len=20, max_indel=3)), (9, dict(alphabet="A", len_range=(5, 30))),
+                         (21, dict(len_range=(2, 12)))):
+            bubbles = gen.random_bubbles(seed, 1200, **kw)
+            flat = flatten_bubbles(bubbles)
+            a = oracle.align(*flat, n_threads=8)
+            b = ctx.align(*flat)
+            assert_msa_equal(a, b, bubbles, f"lanes {lanes} seed {seed}")
+    finally:
+        ctx.close()
+
+
 def test_align_matches_reference_when_available(gpu_ctx, ref):
     bubbles = gen.random_bubbles(99, 4000)
     flat = flatten_bubbles(bubbles)
@@ -73,6 +93,20 @@ def test_empty_batch_and_bad_bubbles(gpu_ctx):
     m = gpu_ctx.align(*flatten_bubbles([["ACGT"], ["ACGT", "ACGA"]]))
     assert m["status"][0] == 5 and m["n_rows"][0] == 0      # PF_BUBBLE_BAD_INPUT
     assert m["status"][1] == 0 and m["n_rows"][1] == 2
+
+
+def test_literal_dash_in_input_is_reported_not_guessed(gpu_ctx, oracle):
+    """'-' is SeqAlign's gap character; an input that already contains one is outside the contract (no caller produces
+    it) and must come back as PF_BUBBLE_BAD_INPUT, the other bubbles of the batch untouched."""
+    bubbles = gen.random_bubbles(22, 600, alphabet="AC-", len_range=(20, 140)) + gen.random_bubbles(23, 600)
+    flat = flatten_bubbles(bubbles)
+    a = oracle.align(*flat, n_threads=8)
+    b = gpu_ctx.align(*flat)
+    for i, bub in enumerate(bubbles):
+        if any("-" in s for s in bub):
+            assert b["status"][i] == 5 and b["n_rows"][i] == 0
+        else:
+            assert msa_bubble(a, i) == msa_bubble(b, i)
 
 
 def test_long_pair_matches_oracle(gpu_ctx, oracle):

@@ -348,15 +348,26 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         gather_gbs = ctx.bench_random_gather(4 << 30)
         int32_gops = ctx.bench_int32()
+        # measured DRAM traffic per launch (ncu, profiles/r01_traffic.json) -- only valid for the workload it was captured on
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        except Exception:
+            pass
+        default_wl = args.batch == 262144 and args.genome_mbp == 100.0 and not args.sharded_db
+        t_lookup = traffic.get("kmc_hash_lookup_kernel", {}).get("bytes") if default_wl and db.index_kind == "hash" else None
+        t_align = traffic.get("align_pipeline", {}).get("bytes") if default_wl else None
         lookups_s = (tot_win / world) / (ms_lookup * 1e-3)       # per GPU, for the per-kernel roofline
         cells_s = (tot_cells / world) / (ms_align * 1e-3)
-        roof_lookup = {"kernel": "kmc_lookup_kernel", "bound": "hbm", "achieved": lookups_s * 64 / 1e9, "peak": hbm_peak,
-                       "unit": "GB/s", "frac": lookups_s * 64 / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+        roof_lookup = {"kernel": "kmc_hash_lookup_kernel" if db.index_kind == "hash" else "kmc_lookup_kernel", "bound": "hbm",
+                       "achieved": lookups_s * 64 / 1e9, "peak": hbm_peak,
+                       "unit": "GB/s", "frac": lookups_s * 64 / 1e9 / hbm_peak, "traffic": t_lookup, "peak_source": peak_src,
                        "algorithmic_bytes_per_lookup": 64, "lookups_per_launch": tot_win / world, "ms": ms_lookup,
                        "random_sector_gather_gbs": gather_gbs, "index": db.index_kind,
                        "index_bytes": db.device_bytes, "frac_of_random_gather": lookups_s * 64 / 1e9 / gather_gbs}
-        roof_align = {"kernel": "msa_lane_kernel (+ msa_warp_kernel for branches > 256 bases), whole alignment pipeline", "bound": "int32", "achieved": cells_s * 18 / 1e9, "peak": int32_gops,
-                      "unit": "Gop/s", "frac": cells_s * 18 / 1e9 / int32_gops, "traffic": None,
+        roof_align = {"kernel": "alignment pipeline: msa_lane_kernel (branches <= 96) + msa_group_kernel<2/2/4/32> (<= 128 / 192 / 256 / longer), concurrent streams",
+                      "bound": "int32", "achieved": cells_s * 18 / 1e9, "peak": int32_gops,
+                      "unit": "Gop/s", "frac": cells_s * 18 / 1e9 / int32_gops, "traffic": t_align,
                       "peak_source": "measured in this run (pf_bench_int32: IADD/IMNMX/LOP mix)", "int32_ops_per_cell": 18,
                       "cells_per_launch": tot_cells / world, "ms": ms_align}
         dominant = roof_align if ms_align >= ms_lookup else roof_lookup

@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--low", type=int, default=2)
     ap.add_argument("--up", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--region-rank", type=int, default=None,
+                    help="diagnostics: take the batch another rank would take (its region of the genome) on this GPU")
     ap.add_argument("--sharded-db", action="store_true",
                     help="partition the KMC index across the ranks (bin % world) and route queries with an NCCL all-to-all "
                          "instead of replicating it (BASELINE config 3 variant)")
@@ -209,7 +211,7 @@ def main():
     t_setup = time.perf_counter()
     db_dir = f"/tmp/pfbench_{os.environ.get('MASTER_PORT', 'solo')}_{args.genome_mbp:g}"
     os.makedirs(db_dir, exist_ok=True)
-    bb, prefix, info = make_workload(args, rank, world, rank == 0, db_dir, str(dev))
+    bb, prefix, info = make_workload(args, rank if args.region_rank is None else args.region_rank, world, rank == 0, db_dir, str(dev))
     if world > 1:
         obj = [info]
         dist.broadcast_object_list(obj, src=0)
@@ -270,6 +272,7 @@ def main():
     torch.cuda.synchronize()
     cells = ctx.last_cells
     retry = ctx.last_retry_count
+    heavy_q = ctx.last_heavy_queued
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -333,7 +336,7 @@ def main():
 
     # ---- reduce over ranks (max time, summed work) ----
     sys.stderr.write(f"[rank {rank}] step {ms_step:.2f} ms (lookup {sum(t_lookup) / len(t_lookup):.2f}, align {sum(t_align) / len(t_align):.2f}), "
-                     f"e2e {ms_e2e:.2f} ms; tiers {ctx.last_tier_counts}; batch {bb.stats()}\n")
+                     f"e2e {ms_e2e:.2f} ms; tiers {ctx.last_tier_counts} heavy-queued {heavy_q}; batch {bb.stats()}\n")
     from ploidyfrost_b200 import shard
     (ms_step, ms_e2e, ms_lookup, ms_align), (tot_bubbles, tot_win, tot_cells) = shard.reduce_step(
         [ms_step, ms_e2e, sum(t_lookup) / len(t_lookup), sum(t_align) / len(t_align)], [bb.n_bubbles, n_win, cells], device=dev)
@@ -384,7 +387,7 @@ def main():
                         "ms_pf_kmc_cov": 1e3 * sum(e2e_cov_times) / len(e2e_cov_times)},
                 "gpu_launches": int(launches),
                 "roofline": dominant, "roofline_lookup": roof_lookup, "roofline_align": roof_align,
-                "bubbles_ok": n_ok, "tier2_retries": int(retry), "setup_s": round(t_setup, 1),
+                "bubbles_ok": n_ok, "tier2_retries": int(retry), "heavy_queued": int(heavy_q), "setup_s": round(t_setup, 1),
                 "batch_stats": bb.stats()}
         if not args.no_cpu_baseline and world >= 1:
             line["cpu_baseline"] = cpu_baseline(args, bb, prefix)

@@ -165,6 +165,9 @@ int pf_align_dev(pf_ctx *ctx, double M, double D, double G, const void *d_bases,
  * (longest branch <= 64/96/128/192/256); out[5] = warp-per-bubble kernel; out[6] = re-runs with the flag matrix in shared
  * memory (long co-optimal searches); out[7] = re-runs with the large limits */
 int pf_align_last_tier_counts(const pf_ctx *ctx, uint32_t *out, int n);
+/* diagnostics: bubbles of the last pf_align* call whose traceback exceeded the first-pass step budget and were handed to the
+ * heavy queue (re-run beside the first pass by a few dedicated one-warp CTAs with the flag matrix in shared memory) */
+uint32_t pf_align_last_heavy_queued(const pf_ctx *ctx);
 /* diagnostics: bubbles of the last pf_align / pf_align_dev call that needed the large (tier-2) work area */
 uint32_t pf_align_last_retry_count(const pf_ctx *ctx);
 /* diagnostics: DP cells (m*n summed over every needlemanWunch fill) executed by the last pf_align* call */

@@ -25,7 +25,7 @@ EXPORTS = ["pf_init", "pf_shutdown", "pf_last_error", "pf_version", "pf_launch_c
            "pf_kmc_close", "pf_kmc_info", "pf_kmc_set_min_count", "pf_kmc_set_max_count", "pf_kmc_reset_min_max",
            "pf_kmc_device_bytes", "pf_kmc_open_ex", "pf_kmc_index_kind", "pf_kmc_open_part", "pf_kmc_local_kmers", "pf_kmc_route_dev", "pf_kmc_lookup_keys_dev",
            "pf_kmc_scatter_dev", "pf_kmc_counts", "pf_kmc_cov", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
-           "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32"]
+           "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_heavy_queued", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32"]
 
 
 class KmcInfo(C.Structure):
@@ -102,6 +102,8 @@ def load():
                                C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(MsaBatch), C.c_void_p]
     L.pf_align_last_retry_count.argtypes = [C.c_void_p]
     L.pf_align_last_retry_count.restype = C.c_uint32
+    L.pf_align_last_heavy_queued.argtypes = [C.c_void_p]
+    L.pf_align_last_heavy_queued.restype = C.c_uint32
     L.pf_align_last_tier_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.pf_align_last_cells.argtypes = [C.c_void_p]
     L.pf_align_last_cells.restype = C.c_uint64
@@ -198,6 +200,10 @@ class Context:
     @property
     def last_retry_count(self) -> int:
         return int(self.lib.pf_align_last_retry_count(self.h))
+
+    @property
+    def last_heavy_queued(self) -> int:
+        return int(self.lib.pf_align_last_heavy_queued(self.h))
 
     @property
     def last_tier_counts(self) -> list:

@@ -27,6 +27,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <type_traits>
 #include <cstring>
 
 using namespace pfalign;
@@ -43,10 +44,9 @@ constexpr int CLS_BIG = N_LANE_CLASSES;        // first pass of the warp kernel
 constexpr int CLS_RETRY_SMEM = N_LANE_CLASSES + 1;  // re-run, warp kernel with the flag bytes in shared memory (long DFS searches)
 constexpr int CLS_RETRY = N_LANE_CLASSES + 2;       // re-run, warp kernel with the large limits
 constexpr int N_TIERS = N_LANE_CLASSES + 3;
-// traceback iterations a lane / group may spend on one bubble before it is handed to the shared-memory-flags tier (typical: ~300,
-// p99.9 ~1500).  Generous on purpose: a 30k-step co-optimal search costs its lane ~2 ms INSIDE the first pass, where other warps
-// hide it; handing it over costs a 3 ms serial re-run after the pass (measured on B200, profiles/r01_summary.md).
-constexpr uint32_t LANE_STEP_LIMIT = 65536;
+// traceback iterations a lane / group may spend on one bubble before it is handed to the heavy queue (bench workload: median 250,
+// p99.9 1 500, p99.99 2 000, a handful per 262 144 bubbles at 3 000 .. 32 000; sweep in profiles/r01_summary.md section 7)
+constexpr uint32_t LANE_STEP_LIMIT = 2048;
 __host__ __device__ constexpr uint32_t lane_nmax(int c) { return c == 0 ? 64u : c == 1 ? 96u : c == 2 ? 128u : c == 3 ? 192u : 256u; }
 constexpr uint32_t LANE_MAX_ROWS = 8;
 
@@ -97,7 +97,7 @@ __device__ __forceinline__ void warp_fill(uint8_t *__restrict__ flags, const CBV
 }
 
 template <bool INTEGRAL>
-struct WarpExec {
+struct WarpExec : SerialHelpers {
     static constexpr bool kDiagFlags = true;
     uint32_t lane;
     unsigned long long cells;
@@ -154,7 +154,7 @@ struct S16Step {
 };
 
 template <int VARIANT>
-struct LaneExec {
+struct LaneExec : SerialHelpers {
     static constexpr bool kDiagFlags = false;
     static constexpr bool INTEGRAL = VARIANT != LANE_FP64;
     int32_t *rowbuf;     // 4 bytes per column: packed score*8+flags (scalar fills) or (U, D) as two int16 (s16x2 fill)
@@ -167,6 +167,7 @@ struct LaneExec {
     __device__ __forceinline__ void sync() const {}
     __device__ __forceinline__ void note_steps(uint64_t) const {}
     __device__ __forceinline__ uint32_t pitch_n(uint32_t n) const { return n; }
+    __device__ __forceinline__ bool prefetch_flags() const { return true; }   // the flag bytes live in HBM / L2
 
     // rows i = 1..m one at a time
     __device__ __forceinline__ void fill_scalar(const BV flags, const CBV A, uint32_t m, uint32_t n, const Scoring &sc) {
@@ -317,8 +318,12 @@ struct GroupExec {
     uint32_t *rb;        // this bubble's score row: element j at rb[j * NB]
     uint8_t *bs;         // this bubble's B characters: element j at bs[j * NB]
     uint32_t pn;         // flag row pitch - 1
+    bool pf;             // flag bytes in HBM (prefetch ahead of the DFS) or in shared memory (heavy kernel)
     unsigned long long cells;
-    __device__ __forceinline__ bool leader() const { return g == 0; }
+    __device__ __forceinline__ bool prefetch_flags() const { return pf; }
+    // Everything outside the fill runs redundantly on all G lanes (identical loads, decisions and stores), so every lane
+    // "is" the leader; the kernel uses g == 0 where something must happen once (queue, counters).
+    __device__ __forceinline__ bool leader() const { return true; }
     __device__ __forceinline__ uint32_t bcast(uint32_t v) const { return __shfl_sync(gmask, v, 0, G); }
     __device__ __forceinline__ int bcast_i(int v) const { return __shfl_sync(gmask, v, 0, G); }
     __device__ __forceinline__ uint32_t bcast_ld(const uint32_t *p) const { return *(const volatile uint32_t *)p; }
@@ -326,7 +331,66 @@ struct GroupExec {
     __device__ __forceinline__ void note_steps(uint64_t) const {}
     __device__ __forceinline__ uint32_t pitch_n(uint32_t) const { return pn; }
 
-    // leader only: the one-row-at-a-time fill (B contains '-': the s16x2 substitution select does not apply)
+    // ---- O(L) helpers spread over the G lanes ----
+    __device__ __forceinline__ uint32_t group_bits(uint32_t ballot) const {   // the group's G bits of a ballot, lane g at bit g
+        return G == 32 ? ballot : ((ballot >> (__ffs(gmask) - 1)) & ((1u << (G & 31)) - 1u));
+    }
+    // variantAnalyze over a move string (see analyze_moves): column p of the alignment is move mv[depth-1-p]; the characters it
+    // consumes sit at the number of earlier non-Left / non-Up moves (ballot + popc), its score term is local, and whether it
+    // opens a gap run depends on the class of the previous column only -- so G columns are handled per step.
+    __device__ __forceinline__ PairKey analyze(const Scoring &sc, const CBV row, const CBV B, const CBV mv, uint32_t depth) const {
+        if (!sc.integral) return analyze_moves(sc, row, B, mv, depth);       // the double accumulation is order dependent
+        const uint32_t ltm = (1u << g) - 1u;
+        int score = 0;
+        uint32_t n_pos = 0, n_indel = 0, ia = 0, jb = 0, carry = 0;
+        for (uint32_t p0 = 0; p0 < depth; p0 += G) {
+            const uint32_t p = p0 + g;
+            const bool live = p < depth;
+            const uint8_t m = live ? mv[depth - 1 - p] : (uint8_t)MV_NONE;
+            const bool use_a = live && m != MV_L, use_b = live && m != MV_U;
+            const uint32_t ma = group_bits(__ballot_sync(gmask, use_a)), mb = group_bits(__ballot_sync(gmask, use_b));
+            const uint8_t a = use_a ? row[ia + __popc(ma & ltm)] : (uint8_t)'-';
+            const uint8_t b = use_b ? B[jb + __popc(mb & ltm)] : (uint8_t)'-';
+            ia += __popc(ma); jb += __popc(mb);
+            const uint32_t c = (!live || a == b) ? 0u : (a == '-' ? 1u : (b == '-' ? 2u : 3u));
+            uint32_t prevc = __shfl_up_sync(gmask, c, 1, G);
+            if (g == 0) prevc = carry;
+            carry = __shfl_sync(gmask, c, G - 1, G);
+            int t_score = !live ? 0 : ((a == '-' || b == '-') ? sc.iG : (a == b ? sc.iM : sc.iD));      // :241-246, gap first
+            uint32_t t_ind = ((c == 1u && prevc != 1u) || (c == 2u && prevc != 2u)) ? 1u : 0u;
+            uint32_t t_pos = (t_ind || c == 3u) ? 1u : 0u;
+#pragma unroll
+            for (int d = G / 2; d; d >>= 1) {
+                t_score += __shfl_xor_sync(gmask, t_score, d, G);
+                t_ind += __shfl_xor_sync(gmask, t_ind, d, G);
+                t_pos += __shfl_xor_sync(gmask, t_pos, d, G);
+            }
+            score += t_score; n_indel += t_ind; n_pos += t_pos;
+        }
+        PairKey k;
+        k.score = score; k.n_pos = n_pos; k.n_indel = n_indel;
+        return k;
+    }
+    __device__ __forceinline__ void copy(const CBV src, const BV dst, uint32_t n) const {
+        for (uint32_t i = g; i < n; i += G) dst[i] = src[i];
+        __syncwarp(gmask);
+    }
+    // project_moves: dst[p] = the p-th column of `src` stretched by the gaps of the move string
+    __device__ __forceinline__ void project(const CBV src, const CBV mv, uint32_t depth, const BV dst, uint8_t gap_move) const {
+        const uint32_t ltm = (1u << g) - 1u;
+        uint32_t ia = 0;
+        for (uint32_t p0 = 0; p0 < depth; p0 += G) {
+            const uint32_t p = p0 + g;
+            const bool live = p < depth;
+            const bool use = live && mv[depth - 1 - p] != gap_move;
+            const uint32_t mu = group_bits(__ballot_sync(gmask, use));
+            if (live) dst[p] = use ? src[ia + __popc(mu & ltm)] : (uint8_t)'-';
+            ia += __popc(mu);
+        }
+        __syncwarp(gmask);
+    }
+
+    // the one-row-at-a-time fill (B contains '-': the s16x2 substitution select does not apply)
     __device__ __forceinline__ void fill_scalar(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n, const Scoring &sc) {
         int32_t *row = (int32_t *)rb;
         const uint32_t W = pn + 1;
@@ -467,9 +531,33 @@ struct MsaArgs {
     uint64_t ws_stride;        // per warp
     uint32_t *counter;
     unsigned long long *stat_cells;  // DP cells filled (m*n per needlemanWunch call), for the roofline figure
+    uint32_t *hq;              // heavy queue (see msa_heavy_kernel); nullptr = none
     Limits lim;
     Scoring sc;
 };
+
+// ---- bubbles whose co-optimal DFS explodes ------------------------------------------------------------------------------
+// One bubble in ~10^5 has a traceback of 10^4 .. 10^6 steps (the DFS enumerates co-optimal paths under the reference's
+// pruning rules, it cannot be cut short).  Such a search is a serial job of milliseconds, so the only way to keep it off the
+// step's critical path is to start it early and run it beside everything else: the first-pass kernels give a bubble a small
+// step budget; a bubble that exceeds it is pushed on a device-side queue, and msa_heavy_kernel -- a handful of one-warp
+// CTAs with the flag matrix AND the move string in shared memory, launched before the first pass and polling that queue --
+// re-runs it concurrently.  When the first pass is over the heavy CTAs stop taking tickets; whatever is still queued (a batch
+// full of explosive bubbles) is re-run by the full-width pass after it.
+// Queue layout (u32 words): [0] tail (producers), [1] head (consumer tickets), [2] done flag, [4..5] bytes of the slot pool
+// handed out, [HQ_HDR ...] bubble ids, 0xFFFFFFFF = not written yet.
+constexpr uint32_t HQ_HDR = 8, HQ_CAP = 4096;
+
+__device__ __forceinline__ void heavy_enqueue(uint32_t *hq, const uint8_t *slot, uint32_t bubble) {
+    const int st = ((const SlotHdr *)slot)->status;
+    if (st != PF_BUBBLE_STEP_LIMIT && st != PF_BUBBLE_CAND_OVERFLOW) return;
+    __threadfence();                                   // slot_ptr / tier of the first pass are written before the hand-over
+    const uint32_t idx = atomicAdd(hq, 1u);
+    if (idx < HQ_CAP) {
+        ((volatile uint32_t *)hq)[HQ_HDR + idx] = bubble;
+        __threadfence();
+    }
+}
 
 // SMEM_FLAGS: one warp per CTA with the flag matrix in dynamic shared memory -- the tier for bubbles whose co-optimal
 // DFS is long (tens of thousands of dependent flag reads: ~30 cycles each from shared memory instead of an L2/HBM trip).
@@ -497,6 +585,87 @@ __global__ void __launch_bounds__(WARP_BLOCK) msa_warp_kernel(const MsaArgs a) {
     }
     if (lane == 0 && x.cells) atomicAdd(a.stat_cells, x.cells);
 }
+
+template <bool I>
+__device__ __forceinline__ void heavy_exec_init(WarpExec<I> &x, uint32_t lane, uint8_t *, uint32_t) { x.lane = lane; x.cells = 0; }
+__device__ __forceinline__ void heavy_exec_init(GroupExec<32> &x, uint32_t lane, uint8_t *row_smem, uint32_t nmax) {
+    x.g = lane; x.gmask = FULL; x.pn = nmax; x.pf = false; x.cells = 0;
+    x.rb = (uint32_t *)row_smem;
+    x.bs = row_smem + 4 * (nmax + 2);
+}
+
+// The consumer side of the heavy queue: one warp per CTA; a.lim = the shared-memory tier's limits, a.slot_base = the slot
+// pool (bump-allocated through hq[4..5]), a.first = pool capacity in KB.
+// MODE 2: the strip-pipelined s16x2 fill of the group kernel with all 32 lanes on the one bubble (row-major flags);
+// MODE 1 / 0: the INT32 / FP64 wavefront of the warp kernel (diagonal-major flags) when the scores do not fit int16.
+// Dynamic shared memory: flag matrix | move string | (MODE 2) score row + B characters.
+template <int MODE>
+__global__ void __launch_bounds__(32) msa_heavy_kernel(const MsaArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_flags[];
+    const uint32_t lane = threadIdx.x & 31;
+    WorkArea ws = carve_work_area(a.ws_base + (uint64_t)blockIdx.x * a.ws_stride, a.lim);
+    const uint64_t flag_bytes = align_up(flag_area_cells(a.lim), 16), mv_bytes = align_up(a.lim.max_alen + a.lim.max_blen, 16);
+    ws.flags = bv(smem_flags);
+    ws.mv = bv(smem_flags + flag_bytes);                                    // the DFS's move string next to the flags
+    typename std::conditional<MODE == 2, GroupExec<32>, WarpExec<MODE == 1>>::type x;
+    heavy_exec_init(x, lane, smem_flags + flag_bytes + mv_bytes, a.lim.max_blen);
+    uint32_t *hq = a.hq;
+    const uint64_t pool_cap = (uint64_t)a.first << 10;
+    if (!hq) {   // drain mode (the pass after the first one): work items [0, n_items) of a.order, slots laid out by the host
+        for (;;) {
+            uint32_t w = 0;
+            if (lane == 0) w = atomicAdd(a.counter, 1u);
+            w = __shfl_sync(FULL, w, 0);
+            if (w >= a.n_items) break;
+            const uint32_t b = a.order[w];
+            const uint32_t s0 = a.bubble_off[b], ns = a.bubble_off[b + 1] - s0;
+            uint8_t *slot = a.slot_base + a.slot_off[w];
+            msa_run(x, a.bases, a.seq_off, s0, ns, ws, a.lim, a.sc, slot);
+            if (lane == 0) { a.slot_ptr[b] = (uint64_t)(uintptr_t)slot; a.tier[b] = a.tier_id; }
+            __syncwarp();
+        }
+        if (lane == 0 && x.cells) atomicAdd(a.stat_cells, x.cells);
+        return;
+    }
+    for (;;) {
+        uint32_t b = 0xFFFFFFFFu;
+        if (lane == 0 && !*(volatile uint32_t *)(hq + 2)) {                  // the first pass is still running: take a ticket
+            const uint32_t t = atomicAdd(hq + 1, 1u);
+            if (t < HQ_CAP) {
+                volatile uint32_t *e = hq + HQ_HDR + t;
+                unsigned long long t0;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                for (;;) {
+                    b = *e;
+                    if (b != 0xFFFFFFFFu) break;
+                    if (*(volatile uint32_t *)(hq + 2)) { b = *e; break; }   // producers are gone: a last look
+                    __nanosleep(1000);
+                    unsigned long long t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    // nothing for 30 ms: give up (a profiler or sanitizer that serialises kernels would otherwise wait forever
+                    // for a first pass that cannot start); whatever is queued later is re-run by the pass after the first one
+                    if (t1 - t0 > 30000000ull) break;
+                }
+            }
+        }
+        b = __shfl_sync(FULL, b, 0);
+        if (b == 0xFFFFFFFFu) break;
+        __threadfence();
+        const uint32_t s0 = a.bubble_off[b], ns = a.bubble_off[b + 1] - s0;
+        const uint64_t bytes = slot_layout(ns, a.seq_off[s0 + ns] - a.seq_off[s0], a.lim).bytes;
+        unsigned long long off = 0;
+        if (lane == 0) off = atomicAdd((unsigned long long *)(hq + 4), (unsigned long long)bytes);
+        off = __shfl_sync(FULL, off, 0);
+        if (off + bytes > pool_cap) continue;                                // left to the pass after the first one
+        uint8_t *slot = a.slot_base + off;
+        msa_run(x, a.bases, a.seq_off, s0, ns, ws, a.lim, a.sc, slot);
+        if (lane == 0) { a.slot_ptr[b] = (uint64_t)(uintptr_t)slot; a.tier[b] = a.tier_id; }
+        __syncwarp();
+    }
+    if (lane == 0 && x.cells) atomicAdd(a.stat_cells, x.cells);
+}
+
+__global__ void heavy_done_kernel(uint32_t *hq) { *(volatile uint32_t *)(hq + 2) = 1u; }
 
 __host__ __device__ constexpr uint32_t lane_smem_per_warp(uint32_t nmax, uint32_t tsize) {
     return 32 * tsize * (nmax + 1) + 32 * nmax;                               // score row + B characters; multiple of 32
@@ -529,6 +698,7 @@ __global__ void __launch_bounds__(LANE_BLOCK, 8) msa_lane_kernel(const MsaArgs a
             msa_run(x, a.bases, a.seq_off, s0, ns, ws, a.lim, a.sc, slot);
             a.slot_ptr[b] = (uint64_t)(uintptr_t)slot;
             a.tier[b] = a.tier_id;
+            if (a.hq) heavy_enqueue(a.hq, slot, b);
         }
         __syncwarp();
     }
@@ -558,6 +728,7 @@ __global__ void __launch_bounds__(GROUP_BLOCK) msa_group_kernel(const MsaArgs a)
     x.rb = (uint32_t *)(smem + (size_t)wib * per_warp) + bi;
     x.bs = smem + (size_t)wib * per_warp + NB * 4 * (nmax + 2) + bi;
     x.pn = nmax;
+    x.pf = true;
     x.cells = 0;
     const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim, NB, bi);
     for (;;) {   // every group pulls its own bubbles: biggest first
@@ -570,7 +741,11 @@ __global__ void __launch_bounds__(GROUP_BLOCK) msa_group_kernel(const MsaArgs a)
         const uint32_t s0 = a.bubble_off[b], ns = a.bubble_off[b + 1] - s0;
         uint8_t *slot = a.slot_base + a.slot_off[w];
         msa_run(x, a.bases, a.seq_off, s0, ns, ws, a.lim, a.sc, slot);
-        if (x.g == 0) { a.slot_ptr[b] = (uint64_t)(uintptr_t)slot; a.tier[b] = a.tier_id; }
+        if (x.g == 0) {
+            a.slot_ptr[b] = (uint64_t)(uintptr_t)slot;
+            a.tier[b] = a.tier_id;
+            if (a.hq) heavy_enqueue(a.hq, slot, b);
+        }
     }
     if (x.g == 0 && x.cells) atomicAdd(a.stat_cells, x.cells);
 }
@@ -732,6 +907,7 @@ struct pf_align_state {
     pf::DevBuf in_bases, in_seq_off, in_bubble_off;
     pf::PinnedBuf h_scalars, h_out[12];
     uint32_t last_retry_count = 0;
+    uint32_t last_heavy_queued = 0;   // bubbles the first pass pushed on the heavy queue
     uint64_t last_cells = 0;
     uint32_t last_class_count[N_TIERS] = {0};
     int lane_blocks_per_sm[3][N_LANE_CLASSES];   // [variant][class]; variants: LANE_FP64, LANE_I32, LANE_S16X2
@@ -739,6 +915,10 @@ struct pf_align_state {
     cudaStream_t aux[N_LANE_CLASSES + 1] = {nullptr};   // the size classes run concurrently
     cudaEvent_t ev_fork = nullptr, ev_join[N_LANE_CLASSES + 1] = {nullptr};
     pf::DevBuf ws_cls[N_LANE_CLASSES];
+    pf::DevBuf hq, heavy_pool, heavy_ws;               // heavy queue, its slot pool and work areas
+    cudaStream_t heavy_stream = nullptr;
+    cudaEvent_t ev_heavy = nullptr;
+    int heavy_ctas = 4;
     int group_lanes[N_LANE_CLASSES] = {1, 1, 2, 2, 4};   // lanes per bubble of each size class (1 = thread-per-bubble kernel)
     bool group_env_done = false;
 };
@@ -746,6 +926,9 @@ struct pf_align_state {
 void pf_align_state_free(pf_align_state *s) {
     if (!s) return;
     for (auto &b : s->ws_cls) b.release();
+    s->hq.release(); s->heavy_pool.release(); s->heavy_ws.release();
+    if (s->heavy_stream) cudaStreamDestroy(s->heavy_stream);
+    if (s->ev_heavy) cudaEventDestroy(s->ev_heavy);
     for (auto &st : s->aux) if (st) cudaStreamDestroy(st);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     for (auto &e : s->ev_join) if (e) cudaEventDestroy(e);
@@ -819,6 +1002,7 @@ void fill_args(MsaArgs &a, pf_align_state *st, int slot_pool, const Limits &lim,
     a.slot_ptr = st->slot_ptr.as<uint64_t>(); a.tier = st->tier.as<uint8_t>(); a.tier_id = (uint8_t)tier_id;
     a.counter = counter; a.lim = lim; a.sc = sc;
     a.stat_cells = (unsigned long long *)(st->counter.as<uint8_t>() + 128);
+    a.hq = nullptr;
 }
 
 // one launch of the warp-per-bubble kernel over work items [first, first + n_items) of `d_order`
@@ -843,26 +1027,42 @@ int launch_warp_tier(pf_ctx *ctx, pf_align_state *st, int pool, const Limits &li
     return PF_OK;
 }
 
-// the shared-memory-flags variant: one warp per CTA, dynamic smem = the flag matrix of `lim`
+// the shared-memory tier in drain mode: one warp per CTA over a host-sized list of bubbles (msa_heavy_kernel)
+int heavy_mode(const Scoring &sc, const Limits &lim) { return lane_variant(sc, lim) == LANE_S16X2 ? 2 : (sc.integral ? 1 : 0); }
+size_t heavy_smem_bytes(const Limits &hl, int hmode) {
+    return (size_t)(align_up(flag_area_cells(hl), 16) + align_up(hl.max_alen + hl.max_blen, 16) + (hmode == 2 ? group_smem_per_warp(hl.max_blen, 1) : 0));
+}
+int heavy_set_attr() {
+    static bool done = false;
+    if (done) return PF_OK;
+    const int big_smem = 200 * 1024;
+    PF_CUDA_TRY(cudaFuncSetAttribute(msa_heavy_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem));
+    PF_CUDA_TRY(cudaFuncSetAttribute(msa_heavy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem));
+    PF_CUDA_TRY(cudaFuncSetAttribute(msa_heavy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem));
+    done = true;
+    return PF_OK;
+}
+void heavy_launch(int hmode, unsigned grid, size_t smem, cudaStream_t s, const MsaArgs &a) {
+    if (hmode == 2) msa_heavy_kernel<2><<<grid, 32, smem, s>>>(a);
+    else if (hmode == 1) msa_heavy_kernel<1><<<grid, 32, smem, s>>>(a);
+    else msa_heavy_kernel<0><<<grid, 32, smem, s>>>(a);
+}
+
 int launch_warp_smem_tier(pf_ctx *ctx, pf_align_state *st, int pool, const Limits &lim, const Scoring &sc, const uint8_t *d_bases,
                           const uint64_t *d_seq_off, const uint32_t *d_bubble_off, const uint32_t *d_order, uint32_t n_items,
                           int tier_id, uint32_t *counter, cudaStream_t s) {
-    const size_t smem = (size_t)align_up(flag_area_cells(lim), 16);
-    static bool attr_done = false;
-    if (!attr_done) {
-        PF_CUDA_TRY(cudaFuncSetAttribute(msa_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PF_CUDA_TRY(cudaFuncSetAttribute(msa_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    const uint64_t ws_bytes = align_up(work_area_bytes(lim), 256);
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>((uint64_t)n_items, (uint64_t)ctx->sm_count);
+    Limits hl = lim;
+    const int hmode = heavy_mode(sc, lim);
+    if (hmode == 2) hl.diag_flags = 0;
     int rc;
+    if ((rc = heavy_set_attr())) return rc;
+    const uint64_t ws_bytes = align_up(work_area_bytes(hl), 256);
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((uint64_t)n_items, (uint64_t)ctx->sm_count);
     if ((rc = st->ws_warp[pool].reserve((uint64_t)blocks * ws_bytes))) return rc;
     MsaArgs a;
-    fill_args(a, st, pool, lim, sc, d_bases, d_seq_off, d_bubble_off, d_order, 0, n_items, tier_id, counter);
+    fill_args(a, st, pool, hl, sc, d_bases, d_seq_off, d_bubble_off, d_order, 0, n_items, tier_id, counter);
     a.ws_base = st->ws_warp[pool].as<uint8_t>(); a.ws_stride = ws_bytes;
-    if (sc.integral) msa_warp_kernel<true, true><<<blocks, 32, smem, s>>>(a);
-    else msa_warp_kernel<false, true><<<blocks, 32, smem, s>>>(a);
+    heavy_launch(hmode, blocks, heavy_smem_bytes(hl, hmode), s, a);
     ctx->launches++;
     PF_CUDA_TRY(cudaGetLastError());
     return PF_OK;
@@ -871,7 +1071,7 @@ int launch_warp_smem_tier(pf_ctx *ctx, pf_align_state *st, int pool, const Limit
 // one launch of the G-lanes-per-bubble kernel over work items [first, first + n_items) of `d_order`
 int launch_group_tier(pf_ctx *ctx, pf_align_state *st, pf::DevBuf &pool, const Limits &lim, int GL, const Scoring &sc,
                       const uint8_t *d_bases, const uint64_t *d_seq_off, const uint32_t *d_bubble_off, const uint32_t *d_order,
-                      uint32_t first, uint32_t n_items, int tier_id, uint32_t *counter, cudaStream_t s) {
+                      uint32_t first, uint32_t n_items, int tier_id, uint32_t *counter, cudaStream_t s, uint32_t *hq = nullptr) {
     const uint32_t NB = 32 / GL, wpb = GROUP_BLOCK / 32;
     const uint64_t ws_bytes = align_up(work_area_bytes(lim, NB), 256);
     const size_t smem = (size_t)wpb * group_smem_per_warp(lim.max_blen, NB);
@@ -889,6 +1089,7 @@ int launch_group_tier(pf_ctx *ctx, pf_align_state *st, pf::DevBuf &pool, const L
     fill_args(a, st, 0, lim, sc, d_bases, d_seq_off, d_bubble_off, d_order, first, n_items, tier_id, counter);
     a.ws_base = pool.as<uint8_t>();
     a.ws_stride = ws_bytes;
+    a.hq = hq;
     group_kernel(GL)<<<grid, GROUP_BLOCK, smem, s>>>(a);
     ctx->launches++;
     PF_CUDA_TRY(cudaGetLastError());
@@ -940,6 +1141,7 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
                 for (int c = 0; c < N_LANE_CLASSES; c++)
                     if (v[c] == 1 || v[c] == 2 || v[c] == 4 || v[c] == 8 || v[c] == 16 || v[c] == 32) st->group_lanes[c] = v[c];
         }
+        if (const char *e = getenv("PF_HEAVY_CTAS")) { const int v = atoi(e); if (v >= 0 && v <= 64) st->heavy_ctas = v; }
         st->group_env_done = true;
     }
     TierTable tt;
@@ -993,6 +1195,39 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
     PF_CUDA_TRY(cudaStreamSynchronize(s));
     if ((rc = st->slots[0].reserve(*h_total + 64))) return rc;
 
+    // ---- heavy queue: a few one-warp CTAs that re-run exploding DFS bubbles beside the first pass ----
+    uint32_t *d_hq = nullptr;
+    if (st->heavy_ctas > 0 && h_bounds[CLS_BIG] > 0) {
+        Limits hl = heavy;
+        const int hmode = heavy_mode(sc, heavy);
+        if (hmode == 2) hl.diag_flags = 0;   // row-major flags, one pitch (the group kernel's fill)
+        // poll mode asks for (almost) a whole SM's shared memory: the one warp that carries a millisecond-scale serial search
+        // should not share its scheduler with first-pass warps
+        const size_t hsmem = std::max<size_t>(heavy_smem_bytes(hl, hmode), 190 * 1024);
+        const uint64_t hws = align_up(work_area_bytes(hl), 256), pool_bytes = 64ull << 20;
+        if ((rc = heavy_set_attr())) return rc;
+        if (!st->heavy_stream) {
+            PF_CUDA_TRY(cudaStreamCreateWithFlags(&st->heavy_stream, cudaStreamNonBlocking));
+            PF_CUDA_TRY(cudaEventCreateWithFlags(&st->ev_heavy, cudaEventDisableTiming));
+        }
+        if ((rc = st->hq.reserve((HQ_HDR + HQ_CAP) * 4))) return rc;
+        if ((rc = st->heavy_pool.reserve(pool_bytes))) return rc;
+        if ((rc = st->heavy_ws.reserve((uint64_t)st->heavy_ctas * hws))) return rc;
+        d_hq = st->hq.as<uint32_t>();
+        PF_CUDA_TRY(cudaMemsetAsync(d_hq, 0, HQ_HDR * 4, s));
+        PF_CUDA_TRY(cudaMemsetAsync(d_hq + HQ_HDR, 0xFF, HQ_CAP * 4, s));
+        PF_CUDA_TRY(cudaEventRecord(st->ev_fork, s));
+        PF_CUDA_TRY(cudaStreamWaitEvent(st->heavy_stream, st->ev_fork, 0));
+        MsaArgs ha;
+        fill_args(ha, st, 0, hl, sc, d_bases, d_seq_off, d_bubble_off, d_order, (uint32_t)(pool_bytes >> 10), 0, CLS_RETRY_SMEM, nullptr);
+        ha.slot_base = st->heavy_pool.as<uint8_t>();
+        ha.ws_base = st->heavy_ws.as<uint8_t>(); ha.ws_stride = hws;
+        ha.hq = d_hq;
+        heavy_launch(hmode, (unsigned)st->heavy_ctas, hsmem, st->heavy_stream, ha);
+        ctx->launches++;
+        PF_CUDA_TRY(cudaGetLastError());
+        PF_CUDA_TRY(cudaEventRecord(st->ev_heavy, st->heavy_stream));
+    }
     // ---- first pass: every non-empty size class on its own stream (they overlap; heaviest first) ----
     PF_CUDA_TRY(cudaEventRecord(st->ev_fork, s));
     {
@@ -1020,9 +1255,10 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         PF_CUDA_TRY(cudaStreamWaitEvent(as, st->ev_fork, 0));
         MsaArgs a;
         fill_args(a, st, 0, tt.lim[c], sc, d_bases, d_seq_off, d_bubble_off, d_order, h_bounds[c], cnt, c, st->counter.as<uint32_t>() + c);
+        a.hq = d_hq;
         if (GL > 1) {   // G lanes per bubble
             if ((rc = launch_group_tier(ctx, st, st->ws_cls[c], tt.lim[c], GL, sc, d_bases, d_seq_off, d_bubble_off, d_order, h_bounds[c], cnt, c,
-                                        st->counter.as<uint32_t>() + c, as))) return rc;
+                                        st->counter.as<uint32_t>() + c, as, d_hq))) return rc;
             ctx->launches--;   // counted once below
         } else {
             const uint64_t ws_bytes = align_up(work_area_bytes(tt.lim[c], 32), 256);
@@ -1041,6 +1277,11 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         PF_CUDA_TRY(cudaEventRecord(st->ev_join[c], as));
         PF_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_join[c], 0));
     }
+    if (d_hq) {   // the first pass is over: the heavy CTAs finish the bubble they hold and stop
+        heavy_done_kernel<<<1, 1, 0, s>>>(d_hq);
+        ctx->launches++;
+        PF_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_heavy, 0));
+    }
     // ---- re-runs: whatever overflowed its tier goes to the shared-memory-flags warp kernel (branches <= 256), and what
     //      still does not fit to the warp kernel with the large limits ----
     st->last_retry_count = 0;
@@ -1051,10 +1292,14 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         ctx->launches++;
         uint32_t *h_cnt = (uint32_t *)(st->h_scalars.as<uint8_t>() + 64);
         PF_CUDA_TRY(cudaMemcpyAsync(h_cnt, d_retry_cnt, 4, cudaMemcpyDeviceToHost, s));
+        if (pass == 0 && d_hq) PF_CUDA_TRY(cudaMemcpyAsync(h_cnt + 1, d_hq, 8, cudaMemcpyDeviceToHost, s));   // queue tail, tickets
         PF_CUDA_TRY(cudaStreamSynchronize(s));
         const uint32_t nr = *h_cnt;
         st->last_class_count[tier] = nr;
-        if (pass == 0) st->last_retry_count = nr;
+        if (pass == 0) {
+            st->last_retry_count = nr;
+            st->last_heavy_queued = d_hq ? h_cnt[1] : 0;
+        }
         if (!nr) break;
         slot_size_kernel<<<(nr + 1 + 255) / 256, 256, 0, s>>>(d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), nullptr, tier, nr, tt,
                                                               st->slot_sizes.as<uint64_t>());
@@ -1198,6 +1443,8 @@ uint32_t pf_align_last_retry_count(const pf_ctx *ctx) { return (ctx && ctx->alig
 uint64_t pf_align_last_cells(const pf_ctx *ctx) { return (ctx && ctx->align) ? ctx->align->last_cells : 0; }
 // diagnostics: bubbles per tier of the last call: [0..4] lane-kernel size classes (<=64/96/128/192/256), [5] warp kernel,
 // [6] re-runs in the shared-memory-flags warp kernel, [7] re-runs with the large limits
+uint32_t pf_align_last_heavy_queued(const pf_ctx *ctx) { return (ctx && ctx->align) ? ctx->align->last_heavy_queued : 0; }
+
 int pf_align_last_tier_counts(const pf_ctx *ctx, uint32_t *out, int n) {
     if (!ctx || !out) return PF_E_INVALID;
     for (int i = 0; i < n; i++) out[i] = (ctx->align && i < N_TIERS) ? ctx->align->last_class_count[i] : 0;

@@ -35,6 +35,15 @@
 
 namespace pfalign {
 
+// hint: the flag byte the DFS will most likely want a few steps from now (no-op on the host)
+PF_HD void prefetch_byte(const uint8_t *p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.L1 [%0];" ::"l"(p));   // generic address: a no-op when the flags live in shared memory
+#else
+    (void)p;
+#endif
+}
+
 enum { F_UP = 1, F_DIAG = 2, F_LEFT = 4 };
 enum { MV_L = 0, MV_U = 1, MV_D = 2, MV_NONE = 0xFF };
 enum { PF_BUBBLE_OUT_OVERFLOW = 6 };  // more variable columns than the output slot holds
@@ -200,21 +209,34 @@ struct TbResult {
 
 // traceback (SeqAlign.cpp:306-478).  flags: diagonal-major bytes written by the fill.
 // Kept alignments go to ext_mv[a*mv_stride ..] with lengths ext_len[a].
-template <bool DIAG>
-PF_HDN inline TbResult traceback(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n,
+template <bool DIAG, class X>
+PF_HDN inline TbResult traceback(X &x, const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n,
                                  const Scoring &sc, const BV mv, const BV ext_mv, const WV ext_len,
                                  uint32_t mv_stride, uint32_t k_aln, uint64_t step_limit, uint32_t pitch_n) {
     TbResult r;
     r.n_aln = 0; r.status = PF_BUBBLE_OK; r.steps = 0;
-    uint32_t i = m, j = n, depth = 0;
-    uint64_t open_a = 0, open_b = 0, cap_a = 5, cap_b = 5;  // indel1, indel2, indel1_max, indel2_max (:312-315)
+    // The loop below is ONE dependent chain per step (flag byte -> decision -> next cell), i.e. pure latency on a GPU lane, so it
+    // is kept to as few instructions as the semantics allow: the cell index moves by a constant per move instead of being
+    // recomputed, (0,0) is cell 0 in both layouts, the last two moves live in registers, counters are 32 bit.
+    // indel1 / indel2 (size_t in the reference, :312-315) may wrap below zero; a 32-bit counter orders against the small caps
+    // exactly like the 64-bit one as long as fewer than 2^31 moves are on the stack.
+    const uint32_t dL = DIAG ? m + 1 : 1u;                     // cell(i, j) - cell(i, j-1)
+    const uint32_t dU = DIAG ? m + 2 : pitch_n + 1;            // cell(i, j) - cell(i-1, j)
+    const uint32_t dD = dL + dU;                               // cell(i, j) - cell(i-1, j-1)
+    uint32_t cell = flag_index<DIAG>(m, n, m, pitch_n);
+    uint32_t depth = 0, steps = 0;
+    const uint32_t budget = step_limit > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)step_limit;
+    uint32_t open_a = 0, open_b = 0, cap_a = 5, cap_b = 5;     // indel1, indel2, indel1_max, indel2_max
     PairKey last;
     last.score = 0; last.n_pos = 0; last.n_indel = 0;
+    const bool pf = x.prefetch_flags();
+    const uint32_t pf_min = 6 * dD;                            // six cells up the diagonal: the path of a good alignment
+    uint32_t lastmv = MV_NONE, prevmv = MV_NONE;               // mv[depth-1], mv[depth-2]
     for (;;) {
-        if (++r.steps > step_limit) { r.status = PF_BUBBLE_STEP_LIMIT; return r; }
-        const uint32_t cell = flag_index<DIAG>(i, j, m, pitch_n);
-        if (i == 0 && j == 0 && open_a <= cap_a && open_b <= cap_b) {   // :322-355
-            const PairKey cand = analyze_moves(sc, A, B, cbv(mv), depth);
+        if (++steps > budget) { r.status = PF_BUBBLE_STEP_LIMIT; r.steps = steps; return r; }
+        if (pf && cell >= pf_min) prefetch_byte(&flags[cell - pf_min]);
+        if (cell == 0 && open_a <= cap_a && open_b <= cap_b) {          // :322-355
+            const PairKey cand = x.analyze(sc, A, B, cbv(mv), depth);
             bool keep = true;
             if (r.n_aln > 0) {
                 const int d = rank_diff(last.score, last.n_pos, last.n_indel, cand.score, cand.n_pos, cand.n_indel);
@@ -222,8 +244,8 @@ PF_HDN inline TbResult traceback(const BV flags, const CBV A, uint32_t m, const 
                 else if (d < 0) r.n_aln = 0;
             }
             if (keep) {
-                if (r.n_aln == k_aln) { r.status = PF_BUBBLE_CAND_OVERFLOW; return r; }
-                copy_bytes(cbv(mv), ext_mv + (uint64_t)r.n_aln * mv_stride, depth);
+                if (r.n_aln == k_aln) { r.status = PF_BUBBLE_CAND_OVERFLOW; r.steps = steps; return r; }
+                x.copy(cbv(mv), ext_mv + (uint64_t)r.n_aln * mv_stride, depth);
                 ext_len[r.n_aln] = depth;
                 r.n_aln++;
                 last = cand;
@@ -231,43 +253,45 @@ PF_HDN inline TbResult traceback(const BV flags, const CBV A, uint32_t m, const 
                 cap_b = open_b;
             }
         }
-        const uint8_t c = flags[cell];
-        const uint8_t w = (uint8_t)(c & 7 & ~(c >> 4));                   // still-untried directions of this cell
-        const uint8_t lastmv = depth ? mv[depth - 1] : (uint8_t)MV_NONE;
+        const uint32_t c = flags[cell];
+        const uint32_t w = c & 7u & ~(c >> 4);                          // still-untried directions of this cell
         if (w & F_LEFT) {                                               // :356-392
             bool take;
             if (open_a < cap_a) { if (lastmv != MV_L) ++open_a; take = true; }
             else if (open_a == cap_a) take = (lastmv == MV_L);
             else take = false;
-            if (!take) { flags[cell] = c & (uint8_t)~F_LEFT; continue; }          // permanent prune of the base matrix
-            flags[cell] = c | (uint8_t)(F_LEFT << 4);
+            if (!take) { flags[cell] = (uint8_t)(c & ~(uint32_t)F_LEFT); continue; }   // permanent prune of the base matrix
+            flags[cell] = (uint8_t)(c | (F_LEFT << 4));
             mv[depth++] = MV_L;
-            j--;
+            prevmv = lastmv; lastmv = MV_L;
+            cell -= dL;
         } else if (w & F_UP) {                                          // :393-424
             bool take;
             if (open_b < cap_b) { if (depth == 0 || lastmv == MV_U) ++open_b; take = true; }  // sic (:397)
             else if (open_b == cap_b) take = (lastmv == MV_U);
             else take = false;
-            if (!take) { flags[cell] = c & (uint8_t)~F_UP; continue; }
-            flags[cell] = c | (uint8_t)(F_UP << 4);
+            if (!take) { flags[cell] = (uint8_t)(c & ~(uint32_t)F_UP); continue; }
+            flags[cell] = (uint8_t)(c | (F_UP << 4));
             mv[depth++] = MV_U;
-            i--;
+            prevmv = lastmv; lastmv = MV_U;
+            cell -= dU;
         } else if (w & F_DIAG) {                                        // :425-431
-            flags[cell] = c | (uint8_t)(F_DIAG << 4);
+            flags[cell] = (uint8_t)(c | (F_DIAG << 4));
             mv[depth++] = MV_D;
-            i--; j--;
+            prevmv = lastmv; lastmv = MV_D;
+            cell -= dD;
         } else {                                                        // :432-474
             if (depth == 0) break;
-            flags[cell] = (uint8_t)(c & 7);                             // matrix_temp[p] = matrix[p]
-            const uint8_t prev = depth >= 2 ? mv[depth - 2] : (uint8_t)MV_NONE;
-            if (lastmv == MV_L && prev != MV_L) --open_a;
-            if (lastmv == MV_U && prev != MV_U) --open_b;               // may wrap below zero, as in the reference
-            if (lastmv == MV_L) j++;
-            else if (lastmv == MV_U) i++;
-            else { i++; j++; }
+            flags[cell] = (uint8_t)(c & 7u);                            // matrix_temp[p] = matrix[p]
+            if (lastmv == MV_L) { if (prevmv != MV_L) --open_a; cell += dL; }
+            else if (lastmv == MV_U) { if (prevmv != MV_U) --open_b; cell += dU; }   // may wrap below zero, as in the reference
+            else cell += dD;
             depth--;
+            lastmv = prevmv;
+            prevmv = depth >= 2 ? (uint32_t)mv[depth - 2] : (uint32_t)MV_NONE;
         }
     }
+    r.steps = steps;
     return r;
 }
 
@@ -346,14 +370,27 @@ PF_HDN inline int scan_candidate(const CBV cand, uint32_t stride, uint32_t nr, u
     bool open = false;
     uint32_t n_snp = 0, n_indel = 0, last_indel_pos = 0, n_var = 0, n_ilen = 0;
     int status = PF_BUBBLE_OK;
-    for (uint32_t j = 0; j < L; j++) {
-        const uint8_t c0 = cand[j];
-        bool multi = false, has_gap = (c0 == '-');
+    // Column summaries (more than one symbol? a gap?) are gathered PF_CH columns at a time -- all loads of a chunk are in
+    // flight together; the state machine then walks the chunk.  Only variable columns (a few per cent) load anything else.
+    for (uint32_t j0 = 0; j0 < L; j0 += PF_CH) {
+      uint32_t multi_m = 0, gap_m = 0;
+      {
+        uint8_t c0[PF_CH];
+#pragma unroll
+        for (uint32_t q = 0; q < PF_CH; q++) c0[q] = j0 + q < L ? cand[j0 + q] : (uint8_t)0;
+#pragma unroll
+        for (uint32_t q = 0; q < PF_CH; q++) gap_m |= (uint32_t)(c0[q] == '-') << q;
         for (uint32_t r = 1; r < nr; r++) {
-            const uint8_t c = cand[(uint64_t)r * stride + j];
-            multi |= (c != c0);
-            has_gap |= (c == '-');
+            uint8_t c[PF_CH];
+#pragma unroll
+            for (uint32_t q = 0; q < PF_CH; q++) c[q] = j0 + q < L ? cand[(uint64_t)r * stride + j0 + q] : (uint8_t)0;
+#pragma unroll
+            for (uint32_t q = 0; q < PF_CH; q++) { multi_m |= (uint32_t)(c[q] != c0[q]) << q; gap_m |= (uint32_t)(c[q] == '-') << q; }
         }
+      }
+      for (uint32_t q = 0; q < PF_CH && j0 + q < L; q++) {
+        const uint32_t j = j0 + q;
+        const bool multi = (multi_m >> q) & 1u, has_gap = (gap_m >> q) & 1u;
         bool number = false;
         int kind = 2;
         if (multi) {
@@ -423,6 +460,7 @@ PF_HDN inline int scan_candidate(const CBV cand, uint32_t stride, uint32_t nr, u
             } else status = PF_BUBBLE_OUT_OVERFLOW;
         }
         if (number) n_var++;
+      }
     }
     key.n_snp = (int)n_snp;
     key.n_indel = (int)n_indel;
@@ -569,12 +607,24 @@ PF_HD SlotLayout slot_layout(uint32_t n_seq, uint64_t sum_len, const Limits &l) 
     return s;
 }
 
+// The helpers a policy offers to the sequential phases.  Policies whose sequential phases run on one thread inherit these;
+// the group kernel overrides them with versions that spread the loop over the lanes of the group.
+struct SerialHelpers {
+    PF_HD bool prefetch_flags() const { return false; }
+    PF_HD PairKey analyze(const Scoring &sc, const CBV row, const CBV B, const CBV mv, uint32_t depth) const { return analyze_moves(sc, row, B, mv, depth); }
+    PF_HD void copy(const CBV src, const BV dst, uint32_t n) const { copy_bytes(src, dst, n); }
+    PF_HD void project(const CBV src, const CBV mv, uint32_t depth, const BV dst, uint8_t gap_move) const { project_moves(src, mv, depth, dst, gap_move); }
+};
+
 // ---- the per-bubble driver: SequenceAlignment (SeqAlign.cpp:550-640) --------------------------------------
 //
 // X is the execution policy:
 //   * generic kernel: a warp (leader = lane 0, fill = wavefront by shuffle, bcast = shuffle), contiguous work area;
 //   * lane kernel: ONE THREAD per bubble (every lane is its own leader, fill = row-by-row with the score row
 //     in shared memory), lane-interleaved work area;
+//   * group kernel: G lanes; the fill is cooperative, and everything else runs REDUNDANTLY on all G lanes (leader() is true
+//     everywhere: same loads, same decisions, same stores to the same addresses -- no extra time under SIMT), which lets
+//     the O(L) helpers (analyze / copy / project) use the G lanes instead of one;
 //   * tests/hostemu: a single CPU thread.
 // X::kDiagFlags selects the flag-byte layout the policy's fill writes.
 template <class X>
@@ -606,7 +656,7 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
             if (m > lim.max_alen) { status = PF_BUBBLE_TOO_LONG; break; }
             x.fill(ws.flags, A, m, B, n, sc, ws.brow);
             if (x.leader()) {
-                const TbResult tb = traceback<X::kDiagFlags>(ws.flags, A, m, B, n, sc, ws.mv, ws.ext_mv, ws.ext_len, mv_stride,
+                const TbResult tb = traceback<X::kDiagFlags>(x, ws.flags, A, m, B, n, sc, ws.mv, ws.ext_mv, ws.ext_len, mv_stride,
                                                              lim.k_aln, steps_left, x.pitch_n(n));
                 steps_left -= tb.steps < steps_left ? tb.steps : steps_left;
                 x.note_steps(tb.steps);
@@ -622,7 +672,7 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
                         const CBV rowj = A + (uint64_t)j * lim.max_alen;
                         for (uint32_t v = 0; v < tb.n_aln; v++) {
                             if (!((alive >> v) & 1)) continue;
-                            const PairKey pk = analyze_moves(sc, rowj, B, cbv(ws.ext_mv + (uint64_t)v * mv_stride), ws.ext_len[v]);
+                            const PairKey pk = x.analyze(sc, rowj, B, cbv(ws.ext_mv + (uint64_t)v * mv_stride), ws.ext_len[v]);
                             const int d = rank_diff(pk.score, pk.n_pos, pk.n_indel, inc.score, inc.n_pos, inc.n_indel);
                             if (d > 0) { inc = pk; best_j = (int)inc.score; alive_j = 1ull << v; }
                             else if (d == 0) { best_j = (int)inc.score; alive_j |= 1ull << v; }
@@ -640,8 +690,8 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
                             const CBV mvv = cbv(ws.ext_mv + (uint64_t)v * mv_stride);
                             const BV dst = ws.cand[cur ^ 1] + nnext * cand_stride;
                             for (uint32_t r = 0; r < i; r++)
-                                project_row(A + (uint64_t)r * lim.max_alen, mvv, depth, dst + (uint64_t)r * lim.max_alen);
-                            project_new(B, mvv, depth, dst + (uint64_t)i * lim.max_alen);
+                                x.project(A + (uint64_t)r * lim.max_alen, mvv, depth, dst + (uint64_t)r * lim.max_alen, (uint8_t)MV_L);
+                            x.project(B, mvv, depth, dst + (uint64_t)i * lim.max_alen, (uint8_t)MV_U);
                             ws.cand_len[cur ^ 1][nnext] = depth;
                             nnext++;
                         }
@@ -693,7 +743,7 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
                     uint32_t nv = 0, nil = 0;
                     status = scan_candidate(win, lim.max_alen, ns, L, Llast, key, true, &sv, &nv, &nil);
                     if (status == PF_BUBBLE_OK) {
-                        for (uint32_t r = 0; r < ns; r++) copy_bytes(win + (uint64_t)r * lim.max_alen, bv(sv.rows + (uint64_t)r * L), L);
+                        for (uint32_t r = 0; r < ns; r++) x.copy(win + (uint64_t)r * lim.max_alen, bv(sv.rows + (uint64_t)r * L), L);
                         hdr->n_rows = ns; hdr->alen = L; hdr->n_var = nv; hdr->n_ilen = nil;
                     }
                 }

@@ -17,7 +17,7 @@ using namespace pfalign;
 namespace {
 
 template <bool DIAG>
-struct HostExec {
+struct HostExec : SerialHelpers {
     static constexpr bool kDiagFlags = DIAG;
     std::vector<int> rowbuf;
     bool leader() const { return true; }

@@ -124,6 +124,43 @@ def test_long_pair_matches_oracle(gpu_ctx, oracle):
     assert_msa_equal(a, b, bubbles, "long pairs")
 
 
+def test_indel_heavy_5kbp_branches(gpu_ctx, oracle):
+    """BASELINE configs[4]: branches up to 5 kbp with long indels, three and four rows -- beyond what the int16 fill can score,
+    so the INT32 wavefront of the warp kernel and the large-limits tier carry it."""
+    rng = np.random.default_rng(17)
+    bubbles = []
+    for L, rows in ((5000, 2), (4200, 3), (3000, 4), (1900, 3)):
+        a = gen.rand_seq(rng, L)
+        out = [a]
+        for r in range(rows - 1):
+            i = int(rng.integers(200, L - 1500))
+            d = int(rng.integers(100, 1200))
+            b = a[:i] + a[i + d:] if r % 2 == 0 else a[:i] + gen.rand_seq(rng, d // 4) + a[i:]
+            out.append(gen.mutate(rng, b, 4, 1))
+        bubbles.append(gen.sort_branching(out))
+    flat = flatten_bubbles(bubbles)
+    a = oracle.align(*flat, n_threads=4)
+    b = gpu_ctx.align(*flat)
+    assert_msa_equal(a, b, bubbles, "5 kbp branches")
+    assert (b["status"] == 0).all()
+
+
+def test_exploding_traceback_goes_through_the_heavy_queue(oracle):
+    """A batch in which many bubbles exceed the first-pass DFS budget (two-letter alphabet: co-optimal paths abound):
+    the heavy queue takes what it can beside the first pass, the pass after it takes the rest; results are the oracle's."""
+    from ploidyfrost_b200 import capi
+    ctx = capi.Context(0)
+    try:
+        bubbles = gen.random_bubbles(31, 4000, alphabet="AC", len_range=(60, 200), max_indel=4, max_indel_len=12)
+        flat = flatten_bubbles(bubbles)
+        a = oracle.align(*flat, n_threads=8)
+        b = ctx.align(*flat)
+        assert_msa_equal(a, b, bubbles, "heavy queue")
+        assert ctx.last_heavy_queued > 0
+    finally:
+        ctx.close()
+
+
 def test_idempotence_and_permutation_properties(gpu_ctx):
     """Size-independent properties: removing gaps from the aligned rows gives back the inputs, in order; all
     rows of a bubble have the same length; the batch result does not depend on batch composition."""

@@ -1,0 +1,235 @@
+"""TEST INFRASTRUCTURE.  Regenerates the rows PloidyFrost writes for the bubbles it aligned (coverage / frequency files, `-t 1`
+dialect) from: the bubbles' raw branch strings, a SequenceAlignment implementation, a KMC lookup implementation.  The logic is a
+restatement of the reference's per-bubble caller -- strict bubbles CDBG.cpp:1186-1330 (= :1998-2189), branching bubbles
+:1440-1660 (= :2190-2575), site k-mers SURVEY.md Appendix C -- used to pin the oracle AND the CUDA path against the unmodified
+reference's own output files (tests/golden/e2e, made by tests/golden/make_golden_e2e.py)."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+from oracle.bindings import flatten_bubbles, flatten_seqs, msa_bubble
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+E2E = os.path.join(HERE, "golden", "e2e")
+
+
+def fmt(x: float) -> str:
+    """ostream << double at default precision == printf %g (6 significant digits)."""
+    return "%g" % x
+
+
+def parse_alignseq(path):
+    """-> [dict(var_id, strict, ent, exit, rows)] in file order (consecutive lines of one VarId are one bubble)."""
+    out = []
+    for ln in open(path):
+        p = ln.rstrip("\n").split("\t")
+        if out and out[-1]["var_id"] == int(p[0]):
+            out[-1]["rows"].append(p[4])
+        else:
+            out.append(dict(var_id=int(p[0]), strict=p[1] == "1", ent=int(p[2]), exit=int(p[3]), rows=[p[4]]))
+    return out
+
+
+def parse_cov_files(d):
+    """-> {var_id: [row string, ...]} over the bi/tri/tetra/penta coverage files."""
+    rows = {}
+    for a in ("bi", "tri", "tetra", "penta"):
+        for ln in open(os.path.join(d, f"P_{a}cov.txt")):
+            p = ln.rstrip("\n").split("\t")
+            rows.setdefault(int(p[-4]), []).append(ln.rstrip("\n"))   # ... type, indelLen, VarId, VarNum, VarDis, ''
+    return rows
+
+
+def site_kmers(rows, c, k, is_indel, n_indel_before):
+    """The k-mer each row contributes at variable column c (CDBG.cpp:2338-2388 indel sites, :2433-2472 SNP sites)."""
+    n = len(rows)
+    if is_indel:
+        cur = [c] * n
+        ext = [""] * n
+        while True:                                       # :2338-2357: extend every row by its next base until they differ
+            chars = set()
+            for r in range(n):
+                while rows[r][cur[r]] == "-":
+                    cur[r] += 1
+                ch = rows[r][cur[r]]
+                cur[r] += 1
+                ext[r] += ch
+                chars.add(ch)
+            if len(chars) > 1:
+                break
+        out = []
+        for r in range(n):
+            e = len(ext[r])
+            if n_indel_before == 0:                       # :2358-2365
+                start = c - k + e
+                assert start >= 0, "substr with a negative start throws in the reference"
+                out.append(rows[r][start:start + k - e] + ext[r])
+            else:                                         # :2366-2388
+                t = rows[r][:c].replace("-", "")
+                if len(t) < k - e:
+                    s = t + ext[r]
+                    x = cur[r]
+                    while len(s) < k:
+                        if rows[r][x] != "-":
+                            s += rows[r][x]
+                        x += 1
+                    out.append(s)
+                else:
+                    out.append(t[len(t) - (k - e):] + ext[r])
+        return out
+    if n_indel_before > 0:                                # :2433-2465
+        out = []
+        for r in range(n):
+            t = rows[r][:c + 1].replace("-", "")
+            if len(t) < k:
+                s = t
+                x = c + 1
+                while len(s) < k:
+                    if rows[r][x] != "-":
+                        s += rows[r][x]
+                    x += 1
+                out.append(s)
+            else:
+                out.append(t[len(t) - k:])
+        return out
+    assert c - k + 1 >= 0
+    return [rows[r][c - k + 1:c + 1] for r in range(n)]    # :2469-2472
+
+
+def var_distance(i, var_site, ent_size, exit_size):
+    """CDBG.cpp:2312-2330 (same in the strict path)."""
+    if i == 0:
+        return min(var_site[1] - var_site[0] - 1, ent_size) if len(var_site) > 1 else min(ent_size, exit_size)
+    if i == len(var_site) - 1:
+        return min(var_site[i] - var_site[i - 1] - 1, exit_size)
+    return min(var_site[i] - var_site[i - 1] - 1, var_site[i + 1] - var_site[i] - 1)
+
+
+def branching_site_plan(bubbles, aligned, k):
+    """Every variable column of every branching bubble with its site k-mers: [(bubble index, site index, column, is_indel,
+    indel sites seen so far incl. this one, offset into the k-mer list)], [k-mer strings]."""
+    plan, kmers = [], []
+    for bi, (b, m) in enumerate(zip(bubbles, aligned)):
+        if not m["rows"] or b["strict"]:
+            continue
+        n_ind = 0
+        for i, c in enumerate(sorted(m["partition"].keys())):
+            is_ind = c in m["indel_pos"]
+            km = site_kmers(m["rows"], c, k, is_ind, n_ind)
+            if is_ind:
+                n_ind += 1
+            plan.append((bi, i, c, is_ind, n_ind, len(kmers)))
+            kmers.extend(km)
+    return plan, kmers
+
+
+def class_coverage(part, kmers, k0, counts, found, low, up):
+    """Coverage per allele class of one site (CDBG.cpp:2393-2418): distinct k-mers per class in std::set order; returns None when
+    the site is dropped."""
+    sets = [dict() for _ in range(max(part))]
+    for j, cl in enumerate(part):
+        sets[cl - 1].setdefault(kmers[k0 + j], k0 + j)
+    tc = []
+    for st in sets:
+        acc = 0.0
+        for s in sorted(st):
+            idx = st[s]
+            assert found[idx], f"k-mer {s} missing: the reference exits here (CDBG.cpp:54)"
+            cval = int(counts[idx])
+            if not (low < cval < up):
+                return None
+            acc += float(cval)
+        tc.append(acc)
+    return tc
+
+
+def regenerate(bubbles, unitig_len, k, low, up, align_fn, cov_fn, kmer_count_fn, site_cov_fn=None):
+    """bubbles: parse_alignseq() records.  align_fn(flat bubbles) -> MSA batch (numpy dict); cov_fn(bases, off) -> pf_cov records
+    (readCov, 'as written else reverse complement'); kmer_count_fn(list of k-mer strings) -> (counts, found).
+    site_cov_fn(msa, bubble index, site index) -> class coverages or None replaces the host-side site k-mer path when given
+    (the device implementation of lookup phase B).  Returns ({var_id: [cov rows]}, {var_id: [frequencies]}, aligned)."""
+    raw = [[r.replace("-", "") for r in b["rows"]] for b in bubbles]
+    msa = align_fn(*flatten_bubbles(raw))
+    aligned = [msa_bubble(msa, i) for i in range(len(bubbles))]
+    bases, off = flatten_seqs([s for b in raw for s in b])
+    cov = cov_fn(bases, off)                               # lookup-A: every branch string
+    plan, kmers = branching_site_plan(bubbles, aligned, k)
+    if site_cov_fn is None:
+        counts, found = kmer_count_fn(kmers) if kmers else (np.zeros(0, np.uint32), np.zeros(0, np.uint8))
+    cov_rows, fre_rows = {}, {}
+    s0 = 0
+    pi = 0
+    for bi, (b, m) in enumerate(zip(bubbles, aligned)):
+        nrow = len(b["rows"])
+        vid = b["var_id"]
+        if m["rows"]:
+            var_site = sorted(m["partition"].keys())
+            ent, ext = unitig_len[b["ent"]], unitig_len[b["exit"]]
+            if b["strict"]:
+                means = [float(cov["sum"][s0 + j]) / float(cov["n_kmers"][s0 + j]) for j in range(nrow)]
+                total = 0.0
+                for x in means:
+                    total += x
+                n_ind = 0
+                for i, c in enumerate(var_site):
+                    part = m["partition"][c]
+                    tc = [0.0] * max(part)
+                    for j, cl in enumerate(part):
+                        tc[cl - 1] += means[j]
+                    il = 0
+                    if c in m["indel_pos"]:
+                        n_ind += 1
+                        il = m["indel_len"][n_ind - 1]
+                    row = "".join(fmt(x) + "\t" for x in tc) + f"1\t{il}\t{vid}\t{len(var_site)}\t{var_distance(i, var_site, ent, ext)}\t"
+                    cov_rows.setdefault(vid, []).append(row)
+                    fre_rows.setdefault(vid, []).extend(fmt(x / total) for x in tc)
+            else:
+                while pi < len(plan) and plan[pi][0] == bi:
+                    _, i, c, is_ind, n_ind, k0 = plan[pi]
+                    pi += 1
+                    if site_cov_fn is not None:
+                        tc = site_cov_fn(msa, bi, i)
+                    else:
+                        tc = class_coverage(m["partition"][c], kmers, k0, counts, found, low, up)
+                    if tc is None:
+                        continue
+                    total = 0.0
+                    for x in tc:
+                        total += x
+                    il = m["indel_len"][n_ind - 1] if is_ind else 0
+                    row = "".join(fmt(x) + "\t" for x in tc) + f"0\t{il}\t{vid}\t{len(var_site)}\t{var_distance(i, var_site, ent, ext)}\t"
+                    cov_rows.setdefault(vid, []).append(row)
+                    fre_rows.setdefault(vid, []).extend(fmt(x / total) for x in tc)
+        s0 += nrow
+    return cov_rows, fre_rows, aligned
+
+
+def load_fixture():
+    meta = json.load(open(os.path.join(E2E, "meta.json")))
+    bubbles = parse_alignseq(os.path.join(E2E, "P_alignseq.txt"))
+    useq = {}
+    for ln in open(os.path.join(E2E, "P_Unitig_Id.txt")):
+        i, s = ln.rstrip("\n").split("\t")
+        useq[int(i)] = s
+    return meta, bubbles, useq, parse_cov_files(E2E)
+
+
+def check_against_reference(align_fn, cov_fn, kmer_count_fn, site_cov_fn=None):
+    """Asserts that (a) SequenceAlignment of the raw branch strings reproduces the reference's aligned rows for every bubble and
+    (b) the regenerated coverage rows equal the reference's files row for row.  Returns (#rows, #branching bubbles)."""
+    meta, bubbles, useq, ref_rows = load_fixture()
+    k = meta["k"]
+    ulen = {i: len(s) for i, s in useq.items()}             # UnitigMap::size is the unitig length in bases
+    cov_rows, fre_rows, aligned = regenerate(bubbles, ulen, k, meta["low"], meta["up"], align_fn, cov_fn, kmer_count_fn, site_cov_fn)
+    for b, m in zip(bubbles, aligned):
+        assert m["rows"] == b["rows"], f"VarId {b['var_id']}: aligned rows differ from the reference's"
+    n = 0
+    for vid, rows in ref_rows.items():
+        mine = sorted(cov_rows.get(vid, []))
+        assert mine == sorted(rows), f"VarId {vid}:\n reference {sorted(rows)}\n ours      {mine}"
+        n += len(rows)
+    assert set(cov_rows) == set(ref_rows)
+    return n, sum(1 for b in bubbles if not b["strict"])

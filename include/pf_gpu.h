@@ -173,6 +173,18 @@ uint32_t pf_align_last_retry_count(const pf_ctx *ctx);
 /* diagnostics: DP cells (m*n summed over every needlemanWunch fill) executed by the last pf_align* call */
 uint64_t pf_align_last_cells(const pf_ctx *ctx);
 
+/* ---- lookup phase B ------------------------------------------------------------------------------------------------ */
+/*
+ * The per-site part of the branching-bubble caller (CDBG.cpp:2295-2509; coloured: CCDBG.cpp:1057-1241): for every variable
+ * column of every bubble of the LAST pf_align / pf_align_dev call on the database's context, the site k-mers are built on
+ * the device from the aligned rows (still resident), the distinct k-mers of each allele class are looked up ('as written,
+ * else reverse complement', CDBG.cpp:38-43) and gated with the strict (low, up) of readCov(string, lower, upper), and the
+ * class coverages are returned.  `skip` (host, one byte per bubble, may be NULL) marks bubbles not to compute -- the strict
+ * bubbles, whose class coverages are sums of branch means (CDBG.cpp:2105-2108).  `out` views pinned host memory owned by the
+ * database handle, valid until the next pf_site_cov on it.
+ */
+int pf_site_cov(pf_kmc *db, uint32_t low, uint32_t up, const uint8_t *skip, pf_site_batch_t *out);
+
 /* ---- roofline denominators measured on this device (bench.py reports them next to the kernels) ------- */
 /* random 32-byte-sector gather rate over a `bytes`-sized table (GB/s of sectors touched) */
 int pf_bench_random_gather(pf_ctx *ctx, uint64_t bytes, double *gb_per_s);

@@ -92,6 +92,29 @@ enum {
     PF_BUBBLE_BAD_INPUT = 5       /* fewer than 2 sequences, or a sequence contains a literal '-'     */
 };
 
+/*
+ * Lookup phase B (pf_site_cov): the allele-class coverages of the variable columns of aligned bubbles, from the site k-mers of
+ * CDBG.cpp:2295-2509.  Sites are the variable columns of the MSA batch in its order (site_off == var_off of that batch);
+ * cov holds, per site, n_rows(bubble) entries of which the first n_class are the class coverages (cov_off == cls_off).
+ */
+typedef struct pf_site_batch {
+    uint32_t n_bubbles;
+    uint32_t reserved;
+    const uint64_t *site_off; /* [n+1]                                                                      */
+    const uint8_t *status;    /* per site: PF_SITE_*                                                        */
+    const uint8_t *n_class;   /* per site: number of allele classes (max class id of the column)            */
+    const uint64_t *cov_off;  /* [n+1]                                                                      */
+    const uint64_t *cov;      /* class coverage = sum of the counters of the class's distinct site k-mers   */
+} pf_site_batch_t;
+
+enum {
+    PF_SITE_OK = 0,
+    PF_SITE_DROPPED = 1,   /* a counter is not inside (low, up): the reference skips the site (CDBG.cpp:2415-2418)            */
+    PF_SITE_MISSING = 2,   /* a site k-mer is not in the database: the reference prints it and exits (CDBG.cpp:52-56)         */
+    PF_SITE_UNDEFINED = 3, /* the reference itself would read outside a row here (substr throws / never returns)             */
+    PF_SITE_SKIPPED = 4    /* the caller asked not to compute this bubble (strict bubbles use the branch means instead)       */
+};
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,8 +24,17 @@ LOOKUP_CANONICAL, LOOKUP_FWD_THEN_RC, LOOKUP_FWD = 0, 1, 2
 EXPORTS = ["pf_init", "pf_shutdown", "pf_last_error", "pf_version", "pf_launch_count", "pf_sync", "pf_kmc_open",
            "pf_kmc_close", "pf_kmc_info", "pf_kmc_set_min_count", "pf_kmc_set_max_count", "pf_kmc_reset_min_max",
            "pf_kmc_device_bytes", "pf_kmc_open_ex", "pf_kmc_index_kind", "pf_kmc_open_part", "pf_kmc_local_kmers", "pf_kmc_route_dev", "pf_kmc_lookup_keys_dev",
-           "pf_kmc_scatter_dev", "pf_kmc_counts", "pf_kmc_cov", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
+           "pf_kmc_scatter_dev", "pf_kmc_counts", "pf_kmc_cov", "pf_site_cov", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
            "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_heavy_queued", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32"]
+
+
+class SiteBatch(C.Structure):
+    _fields_ = [("n_bubbles", C.c_uint32), ("reserved", C.c_uint32), ("site_off", C.POINTER(C.c_uint64)),
+                ("status", C.POINTER(C.c_uint8)), ("n_class", C.POINTER(C.c_uint8)), ("cov_off", C.POINTER(C.c_uint64)),
+                ("cov", C.POINTER(C.c_uint64))]
+
+
+SITE_OK, SITE_DROPPED, SITE_MISSING, SITE_UNDEFINED, SITE_SKIPPED = 0, 1, 2, 3, 4
 
 
 class KmcInfo(C.Structure):
@@ -75,6 +84,7 @@ def load():
     L.pf_kmc_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
     L.pf_kmc_open_ex.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p)]
     L.pf_kmc_index_kind.argtypes = [C.c_void_p]
+    L.pf_site_cov.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(SiteBatch)]
     L.pf_kmc_open_part.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.pf_kmc_local_kmers.argtypes = [C.c_void_p]
     L.pf_kmc_local_kmers.restype = C.c_uint64
@@ -248,6 +258,22 @@ class KmcDb:
         self.h = h
         self.refresh_info()
         self.k = self.info["kmer_length"]
+
+    def site_cov(self, low, up, skip=None):
+        """pf_site_cov: class coverages of the variable columns of the context's last alignment (lookup phase B)."""
+        sb = SiteBatch()
+        sk = None
+        if skip is not None:
+            sk = np.ascontiguousarray(skip, dtype=np.uint8)
+        _check(self.lib.pf_site_cov(self.h, low, up, sk.ctypes.data if sk is not None else None, C.byref(sb)), "pf_site_cov")
+        n = sb.n_bubbles
+        site_off = np.ctypeslib.as_array(sb.site_off, shape=(n + 1,)).copy()
+        cov_off = np.ctypeslib.as_array(sb.cov_off, shape=(n + 1,)).copy()
+        ns, nc = int(site_off[-1]), int(cov_off[-1])
+        return {"site_off": site_off, "cov_off": cov_off,
+                "status": np.ctypeslib.as_array(sb.status, shape=(ns,)).copy() if ns else np.zeros(0, np.uint8),
+                "n_class": np.ctypeslib.as_array(sb.n_class, shape=(ns,)).copy() if ns else np.zeros(0, np.uint8),
+                "cov": np.ctypeslib.as_array(sb.cov, shape=(nc,)).copy() if nc else np.zeros(0, np.uint64)}
 
     @property
     def device_bytes(self) -> int:

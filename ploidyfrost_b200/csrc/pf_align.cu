@@ -907,6 +907,8 @@ struct pf_align_state {
     pf::DevBuf in_bases, in_seq_off, in_bubble_off;
     pf::PinnedBuf h_scalars, h_out[12];
     uint32_t last_retry_count = 0;
+    uint32_t last_n = 0;              // bubbles of the last call; its compacted result is still in the buffers below
+    uint64_t last_tot[4] = {0, 0, 0, 0};   // rows bytes, variable columns, class entries, indel lengths
     uint32_t last_heavy_queued = 0;   // bubbles the first pass pushed on the heavy queue
     uint64_t last_cells = 0;
     uint32_t last_class_count[N_TIERS] = {0};
@@ -1339,6 +1341,8 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
     PF_CUDA_TRY(cudaStreamSynchronize(s));
     st->last_cells = h_tot[4];
     res.tot_rows = h_tot[0]; res.tot_var = h_tot[1]; res.tot_cls = h_tot[2]; res.tot_ilen = h_tot[3];
+    st->last_n = n;
+    for (int i = 0; i < 4; i++) st->last_tot[i] = h_tot[i];
     if ((rc = st->rows.reserve(res.tot_rows + 16))) return rc;
     if ((rc = st->var_col.reserve(res.tot_var * 4 + 16))) return rc;
     if ((rc = st->var_kind.reserve(res.tot_var + 16))) return rc;
@@ -1443,6 +1447,26 @@ uint32_t pf_align_last_retry_count(const pf_ctx *ctx) { return (ctx && ctx->alig
 uint64_t pf_align_last_cells(const pf_ctx *ctx) { return (ctx && ctx->align) ? ctx->align->last_cells : 0; }
 // diagnostics: bubbles per tier of the last call: [0..4] lane-kernel size classes (<=64/96/128/192/256), [5] warp kernel,
 // [6] re-runs in the shared-memory-flags warp kernel, [7] re-runs with the large limits
+}  // extern "C"
+
+// internal (pf_kmc.cu: lookup phase B): device pointers of the last alignment result of this context
+int pf_align_last_dev(pf_ctx *ctx, pf_msa_batch_t *out_dev, uint64_t totals[4]) {
+    if (!ctx || !ctx->align || !ctx->align->last_n) return PF_E_INVALID;
+    pf_align_state *st = ctx->align;
+    memset(out_dev, 0, sizeof(*out_dev));
+    out_dev->n_bubbles = st->last_n;
+    out_dev->status = st->status.as<int32_t>(); out_dev->n_rows = st->n_rows.as<uint32_t>();
+    out_dev->aln_len = st->aln_len.as<uint32_t>(); out_dev->rows_off = st->off[0].as<uint64_t>();
+    out_dev->rows = st->rows.as<char>(); out_dev->var_off = st->off[1].as<uint64_t>();
+    out_dev->var_col = st->var_col.as<uint32_t>(); out_dev->var_kind = st->var_kind.as<uint8_t>();
+    out_dev->cls_off = st->off[2].as<uint64_t>(); out_dev->cls = st->cls.as<uint16_t>();
+    out_dev->ilen_off = st->off[3].as<uint64_t>(); out_dev->ilen = st->ilen.as<uint32_t>();
+    for (int i = 0; i < 4; i++) totals[i] = st->last_tot[i];
+    return PF_OK;
+}
+
+extern "C" {
+
 uint32_t pf_align_last_heavy_queued(const pf_ctx *ctx) { return (ctx && ctx->align) ? ctx->align->last_heavy_queued : 0; }
 
 int pf_align_last_tier_counts(const pf_ctx *ctx, uint32_t *out, int n) {

@@ -42,6 +42,8 @@ struct PinnedBuf {
 }  // namespace pf
 
 struct pf_align_state;  // defined in pf_align.cu
+// device pointers + totals {row bytes, variable columns, class entries, indel lengths} of the context's last alignment result
+int pf_align_last_dev(pf_ctx *ctx, pf_msa_batch_t *out_dev, uint64_t totals[4]);
 
 struct pf_ctx {
     int device = 0;

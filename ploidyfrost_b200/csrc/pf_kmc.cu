@@ -478,6 +478,172 @@ __global__ void kmc_cov_from_counts_kernel(const uint64_t *__restrict__ win_off,
     cov[s] = c;
 }
 
+// ---- lookup phase B: site k-mers of branching bubbles --------------------------------------------------------------------
+// CDBG.cpp:2295-2509.  For every variable column of an aligned bubble the reference builds, per row, the
+// k-mer that ENDS at the site (SNP) or ends where the rows start to differ after the gap (indel), de-duplicates the strings per
+// allele class in a std::set, looks each distinct string up with readCov(string, lower, upper) -- 'as written, else reverse
+// complement', strict gate -- and sums per class; a count outside the gate drops the site, a missing k-mer ends the program.
+// One thread per bubble: the running number of indel sites makes the sites of a bubble sequential, everything else is a few
+// dozen byte loads per row.  Row r of bubble b is rows[rows_off[b] + r * aln_len[b] ...].
+constexpr uint32_t SITE_MAX_ROWS = 16;
+
+struct SiteArgs {
+    KmcView db;
+    pfkmc::HashView hv;
+    int hash_on, both_strands;
+    uint32_t n;
+    const int32_t *status;
+    const uint32_t *n_rows, *aln_len;
+    const uint64_t *rows_off;
+    const char *rows;
+    const uint64_t *var_off;
+    const uint32_t *var_col;
+    const uint8_t *var_kind;
+    const uint64_t *cls_off;
+    const uint16_t *cls;
+    const uint8_t *skip;
+    uint32_t low, up;
+    uint8_t *site_status, *site_ncls;
+    unsigned long long *site_cov;
+};
+
+__device__ __forceinline__ bool site_lookup_one(const SiteArgs &a, uint64_t key, uint32_t &cnt) {
+    if (a.hash_on) {
+        const bool ok = pfkmc::hash_find(a.hv, key, cnt);
+        return ok && cnt >= a.db.min_count && (uint64_t)cnt <= a.db.max_count;
+    }
+    uint32_t bin = 0;
+    if (a.db.is_kmc2) {
+        const uint32_t m = a.db.sig_len;
+        const uint64_t mask = (1ull << (2 * m)) - 1;
+        uint32_t sig = 0xFFFFFFFFu;
+        for (uint32_t j = 0; j + m <= a.db.k; j++) sig = min(sig, __ldg(a.db.norm + ((key >> (2 * (a.db.k - m - j))) & mask)));
+        bin = __ldg(a.db.sigmap + sig);
+    }
+    return kmc_search(a.db, key, bin, cnt);
+}
+
+// One row's site k-mer.  `end` = one past the last column that belongs to the left part, `need` = characters wanted from the
+// left, `tail` / `tail_len` = the characters already fixed after them (the indel extension), `fwd` = where to go on reading if
+// the row's left part is too short.  contiguous: the left part is the `need` columns before `end` exactly as they are
+// (no indel site so far, :2358-2365, :2469-2472); otherwise gaps are skipped (:2366-2388, :2433-2465).
+// Returns 0 ok, PF_SITE_UNDEFINED when the reference itself would read outside the row.
+__device__ __forceinline__ int site_row_kmer(const char *row, uint32_t L, uint32_t k, uint32_t end, uint32_t need, uint64_t tail,
+                                             uint32_t tail_len, uint32_t fwd, bool contiguous, uint64_t &key) {
+    uint64_t back = 0;
+    uint32_t got = 0;
+    if (contiguous) {
+        if (end < need) return PF_SITE_UNDEFINED;                // substr with a wrapped start position throws
+        for (uint32_t q = 0; q < need; q++) {
+            const uint32_t code = base_code((uint8_t)row[end - 1 - q]);
+            if (code > 3) return PF_SITE_UNDEFINED;              // a '-' inside the window: not a k-mer, outcome order dependent
+            back |= (uint64_t)code << (2 * q);
+        }
+        got = need;
+    } else {
+        for (uint32_t j = end; j > 0 && got < need; j--) {
+            const uint8_t ch = (uint8_t)row[j - 1];
+            if (ch == '-') continue;
+            const uint32_t code = base_code(ch);
+            if (code > 3) return PF_SITE_UNDEFINED;
+            back |= (uint64_t)code << (2 * got);
+            got++;
+        }
+    }
+    key = tail_len ? (((tail_len >= 32 ? 0ull : back << (2 * tail_len))) | tail) : back;
+    uint32_t have = got + tail_len;
+    for (uint32_t x = fwd; have < k; x++) {                       // the left part was shorter than wanted: extend to the right
+        if (x >= L) return PF_SITE_UNDEFINED;                    // the reference never terminates / throws here
+        const uint8_t ch = (uint8_t)row[x];
+        if (ch == '-') continue;
+        const uint32_t code = base_code(ch);
+        if (code > 3) return PF_SITE_UNDEFINED;
+        key = (key << 2) | code;
+        have++;
+    }
+    return PF_SITE_OK;
+}
+
+__global__ void site_cov_kernel(const SiteArgs a) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.n) return;
+    const uint64_t v0 = a.var_off[b], v1 = a.var_off[b + 1];
+    if (v0 == v1) return;
+    const uint32_t nr = a.n_rows[b], L = a.aln_len[b], k = a.db.k;
+    const char *R = a.rows + a.rows_off[b];
+    const uint16_t *C = a.cls + a.cls_off[b];
+    unsigned long long *cov_out = a.site_cov + a.cls_off[b];
+    const bool skipped = a.skip && a.skip[b];
+    uint32_t n_ind = 0;
+    for (uint64_t v = v0; v < v1; v++) {
+        const uint32_t c = a.var_col[v];
+        const bool is_ind = a.var_kind[v] == 1;
+        const uint16_t *cl = C + (v - v0) * nr;
+        unsigned long long *cov = cov_out + (v - v0) * nr;
+        uint32_t ncls = 0;
+        for (uint32_t r = 0; r < nr; r++) { ncls = max(ncls, (uint32_t)cl[r]); cov[r] = 0; }
+        a.site_ncls[v] = (uint8_t)min(ncls, 255u);
+        int st = PF_SITE_OK;
+        uint64_t key[SITE_MAX_ROWS];
+        if (skipped) st = PF_SITE_SKIPPED;
+        else if (nr > SITE_MAX_ROWS || k > 32) st = PF_SITE_UNDEFINED;
+        else if (!a.both_strands) st = PF_SITE_OK;               // readCov(string) does nothing on a strand-specific database (CDBG.cpp:34)
+        else if (is_ind) {
+            uint32_t cur[SITE_MAX_ROWS];
+            uint64_t ext[SITE_MAX_ROWS];
+            for (uint32_t r = 0; r < nr; r++) { cur[r] = c; ext[r] = 0; }
+            uint32_t e = 0;
+            for (;;) {                                            // :2338-2357: one more base per row until the rows differ
+                bool differ = false;
+                uint32_t first = 0;
+                for (uint32_t r = 0; r < nr && st == PF_SITE_OK; r++) {
+                    const char *row = R + (uint64_t)r * L;
+                    while (cur[r] < L && row[cur[r]] == '-') cur[r]++;
+                    if (cur[r] >= L) { st = PF_SITE_UNDEFINED; break; }
+                    const uint32_t code = base_code((uint8_t)row[cur[r]]);
+                    if (code > 3) { st = PF_SITE_UNDEFINED; break; }
+                    cur[r]++;
+                    ext[r] = (ext[r] << 2) | code;
+                    if (r == 0) first = code; else differ |= code != first;
+                }
+                if (st != PF_SITE_OK) break;
+                e++;
+                if (differ) break;
+                if (e >= k) { st = PF_SITE_UNDEFINED; break; }
+            }
+            for (uint32_t r = 0; r < nr && st == PF_SITE_OK; r++)
+                st = site_row_kmer(R + (uint64_t)r * L, L, k, c, k - e, ext[r], e, cur[r], n_ind == 0, key[r]);
+        } else {
+            for (uint32_t r = 0; r < nr && st == PF_SITE_OK; r++)
+                st = site_row_kmer(R + (uint64_t)r * L, L, k, c + 1, k, 0, 0, c + 1, n_ind == 0, key[r]);
+        }
+        if (is_ind) n_ind++;                                      // :2390, before the lookups
+        if (st == PF_SITE_OK && a.both_strands) {
+            for (uint32_t q = 1; q <= ncls && st == PF_SITE_OK; q++) {          // classes in order, strings in std::set order
+                unsigned long long acc = 0;
+                bool have_last = false;
+                uint64_t last = 0;
+                for (;;) {
+                    bool found = false;
+                    uint64_t best = 0;
+                    for (uint32_t r = 0; r < nr; r++)
+                        if (cl[r] == q && (!have_last || key[r] > last) && (!found || key[r] < best)) { best = key[r]; found = true; }
+                    if (!found) break;
+                    last = best; have_last = true;
+                    uint32_t cnt = 0;
+                    bool ok = site_lookup_one(a, best, cnt);                       // CDBG.cpp:38-43
+                    if (!ok) ok = site_lookup_one(a, revcomp64(best, k), cnt);
+                    if (!ok) { st = PF_SITE_MISSING; break; }                      // the reference exits (CDBG.cpp:52-56)
+                    if (!(cnt > a.low && cnt < a.up)) { st = PF_SITE_DROPPED; break; }
+                    acc += cnt;
+                }
+                cov[q - 1] = acc;
+            }
+        }
+        a.site_status[v] = (uint8_t)st;
+    }
+}
+
 bool slurp(const std::string &path, std::vector<unsigned char> &buf) {
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) return false;
@@ -522,6 +688,8 @@ struct pf_kmc {
     void *d_hash = nullptr;
     uint32_t build_status = 0;
     pf::DevBuf tile_seq;   // per-call scratch of the hash lookup (grow-only)
+    pf::DevBuf site_status, site_ncls, site_cov, site_skip;   // pf_site_cov outputs (grow-only)
+    pf::PinnedBuf h_site[5];
 };
 
 struct pf_kmc_route_state {   // scratch of pf_kmc_route_dev (grow-only)
@@ -808,6 +976,8 @@ int pf_kmc_close(pf_kmc *db) {
     cudaFree(db->d_lut); cudaFree(db->d_sigmap); cudaFree(db->d_norm);
     cudaFree(db->d_rec); cudaFree(db->d_suf); cudaFree(db->d_cnt); cudaFree(db->d_hash);
     db->tile_seq.release();
+    db->site_status.release(); db->site_ncls.release(); db->site_cov.release(); db->site_skip.release();
+    for (auto &b : db->h_site) b.release();
     delete db;
     return PF_OK;
 }
@@ -996,6 +1166,50 @@ int pf_kmc_scatter_dev(pf_kmc *db, const void *d_send_idx, uint64_t n_sent, cons
         ctx->launches++;
     }
     PF_CUDA_TRY(cudaGetLastError());
+    return PF_OK;
+}
+
+int pf_site_cov(pf_kmc *db, uint32_t low, uint32_t up, const uint8_t *skip, pf_site_batch_t *out) {
+    if (!db || !out) { pf::set_error("pf_site_cov: null argument"); return PF_E_INVALID; }
+    if (db->view.n_parts > 1) { pf::set_error("pf_site_cov: this index holds one partition of the database"); return PF_E_INVALID; }
+    pf_ctx *ctx = db->ctx;
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    pf_msa_batch_t m;
+    uint64_t tot[4];
+    if (pf_align_last_dev(ctx, &m, tot) != PF_OK) { pf::set_error("pf_site_cov: no alignment result on this context (call pf_align / pf_align_dev first)"); return PF_E_INVALID; }
+    const uint32_t n = m.n_bubbles;
+    const uint64_t n_var = tot[1], n_cls = tot[2];
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = db->site_status.reserve(n_var + 16))) return rc;
+    if ((rc = db->site_ncls.reserve(n_var + 16))) return rc;
+    if ((rc = db->site_cov.reserve(n_cls * 8 + 16))) return rc;
+    if (skip) {
+        if ((rc = db->site_skip.reserve(n + 16))) return rc;
+        PF_CUDA_TRY(cudaMemcpyAsync(db->site_skip.p, skip, n, cudaMemcpyHostToDevice, st));
+    }
+    SiteArgs a;
+    a.db = db->view; a.hv = db->hview; a.hash_on = db->hash_on ? 1 : 0; a.both_strands = (int)db->info.both_strands;
+    a.n = n; a.status = m.status; a.n_rows = m.n_rows; a.aln_len = m.aln_len; a.rows_off = m.rows_off; a.rows = m.rows;
+    a.var_off = m.var_off; a.var_col = m.var_col; a.var_kind = m.var_kind; a.cls_off = m.cls_off; a.cls = m.cls;
+    a.skip = skip ? db->site_skip.as<uint8_t>() : nullptr; a.low = low; a.up = up;
+    a.site_status = db->site_status.as<uint8_t>(); a.site_ncls = db->site_ncls.as<uint8_t>();
+    a.site_cov = db->site_cov.as<unsigned long long>();
+    site_cov_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+    ctx->launches++;
+    PF_CUDA_TRY(cudaGetLastError());
+    const uint64_t n1 = (uint64_t)n + 1;
+    const void *src[5] = {m.var_off, db->site_status.p, db->site_ncls.p, m.cls_off, db->site_cov.p};
+    const uint64_t bytes[5] = {n1 * 8, n_var, n_var, n1 * 8, n_cls * 8};
+    for (int i = 0; i < 5; i++) {
+        if ((rc = db->h_site[i].reserve(bytes[i] + 16))) return rc;
+        if (bytes[i]) PF_CUDA_TRY(cudaMemcpyAsync(db->h_site[i].p, src[i], bytes[i], cudaMemcpyDeviceToHost, st));
+    }
+    PF_CUDA_TRY(cudaStreamSynchronize(st));
+    out->n_bubbles = n;
+    out->site_off = db->h_site[0].as<uint64_t>(); out->status = db->h_site[1].as<uint8_t>(); out->n_class = db->h_site[2].as<uint8_t>();
+    out->cov_off = db->h_site[3].as<uint64_t>(); out->cov = db->h_site[4].as<uint64_t>();
     return PF_OK;
 }
 

@@ -108,6 +108,29 @@ def make_workload(args, rank, world, need_db_files, db_dir, device=None):
     return bb, prefix, info
 
 
+def site_kmer_proxy(msa, strict, k):
+    """CPU legs only: the lookup-B workload of an alignment result as a flat k-mer batch -- for every variable column of every
+    branching bubble and every row, the k characters ending at the column (the reference's site k-mer when no indel precedes the
+    site, CDBG.cpp:2469-2472); windows that touch a gap or start before the row are left out.  A proxy for the reference's own
+    string handling (which cannot be driven without its Bifrost graph): same number and kind of database lookups."""
+    nv = np.diff(msa["var_off"]).astype(np.int64)
+    b_of_site = np.repeat(np.arange(len(nv)), nv)
+    keep = strict[b_of_site] == 0
+    b_of_site = b_of_site[keep]
+    col = msa["var_col"].astype(np.int64)[keep]
+    nr = msa["n_rows"].astype(np.int64)[b_of_site]
+    site_of_row = np.repeat(np.arange(len(b_of_site)), nr)
+    r = np.arange(len(site_of_row)) - np.repeat(np.cumsum(nr) - nr, nr)
+    b = b_of_site[site_of_row]
+    L = msa["aln_len"].astype(np.int64)[b]
+    c = col[site_of_row]
+    ok = c - k + 1 >= 0
+    start = (msa["rows_off"].astype(np.int64)[b] + r * L + c - k + 1)[ok]
+    win = msa["rows"][start[:, None] + np.arange(k)[None, :]]
+    win = win[~(win == ord("-")).any(axis=1)]
+    return np.ascontiguousarray(win.reshape(-1)), (np.arange(len(win) + 1, dtype=np.uint64) * k)
+
+
 def reference_arm(args, rank, world):
     """The reference's own CPU implementation (unmodified SeqAlign + KMC API in oracle/_ref, driven by
     oracle/ref_shim.cpp with PloidyFrost's readCov call pattern), all host threads, bounded sample per step."""
@@ -136,11 +159,18 @@ def reference_arm(args, rank, world):
         h = ref.kmc_open(prefix)
         times = []
         n_lookups = int(np.maximum(np.diff(lo).astype(np.int64) - K + 1, 0).sum())
+        n_site_kmers = 0
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             ref.kmc_cov(h, lb, lo, mode=1, low=args.low, up=args.up, n_threads=cores)
-            ref.align(sample.bases, sample.seq_off, sample.bubble_off, n_threads=cores)
-            dt = time.perf_counter() - t0
+            msa = ref.align(sample.bases, sample.seq_off, sample.bubble_off, n_threads=cores)
+            t1 = time.perf_counter()
+            sb, so = site_kmer_proxy(msa, sample.bubble_type, K)       # untimed: stands in for the reference's string handling
+            t2 = time.perf_counter()
+            if len(so) > 1:
+                ref.kmc_counts(h, sb, so, K, mode=1, n_threads=cores)  # lookup-B
+            n_site_kmers = len(so) - 1
+            dt = (time.perf_counter() - t2) + (t1 - t0)
             if it >= args.warmup:
                 times.append(dt)
         ref.kmc_close(h)
@@ -152,7 +182,7 @@ def reference_arm(args, rank, world):
             "config": workload_config(args, sample.n_bubbles, info),
             "kmc_lookups_per_s": n_lookups / (ms * 1e-3),
             "cpu_baseline": {"value": val, "unit": "bubbles/s", "cores": cores, "kind": kind,
-                             "sample": f"{sample.n_bubbles} bubbles ({n_lookups} k-mer lookups) of the same batch per step"},
+                             "sample": f"{sample.n_bubbles} bubbles ({n_lookups} k-mer lookups + {n_site_kmers} site k-mer lookups) of the same batch per step"},
             "e2e": {"value": val, "unit": "bubbles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -161,7 +191,7 @@ def workload_config(args, n_bubbles, info):
     return {"workload": f"configs[1]: synthetic tetraploid {args.genome_mbp:g} Mbp (4 haplotypes, 1% SNP, 0.1% indel), "
                         f"60x-equivalent KMC2 db (k=25, p=9, sig 9, 512 bins), -z 8, M/D/G = 2/-1/-3",
             "batch_bubbles": int(n_bubbles), "db_kmers": (info or {}).get("N"),
-            "step": "lookup-A (readCov of entrance + branch unitigs) + SequenceAlignment per bubble",
+            "step": "lookup-A (readCov of entrance + branch unitigs) + SequenceAlignment per bubble + lookup-B (site k-mers of the branching bubbles)",
             "l2": "flushed between timed steps (256 MiB memset); KMC index (>2 GB) exceeds L2",
             "kmc_index": "partitioned by bin % n_gpus, queries routed by NCCL all-to-all" if getattr(args, "sharded_db", False)
                          else "replicated on every GPU"}
@@ -241,6 +271,9 @@ def main():
     d_ab = torch.from_numpy(bb.bases).to(dev)
     d_ao = torch.from_numpy(bb.seq_off.astype(np.int64)).to(dev)
     d_bo = torch.from_numpy(bb.bubble_off.astype(np.int32)).to(dev)
+    skip_np = np.ascontiguousarray(bb.bubble_type.astype(np.uint8))        # strict bubbles: class coverage = sum of branch means, no site k-mers
+    d_skip = torch.from_numpy(skip_np).to(dev)
+    do_sites = not args.sharded_db                                          # lookup phase B needs the whole index on this GPU
     seq_len = np.diff(bb.seq_off)
     max_len, max_rows = int(seq_len.max()), int(np.diff(bb.bubble_off).max())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -265,6 +298,10 @@ def main():
                       stream=sptr)
         if ev:
             ev[2].record(stream)
+        if do_sites:
+            db.site_cov_dev(args.low, args.up, d_skip.data_ptr(), sptr)
+        if ev:
+            ev[3].record(stream)
 
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 1)):
@@ -279,7 +316,7 @@ def main():
     barrier()
     torch.cuda.synchronize()
     launches0 = ctx.launches
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     with torch.cuda.stream(stream):
         for it in range(args.steps):
             flush.fill_(it & 0xFF)
@@ -289,7 +326,8 @@ def main():
     launches = ctx.launches - launches0
     t_lookup = [e[0].elapsed_time(e[1]) for e in evs]
     t_align = [e[1].elapsed_time(e[2]) for e in evs]
-    t_step = [e[0].elapsed_time(e[2]) for e in evs]
+    t_site = [e[2].elapsed_time(e[3]) for e in evs]
+    t_step = [e[0].elapsed_time(e[3]) for e in evs]
     ms_step = sum(t_step) / len(t_step)
 
     # ---- e2e: host-pointer C ABI from pinned host buffers ----
@@ -322,24 +360,29 @@ def main():
             cov = db.cov(h_lb[1], h_lo[1], mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up, out=cov_out)
         t1 = time.perf_counter()
         msa = ctx.align(h_ab[1], h_ao[1], h_bo[1], copy=False)   # views of the pinned result arena (C-ABI ownership rule)
+        sites = db.site_cov(args.low, args.up, skip_np) if do_sites else None
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if it >= 2:
             e2e_times.append(dt)
             e2e_cov_times.append(t1 - t0)
         d2h_bytes = cov.nbytes + sum(v.nbytes for v in msa.values() if isinstance(v, np.ndarray))
+        if sites is not None:
+            d2h_bytes += sum(v.nbytes for v in sites.values())
     sampler.stop_flag = True
     sampler.join(timeout=2)
     ms_e2e = 1e3 * sum(e2e_times) / len(e2e_times)
-    h2d_bytes = lb.nbytes + lo.nbytes + wo.nbytes + bb.bases.nbytes + bb.seq_off.nbytes + bb.bubble_off.nbytes
+    h2d_bytes = lb.nbytes + lo.nbytes + wo.nbytes + bb.bases.nbytes + bb.seq_off.nbytes + bb.bubble_off.nbytes + (skip_np.nbytes if do_sites else 0)
+    site_hist = np.bincount(sites["status"], minlength=5).tolist() if sites is not None else None
+    n_sites = int(len(sites["status"])) if sites is not None else 0
     n_ok = int((msa["status"] == 0).sum())
 
     # ---- reduce over ranks (max time, summed work) ----
-    sys.stderr.write(f"[rank {rank}] step {ms_step:.2f} ms (lookup {sum(t_lookup) / len(t_lookup):.2f}, align {sum(t_align) / len(t_align):.2f}), "
+    sys.stderr.write(f"[rank {rank}] step {ms_step:.2f} ms (lookup {sum(t_lookup) / len(t_lookup):.2f}, align {sum(t_align) / len(t_align):.2f}, sites {sum(t_site) / len(t_site):.2f}), "
                      f"e2e {ms_e2e:.2f} ms; tiers {ctx.last_tier_counts} heavy-queued {heavy_q}; batch {bb.stats()}\n")
     from ploidyfrost_b200 import shard
-    (ms_step, ms_e2e, ms_lookup, ms_align), (tot_bubbles, tot_win, tot_cells) = shard.reduce_step(
-        [ms_step, ms_e2e, sum(t_lookup) / len(t_lookup), sum(t_align) / len(t_align)], [bb.n_bubbles, n_win, cells], device=dev)
+    (ms_step, ms_e2e, ms_lookup, ms_align, ms_site), (tot_bubbles, tot_win, tot_cells) = shard.reduce_step(
+        [ms_step, ms_e2e, sum(t_lookup) / len(t_lookup), sum(t_align) / len(t_align), sum(t_site) / len(t_site)], [bb.n_bubbles, n_win, cells], device=dev)
 
     if rank == 0:
         peaks = {}
@@ -380,7 +423,8 @@ def main():
                 "config": workload_config(args, bb.n_bubbles, info),
                 "kmc_lookups_per_s": tot_win / (ms_step * 1e-3), "kmc_lookups_per_s_kernel": tot_win / (ms_lookup * 1e-3),
                 "dp_cells_per_s_kernel": tot_cells / (ms_align * 1e-3),
-                "ms_lookup_kernel": ms_lookup, "ms_align_pipeline": ms_align,
+                "ms_lookup_kernel": ms_lookup, "ms_align_pipeline": ms_align, "ms_site_cov_kernel": ms_site,
+                "site_columns_per_step": n_sites, "site_status_hist(ok,dropped,missing,undefined,skipped)": site_hist,
                 "clocks": sampler.summary(),
                 "e2e": {"value": tot_bubbles / (ms_e2e * 1e-3), "unit": "bubbles/s", "h2d_bytes_per_step": int(h2d_bytes),
                         "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e,
@@ -421,13 +465,19 @@ def cpu_baseline(args, bb, prefix):
     t0 = time.perf_counter()
     ref.kmc_cov(h, lb, lo, mode=1, low=args.low, up=args.up, n_threads=cores)
     t1 = time.perf_counter()
-    ref.align(sample.bases, sample.seq_off, sample.bubble_off, n_threads=cores)
+    msa = ref.align(sample.bases, sample.seq_off, sample.bubble_off, n_threads=cores)
     t2 = time.perf_counter()
+    sb, so = site_kmer_proxy(msa, sample.bubble_type, K)               # untimed: stands in for the reference's string handling
+    t3 = time.perf_counter()
+    if len(so) > 1:
+        ref.kmc_counts(h, sb, so, K, mode=1, n_threads=cores)          # lookup-B
+    t4 = time.perf_counter()
     ref.kmc_close(h)
-    return {"value": sample.n_bubbles / (t2 - t0), "unit": "bubbles/s", "cores": cores, "kind": kind,
-            "sample": f"{sample.n_bubbles} bubbles / {n_lookups} k-mer lookups of the same batch, one pass, same KMC db",
+    total = (t2 - t0) + (t4 - t3)
+    return {"value": sample.n_bubbles / total, "unit": "bubbles/s", "cores": cores, "kind": kind,
+            "sample": f"{sample.n_bubbles} bubbles / {n_lookups} k-mer lookups + {len(so) - 1} site k-mer lookups of the same batch, one pass, same KMC db",
             "kmc_lookups_per_s": n_lookups / (t1 - t0), "align_bubbles_per_s": sample.n_bubbles / (t2 - t1),
-            "seconds": round(t2 - t0, 2)}
+            "site_kmer_lookups_per_s": (len(so) - 1) / max(t4 - t3, 1e-9), "seconds": round(total, 2)}
 
 
 if __name__ == "__main__":

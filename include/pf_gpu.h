@@ -184,6 +184,8 @@ uint64_t pf_align_last_cells(const pf_ctx *ctx);
  * database handle, valid until the next pf_site_cov on it.
  */
 int pf_site_cov(pf_kmc *db, uint32_t low, uint32_t up, const uint8_t *skip, pf_site_batch_t *out);
+/* device-resident form: `d_skip` is a device pointer (or NULL), `out_dev` (may be NULL) receives DEVICE pointers; asynchronous on the stream */
+int pf_site_cov_dev(pf_kmc *db, uint32_t low, uint32_t up, const void *d_skip, pf_site_batch_t *out_dev, void *cuda_stream);
 
 /* ---- roofline denominators measured on this device (bench.py reports them next to the kernels) ------- */
 /* random 32-byte-sector gather rate over a `bytes`-sized table (GB/s of sectors touched) */

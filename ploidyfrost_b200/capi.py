@@ -24,7 +24,7 @@ LOOKUP_CANONICAL, LOOKUP_FWD_THEN_RC, LOOKUP_FWD = 0, 1, 2
 EXPORTS = ["pf_init", "pf_shutdown", "pf_last_error", "pf_version", "pf_launch_count", "pf_sync", "pf_kmc_open",
            "pf_kmc_close", "pf_kmc_info", "pf_kmc_set_min_count", "pf_kmc_set_max_count", "pf_kmc_reset_min_max",
            "pf_kmc_device_bytes", "pf_kmc_open_ex", "pf_kmc_index_kind", "pf_kmc_open_part", "pf_kmc_local_kmers", "pf_kmc_route_dev", "pf_kmc_lookup_keys_dev",
-           "pf_kmc_scatter_dev", "pf_kmc_counts", "pf_kmc_cov", "pf_site_cov", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
+           "pf_kmc_scatter_dev", "pf_kmc_counts", "pf_kmc_cov", "pf_site_cov", "pf_site_cov_dev", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
            "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_heavy_queued", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32"]
 
 
@@ -85,6 +85,7 @@ def load():
     L.pf_kmc_open_ex.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p)]
     L.pf_kmc_index_kind.argtypes = [C.c_void_p]
     L.pf_site_cov.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(SiteBatch)]
+    L.pf_site_cov_dev.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pf_kmc_open_part.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.pf_kmc_local_kmers.argtypes = [C.c_void_p]
     L.pf_kmc_local_kmers.restype = C.c_uint64
@@ -258,6 +259,10 @@ class KmcDb:
         self.h = h
         self.refresh_info()
         self.k = self.info["kmer_length"]
+
+    def site_cov_dev(self, low, up, d_skip=None, stream=None):
+        """pf_site_cov_dev: asynchronous, results stay on the device."""
+        _check(self.lib.pf_site_cov_dev(self.h, low, up, d_skip, None, stream), "pf_site_cov_dev")
 
     def site_cov(self, low, up, skip=None):
         """pf_site_cov: class coverages of the variable columns of the context's last alignment (lookup phase B)."""

@@ -483,9 +483,11 @@ __global__ void kmc_cov_from_counts_kernel(const uint64_t *__restrict__ win_off,
 // k-mer that ENDS at the site (SNP) or ends where the rows start to differ after the gap (indel), de-duplicates the strings per
 // allele class in a std::set, looks each distinct string up with readCov(string, lower, upper) -- 'as written, else reverse
 // complement', strict gate -- and sums per class; a count outside the gate drops the site, a missing k-mer ends the program.
-// One thread per bubble: the running number of indel sites makes the sites of a bubble sequential, everything else is a few
-// dozen byte loads per row.  Row r of bubble b is rows[rows_off[b] + r * aln_len[b] ...].
+// SITE_TPB threads per bubble, thread t takes the bubble's sites t, t + SITE_TPB, ...; the number of indel sites before a
+// site (the only thing that couples the sites of a bubble) is a count over var_kind.  Everything else is a few dozen byte
+// loads per row.  Row r of bubble b is rows[rows_off[b] + r * aln_len[b] ...].
 constexpr uint32_t SITE_MAX_ROWS = 16;
+constexpr uint32_t SITE_TPB = 4;
 
 struct SiteArgs {
     KmcView db;
@@ -565,17 +567,20 @@ __device__ __forceinline__ int site_row_kmer(const char *row, uint32_t L, uint32
 }
 
 __global__ void site_cov_kernel(const SiteArgs a) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = gt / SITE_TPB, t0 = gt % SITE_TPB;
     if (b >= a.n) return;
     const uint64_t v0 = a.var_off[b], v1 = a.var_off[b + 1];
-    if (v0 == v1) return;
+    if (v0 + t0 >= v1) return;
     const uint32_t nr = a.n_rows[b], L = a.aln_len[b], k = a.db.k;
     const char *R = a.rows + a.rows_off[b];
     const uint16_t *C = a.cls + a.cls_off[b];
     unsigned long long *cov_out = a.site_cov + a.cls_off[b];
     const bool skipped = a.skip && a.skip[b];
     uint32_t n_ind = 0;
-    for (uint64_t v = v0; v < v1; v++) {
+    uint64_t counted = v0;                                        // var_kind[v0 .. counted) is already in n_ind
+    for (uint64_t v = v0 + t0; v < v1; v += SITE_TPB) {
+        for (; counted < v; counted++) n_ind += a.var_kind[counted] == 1;
         const uint32_t c = a.var_col[v];
         const bool is_ind = a.var_kind[v] == 1;
         const uint16_t *cl = C + (v - v0) * nr;
@@ -617,7 +622,6 @@ __global__ void site_cov_kernel(const SiteArgs a) {
             for (uint32_t r = 0; r < nr && st == PF_SITE_OK; r++)
                 st = site_row_kmer(R + (uint64_t)r * L, L, k, c + 1, k, 0, 0, c + 1, n_ind == 0, key[r]);
         }
-        if (is_ind) n_ind++;                                      // :2390, before the lookups
         if (st == PF_SITE_OK && a.both_strands) {
             for (uint32_t q = 1; q <= ncls && st == PF_SITE_OK; q++) {          // classes in order, strings in std::set order
                 unsigned long long acc = 0;
@@ -690,6 +694,7 @@ struct pf_kmc {
     pf::DevBuf tile_seq;   // per-call scratch of the hash lookup (grow-only)
     pf::DevBuf site_status, site_ncls, site_cov, site_skip;   // pf_site_cov outputs (grow-only)
     pf::PinnedBuf h_site[5];
+    uint64_t site_totals[2] = {0, 0};   // variable columns, class entries of the last pf_site_cov*
 };
 
 struct pf_kmc_route_state {   // scratch of pf_kmc_route_dev (grow-only)
@@ -1169,38 +1174,61 @@ int pf_kmc_scatter_dev(pf_kmc *db, const void *d_send_idx, uint64_t n_sent, cons
     return PF_OK;
 }
 
-int pf_site_cov(pf_kmc *db, uint32_t low, uint32_t up, const uint8_t *skip, pf_site_batch_t *out) {
-    if (!db || !out) { pf::set_error("pf_site_cov: null argument"); return PF_E_INVALID; }
+// device-resident form: d_skip is a device pointer (or NULL); results stay in the handle's device buffers, `out_dev` gets DEVICE pointers
+int pf_site_cov_dev(pf_kmc *db, uint32_t low, uint32_t up, const void *d_skip, pf_site_batch_t *out_dev, void *cuda_stream) {
+    if (!db) { pf::set_error("pf_site_cov_dev: null database"); return PF_E_INVALID; }
     if (db->view.n_parts > 1) { pf::set_error("pf_site_cov: this index holds one partition of the database"); return PF_E_INVALID; }
     pf_ctx *ctx = db->ctx;
     PF_CUDA_TRY(cudaSetDevice(ctx->device));
-    memset(out, 0, sizeof(*out));
     pf_msa_batch_t m;
     uint64_t tot[4];
     if (pf_align_last_dev(ctx, &m, tot) != PF_OK) { pf::set_error("pf_site_cov: no alignment result on this context (call pf_align / pf_align_dev first)"); return PF_E_INVALID; }
     const uint32_t n = m.n_bubbles;
     const uint64_t n_var = tot[1], n_cls = tot[2];
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     int rc;
     if ((rc = db->site_status.reserve(n_var + 16))) return rc;
     if ((rc = db->site_ncls.reserve(n_var + 16))) return rc;
     if ((rc = db->site_cov.reserve(n_cls * 8 + 16))) return rc;
-    if (skip) {
-        if ((rc = db->site_skip.reserve(n + 16))) return rc;
-        PF_CUDA_TRY(cudaMemcpyAsync(db->site_skip.p, skip, n, cudaMemcpyHostToDevice, st));
-    }
     SiteArgs a;
     a.db = db->view; a.hv = db->hview; a.hash_on = db->hash_on ? 1 : 0; a.both_strands = (int)db->info.both_strands;
     a.n = n; a.status = m.status; a.n_rows = m.n_rows; a.aln_len = m.aln_len; a.rows_off = m.rows_off; a.rows = m.rows;
     a.var_off = m.var_off; a.var_col = m.var_col; a.var_kind = m.var_kind; a.cls_off = m.cls_off; a.cls = m.cls;
-    a.skip = skip ? db->site_skip.as<uint8_t>() : nullptr; a.low = low; a.up = up;
+    a.skip = (const uint8_t *)d_skip; a.low = low; a.up = up;
     a.site_status = db->site_status.as<uint8_t>(); a.site_ncls = db->site_ncls.as<uint8_t>();
     a.site_cov = db->site_cov.as<unsigned long long>();
-    site_cov_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+    site_cov_kernel<<<(unsigned)(((uint64_t)n * SITE_TPB + 127) / 128), 128, 0, st>>>(a);
     ctx->launches++;
     PF_CUDA_TRY(cudaGetLastError());
-    const uint64_t n1 = (uint64_t)n + 1;
-    const void *src[5] = {m.var_off, db->site_status.p, db->site_ncls.p, m.cls_off, db->site_cov.p};
+    if (out_dev) {
+        memset(out_dev, 0, sizeof(*out_dev));
+        out_dev->n_bubbles = n;
+        out_dev->site_off = m.var_off; out_dev->status = db->site_status.as<uint8_t>(); out_dev->n_class = db->site_ncls.as<uint8_t>();
+        out_dev->cov_off = m.cls_off; out_dev->cov = db->site_cov.as<uint64_t>();
+    }
+    db->site_totals[0] = n_var; db->site_totals[1] = n_cls;
+    return PF_OK;
+}
+
+int pf_site_cov(pf_kmc *db, uint32_t low, uint32_t up, const uint8_t *skip, pf_site_batch_t *out) {
+    if (!db || !out) { pf::set_error("pf_site_cov: null argument"); return PF_E_INVALID; }
+    pf_ctx *ctx = db->ctx;
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    cudaStream_t st = ctx->stream;
+    pf_msa_batch_t m;
+    uint64_t tot[4];
+    if (pf_align_last_dev(ctx, &m, tot) != PF_OK) { pf::set_error("pf_site_cov: no alignment result on this context (call pf_align / pf_align_dev first)"); return PF_E_INVALID; }
+    const uint32_t n = m.n_bubbles;
+    int rc;
+    if (skip) {
+        if ((rc = db->site_skip.reserve(n + 16))) return rc;
+        PF_CUDA_TRY(cudaMemcpyAsync(db->site_skip.p, skip, n, cudaMemcpyHostToDevice, st));
+    }
+    pf_site_batch_t d;
+    if ((rc = pf_site_cov_dev(db, low, up, skip ? db->site_skip.p : nullptr, &d, st))) return rc;
+    const uint64_t n1 = (uint64_t)n + 1, n_var = db->site_totals[0], n_cls = db->site_totals[1];
+    const void *src[5] = {d.site_off, d.status, d.n_class, d.cov_off, d.cov};
     const uint64_t bytes[5] = {n1 * 8, n_var, n_var, n1 * 8, n_cls * 8};
     for (int i = 0; i < 5; i++) {
         if ((rc = db->h_site[i].reserve(bytes[i] + 16))) return rc;

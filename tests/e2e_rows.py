@@ -233,3 +233,25 @@ def check_against_reference(align_fn, cov_fn, kmer_count_fn, site_cov_fn=None):
         n += len(rows)
     assert set(cov_rows) == set(ref_rows)
     return n, sum(1 for b in bubbles if not b["strict"])
+
+
+def device_site_cov_hook(db, meta, bubbles):
+    """site_cov_fn for check_against_reference() that takes lookup phase B from the device (pf_site_cov over the rows pf_align left
+    in HBM).  Returns (hook, state); state["sc"] holds the raw pf_site_cov result after the first call."""
+    from ploidyfrost_b200 import capi
+    state = {}
+
+    def site_cov(msa, bi, i):
+        if "sc" not in state:
+            skip = np.array([1 if b["strict"] else 0 for b in bubbles], np.uint8)
+            state["sc"] = db.site_cov(meta["low"], meta["up"], skip)
+            state["nrows"] = msa["n_rows"]
+        sc = state["sc"]
+        v = int(sc["site_off"][bi]) + i
+        st = int(sc["status"][v])
+        assert st in (capi.SITE_OK, capi.SITE_DROPPED), f"bubble {bi} site {i}: status {st}"
+        if st == capi.SITE_DROPPED:
+            return None
+        c0 = int(sc["cov_off"][bi]) + i * int(state["nrows"][bi])
+        return [float(x) for x in sc["cov"][c0:c0 + int(sc["n_class"][v])]]
+    return site_cov, state

@@ -34,21 +34,8 @@ def test_reference_rows_with_lookup_phase_b_on_the_device(gpu_ctx, index):
     from ploidyfrost_b200 import capi
     meta, bubbles, _, _ = e2e_rows.load_fixture()
     db = capi.KmcDb(gpu_ctx, os.path.join(e2e_rows.E2E, "db"), index=index)
-    state = {}
     try:
-        def site_cov(msa, bi, i):
-            if "sc" not in state:
-                skip = np.array([1 if b["strict"] else 0 for b in bubbles], np.uint8)
-                state["sc"] = db.site_cov(meta["low"], meta["up"], skip)
-                state["nrows"] = msa["n_rows"]
-            sc = state["sc"]
-            v = int(sc["site_off"][bi]) + i
-            st = int(sc["status"][v])
-            assert st in (capi.SITE_OK, capi.SITE_DROPPED), f"bubble {bi} site {i}: status {st}"
-            if st == capi.SITE_DROPPED:
-                return None
-            c0 = int(sc["cov_off"][bi]) + i * int(state["nrows"][bi])
-            return [float(x) for x in sc["cov"][c0:c0 + int(sc["n_class"][v])]]
+        site_cov, state = e2e_rows.device_site_cov_hook(db, meta, bubbles)
         n_rows, n_branching = e2e_rows.check_against_reference(
             lambda *f: gpu_ctx.align(*f), lambda b, off: db.cov(b, off, mode=capi.LOOKUP_FWD_THEN_RC, low=2, up=1000), None, site_cov)
         assert n_rows == 493 and n_branching == 114

@@ -532,6 +532,7 @@ struct MsaArgs {
     uint32_t *counter;
     unsigned long long *stat_cells;  // DP cells filled (m*n per needlemanWunch call), for the roofline figure
     uint32_t *hq;              // heavy queue (see msa_heavy_kernel); nullptr = none
+    uint32_t warp_dequeue;     // group kernel: 1 = the warp's groups start their bubbles together, 0 = every group on its own
     Limits lim;
     Scoring sc;
 };
@@ -547,6 +548,7 @@ struct MsaArgs {
 // Queue layout (u32 words): [0] tail (producers), [1] head (consumer tickets), [2] done flag, [4..5] bytes of the slot pool
 // handed out, [HQ_HDR ...] bubble ids, 0xFFFFFFFF = not written yet.
 constexpr uint32_t HQ_HDR = 8, HQ_CAP = 4096;
+constexpr uint32_t HQ_TRACE = HQ_HDR + HQ_CAP;   // u32 index of the trace area: per ticket {bubble, t_taken, t_done} as u64 (PF_HEAVY_TRACE)
 
 __device__ __forceinline__ void heavy_enqueue(uint32_t *hq, const uint8_t *slot, uint32_t bubble) {
     const int st = ((const SlotHdr *)slot)->status;
@@ -658,8 +660,18 @@ __global__ void __launch_bounds__(32) msa_heavy_kernel(const MsaArgs a) {
         off = __shfl_sync(FULL, off, 0);
         if (off + bytes > pool_cap) continue;                                // left to the pass after the first one
         uint8_t *slot = a.slot_base + off;
+        unsigned long long tt0, tt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt0));
         msa_run(x, a.bases, a.seq_off, s0, ns, ws, a.lim, a.sc, slot);
-        if (lane == 0) { a.slot_ptr[b] = (uint64_t)(uintptr_t)slot; a.tier[b] = a.tier_id; }
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt1));
+        if (lane == 0) {
+            a.slot_ptr[b] = (uint64_t)(uintptr_t)slot; a.tier[b] = a.tier_id;
+            const uint32_t tr = atomicAdd(hq + 3, 1u);
+            if (tr < HQ_CAP) {
+                unsigned long long *T = (unsigned long long *)(hq + HQ_TRACE) + 3ull * tr;
+                T[0] = b; T[1] = tt0; T[2] = tt1;
+            }
+        }
         __syncwarp();
     }
     if (lane == 0 && x.cells) atomicAdd(a.stat_cells, x.cells);
@@ -731,20 +743,46 @@ __global__ void __launch_bounds__(GROUP_BLOCK) msa_group_kernel(const MsaArgs a)
     x.pf = true;
     x.cells = 0;
     const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim, NB, bi);
-    for (;;) {   // every group pulls its own bubbles: biggest first
-        uint32_t q = 0;
-        if (x.g == 0) q = atomicAdd(a.counter, 1u);
-        q = __shfl_sync(x.gmask, q, 0, G);
-        if (q >= a.n_items) break;
-        const uint32_t w = a.first + (a.n_items - 1 - q);
-        const uint32_t b = a.order[w];
-        const uint32_t s0 = a.bubble_off[b], ns = a.bubble_off[b + 1] - s0;
-        uint8_t *slot = a.slot_base + a.slot_off[w];
-        msa_run(x, a.bases, a.seq_off, s0, ns, ws, a.lim, a.sc, slot);
-        if (x.g == 0) {
-            a.slot_ptr[b] = (uint64_t)(uintptr_t)slot;
-            a.tier[b] = a.tier_id;
-            if (a.hq) heavy_enqueue(a.hq, slot, b);
+    if (a.warp_dequeue) {
+        // The warp pulls NB neighbouring bubbles of the size-sorted list at a time and its groups start them together: alike
+        // bubbles stay in the same phase (fill with fill, traceback with traceback), i.e. little SIMT divergence between
+        // the groups of a warp; a group that finishes early waits for the others.
+        for (;;) {
+            uint32_t q = 0;
+            if (lane == 0) q = atomicAdd(a.counter, NB);
+            q = __shfl_sync(FULL, q, 0);
+            if (q >= a.n_items) break;
+            const uint32_t item = q + bi;
+            if (item < a.n_items) {
+                const uint32_t w = a.first + (a.n_items - 1 - item);
+                const uint32_t b = a.order[w];
+                const uint32_t s0 = a.bubble_off[b], ns = a.bubble_off[b + 1] - s0;
+                uint8_t *slot = a.slot_base + a.slot_off[w];
+                msa_run(x, a.bases, a.seq_off, s0, ns, ws, a.lim, a.sc, slot);
+                if (x.g == 0) {
+                    a.slot_ptr[b] = (uint64_t)(uintptr_t)slot;
+                    a.tier[b] = a.tier_id;
+                    if (a.hq) heavy_enqueue(a.hq, slot, b);
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        for (;;) {   // every group pulls its own bubbles: biggest first
+            uint32_t q = 0;
+            if (x.g == 0) q = atomicAdd(a.counter, 1u);
+            q = __shfl_sync(x.gmask, q, 0, G);
+            if (q >= a.n_items) break;
+            const uint32_t w = a.first + (a.n_items - 1 - q);
+            const uint32_t b = a.order[w];
+            const uint32_t s0 = a.bubble_off[b], ns = a.bubble_off[b + 1] - s0;
+            uint8_t *slot = a.slot_base + a.slot_off[w];
+            msa_run(x, a.bases, a.seq_off, s0, ns, ws, a.lim, a.sc, slot);
+            if (x.g == 0) {
+                a.slot_ptr[b] = (uint64_t)(uintptr_t)slot;
+                a.tier[b] = a.tier_id;
+                if (a.hq) heavy_enqueue(a.hq, slot, b);
+            }
         }
     }
     if (x.g == 0 && x.cells) atomicAdd(a.stat_cells, x.cells);
@@ -921,7 +959,7 @@ struct pf_align_state {
     cudaStream_t heavy_stream = nullptr;
     cudaEvent_t ev_heavy = nullptr;
     int heavy_ctas = 4;
-    int group_lanes[N_LANE_CLASSES] = {1, 1, 2, 2, 4};   // lanes per bubble of each size class (1 = thread-per-bubble kernel)
+    int group_lanes[N_LANE_CLASSES] = {1, 1, 2, 4, 8};   // lanes per bubble of each size class (1 = thread-per-bubble kernel)
     bool group_env_done = false;
 };
 
@@ -1005,6 +1043,8 @@ void fill_args(MsaArgs &a, pf_align_state *st, int slot_pool, const Limits &lim,
     a.counter = counter; a.lim = lim; a.sc = sc;
     a.stat_cells = (unsigned long long *)(st->counter.as<uint8_t>() + 128);
     a.hq = nullptr;
+    static const int wd = getenv("PF_GROUP_WARP_DEQUEUE") ? atoi(getenv("PF_GROUP_WARP_DEQUEUE")) : 0;   // measured: no difference (profiles/r01_summary.md section 9)
+    a.warp_dequeue = (uint32_t)wd;
 }
 
 // one launch of the warp-per-bubble kernel over work items [first, first + n_items) of `d_order`
@@ -1212,7 +1252,7 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
             PF_CUDA_TRY(cudaStreamCreateWithFlags(&st->heavy_stream, cudaStreamNonBlocking));
             PF_CUDA_TRY(cudaEventCreateWithFlags(&st->ev_heavy, cudaEventDisableTiming));
         }
-        if ((rc = st->hq.reserve((HQ_HDR + HQ_CAP) * 4))) return rc;
+        if ((rc = st->hq.reserve((HQ_HDR + HQ_CAP) * 4 + (uint64_t)HQ_CAP * 24 + 64))) return rc;
         if ((rc = st->heavy_pool.reserve(pool_bytes))) return rc;
         if ((rc = st->heavy_ws.reserve((uint64_t)st->heavy_ctas * hws))) return rc;
         d_hq = st->hq.as<uint32_t>();
@@ -1301,6 +1341,19 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         if (pass == 0) {
             st->last_retry_count = nr;
             st->last_heavy_queued = d_hq ? h_cnt[1] : 0;
+            if (d_hq && getenv("PF_HEAVY_TRACE")) {   // diagnostics: when each queued bubble was taken and finished
+                std::vector<unsigned long long> T(3 * HQ_CAP);
+                uint32_t hdr[HQ_HDR];
+                cudaMemcpy(hdr, d_hq, sizeof(hdr), cudaMemcpyDeviceToHost);
+                cudaMemcpy(T.data(), d_hq + HQ_TRACE, T.size() * 8, cudaMemcpyDeviceToHost);
+                const uint32_t nt = std::min(hdr[3], HQ_CAP);
+                unsigned long long t_min = ~0ull;
+                for (uint32_t i = 0; i < nt; i++) t_min = std::min(t_min, T[3 * i + 1]);
+                fprintf(stderr, "[heavy] queued %u, taken %u, traced %u\n", hdr[0], hdr[1], nt);
+                for (uint32_t i = 0; i < nt; i++)
+                    fprintf(stderr, "[heavy]   bubble %llu taken +%.3f ms, ran %.3f ms\n", T[3 * i], (T[3 * i + 1] - t_min) * 1e-6,
+                            (T[3 * i + 2] - T[3 * i + 1]) * 1e-6);
+            }
         }
         if (!nr) break;
         slot_size_kernel<<<(nr + 1 + 255) / 256, 256, 0, s>>>(d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), nullptr, tier, nr, tt,

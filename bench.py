@@ -360,7 +360,7 @@ def main():
             cov = db.cov(h_lb[1], h_lo[1], mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up, out=cov_out)
         t1 = time.perf_counter()
         msa = ctx.align(h_ab[1], h_ao[1], h_bo[1], copy=False)   # views of the pinned result arena (C-ABI ownership rule)
-        sites = db.site_cov(args.low, args.up, skip_np) if do_sites else None
+        sites = db.site_cov(args.low, args.up, skip_np, copy=False) if do_sites else None   # views, like the alignment result
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if it >= 2:

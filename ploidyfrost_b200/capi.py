@@ -264,21 +264,23 @@ class KmcDb:
         """pf_site_cov_dev: asynchronous, results stay on the device."""
         _check(self.lib.pf_site_cov_dev(self.h, low, up, d_skip, None, stream), "pf_site_cov_dev")
 
-    def site_cov(self, low, up, skip=None):
-        """pf_site_cov: class coverages of the variable columns of the context's last alignment (lookup phase B)."""
+    def site_cov(self, low, up, skip=None, copy=True):
+        """pf_site_cov: class coverages of the variable columns of the context's last alignment (lookup phase B).
+        copy=False returns views of the handle's pinned result arena (valid until the next pf_site_cov on this handle)."""
         sb = SiteBatch()
         sk = None
         if skip is not None:
             sk = np.ascontiguousarray(skip, dtype=np.uint8)
         _check(self.lib.pf_site_cov(self.h, low, up, sk.ctypes.data if sk is not None else None, C.byref(sb)), "pf_site_cov")
         n = sb.n_bubbles
-        site_off = np.ctypeslib.as_array(sb.site_off, shape=(n + 1,)).copy()
-        cov_off = np.ctypeslib.as_array(sb.cov_off, shape=(n + 1,)).copy()
+        fin = (lambda a: a.copy()) if copy else (lambda a: a)
+        site_off = np.ctypeslib.as_array(sb.site_off, shape=(n + 1,))
+        cov_off = np.ctypeslib.as_array(sb.cov_off, shape=(n + 1,))
         ns, nc = int(site_off[-1]), int(cov_off[-1])
-        return {"site_off": site_off, "cov_off": cov_off,
-                "status": np.ctypeslib.as_array(sb.status, shape=(ns,)).copy() if ns else np.zeros(0, np.uint8),
-                "n_class": np.ctypeslib.as_array(sb.n_class, shape=(ns,)).copy() if ns else np.zeros(0, np.uint8),
-                "cov": np.ctypeslib.as_array(sb.cov, shape=(nc,)).copy() if nc else np.zeros(0, np.uint64)}
+        return {"site_off": fin(site_off), "cov_off": fin(cov_off),
+                "status": fin(np.ctypeslib.as_array(sb.status, shape=(ns,))) if ns else np.zeros(0, np.uint8),
+                "n_class": fin(np.ctypeslib.as_array(sb.n_class, shape=(ns,))) if ns else np.zeros(0, np.uint8),
+                "cov": fin(np.ctypeslib.as_array(sb.cov, shape=(nc,))) if nc else np.zeros(0, np.uint64)}
 
     @property
     def device_bytes(self) -> int:

@@ -159,6 +159,7 @@ struct LaneExec : SerialHelpers {
     static constexpr bool INTEGRAL = VARIANT != LANE_FP64;
     int32_t *rowbuf;     // 4 bytes per column: packed score*8+flags (scalar fills) or (U, D) as two int16 (s16x2 fill)
     uint8_t *bs;
+    uint32_t pitch;      // flag row pitch shared by the 32 bubbles of the warp (0: every bubble its own n + 1)
     unsigned long long cells;
     __device__ __forceinline__ bool leader() const { return true; }
     __device__ __forceinline__ uint32_t bcast(uint32_t v) const { return v; }
@@ -166,7 +167,7 @@ struct LaneExec : SerialHelpers {
     __device__ __forceinline__ uint32_t bcast_ld(const uint32_t *p) const { return *p; }
     __device__ __forceinline__ void sync() const {}
     __device__ __forceinline__ void note_steps(uint64_t) const {}
-    __device__ __forceinline__ uint32_t pitch_n(uint32_t n) const { return n; }
+    __device__ __forceinline__ uint32_t pitch_n(uint32_t n) const { return pitch ? pitch - 1 : n; }
     __device__ __forceinline__ bool prefetch_flags() const { return true; }   // the flag bytes live in HBM / L2
 
     // rows i = 1..m one at a time
@@ -177,7 +178,7 @@ struct LaneExec : SerialHelpers {
             rowbuf[j * 32] = pack_sf(border_score(sc, j), F_LEFT);
             flags[j] = (uint8_t)F_LEFT;
         }
-        const uint32_t W = n + 1;
+        const uint32_t W = pitch ? pitch : n + 1;
         uint8_t a_next = m ? A[0] : (uint8_t)0;
         for (uint32_t i = 1; i <= m; i++) {
             const uint8_t a = a_next;
@@ -229,7 +230,7 @@ struct LaneExec : SerialHelpers {
     // Needs n >= 1, integral scoring, every |score| + 1 < 16000 and no '-' in B (the launcher / caller check).
     __device__ __forceinline__ void fill_s16x2(const BV flags, const CBV A, uint32_t m, uint32_t n, const Scoring &sc) {
         uint32_t *rb = (uint32_t *)rowbuf;
-        const uint32_t W = n + 1;
+        const uint32_t W = pitch ? pitch : n + 1;
         const int G = sc.iG;
         flags[0] = 0;
         rb[0] = pack2(0, 0);                                                 // (0,0): no flags
@@ -532,6 +533,7 @@ struct MsaArgs {
     uint32_t *counter;
     unsigned long long *stat_cells;  // DP cells filled (m*n per needlemanWunch call), for the roofline figure
     uint32_t *hq;              // heavy queue (see msa_heavy_kernel); nullptr = none
+    uint32_t lane_pitch;       // lane kernel: 1 = one flag row pitch per launch (lanes at the same cell share a sector)
     uint32_t warp_dequeue;     // group kernel: 1 = the warp's groups start their bubbles together, 0 = every group on its own
     Limits lim;
     Scoring sc;
@@ -693,6 +695,7 @@ __global__ void __launch_bounds__(LANE_BLOCK, 8) msa_lane_kernel(const MsaArgs a
     LaneExec<VARIANT> x;
     x.rowbuf = (int32_t *)(smem + (size_t)wib * per_warp) + lane;
     x.bs = smem + (size_t)wib * per_warp + 32 * 4 * (nmax + 1) + lane;
+    x.pitch = a.lane_pitch ? nmax + 1 : 0;
     x.cells = 0;
     const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim, 32, lane);
     for (;;) {
@@ -1045,6 +1048,8 @@ void fill_args(MsaArgs &a, pf_align_state *st, int slot_pool, const Limits &lim,
     a.hq = nullptr;
     static const int wd = getenv("PF_GROUP_WARP_DEQUEUE") ? atoi(getenv("PF_GROUP_WARP_DEQUEUE")) : 0;   // measured: no difference (profiles/r01_summary.md section 9)
     a.warp_dequeue = (uint32_t)wd;
+    static const int lp = getenv("PF_LANE_PITCH") ? atoi(getenv("PF_LANE_PITCH")) : 1;
+    a.lane_pitch = (uint32_t)lp;
 }
 
 // one launch of the warp-per-bubble kernel over work items [first, first + n_items) of `d_order`

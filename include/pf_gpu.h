@@ -99,6 +99,15 @@ int pf_kmc_cov(pf_kmc *db, const char *bases, const uint64_t *seq_off, uint32_t 
                uint32_t low, uint32_t up, pf_cov_t *out);
 
 /*
+ * Asynchronous pf_kmc_cov: enqueues copy-in, lookup and copy-out on the handle's own stream and returns; `bases`, `seq_off` and
+ * `out` must stay valid (and should be pinned for the copies to be truly asynchronous) until pf_kmc_wait(db) returns.  Lets the
+ * lookups of a batch run beside pf_align / pf_site_cov of the same context.  One outstanding call per handle.
+ */
+int pf_kmc_cov_async(pf_kmc *db, const char *bases, const uint64_t *seq_off, uint32_t n_seq, int mode, uint32_t low, uint32_t up,
+                     pf_cov_t *out);
+int pf_kmc_wait(pf_kmc *db);
+
+/*
  * Device-resident forms.  d_bases (n_bases chars), d_seq_off (n_seq+1 x u64) and d_win_off
  * (n_seq+1 x u64, exclusive prefix sum of max(len-k+1,0); pf_window_offsets computes it on the host)
  * are device pointers; d_seq_off[0] must be 0 and d_bases should be 16-byte aligned (it is staged with

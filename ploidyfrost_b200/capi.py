@@ -24,7 +24,7 @@ LOOKUP_CANONICAL, LOOKUP_FWD_THEN_RC, LOOKUP_FWD = 0, 1, 2
 EXPORTS = ["pf_init", "pf_shutdown", "pf_last_error", "pf_version", "pf_launch_count", "pf_sync", "pf_kmc_open",
            "pf_kmc_close", "pf_kmc_info", "pf_kmc_set_min_count", "pf_kmc_set_max_count", "pf_kmc_reset_min_max",
            "pf_kmc_device_bytes", "pf_kmc_open_ex", "pf_kmc_index_kind", "pf_kmc_open_part", "pf_kmc_local_kmers", "pf_kmc_route_dev", "pf_kmc_lookup_keys_dev",
-           "pf_kmc_scatter_dev", "pf_kmc_counts", "pf_kmc_cov", "pf_site_cov", "pf_site_cov_dev", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
+           "pf_kmc_scatter_dev", "pf_kmc_counts", "pf_kmc_cov", "pf_kmc_cov_async", "pf_kmc_wait", "pf_site_cov", "pf_site_cov_dev", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
            "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_heavy_queued", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32"]
 
 
@@ -103,6 +103,8 @@ def load():
     L.pf_kmc_device_bytes.restype = C.c_uint64
     L.pf_kmc_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
     L.pf_kmc_cov.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.pf_kmc_cov_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.pf_kmc_wait.argtypes = [C.c_void_p]
     L.pf_kmc_lookup_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,
                                     C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pf_window_offsets.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
@@ -355,6 +357,18 @@ class KmcDb:
         _check(self.lib.pf_kmc_cov(self.h, bases.ctypes.data, seq_off.ctypes.data, n, mode, low, up, out.ctypes.data),
                "pf_kmc_cov")
         return out[:n]
+
+    def cov_async(self, bases, seq_off, out, mode=LOOKUP_FWD_THEN_RC, low=0, up=0xFFFFFFFF):
+        """pf_kmc_cov_async: returns at once; `bases`, `seq_off`, `out` (contiguous, ideally pinned) must live until wait()."""
+        assert bases.dtype == np.uint8 and bases.flags.c_contiguous and seq_off.dtype == np.uint64 and seq_off.flags.c_contiguous
+        n = len(seq_off) - 1
+        assert out.dtype == COV_DTYPE and len(out) >= n and out.flags.c_contiguous
+        _check(self.lib.pf_kmc_cov_async(self.h, bases.ctypes.data, seq_off.ctypes.data, n, mode, low, up, out.ctypes.data),
+               "pf_kmc_cov_async")
+        return out[:n]
+
+    def wait(self):
+        _check(self.lib.pf_kmc_wait(self.h), "pf_kmc_wait")
 
     def lookup_dev(self, d_bases, n_bases, d_seq_off, d_win_off, n_seq, n_windows, mode=LOOKUP_CANONICAL, low=0,
                    up=0xFFFFFFFF, d_counts=None, d_found=None, d_cov=None, stream=None):

@@ -694,7 +694,11 @@ struct pf_kmc {
     pf::DevBuf tile_seq;   // per-call scratch of the hash lookup (grow-only)
     pf::DevBuf site_status, site_ncls, site_cov, site_skip;   // pf_site_cov outputs (grow-only)
     pf::PinnedBuf h_site[5];
-    uint64_t site_totals[2] = {0, 0};   // variable columns, class entries of the last pf_site_cov*
+    uint64_t site_totals[2] = {0, 0};
+    // host-pointer calls: the handle's own stream, staging and device buffers
+    cudaStream_t k_stream = nullptr;
+    pf::PinnedBuf k_stage;
+    pf::DevBuf k_in[3], k_out[3];   // variable columns, class entries of the last pf_site_cov*
 };
 
 struct pf_kmc_route_state {   // scratch of pf_kmc_route_dev (grow-only)
@@ -983,6 +987,10 @@ int pf_kmc_close(pf_kmc *db) {
     db->tile_seq.release();
     db->site_status.release(); db->site_ncls.release(); db->site_cov.release(); db->site_skip.release();
     for (auto &b : db->h_site) b.release();
+    if (db->k_stream) { cudaStreamSynchronize(db->k_stream); cudaStreamDestroy(db->k_stream); }
+    db->k_stage.release();
+    for (auto &b : db->k_in) b.release();
+    for (auto &b : db->k_out) b.release();
     delete db;
     return PF_OK;
 }
@@ -1241,51 +1249,68 @@ int pf_site_cov(pf_kmc *db, uint32_t low, uint32_t up, const uint8_t *skip, pf_s
     return PF_OK;
 }
 
+// Host-pointer lookups.  Staging and device buffers belong to the database handle (not to the context) so that an asynchronous
+// call can run beside pf_align / pf_site_cov of the same context; `async`: enqueue on the handle's own stream and return.
 static int kmc_host_call(pf_kmc *db, const char *bases, const uint64_t *seq_off, uint32_t n_seq, int mode, uint32_t low,
-                         uint32_t up, uint32_t *counts, uint8_t *found, pf_cov_t *cov) {
+                         uint32_t up, uint32_t *counts, uint8_t *found, pf_cov_t *cov, bool async) {
     if (!db || !seq_off || (!bases && n_seq && seq_off[n_seq] > 0)) { pf::set_error("pf_kmc: null argument"); return PF_E_INVALID; }
     pf_ctx *ctx = db->ctx;
     PF_CUDA_TRY(cudaSetDevice(ctx->device));
     if (n_seq == 0) return PF_OK;
     if (db->view.n_parts > 1) { pf::set_error("pf_kmc_counts/cov: this index holds one partition of the database; use the route / lookup_keys / scatter calls"); return PF_E_INVALID; }
+    if (!db->k_stream) PF_CUDA_TRY(cudaStreamCreateWithFlags(&db->k_stream, cudaStreamNonBlocking));
+    PF_CUDA_TRY(cudaStreamSynchronize(db->k_stream));   // an earlier asynchronous call still owns the staging buffers
     const uint64_t n_bases = seq_off[n_seq] - seq_off[0];
     int rc;
     // rebased offsets + window offsets are built straight into pinned staging (one async copy each, no bounce buffer)
-    if ((rc = ctx->h_stage[0].reserve((uint64_t)(n_seq + 1) * 16))) return rc;
-    uint64_t *off = ctx->h_stage[0].as<uint64_t>(), *woff = off + (n_seq + 1);
+    if ((rc = db->k_stage.reserve((uint64_t)(n_seq + 1) * 16))) return rc;
+    uint64_t *off = db->k_stage.as<uint64_t>(), *woff = off + (n_seq + 1);
     for (uint32_t s = 0; s <= n_seq; s++) off[s] = seq_off[s] - seq_off[0];
     const uint64_t W = pf_window_offsets(off, n_seq, db->info.kmer_length, woff);
-    cudaStream_t st = ctx->stream;
-    if ((rc = ctx->d_in[0].reserve(n_bases + 16))) return rc;
-    if ((rc = ctx->d_in[1].reserve((n_seq + 1) * 8))) return rc;
-    if ((rc = ctx->d_in[2].reserve((n_seq + 1) * 8))) return rc;
-    if (counts && (rc = ctx->d_out[0].reserve(W * 4 + 4))) return rc;
-    if (found && (rc = ctx->d_out[1].reserve(W + 4))) return rc;
-    if (cov && (rc = ctx->d_out[2].reserve((uint64_t)n_seq * sizeof(pf_cov_t)))) return rc;
-    if (n_bases) PF_CUDA_TRY(cudaMemcpyAsync(ctx->d_in[0].p, bases + seq_off[0], n_bases, cudaMemcpyHostToDevice, st));
-    PF_CUDA_TRY(cudaMemcpyAsync(ctx->d_in[1].p, off, (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
-    PF_CUDA_TRY(cudaMemcpyAsync(ctx->d_in[2].p, woff, (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
-    rc = pf_kmc_lookup_dev(db, ctx->d_in[0].p, n_bases, ctx->d_in[1].p, ctx->d_in[2].p, n_seq, W, mode, low, up,
-                           counts ? ctx->d_out[0].p : nullptr, found ? ctx->d_out[1].p : nullptr,
-                           cov ? ctx->d_out[2].p : nullptr, st);
+    cudaStream_t st = db->k_stream;
+    if ((rc = db->k_in[0].reserve(n_bases + 16))) return rc;
+    if ((rc = db->k_in[1].reserve((n_seq + 1) * 8))) return rc;
+    if ((rc = db->k_in[2].reserve((n_seq + 1) * 8))) return rc;
+    if (counts && (rc = db->k_out[0].reserve(W * 4 + 4))) return rc;
+    if (found && (rc = db->k_out[1].reserve(W + 4))) return rc;
+    if (cov && (rc = db->k_out[2].reserve((uint64_t)n_seq * sizeof(pf_cov_t)))) return rc;
+    if (n_bases) PF_CUDA_TRY(cudaMemcpyAsync(db->k_in[0].p, bases + seq_off[0], n_bases, cudaMemcpyHostToDevice, st));
+    PF_CUDA_TRY(cudaMemcpyAsync(db->k_in[1].p, off, (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+    PF_CUDA_TRY(cudaMemcpyAsync(db->k_in[2].p, woff, (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+    rc = pf_kmc_lookup_dev(db, db->k_in[0].p, n_bases, db->k_in[1].p, db->k_in[2].p, n_seq, W, mode, low, up,
+                           counts ? db->k_out[0].p : nullptr, found ? db->k_out[1].p : nullptr,
+                           cov ? db->k_out[2].p : nullptr, st);
     if (rc) return rc;
-    if (counts && W) PF_CUDA_TRY(cudaMemcpyAsync(counts, ctx->d_out[0].p, W * 4, cudaMemcpyDeviceToHost, st));
-    if (found && W) PF_CUDA_TRY(cudaMemcpyAsync(found, ctx->d_out[1].p, W, cudaMemcpyDeviceToHost, st));
-    if (cov) PF_CUDA_TRY(cudaMemcpyAsync(cov, ctx->d_out[2].p, (uint64_t)n_seq * sizeof(pf_cov_t), cudaMemcpyDeviceToHost, st));
-    PF_CUDA_TRY(cudaStreamSynchronize(st));
+    if (counts && W) PF_CUDA_TRY(cudaMemcpyAsync(counts, db->k_out[0].p, W * 4, cudaMemcpyDeviceToHost, st));
+    if (found && W) PF_CUDA_TRY(cudaMemcpyAsync(found, db->k_out[1].p, W, cudaMemcpyDeviceToHost, st));
+    if (cov) PF_CUDA_TRY(cudaMemcpyAsync(cov, db->k_out[2].p, (uint64_t)n_seq * sizeof(pf_cov_t), cudaMemcpyDeviceToHost, st));
+    if (!async) PF_CUDA_TRY(cudaStreamSynchronize(st));
+    return PF_OK;
+}
+
+int pf_kmc_cov_async(pf_kmc *db, const char *bases, const uint64_t *seq_off, uint32_t n_seq, int mode, uint32_t low, uint32_t up,
+                     pf_cov_t *out) {
+    if (!out) { pf::set_error("pf_kmc_cov_async: null output"); return PF_E_INVALID; }
+    return kmc_host_call(db, bases, seq_off, n_seq, mode, low, up, nullptr, nullptr, out, true);
+}
+
+int pf_kmc_wait(pf_kmc *db) {
+    if (!db) return PF_E_INVALID;
+    PF_CUDA_TRY(cudaSetDevice(db->ctx->device));
+    if (db->k_stream) PF_CUDA_TRY(cudaStreamSynchronize(db->k_stream));
     return PF_OK;
 }
 
 int pf_kmc_counts(pf_kmc *db, const char *bases, const uint64_t *seq_off, uint32_t n_seq, int mode, uint32_t *counts,
                   uint8_t *found) {
     if (!counts && !found) { pf::set_error("pf_kmc_counts: no output requested"); return PF_E_INVALID; }
-    return kmc_host_call(db, bases, seq_off, n_seq, mode, 0, 0xFFFFFFFFu, counts, found, nullptr);
+    return kmc_host_call(db, bases, seq_off, n_seq, mode, 0, 0xFFFFFFFFu, counts, found, nullptr, false);
 }
 
 int pf_kmc_cov(pf_kmc *db, const char *bases, const uint64_t *seq_off, uint32_t n_seq, int mode, uint32_t low, uint32_t up,
                pf_cov_t *out) {
     if (!out) { pf::set_error("pf_kmc_cov: null output"); return PF_E_INVALID; }
-    return kmc_host_call(db, bases, seq_off, n_seq, mode, low, up, nullptr, nullptr, out);
+    return kmc_host_call(db, bases, seq_off, n_seq, mode, low, up, nullptr, nullptr, out, false);
 }
 
 }  // extern "C"

@@ -25,6 +25,7 @@
 #include "pf_kmc_hash.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstring>
@@ -334,6 +335,15 @@ kmc_lookup_kernel(const KmcView db, const uint8_t *__restrict__ bases, const uin
         }
         __syncthreads();  // smem is reused by the next tile
     }
+}
+
+// window counts max(len - k + 1, 0) of every sequence (+ a 0 for the end of the exclusive scan that makes win_off)
+__global__ void win_len_kernel(const uint64_t *__restrict__ seq_off, uint32_t n_seq, uint32_t k, uint64_t *__restrict__ wlen) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_seq) return;
+    if (s == n_seq) { wlen[s] = 0; return; }
+    const uint64_t len = seq_off[s + 1] - seq_off[s];
+    wlen[s] = len >= k ? len - k + 1 : 0;
 }
 
 __global__ void cov_init_kernel(pf_cov_t *cov, const uint64_t *__restrict__ win_off, uint32_t n_seq) {
@@ -1262,6 +1272,32 @@ static int kmc_host_call(pf_kmc *db, const char *bases, const uint64_t *seq_off,
     PF_CUDA_TRY(cudaStreamSynchronize(db->k_stream));   // an earlier asynchronous call still owns the staging buffers
     const uint64_t n_bases = seq_off[n_seq] - seq_off[0];
     int rc;
+    if (cov && !counts && !found && seq_off[0] == 0) {
+        // coverage only, offsets already zero-based: nothing is touched on the host -- the caller's offsets are copied as they
+        // are and the window offsets are an exclusive scan on the device
+        cudaStream_t st = db->k_stream;
+        if ((rc = db->k_in[0].reserve(n_bases + 16))) return rc;
+        if ((rc = db->k_in[1].reserve((uint64_t)(n_seq + 1) * 8))) return rc;
+        if ((rc = db->k_in[2].reserve((uint64_t)(n_seq + 1) * 8))) return rc;
+        if ((rc = db->k_out[1].reserve((uint64_t)(n_seq + 1) * 8))) return rc;                 // window counts
+        if ((rc = db->k_out[2].reserve((uint64_t)n_seq * sizeof(pf_cov_t)))) return rc;
+        if (n_bases) PF_CUDA_TRY(cudaMemcpyAsync(db->k_in[0].p, bases, n_bases, cudaMemcpyHostToDevice, st));
+        PF_CUDA_TRY(cudaMemcpyAsync(db->k_in[1].p, seq_off, (uint64_t)(n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+        win_len_kernel<<<(n_seq + 1 + 255) / 256, 256, 0, st>>>(db->k_in[1].as<uint64_t>(), n_seq, db->info.kmer_length, db->k_out[1].as<uint64_t>());
+        size_t tmp = 0;
+        PF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp, db->k_out[1].as<uint64_t>(), db->k_in[2].as<uint64_t>(), (int)(n_seq + 1), st));
+        if ((rc = db->k_out[0].reserve(tmp + 16))) return rc;
+        tmp = db->k_out[0].cap;
+        PF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(db->k_out[0].p, tmp, db->k_out[1].as<uint64_t>(), db->k_in[2].as<uint64_t>(), (int)(n_seq + 1), st));
+        ctx->launches += 3;
+        // the number of windows is only an upper bound here (no per-window output is written)
+        rc = pf_kmc_lookup_dev(db, db->k_in[0].p, n_bases, db->k_in[1].p, db->k_in[2].p, n_seq, std::max<uint64_t>(n_bases, 1), mode, low, up,
+                               nullptr, nullptr, db->k_out[2].p, st);
+        if (rc) return rc;
+        PF_CUDA_TRY(cudaMemcpyAsync(cov, db->k_out[2].p, (uint64_t)n_seq * sizeof(pf_cov_t), cudaMemcpyDeviceToHost, st));
+        if (!async) PF_CUDA_TRY(cudaStreamSynchronize(st));
+        return PF_OK;
+    }
     // rebased offsets + window offsets are built straight into pinned staging (one async copy each, no bounce buffer)
     if ((rc = db->k_stage.reserve((uint64_t)(n_seq + 1) * 16))) return rc;
     uint64_t *off = db->k_stage.as<uint64_t>(), *woff = off + (n_seq + 1);

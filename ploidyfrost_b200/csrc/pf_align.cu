@@ -34,6 +34,12 @@ using namespace pfalign;
 
 namespace {
 
+#ifndef PF_LANE_MINB
+#define PF_LANE_MINB 8     // minimum resident CTAs per SM the compiler must allow for (register cap = 65536 / (64 * MINB))
+#endif
+#ifndef PF_GROUP_MINB
+#define PF_GROUP_MINB 8
+#endif
 constexpr int WARP_BLOCK = 128;  // msa_warp_kernel: 4 warps per CTA
 constexpr int LANE_BLOCK = 64;   // msa_lane_kernel: 2 warps per CTA (shared memory is per warp, small CTAs pack SMs tighter)
 constexpr uint32_t FULL = 0xffffffffu;
@@ -686,7 +692,7 @@ __host__ __device__ constexpr uint32_t lane_smem_per_warp(uint32_t nmax, uint32_
 }
 
 template <int VARIANT>
-__global__ void __launch_bounds__(LANE_BLOCK, 8) msa_lane_kernel(const MsaArgs a) {
+__global__ void __launch_bounds__(LANE_BLOCK, PF_LANE_MINB) msa_lane_kernel(const MsaArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -729,7 +735,7 @@ __host__ __device__ constexpr uint32_t group_smem_per_warp(uint32_t nmax, uint32
 }
 
 template <int G>
-__global__ void __launch_bounds__(GROUP_BLOCK) msa_group_kernel(const MsaArgs a) {
+__global__ void __launch_bounds__(GROUP_BLOCK, PF_GROUP_MINB) msa_group_kernel(const MsaArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr uint32_t NB = 32 / G;
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

@@ -225,3 +225,36 @@ def test_dense_buckets_and_tiny_tables(gpu_ctx, oracle, tmp_path):
         finally:
             oracle.kmc_close(ho)
             db.close()
+
+
+def test_async_cov_beside_an_alignment(gpu_ctx, oracle, tmp_path):
+    """pf_kmc_cov_async + pf_kmc_wait: same records as the synchronous call, with a pf_align of the same context in between."""
+    import torch
+    from oracle.bindings import flatten_bubbles
+    from ploidyfrost_b200 import capi
+    from tests.util import assert_msa_equal
+    prefix, g, u, c = gen.make_genome_db(tmp_path, seed=41, k=25, version=0x200, p=9, genome_len=60000)
+    db = capi.KmcDb(gpu_ctx, prefix)
+    try:
+        rng = np.random.default_rng(41)
+        bases, off = flatten_seqs(gen.query_sequences(rng, g, 20000, k=25))
+        hb = torch.from_numpy(bases).pin_memory()
+        ho = torch.from_numpy(off).pin_memory()
+        out = torch.zeros(len(off) - 1, dtype=torch.uint8).new_zeros((len(off) - 1) * 24).pin_memory()
+        rec = out.numpy().view(capi.COV_DTYPE)
+        want = db.cov(bases, off, mode=1, low=1, up=1000).copy()
+        bubbles = gen.random_bubbles(5, 3000)
+        flat = flatten_bubbles(bubbles)
+        for _ in range(3):
+            rec[:] = 0
+            db.cov_async(hb.numpy(), ho.numpy(), rec, mode=1, low=1, up=1000)
+            m = gpu_ctx.align(*flat)
+            db.wait()
+            assert np.array_equal(rec, want)
+        assert_msa_equal(oracle.align(*flat, n_threads=8), m, bubbles, "align beside async lookups")
+        # offsets that do not start at zero take the staging path
+        sub = off[100:]
+        a = db.cov(bases, sub, mode=1, low=1, up=1000)
+        assert np.array_equal(a, want[100:])
+    finally:
+        db.close()

@@ -569,15 +569,11 @@ __device__ __forceinline__ void heavy_enqueue(uint32_t *hq, const uint8_t *slot,
     }
 }
 
-// SMEM_FLAGS: one warp per CTA with the flag matrix in dynamic shared memory -- the tier for bubbles whose co-optimal
-// DFS is long (tens of thousands of dependent flag reads: ~30 cycles each from shared memory instead of an L2/HBM trip).
-template <bool INTEGRAL, bool SMEM_FLAGS>
+template <bool INTEGRAL>
 __global__ void __launch_bounds__(WARP_BLOCK) msa_warp_kernel(const MsaArgs a) {
-    extern __shared__ __align__(16) uint8_t smem_flags[];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim);
-    if (SMEM_FLAGS) ws.flags = bv(smem_flags);
     WarpExec<INTEGRAL> x;
     x.lane = lane;
     x.cells = 0;
@@ -968,6 +964,7 @@ struct pf_align_state {
     cudaStream_t heavy_stream = nullptr;
     cudaEvent_t ev_heavy = nullptr;
     int heavy_ctas = 4;
+    bool heavy_attr_done = false;
     int group_lanes[N_LANE_CLASSES] = {1, 1, 2, 4, 8};   // lanes per bubble of each size class (1 = thread-per-bubble kernel)
     bool group_env_done = false;
 };
@@ -1073,8 +1070,8 @@ int launch_warp_tier(pf_ctx *ctx, pf_align_state *st, int pool, const Limits &li
     MsaArgs a;
     fill_args(a, st, pool, lim, sc, d_bases, d_seq_off, d_bubble_off, d_order, first, n_items, tier_id, counter);
     a.ws_base = st->ws_warp[pool].as<uint8_t>(); a.ws_stride = ws_bytes;
-    if (sc.integral) msa_warp_kernel<true, false><<<blocks, WARP_BLOCK, 0, s>>>(a);
-    else msa_warp_kernel<false, false><<<blocks, WARP_BLOCK, 0, s>>>(a);
+    if (sc.integral) msa_warp_kernel<true><<<blocks, WARP_BLOCK, 0, s>>>(a);
+    else msa_warp_kernel<false><<<blocks, WARP_BLOCK, 0, s>>>(a);
     ctx->launches++;
     PF_CUDA_TRY(cudaGetLastError());
     return PF_OK;
@@ -1085,8 +1082,7 @@ int heavy_mode(const Scoring &sc, const Limits &lim) { return lane_variant(sc, l
 size_t heavy_smem_bytes(const Limits &hl, int hmode) {
     return (size_t)(align_up(flag_area_cells(hl), 16) + align_up(hl.max_alen + hl.max_blen, 16) + (hmode == 2 ? group_smem_per_warp(hl.max_blen, 1) : 0));
 }
-int heavy_set_attr() {
-    static bool done = false;
+int heavy_set_attr(bool &done) {   // function attributes are per device: remembered per context, not per process
     if (done) return PF_OK;
     const int big_smem = 200 * 1024;
     PF_CUDA_TRY(cudaFuncSetAttribute(msa_heavy_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem));
@@ -1108,7 +1104,7 @@ int launch_warp_smem_tier(pf_ctx *ctx, pf_align_state *st, int pool, const Limit
     const int hmode = heavy_mode(sc, lim);
     if (hmode == 2) hl.diag_flags = 0;
     int rc;
-    if ((rc = heavy_set_attr())) return rc;
+    if ((rc = heavy_set_attr(st->heavy_attr_done))) return rc;
     const uint64_t ws_bytes = align_up(work_area_bytes(hl), 256);
     const uint32_t blocks = (uint32_t)std::min<uint64_t>((uint64_t)n_items, (uint64_t)ctx->sm_count);
     if ((rc = st->ws_warp[pool].reserve((uint64_t)blocks * ws_bytes))) return rc;
@@ -1258,7 +1254,7 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         // should not share its scheduler with first-pass warps
         const size_t hsmem = std::max<size_t>(heavy_smem_bytes(hl, hmode), 190 * 1024);
         const uint64_t hws = align_up(work_area_bytes(hl), 256), pool_bytes = 64ull << 20;
-        if ((rc = heavy_set_attr())) return rc;
+        if ((rc = heavy_set_attr(st->heavy_attr_done))) return rc;
         if (!st->heavy_stream) {
             PF_CUDA_TRY(cudaStreamCreateWithFlags(&st->heavy_stream, cudaStreamNonBlocking));
             PF_CUDA_TRY(cudaEventCreateWithFlags(&st->ev_heavy, cudaEventDisableTiming));

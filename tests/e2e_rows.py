@@ -207,20 +207,21 @@ def regenerate(bubbles, unitig_len, k, low, up, align_fn, cov_fn, kmer_count_fn,
     return cov_rows, fre_rows, aligned
 
 
-def load_fixture():
-    meta = json.load(open(os.path.join(E2E, "meta.json")))
-    bubbles = parse_alignseq(os.path.join(E2E, "P_alignseq.txt"))
+def load_fixture(d=None):
+    d = d or E2E
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    bubbles = parse_alignseq(os.path.join(d, "P_alignseq.txt"))
     useq = {}
-    for ln in open(os.path.join(E2E, "P_Unitig_Id.txt")):
+    for ln in open(os.path.join(d, "P_Unitig_Id.txt")):
         i, s = ln.rstrip("\n").split("\t")
         useq[int(i)] = s
-    return meta, bubbles, useq, parse_cov_files(E2E)
+    return meta, bubbles, useq, parse_cov_files(d)
 
 
-def check_against_reference(align_fn, cov_fn, kmer_count_fn, site_cov_fn=None):
+def check_against_reference(align_fn, cov_fn, kmer_count_fn, site_cov_fn=None, fixture_dir=None):
     """Asserts that (a) SequenceAlignment of the raw branch strings reproduces the reference's aligned rows for every bubble and
     (b) the regenerated coverage rows equal the reference's files row for row.  Returns (#rows, #branching bubbles)."""
-    meta, bubbles, useq, ref_rows = load_fixture()
+    meta, bubbles, useq, ref_rows = load_fixture(fixture_dir)
     k = meta["k"]
     ulen = {i: len(s) for i, s in useq.items()}             # UnitigMap::size is the unitig length in bases
     cov_rows, fre_rows, aligned = regenerate(bubbles, ulen, k, meta["low"], meta["up"], align_fn, cov_fn, kmer_count_fn, site_cov_fn)
@@ -255,3 +256,45 @@ def device_site_cov_hook(db, meta, bubbles):
         c0 = int(sc["cov_off"][bi]) + i * int(state["nrows"][bi])
         return [float(x) for x in sc["cov"][c0:c0 + int(sc["n_class"][v])]]
     return site_cov, state
+
+
+# ---- BASELINE configs[0]: the reference run here and now ----------------------------------------------------------------------
+def reference_binaries():
+    """(PloidyFrost, Bifrost) of oracle/_ref (built by `make -C oracle ref_full` in the dev container; they travel to the GPU box
+    with the snapshot and need nothing from /root/reference at run time), or None."""
+    ref = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
+    pf, bf = os.path.join(ref, "PloidyFrost"), os.path.join(ref, "Bifrost")
+    return (pf, bf) if os.path.exists(pf) and os.path.exists(bf) else None
+
+
+def run_reference_config0(workdir, genome=200000, depth=30, read_len=150, k=25, low=2, up=1000, seed=20261017, threads=1):
+    """BASELINE configs[0], scaled by `genome`: synthetic diploid (1 % SNP, 0.1 % indel), `depth`x error-free reads of random
+    strand, Bifrost graph of the reads, KMC database = canonical k-mer counts of the reads; the unmodified PloidyFrost is run on
+    it and its output directory is returned in the shape load_fixture() reads."""
+    import subprocess
+    from ploidyfrost_b200.synth import kmcdb, workload as wl
+    pf, bf = reference_binaries()
+    w = wl.Workload(seed, genome, 2, p_snp=0.01, p_indel=0.001, n_threads=2)
+    haps = [bytes(w.haplotype(i)).decode() for i in range(2)]
+    w.close()
+    rng = np.random.default_rng(seed)
+    comp = str.maketrans("ACGT", "TGCA")
+    reads = []
+    for h in haps:
+        n = depth * len(h) // (2 * read_len)
+        for a in rng.integers(0, len(h) - read_len, n):
+            r = h[a:a + read_len]
+            reads.append(r.translate(comp)[::-1] if rng.random() < 0.5 else r)
+    with open(os.path.join(workdir, "reads.fa"), "w") as f:
+        for i, r in enumerate(reads):
+            f.write(f">r{i}\n{r}\n")
+    u, c = kmcdb.count_canonical_kmers(reads, k)
+    kmcdb.write_kmc_db(os.path.join(workdir, "db"), u, c.astype(np.uint64), k, version=0x200, lut_prefix_len=5, counter_size=2, n_bins=64,
+                       sig_len=9)
+    subprocess.run([bf, "build", "-r", "reads.fa", "-k", str(k), "-i", "-d", "-o", "dbg", "-t", "4"], cwd=workdir, check=True,
+                   capture_output=True)
+    subprocess.run([pf, "-g", "dbg.gfa", "-d", "db", "-t", str(threads), "-l", str(low), "-u", str(up), "-o", "P"], cwd=workdir, check=True,
+                   capture_output=True)
+    out = os.path.join(workdir, "PloidyFrost_output")
+    json.dump({"k": k, "low": low, "up": up, "genome": genome, "db_kmers": int(len(u))}, open(os.path.join(out, "meta.json"), "w"))
+    return out, os.path.join(workdir, "db")

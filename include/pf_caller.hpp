@@ -1,0 +1,193 @@
+// pf_caller.hpp -- the per-bubble caller of PloidyFrost over the C ABI, batched (header-only, C++11).
+//
+// What the reference does for ONE superbubble inside CDBG::PloidyEstimation -- look the branches up, order them, align them,
+// turn every variable column into allele-class coverages and append rows to its output streams (strict bubbles:
+// src/CDBG.cpp:1186-1330 = :1998-2189; branching bubbles: :1440-1660 = :2190-2575) -- done here for a whole batch of bubbles
+// with three device calls (pf_kmc_cov, pf_align, pf_site_cov).  The graph side stays with the host program: it finds the
+// superbubbles on its Bifrost graph and hands over, per bubble, the branch strings and the four numbers the rows need.
+// The text produced is the reference's `-t 1` dialect, byte for byte (tests/dropin/caller_test.cpp compares it with the
+// unmodified reference's own files, tests/golden/e2e).
+#ifndef PF_CALLER_HPP
+#define PF_CALLER_HPP
+
+#include <algorithm>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "pf_gpu.h"
+
+namespace pfdropin {
+
+struct Bubble {
+    unsigned entrance_id = 0, exit_id = 0;     // MyUnitig ids as the reference prints them (P_Unitig_Id.txt)
+    size_t entrance_size = 0, exit_size = 0;   // UnitigMap::size of entrance / exit (bases); they bound VarDis (CDBG.cpp:2312-2330)
+    bool strict = false;                       // MyUnitig::isStrict: every branch is one unitig
+    // strict: mappedSequenceToString() of every successor, in successor order (CDBG.cpp:2016-2048);
+    // branching: the strings from the last k-mer of the entrance to the first k-mer of the exit (:2226), any order
+    std::vector<std::string> branches;
+    // strict only, optional: referenceUnitigToString() of every branch -- the tie-break of sortSeq_simple (:482-551) when two
+    // branches have exactly the same mean coverage; empty = the branch strings themselves
+    std::vector<std::string> sort_keys;
+};
+
+struct CallerFiles {   // what the reference appends to its streams (Appendix D of SURVEY.md), `-t 1` dialect
+    std::string alignseq;            // P_alignseq.txt
+    std::string cov[4], fre[4];      // P_{bi,tri,tetra,penta}{cov,fre}.txt
+    std::string allele_frequency;    // P_allele_frequency.txt
+    size_t alleles[4] = {0, 0, 0, 0};
+    size_t bubbles_called = 0;
+};
+
+class BubbleCaller {
+  public:
+    BubbleCaller(pf_ctx *ctx, pf_kmc *db, double match, double mismatch, double gap, unsigned lower, unsigned upper)
+        : ctx_(ctx), db_(db), M_(match), D_(mismatch), G_(gap), lower_(lower), upper_(upper) {}
+
+    const std::string &error() const { return err_; }
+
+    // Calls one batch.  `var_id` is the reference's running variant counter (var_count_all; start it at 1 for the `-t 1` files)
+    // and advances by one for every bubble whose alignment is not empty.  Returns false where the reference would have ended
+    // the program (a k-mer of a branch or of a site is not in the database, CDBG.cpp:52-56) or on a device error; error() says which.
+    bool call(const std::vector<Bubble> &batch, size_t &var_id, CallerFiles &out) {
+        err_.clear();
+        // ---- lookup-A: readCov of every branch of the strict bubbles (CDBG.cpp:66-120) ----
+        std::string lbases;
+        std::vector<uint64_t> loff(1, 0);
+        for (const Bubble &b : batch)
+            if (b.strict)
+                for (const std::string &s : b.branches) { lbases += s; loff.push_back(lbases.size()); }
+        std::vector<pf_cov_t> cov(loff.size() - 1);
+        if (!cov.empty() && pf_kmc_cov(db_, lbases.data(), loff.data(), (uint32_t)cov.size(), PF_LOOKUP_FWD_THEN_RC, 0, 0xFFFFFFFFu,
+                                       cov.data()) != PF_OK)
+            return fail(pf_last_error());
+        // ---- gate + order the branches; build the alignment batch ----
+        struct Kept { size_t src; std::vector<size_t> order; std::vector<double> means; double sum; };
+        std::vector<Kept> kept;
+        std::string abases;
+        std::vector<uint64_t> aoff(1, 0);
+        std::vector<uint32_t> boff(1, 0);
+        std::vector<uint8_t> skip;
+        size_t ci = 0;
+        for (size_t bi = 0; bi < batch.size(); bi++) {
+            const Bubble &b = batch[bi];
+            Kept kb;
+            kb.src = bi; kb.sum = 0;
+            const size_t n = b.branches.size();
+            if (b.strict) {
+                bool ok = true;
+                for (size_t j = 0; j < n; j++, ci++) {
+                    const pf_cov_t &c = cov[ci];
+                    if (!ok) continue;                                             // the reference stopped reading at the first failure (:2027-2031)
+                    if (c.first_missing >= 0) return fail("a k-mer of a branch unitig is not in the database: the reference exits here (CDBG.cpp:94)");
+                    if (c.min > lower_ && c.min < upper_) {                       // :2021 (min count of the branch inside the thresholds)
+                        const double m = (double)c.sum / (double)c.n_kmers;
+                        kb.means.push_back(m);
+                        kb.sum += m;                                               // in successor order (:2024)
+                    } else ok = false;                                             // :2027-2031: the bubble is dropped
+                }
+                if (!ok || n < 2) continue;
+                kb.order.resize(n);
+                for (size_t j = 0; j < n; j++) kb.order[j] = j;
+                const std::vector<std::string> &keys = b.sort_keys.size() == n ? b.sort_keys : b.branches;
+                std::sort(kb.order.begin(), kb.order.end(), [&](size_t x, size_t y) {          // sortSeq_simple's order (:482-551)
+                    if (kb.means[x] != kb.means[y]) return kb.means[x] > kb.means[y];
+                    return std::strcmp(keys[x].c_str(), keys[y].c_str()) > 0;
+                });
+            } else {
+                if (n < 2) continue;
+                kb.order.resize(n);
+                for (size_t j = 0; j < n; j++) kb.order[j] = j;
+                std::sort(kb.order.begin(), kb.order.end(), [&](size_t x, size_t y) {          // sortSeq_branching: longer first, then larger
+                    if (b.branches[x].size() != b.branches[y].size()) return b.branches[x].size() > b.branches[y].size();
+                    return b.branches[x] > b.branches[y];
+                });
+            }
+            for (size_t j : kb.order) { abases += b.branches[j]; aoff.push_back(abases.size()); }
+            boff.push_back((uint32_t)(aoff.size() - 1));
+            skip.push_back(b.strict ? 1 : 0);
+            kept.push_back(std::move(kb));
+        }
+        if (kept.empty()) return true;
+        // ---- SequenceAlignment of every kept bubble, then the site k-mers of the branching ones ----
+        pf_msa_batch_t m;
+        if (pf_align(ctx_, M_, D_, G_, abases.data(), aoff.data(), boff.data(), (uint32_t)kept.size(), &m) != PF_OK) return fail(pf_last_error());
+        pf_site_batch_t sc;
+        if (pf_site_cov(db_, lower_, upper_, skip.data(), &sc) != PF_OK) return fail(pf_last_error());
+        // ---- rows ----
+        static const char *kNames[4] = {"bi", "tri", "tetra", "penta"};
+        (void)kNames;
+        for (size_t q = 0; q < kept.size(); q++) {
+            const Kept &kb = kept[q];
+            const Bubble &b = batch[kb.src];
+            if (m.status[q] != PF_BUBBLE_OK) return fail("a bubble does not fit the device limits (status " + std::to_string(m.status[q]) + ")");
+            const uint32_t nr = m.n_rows[q], L = m.aln_len[q];
+            if (nr == 0) continue;                                                 // str_vec came back empty (:2051, :2273)
+            const size_t var_count = var_id++;
+            out.bubbles_called++;
+            const char *rows = m.rows + m.rows_off[q];
+            for (uint32_t r = 0; r < nr; r++) {
+                std::ostringstream ln;
+                ln << var_count << "\t" << (b.strict ? 1 : 0) << "\t" << b.entrance_id << "\t" << b.exit_id << "\t";
+                out.alignseq += ln.str();
+                out.alignseq.append(rows + (size_t)r * L, L);
+                out.alignseq += "\n";
+            }
+            const uint64_t v0 = m.var_off[q], v1 = m.var_off[q + 1];
+            const size_t n_var = (size_t)(v1 - v0);
+            const uint16_t *cls = m.cls + m.cls_off[q];
+            const uint32_t *ilen = m.ilen + m.ilen_off[q];
+            const size_t n_ilen = (size_t)(m.ilen_off[q + 1] - m.ilen_off[q]);
+            size_t indel = 0;
+            for (size_t i = 0; i < n_var; i++) {
+                const uint32_t col = m.var_col[v0 + i];
+                const bool is_indel = m.var_kind[v0 + i] == 1;
+                size_t var_distance;                                               // :2312-2330
+                auto gap_to = [&](size_t a, size_t c) { return (size_t)(m.var_col[v0 + c] - m.var_col[v0 + a] - 1); };
+                if (i == 0) var_distance = n_var > 1 ? std::min(gap_to(0, 1), b.entrance_size) : std::min(b.entrance_size, b.exit_size);
+                else if (i == n_var - 1) var_distance = std::min(gap_to(i - 1, i), b.exit_size);
+                else var_distance = std::min(gap_to(i - 1, i), gap_to(i, i + 1));
+                (void)col;
+                unsigned maxnum = 0;
+                for (uint32_t r = 0; r < nr; r++) maxnum = std::max<unsigned>(maxnum, cls[i * nr + r]);
+                std::vector<double> tc(maxnum, 0.0);
+                double sum = 0;
+                if (is_indel) indel++;                                             // :2390 / strict :2127, before anything can skip the site
+                if (b.strict) {
+                    for (uint32_t r = 0; r < nr; r++) tc[cls[i * nr + r] - 1] += kb.means[kb.order[r]];   // :2105-2108
+                    sum = kb.sum;
+                } else {
+                    const uint8_t st = sc.status[sc.site_off[q] + i];
+                    if (st == PF_SITE_DROPPED) continue;                           // :2415-2418
+                    if (st == PF_SITE_MISSING) return fail("a site k-mer is not in the database: the reference exits here (CDBG.cpp:54)");
+                    if (st != PF_SITE_OK) return fail("a site k-mer cannot be formed (the reference reads outside the aligned row here)");
+                    const uint64_t *cv = sc.cov + sc.cov_off[q] + i * nr;
+                    for (unsigned c = 0; c < maxnum; c++) { tc[c] = (double)cv[c]; sum += tc[c]; }
+                }
+                std::ostringstream cov_info, fre_info;
+                for (double c : tc) { cov_info << c << "\t"; fre_info << c / sum << "\n"; }
+                const uint32_t il = is_indel ? (indel - 1 < n_ilen ? ilen[indel - 1] : 0u) : 0u;
+                cov_info << (b.strict ? 1 : 0) << "\t" << il << "\t" << var_count << "\t" << n_var << "\t" << var_distance << "\t\n";
+                if (maxnum >= 2 && maxnum <= 5) {                                  // switch (maxnum), :2126-2147
+                    out.alleles[maxnum - 2]++;
+                    out.cov[maxnum - 2] += cov_info.str();
+                    out.fre[maxnum - 2] += fre_info.str();
+                    out.allele_frequency += fre_info.str();                        // -t 1: every site in site order (:1318, :1630)
+                }
+            }
+        }
+        return true;
+    }
+
+  private:
+    bool fail(const std::string &why) { err_ = why; return false; }
+    pf_ctx *ctx_;
+    pf_kmc *db_;
+    double M_, D_, G_;
+    unsigned lower_, upper_;
+    std::string err_;
+};
+
+}  // namespace pfdropin
+#endif  // PF_CALLER_HPP

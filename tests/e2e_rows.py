@@ -264,6 +264,9 @@ def reference_binaries():
     with the snapshot and need nothing from /root/reference at run time), or None."""
     ref = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
     pf, bf = os.path.join(ref, "PloidyFrost"), os.path.join(ref, "Bifrost")
+    if not (os.path.exists(pf) and os.path.exists(bf)) and os.path.isdir("/root/reference/src"):   # dev container: build them
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(os.path.dirname(HERE), "oracle"), "ref_full"], check=False, capture_output=True)
     return (pf, bf) if os.path.exists(pf) and os.path.exists(bf) else None
 
 

@@ -301,3 +301,22 @@ def run_reference_config0(workdir, genome=200000, depth=30, read_len=150, k=25, 
     out = os.path.join(workdir, "PloidyFrost_output")
     json.dump({"k": k, "low": low, "up": up, "genome": genome, "db_kmers": int(len(u))}, open(os.path.join(out, "meta.json"), "w"))
     return out, os.path.join(workdir, "db")
+
+
+def site_outcome(part, kmers, k0, counts, found, low, up):
+    """(status, class coverages) of one site in the reference's iteration order (classes ascending, distinct k-mers of a class in
+    std::set order): 0 ok, 1 dropped at the first counter outside (low, up), 2 a missing k-mer reached first (the reference exits)."""
+    sets = [dict() for _ in range(max(part))]
+    for j, cl in enumerate(part):
+        sets[cl - 1].setdefault(kmers[k0 + j], k0 + j)
+    tc = [0] * len(sets)
+    for q, st in enumerate(sets):
+        for s in sorted(st):
+            idx = st[s]
+            if not found[idx]:
+                return 2, tc
+            cval = int(counts[idx])
+            if not (low < cval < up):
+                return 1, tc
+            tc[q] += cval
+    return 0, tc

@@ -64,3 +64,62 @@ def test_config0_reference_run_from_the_cuda_path(gpu_ctx, tmp_path):
         assert n_rows > 1000 and n_branching > 50
     finally:
         db.close()
+
+
+def test_site_cov_statuses_against_the_host_logic(gpu_ctx, oracle, tmp_path):
+    """pf_site_cov on synthetic bubbles whose variant alleles are only partly in the database and with a tight (low, up):
+    every site's status (ok / dropped / missing) and class coverages must equal the reference's iteration order as restated
+    in tests/e2e_rows.py (site_kmers + site_outcome) over oracle lookups."""
+    from oracle.bindings import flatten_bubbles, msa_bubble
+    from ploidyfrost_b200 import capi
+    from ploidyfrost_b200.synth import kmcdb
+    from tests import gen
+    k = 25
+    rng = np.random.default_rng(77)
+    g = gen.rand_seq(rng, 60000)
+    bubbles, extra = [], []
+    for _ in range(1500):
+        a = int(rng.integers(0, len(g) - 200))
+        ln = int(rng.integers(2 * k + 5, 150))
+        base = g[a:a + ln]
+        rows = [base]
+        for r in range(int(rng.integers(1, 4))):
+            inner = gen.mutate(rng, base[k:-k], int(rng.integers(1, 3)), int(rng.integers(0, 2)), max_indel=4)
+            alt = base[:k] + inner + base[-k:]
+            if alt not in rows and len(alt) >= 2 * k:
+                rows.append(alt)
+                if rng.random() < 0.6:
+                    extra.append(alt)                      # this allele is in the database, the others are not
+        if len(rows) >= 2:
+            bubbles.append(gen.sort_branching(rows))
+    u, c = kmcdb.count_canonical_kmers([g] + extra, k)
+    c = (c + rng.integers(0, 4, len(c))).astype(np.uint64)  # counts 1..: a (1, 4) gate drops some sites
+    prefix = str(tmp_path / "sites")
+    kmcdb.write_kmc_db(prefix, u, c, k, version=0x200, lut_prefix_len=5, counter_size=2, n_bins=32, sig_len=9)
+    low, up = 1, 4
+    h = oracle.kmc_open(prefix)
+    db = capi.KmcDb(gpu_ctx, prefix)
+    try:
+        flat = flatten_bubbles(bubbles)
+        msa = gpu_ctx.align(*flat)
+        sc = db.site_cov(low, up, None)
+        aligned = [msa_bubble(msa, i) for i in range(len(bubbles))]
+        fake = [dict(strict=False) for _ in bubbles]
+        plan, kmers = e2e_rows.branching_site_plan(fake, aligned, k)
+        b, off = flatten_seqs(kmers)
+        counts, found = oracle.kmc_counts(h, b, off, k, mode=1)
+        seen = np.zeros(5, int)
+        for bi, i, col, is_ind, n_ind, k0 in plan:
+            part = aligned[bi]["partition"][col]
+            st, tc = e2e_rows.site_outcome(part, kmers, k0, counts, found, low, up)
+            v = int(sc["site_off"][bi]) + i
+            assert int(sc["status"][v]) == st, (bi, i, int(sc["status"][v]), st)
+            assert int(sc["n_class"][v]) == max(part)
+            if st == 0:
+                c0 = int(sc["cov_off"][bi]) + i * int(msa["n_rows"][bi])
+                assert [int(x) for x in sc["cov"][c0:c0 + max(part)]] == tc
+            seen[st] += 1
+        assert seen[0] > 100 and seen[1] > 20 and seen[2] > 100, seen
+    finally:
+        oracle.kmc_close(h)
+        db.close()

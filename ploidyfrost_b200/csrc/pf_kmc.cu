@@ -493,11 +493,16 @@ __global__ void kmc_cov_from_counts_kernel(const uint64_t *__restrict__ win_off,
 // k-mer that ENDS at the site (SNP) or ends where the rows start to differ after the gap (indel), de-duplicates the strings per
 // allele class in a std::set, looks each distinct string up with readCov(string, lower, upper) -- 'as written, else reverse
 // complement', strict gate -- and sums per class; a count outside the gate drops the site, a missing k-mer ends the program.
-// SITE_TPB threads per bubble, thread t takes the bubble's sites t, t + SITE_TPB, ...; the number of indel sites before a
-// site (the only thing that couples the sites of a bubble) is a count over var_kind.  Everything else is a few dozen byte
+// One thread per SITE (site_map_kernel first writes the bubble of every variable column): the number of indel sites before a
+// site -- the only thing that couples the sites of a bubble -- is a count over var_kind.  Everything else is a few dozen byte
 // loads per row.  Row r of bubble b is rows[rows_off[b] + r * aln_len[b] ...].
 constexpr uint32_t SITE_MAX_ROWS = 16;
-constexpr uint32_t SITE_TPB = 4;
+
+__global__ void site_map_kernel(const uint64_t *__restrict__ var_off, uint32_t n, uint32_t *__restrict__ site_bubble) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    for (uint64_t v = var_off[b]; v < var_off[b + 1]; v++) site_bubble[v] = b;
+}
 
 struct SiteArgs {
     KmcView db;
@@ -517,6 +522,8 @@ struct SiteArgs {
     uint32_t low, up;
     uint8_t *site_status, *site_ncls;
     unsigned long long *site_cov;
+    const uint32_t *site_bubble;
+    uint64_t n_sites;
 };
 
 __device__ __forceinline__ bool site_lookup_one(const SiteArgs &a, uint64_t key, uint32_t &cnt) {
@@ -577,20 +584,19 @@ __device__ __forceinline__ int site_row_kmer(const char *row, uint32_t L, uint32
 }
 
 __global__ void site_cov_kernel(const SiteArgs a) {
-    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t b = gt / SITE_TPB, t0 = gt % SITE_TPB;
-    if (b >= a.n) return;
-    const uint64_t v0 = a.var_off[b], v1 = a.var_off[b + 1];
-    if (v0 + t0 >= v1) return;
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.n_sites) return;
+    const uint32_t b = a.site_bubble[v];
+    const uint64_t v0 = a.var_off[b];
     const uint32_t nr = a.n_rows[b], L = a.aln_len[b], k = a.db.k;
     const char *R = a.rows + a.rows_off[b];
     const uint16_t *C = a.cls + a.cls_off[b];
     unsigned long long *cov_out = a.site_cov + a.cls_off[b];
     const bool skipped = a.skip && a.skip[b];
     uint32_t n_ind = 0;
-    uint64_t counted = v0;                                        // var_kind[v0 .. counted) is already in n_ind
-    for (uint64_t v = v0 + t0; v < v1; v += SITE_TPB) {
-        for (; counted < v; counted++) n_ind += a.var_kind[counted] == 1;
+    if (!skipped)
+        for (uint64_t u = v0; u < v; u++) n_ind += a.var_kind[u] == 1;     // indel sites before this one (:2390)
+    {
         const uint32_t c = a.var_col[v];
         const bool is_ind = a.var_kind[v] == 1;
         const uint16_t *cl = C + (v - v0) * nr;
@@ -702,7 +708,7 @@ struct pf_kmc {
     void *d_hash = nullptr;
     uint32_t build_status = 0;
     pf::DevBuf tile_seq;   // per-call scratch of the hash lookup (grow-only)
-    pf::DevBuf site_status, site_ncls, site_cov, site_skip;   // pf_site_cov outputs (grow-only)
+    pf::DevBuf site_status, site_ncls, site_cov, site_skip, site_map;   // pf_site_cov outputs (grow-only)
     pf::PinnedBuf h_site[5];
     uint64_t site_totals[2] = {0, 0};
     // host-pointer calls: the handle's own stream, staging and device buffers
@@ -995,7 +1001,7 @@ int pf_kmc_close(pf_kmc *db) {
     cudaFree(db->d_lut); cudaFree(db->d_sigmap); cudaFree(db->d_norm);
     cudaFree(db->d_rec); cudaFree(db->d_suf); cudaFree(db->d_cnt); cudaFree(db->d_hash);
     db->tile_seq.release();
-    db->site_status.release(); db->site_ncls.release(); db->site_cov.release(); db->site_skip.release();
+    db->site_status.release(); db->site_ncls.release(); db->site_cov.release(); db->site_skip.release(); db->site_map.release();
     for (auto &b : db->h_site) b.release();
     if (db->k_stream) { cudaStreamSynchronize(db->k_stream); cudaStreamDestroy(db->k_stream); }
     db->k_stage.release();
@@ -1215,7 +1221,13 @@ int pf_site_cov_dev(pf_kmc *db, uint32_t low, uint32_t up, const void *d_skip, p
     a.skip = (const uint8_t *)d_skip; a.low = low; a.up = up;
     a.site_status = db->site_status.as<uint8_t>(); a.site_ncls = db->site_ncls.as<uint8_t>();
     a.site_cov = db->site_cov.as<unsigned long long>();
-    site_cov_kernel<<<(unsigned)(((uint64_t)n * SITE_TPB + 127) / 128), 128, 0, st>>>(a);
+    if ((rc = db->site_map.reserve(n_var * 4 + 16))) return rc;
+    a.site_bubble = db->site_map.as<uint32_t>(); a.n_sites = n_var;
+    if (n_var) {
+        site_map_kernel<<<(n + 255) / 256, 256, 0, st>>>(m.var_off, n, db->site_map.as<uint32_t>());
+        site_cov_kernel<<<(unsigned)((n_var + 127) / 128), 128, 0, st>>>(a);
+        ctx->launches++;
+    }
     ctx->launches++;
     PF_CUDA_TRY(cudaGetLastError());
     if (out_dev) {

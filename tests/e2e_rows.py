@@ -270,21 +270,22 @@ def reference_binaries():
     return (pf, bf) if os.path.exists(pf) and os.path.exists(bf) else None
 
 
-def run_reference_config0(workdir, genome=200000, depth=30, read_len=150, k=25, low=2, up=1000, seed=20261017, threads=1):
+def run_reference_config0(workdir, genome=200000, depth=30, read_len=150, k=25, low=2, up=1000, seed=20261017, threads=1, haplotypes=2,
+                          p_snp=0.01, p_indel=0.001):
     """BASELINE configs[0], scaled by `genome`: synthetic diploid (1 % SNP, 0.1 % indel), `depth`x error-free reads of random
     strand, Bifrost graph of the reads, KMC database = canonical k-mer counts of the reads; the unmodified PloidyFrost is run on
     it and its output directory is returned in the shape load_fixture() reads."""
     import subprocess
     from ploidyfrost_b200.synth import kmcdb, workload as wl
     pf, bf = reference_binaries()
-    w = wl.Workload(seed, genome, 2, p_snp=0.01, p_indel=0.001, n_threads=2)
-    haps = [bytes(w.haplotype(i)).decode() for i in range(2)]
+    w = wl.Workload(seed, genome, haplotypes, p_snp=p_snp, p_indel=p_indel, n_threads=2)
+    haps = [bytes(w.haplotype(i)).decode() for i in range(haplotypes)]
     w.close()
     rng = np.random.default_rng(seed)
     comp = str.maketrans("ACGT", "TGCA")
     reads = []
     for h in haps:
-        n = depth * len(h) // (2 * read_len)
+        n = depth * len(h) // (haplotypes * read_len)
         for a in rng.integers(0, len(h) - read_len, n):
             r = h[a:a + read_len]
             reads.append(r.translate(comp)[::-1] if rng.random() < 0.5 else r)

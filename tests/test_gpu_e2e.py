@@ -46,14 +46,21 @@ def test_reference_rows_with_lookup_phase_b_on_the_device(gpu_ctx, index):
         db.close()
 
 
-def test_config0_reference_run_from_the_cuda_path(gpu_ctx, tmp_path):
+LIVE_CASES = [(2, 200000, 0.001, 0.01),      # BASELINE configs[0] (scaled; PF_E2E_GENOME = 1000000 for the full size)
+              (4, 300000, 0.003, 0.01),      # tetraploid, three times the indel rate: 3-8 branches, sites after indels
+              (2, 300000, 0.005, 0.02)]      # variant-dense diploid: bubbles of up to 8 paths
+
+
+@pytest.mark.parametrize("hap,genome,p_indel,p_snp", LIVE_CASES)
+def test_config0_reference_run_from_the_cuda_path(gpu_ctx, tmp_path, hap, genome, p_indel, p_snp):
     """BASELINE configs[0] (diploid, 30x reads, k = 25; scaled to 200 kbp, PF_E2E_GENOME overrides): the unmodified PloidyFrost and
     Bifrost binaries of oracle/_ref run end to end on this box, then lookup-A, SequenceAlignment and lookup-B (pf_site_cov) of the
     CUDA path must regenerate every aligned row and every coverage row the reference wrote."""
     from ploidyfrost_b200 import capi
     if e2e_rows.reference_binaries() is None:
         pytest.skip("oracle/_ref/PloidyFrost not built (make -C oracle ref_full in the dev container)")
-    out, dbp = e2e_rows.run_reference_config0(str(tmp_path), genome=int(os.environ.get("PF_E2E_GENOME", "200000")))
+    out, dbp = e2e_rows.run_reference_config0(str(tmp_path), genome=int(os.environ.get("PF_E2E_GENOME", str(genome))) if hap == 2 and p_indel == 0.001 else genome,
+                                              haplotypes=hap, p_indel=p_indel, p_snp=p_snp, depth=15 * hap)
     meta, bubbles, _, _ = e2e_rows.load_fixture(out)
     db = capi.KmcDb(gpu_ctx, dbp)
     try:
@@ -61,7 +68,7 @@ def test_config0_reference_run_from_the_cuda_path(gpu_ctx, tmp_path):
         n_rows, n_branching = e2e_rows.check_against_reference(
             lambda *f: gpu_ctx.align(*f), lambda b, off: db.cov(b, off, mode=capi.LOOKUP_FWD_THEN_RC, low=2, up=1000), None, site_cov,
             fixture_dir=out)
-        assert n_rows > 1000 and n_branching > 50
+        assert n_rows > 1000 and n_branching > 50, (n_rows, n_branching)
     finally:
         db.close()
 

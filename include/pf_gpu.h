@@ -66,6 +66,9 @@ enum { PF_KMC_INDEX_AUTO = 0, PF_KMC_INDEX_VERBATIM = 1, PF_KMC_INDEX_HASH = 2 }
 int pf_kmc_open_ex(pf_ctx *ctx, const char *prefix, uint32_t flags, pf_kmc **db);
 /* PF_KMC_INDEX_VERBATIM or PF_KMC_INDEX_HASH: the layout this handle ended up with */
 int pf_kmc_index_kind(const pf_kmc *db);
+/* diagnostics: result of the open-time verification (bit 0: a prefix bucket is not strictly ascending, bit 1: a record is not
+ * in the bin its signature maps to, bit 2: a key is not the canonical form, bit 3: hash table overflow) */
+uint32_t pf_kmc_build_status(const pf_kmc *db);
 /* CKMCFile::Close (kmc_file.cpp:631) */
 int pf_kmc_close(pf_kmc *db);
 /* CKMCFile::Info (kmc_file.cpp Info(CKMCFileInfo&)) */
@@ -132,6 +135,11 @@ uint64_t pf_window_offsets(const uint64_t *seq_off, uint32_t n_seq, uint32_t k, 
  * Results equal the unpartitioned calls (PF_LOOKUP_FWD_THEN_RC is routed as the canonical key, which is the same
  * lookup on a both-strands database and refused otherwise). */
 int pf_kmc_open_part(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, pf_kmc **db);
+/* same with PF_KMC_INDEX_* flags.  By default a partition is a slice of the one-sector hash index -- keys are owned by
+ * mix(key) % n_parts, every rank stages the whole database once at open time and keeps its own keys -- and falls back to the
+ * bin / prefix partition of the verbatim image (PF_KMC_INDEX_VERBATIM forces it) when the database fails the verification.
+ * All ranks of a job must use the same layout (they route by the same owner function). */
+int pf_kmc_open_part_ex(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, uint32_t flags, pf_kmc **db);
 /* records held by this index (== total_kmers unless partitioned) */
 uint64_t pf_kmc_local_kmers(const pf_kmc *db);
 /* d_send_keys: u64[n_windows], d_send_idx: u32[n_windows] (device, caller-allocated).  On return h_send_off[0..n_parts]

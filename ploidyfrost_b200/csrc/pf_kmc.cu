@@ -381,7 +381,10 @@ __global__ void repack_records_kernel(const uint8_t *__restrict__ raw, uint64_t 
 // (any of these keeps the verbatim index) and whether every key is the canonical form of its k-mer:
 //   bit 2  key > reverse complement                                      -> FWD_THEN_RC stays a two-probe lookup
 enum { HB_UNSORTED = 1, HB_WRONG_BIN = 2, HB_NOT_CANONICAL = 4, HB_OVERFLOW = 8 };
-__global__ void kmc_hash_build_kernel(const KmcView db, const pfkmc::HashView hv, uint32_t *__restrict__ status) {
+// part / n_parts: a partition of the index inserts only the keys it owns (owner = mix(key) % n_parts, pfkmc::hash_owner); every
+// record is still verified.  status[1] (as u64 at status + 2) counts the inserted keys.
+__global__ void kmc_hash_build_kernel(const KmcView db, const pfkmc::HashView hv, uint32_t *__restrict__ status, uint32_t part,
+                                      uint32_t n_parts) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= db.N) return;
     if (lut_at(db, 0) > i) return;                     // before the first bucket: no prefix reaches it
@@ -416,7 +419,10 @@ __global__ void kmc_hash_build_kernel(const KmcView db, const pfkmc::HashView hv
         if (__ldg(db.sigmap + sig) != bin) st |= HB_WRONG_BIN;
     }
     if (key > revcomp64(key, db.k)) st |= HB_NOT_CANONICAL;
-    if (!pfkmc::hash_insert(hv, key, c)) st |= HB_OVERFLOW;
+    if (n_parts <= 1 || pfkmc::hash_owner(key, hv.kbits, n_parts) == part) {
+        if (!pfkmc::hash_insert(hv, key, c)) st |= HB_OVERFLOW;
+        else atomicAdd((unsigned long long *)(status + 2), 1ull);
+    }
     if (st) atomicOr(status, st);
 }
 
@@ -707,6 +713,7 @@ struct pf_kmc {
     pfkmc::HashView hview{};
     void *d_hash = nullptr;
     uint32_t build_status = 0;
+    uint64_t hash_inserted = 0;   // keys in the hash index (== total_kmers unless this handle is one partition)
     pf::DevBuf tile_seq;   // per-call scratch of the hash lookup (grow-only)
     pf::DevBuf site_status, site_ncls, site_cov, site_skip, site_map;   // pf_site_cov outputs (grow-only)
     pf::PinnedBuf h_site[5];
@@ -728,41 +735,53 @@ namespace {
 // (KMC2: bins with bin % n_parts == part; KMC1: the part-th range of ceil(4^p / n_parts) prefixes).
 // Re-hash the verbatim image into the one-sector index; on success the prefix table and the record arrays are released.
 // Returns PF_OK also when the hash index is not used (database fails the verification, or the slot does not fit).
-int kmc_build_hash(pf_kmc *db) {
+int kmc_build_hash(pf_kmc *db, uint32_t part = 0, uint32_t n_parts = 1) {
     pf_ctx *ctx = db->ctx;
     const KmcView &V = db->view;
     const uint64_t N = V.N;
     if (!N) return PF_OK;
+    const uint64_t n_local = n_parts > 1 ? N / n_parts + N / (4 * n_parts) + 1024 : N;   // a partition holds ~N / n_parts keys (+25 % slack)
     uint32_t b = 4;
-    while (b < 40 && (2ull << b) < N) b++;                                  // <= 2 keys per 4-slot bucket on average
+    while (b < 40 && (3ull << b) < 2 * n_local) b++;                        // <= 1.5 keys per 4-slot bucket on average
     const int need = (int)(2 * V.k + 8 * V.C + pfkmc::H_DIST_BITS) - 63;    // dist + rem + counter must leave the all-ones slot free
     if (need > (int)b) {
         if (need > 23 || need > 2 * (int)V.k) return PF_OK;                 // would inflate a small table past 256 MB: keep the verbatim index
         b = (uint32_t)need;
     }
     if (b > 2 * V.k) b = 2 * V.k;
-    if ((2 * V.k - b) + 8 * V.C + pfkmc::H_DIST_BITS > 63) return PF_OK;
     pfkmc::HashView hv;
-    hv.bucket_bits = b; hv.rem_bits = 2 * V.k - b; hv.cbits = 8 * V.C; hv.kbits = 2 * V.k;
-    const uint64_t bytes = 32ull << b;
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < bytes + (256ull << 20)) { cudaGetLastError(); return PF_OK; }
-    void *tab = nullptr, *d_status = nullptr;
-    if (cudaMalloc(&tab, bytes) != cudaSuccess) { cudaGetLastError(); return PF_OK; }
-    hv.tab = (unsigned long long *)tab;
-    cudaStream_t st = ctx->stream;
+    void *tab = nullptr;
+    uint64_t bytes = 0;
     uint32_t status = 0;
-    PF_CUDA_TRY(cudaMalloc(&d_status, 4));
-    PF_CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, st));
-    PF_CUDA_TRY(cudaMemsetAsync(tab, 0xFF, bytes, st));
-    kmc_hash_build_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(V, hv, (uint32_t *)d_status);
-    ctx->launches++;
-    PF_CUDA_TRY(cudaGetLastError());
-    PF_CUDA_TRY(cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, st));
-    PF_CUDA_TRY(cudaStreamSynchronize(st));
-    cudaFree(d_status);
-    db->build_status = status;
-    if (status & (HB_UNSORTED | HB_WRONG_BIN | HB_OVERFLOW)) { cudaFree(tab); return PF_OK; }
+    for (int attempt = 0;; attempt++) {   // a table that overflows (a key more than H_MAX_DIST buckets from home) is rebuilt once, twice as large
+        if (b > 2 * V.k || (2 * V.k - b) + 8 * V.C + pfkmc::H_DIST_BITS > 63) return PF_OK;
+        hv.bucket_bits = b; hv.rem_bits = 2 * V.k - b; hv.cbits = 8 * V.C; hv.kbits = 2 * V.k;
+        bytes = 32ull << b;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < bytes + (256ull << 20)) { cudaGetLastError(); return PF_OK; }
+        void *d_status = nullptr;
+        if (cudaMalloc(&tab, bytes) != cudaSuccess) { cudaGetLastError(); return PF_OK; }
+        hv.tab = (unsigned long long *)tab;
+        cudaStream_t st = ctx->stream;
+        uint32_t h_status[4] = {0, 0, 0, 0};
+        PF_CUDA_TRY(cudaMalloc(&d_status, 16));
+        PF_CUDA_TRY(cudaMemsetAsync(d_status, 0, 16, st));
+        PF_CUDA_TRY(cudaMemsetAsync(tab, 0xFF, bytes, st));
+        kmc_hash_build_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(V, hv, (uint32_t *)d_status, part, n_parts);
+        ctx->launches++;
+        PF_CUDA_TRY(cudaGetLastError());
+        PF_CUDA_TRY(cudaMemcpyAsync(h_status, d_status, 16, cudaMemcpyDeviceToHost, st));
+        PF_CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(d_status);
+        status = h_status[0];
+        db->build_status = status;
+        db->hash_inserted = (uint64_t)h_status[2] | ((uint64_t)h_status[3] << 32);
+        if (!(status & (HB_UNSORTED | HB_WRONG_BIN | HB_OVERFLOW))) break;
+        cudaFree(tab);
+        tab = nullptr;
+        if ((status & (HB_UNSORTED | HB_WRONG_BIN)) || attempt == 1) return PF_OK;
+        b++;
+    }
     db->hash_on = true;
     db->canonical_ok = !(status & HB_NOT_CANONICAL);
     db->hview = hv;
@@ -771,6 +790,27 @@ int kmc_build_hash(pf_kmc *db) {
     db->d_lut = db->d_rec = db->d_suf = db->d_cnt = nullptr;
     db->view.lut = nullptr; db->view.rec = nullptr; db->view.suf = nullptr; db->view.cnt = nullptr;
     db->device_bytes = bytes + (V.is_kmc2 ? ((1ull << (2 * V.sig_len)) * 8 + 4) : 0);
+    return PF_OK;
+}
+
+int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, uint32_t flags, pf_kmc **out);
+
+// A partition of the hash index: the whole database is staged once (verbatim image), the keys this partition owns
+// (mix(key) % n_parts == part) are inserted into a table sized for N / n_parts, the image is released.  Falls back to the
+// bin / prefix partition of the verbatim layout when the database fails the verification.
+int kmc_open_hash_part(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, pf_kmc **out) {
+    pf_kmc *db = nullptr;
+    int rc = kmc_open_impl(ctx, prefix, 0, 1, PF_KMC_INDEX_VERBATIM, &db);
+    if (rc) return rc;
+    rc = kmc_build_hash(db, part, n_parts);
+    if (rc) { pf_kmc_close(db); return rc; }
+    if (!db->hash_on) {   // not hashable: the verbatim partition
+        pf_kmc_close(db);
+        return kmc_open_impl(ctx, prefix, part, n_parts, PF_KMC_INDEX_VERBATIM, out);
+    }
+    db->view.n_parts = n_parts; db->view.part = part;
+    db->local_kmers = db->hash_inserted;
+    *out = db;
     return PF_OK;
 }
 
@@ -980,10 +1020,21 @@ int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **out) { return kmc_open
 
 int pf_kmc_open_ex(pf_ctx *ctx, const char *prefix, uint32_t flags, pf_kmc **out) { return kmc_open_impl(ctx, prefix, 0, 1, flags, out); }
 
+/* diagnostics: what the open-time verification found (bit 0 unsorted bucket, 1 record in the wrong bin, 2 non-canonical key,
+ * 3 table overflow); 0 for a handle that never tried the hash index */
+uint32_t pf_kmc_build_status(const pf_kmc *db) { return db ? db->build_status : 0; }
+
 int pf_kmc_index_kind(const pf_kmc *db) { return db ? (db->hash_on ? PF_KMC_INDEX_HASH : PF_KMC_INDEX_VERBATIM) : PF_E_INVALID; }
 
+int pf_kmc_open_part_ex(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, uint32_t flags, pf_kmc **out) {
+    if (!ctx || !prefix || !out) { pf::set_error("pf_kmc_open_part: null argument"); return PF_E_INVALID; }
+    if (n_parts == 0 || part >= n_parts || n_parts > 254) { pf::set_error("pf_kmc_open_part: bad partition %u of %u", part, n_parts); return PF_E_INVALID; }
+    if (n_parts > 1 && !(flags & PF_KMC_INDEX_VERBATIM)) return kmc_open_hash_part(ctx, prefix, part, n_parts, out);
+    return kmc_open_impl(ctx, prefix, part, n_parts, flags | (n_parts > 1 ? (uint32_t)PF_KMC_INDEX_VERBATIM : 0u), out);
+}
+
 int pf_kmc_open_part(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, pf_kmc **out) {
-    return kmc_open_impl(ctx, prefix, part, n_parts, PF_KMC_INDEX_VERBATIM, out);
+    return pf_kmc_open_part_ex(ctx, prefix, part, n_parts, env_open_flags(), out);
 }
 
 uint64_t pf_kmc_local_kmers(const pf_kmc *db) { return db ? db->local_kmers : 0; }
@@ -1077,11 +1128,12 @@ int pf_kmc_lookup_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const v
         ctx->launches++;
         static int per_sm = 0;
         if (!per_sm) {
-            PF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pfkmc::kmc_hash_lookup_kernel, pfkmc::HL_THREADS, 0));
+            PF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pfkmc::kmc_hash_lookup_kernel<false>, pfkmc::HL_THREADS, 0));
             if (per_sm < 1) per_sm = 1;
         }
         const unsigned hgrid = (unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)ctx->sm_count * per_sm);
-        pfkmc::kmc_hash_lookup_kernel<<<hgrid, pfkmc::HL_THREADS, 0, st>>>(a);
+        a.n_parts = 1; a.route_keys = nullptr; a.route_owner = nullptr;
+        pfkmc::kmc_hash_lookup_kernel<false><<<hgrid, pfkmc::HL_THREADS, 0, st>>>(a);
         ctx->launches++;
         PF_CUDA_TRY(cudaGetLastError());
         return PF_OK;
@@ -1124,11 +1176,28 @@ int pf_kmc_route_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const vo
     if ((rc = R->h_bounds.reserve((P + 2) * 8))) return rc;
     // windows shorter sequences never produce stay 0xFF (not sent)
     PF_CUDA_TRY(cudaMemsetAsync(R->owner.p, 0xFF, n_windows, st));
+    if (db->hash_on) {   // partition of the hash index: keys are owned by mix(key) % n_parts
+        pfkmc::HashLookupArgs a;
+        a.hv = db->hview; a.k = db->view.k; a.min_count = db->view.min_count; a.max_count = db->view.max_count;
+        a.mode = mode == PF_LOOKUP_FWD ? (int)PF_LOOKUP_FWD : (int)PF_LOOKUP_CANONICAL;   // FWD_THEN_RC travels as the canonical key
+        a.bases = (const uint8_t *)d_bases; a.n_bases = n_bases; a.seq_off = (const uint64_t *)d_seq_off;
+        a.win_off = (const uint64_t *)d_win_off; a.n_seq = n_seq; a.low = 0; a.up = 0;
+        a.counts = nullptr; a.found = nullptr; a.cov = nullptr;
+        a.n_tiles = (n_bases + pfkmc::HL_TILE - 1) / pfkmc::HL_TILE;
+        if ((rc = db->tile_seq.reserve((a.n_tiles + 1) * 4))) return rc;
+        a.tile_seq = db->tile_seq.as<uint32_t>();
+        a.n_parts = P; a.route_keys = R->keys.as<unsigned long long>(); a.route_owner = R->owner.as<uint8_t>();
+        pfkmc::tile_seq_kernel<<<(unsigned)((a.n_tiles + 1 + 255) / 256), 256, 0, st>>>(a.seq_off, n_seq, a.n_tiles, db->tile_seq.as<uint32_t>());
+        const unsigned hgrid = (unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)ctx->sm_count * 3);
+        pfkmc::kmc_hash_lookup_kernel<true><<<hgrid, pfkmc::HL_THREADS, 0, st>>>(a);
+        ctx->launches++;
+    } else {
     const uint64_t n_tiles = (n_bases + LK_TILE - 1) / LK_TILE;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 6);
     kmc_lookup_kernel<true><<<grid, LK_THREADS, 0, st>>>(db->view, (const uint8_t *)d_bases, n_bases, (const uint64_t *)d_seq_off,
                                                         (const uint64_t *)d_win_off, n_seq, mode, 0, 0, nullptr, nullptr, nullptr, n_tiles,
                                                         R->keys.as<unsigned long long>(), R->owner.as<uint8_t>());
+    }
     // bucket by owner: stable radix sort of (owner, window index) on the 8 owner bits
     {
         uint32_t *idx = R->idx.as<uint32_t>();   // window indices 0..n-1 as the sort's value array

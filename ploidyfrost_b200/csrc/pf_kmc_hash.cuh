@@ -50,6 +50,11 @@ __host__ __device__ __forceinline__ uint64_t hash_mix(uint64_t key, uint32_t kbi
     return h;
 }
 
+// which partition of a partitioned hash index owns a key: the low end of the mixed value (the bucket uses the high end)
+__host__ __device__ __forceinline__ uint32_t hash_owner(uint64_t key, uint32_t kbits, uint32_t n_parts) {
+    return (uint32_t)(hash_mix(key, kbits) % n_parts);
+}
+
 __device__ __forceinline__ void ld_bucket(const unsigned long long *p, unsigned long long v[4]) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3])
@@ -128,6 +133,9 @@ struct HashLookupArgs {
     uint8_t *found;
     pf_cov_t *cov;
     uint64_t n_tiles;
+    uint32_t n_parts;                      // ROUTE instantiation: partitions of the index
+    unsigned long long *route_keys;        // ROUTE: key of every live window ...
+    uint8_t *route_owner;                  // ... and the partition that owns it (windows that are not looked up keep 0xFF)
     const uint32_t *tile_seq;   // [n_tiles + 1] sequence containing the first base of each tile (tile_seq_kernel)
 };
 
@@ -163,6 +171,9 @@ struct CovRun {   // readCov partials of one (thread, sequence) run  (CDBG.cpp:2
 // window starts, takes its first k-mer from three packed words, rolls the forward and reverse-complement values from
 // base to base in registers, and keeps four bucket loads in flight at a time.  The readCov reductions are accumulated
 // per (thread, sequence) run and leave the warp as one set of atomics per (warp, sequence).
+// ROUTE = true (partitioned index): nothing is looked up here -- the key of every live window and the partition that owns it
+// are written out for the exchange (pf_kmc_route_dev).
+template <bool ROUTE>
 __global__ void __launch_bounds__(HL_THREADS, 3) kmc_hash_lookup_kernel(const HashLookupArgs a) {
     __shared__ uint32_t s_pk[HL_WORDS];
     __shared__ uint32_t s_bad[HL_WORDS];
@@ -289,12 +300,15 @@ __global__ void __launch_bounds__(HL_THREADS, 3) kmc_hash_lookup_kernel(const Ha
                     const uint64_t key = a.mode == PF_LOOKUP_CANONICAL ? (fwd < rc ? fwd : rc) : fwd;
                     alt[u] = rc;
                     hk[u] = hash_mix(key, a.hv.kbits);
-                    if (st[u] == 2) ld_bucket(a.hv.tab + 4 * (hk[u] >> a.hv.rem_bits), bk[u]);
+                    if (ROUTE) {
+                        if (st[u] == 2) { a.route_keys[wi[u]] = key; a.route_owner[wi[u]] = (uint8_t)(hk[u] % a.n_parts); }
+                    } else if (st[u] == 2) ld_bucket(a.hv.tab + 4 * (hk[u] >> a.hv.rem_bits), bk[u]);
                     const uint64_t c = rest >> 62;                           // roll to the next window
                     rest <<= 2;
                     fwd = ((fwd << 2) | c) & kmask;
                     rc = (rc >> 2) | ((3ull - c) << rc_shift);
                 }
+                if (ROUTE) continue;
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     if (st[u] == 0) continue;
@@ -322,7 +336,7 @@ __global__ void __launch_bounds__(HL_THREADS, 3) kmc_hash_lookup_kernel(const Ha
                 }
             }
         }
-        if (a.cov) {   // the thread's last run leaves through the warp: one set of atomics per (warp, sequence)
+        if (!ROUTE && a.cov) {   // the thread's last run leaves through the warp: one set of atomics per (warp, sequence)
             const uint32_t grp = __match_any_sync(0xffffffffu, run.s);
             const uint32_t leader = __ffs(grp) - 1;
             const uint32_t s_lo = __reduce_add_sync(grp, (uint32_t)(run.sum & 0xFFFFFu));

@@ -24,8 +24,9 @@ def _dev_batch(seqs, k, dev):
     return bases, off, wo, d_b, torch.from_numpy(off.astype(np.int64)).to(dev), torch.from_numpy(wo.astype(np.int64)).to(dev)
 
 
+@pytest.mark.parametrize("index", ["auto", "verbatim"])
 @pytest.mark.parametrize("ver,p,n_parts", [(0x200, 5, 4), (0x200, 9, 3), (0, 5, 4), (0, 1, 8), (0, 9, 5), (0x200, 5, 1)])
-def test_partitioned_lookup_equals_replicated(gpu_ctx, tmp_path, ver, p, n_parts):
+def test_partitioned_lookup_equals_replicated(gpu_ctx, tmp_path, ver, p, n_parts, index):
     from ploidyfrost_b200 import capi
     k = 25
     dev = torch.device("cuda", 0)
@@ -35,8 +36,9 @@ def test_partitioned_lookup_equals_replicated(gpu_ctx, tmp_path, ver, p, n_parts
     bases, off, wo, d_b, d_o, d_w = _dev_batch(seqs, k, dev)
     nw, ns = int(wo[-1]), len(off) - 1
     full = capi.KmcDb(gpu_ctx, prefix)
-    parts = [capi.KmcDb(gpu_ctx, prefix, part=r, n_parts=n_parts) for r in range(n_parts)]
+    parts = [capi.KmcDb(gpu_ctx, prefix, part=r, n_parts=n_parts, index=index) for r in range(n_parts)]
     try:
+        assert all(d.index_kind == ("hash" if index == "auto" else "verbatim") for d in parts)
         assert sum(d.local_kmers for d in parts) == full.info["total_kmers"]
         if n_parts > 1:
             assert max(d.local_kmers for d in parts) < full.info["total_kmers"]

@@ -194,8 +194,10 @@ def workload_config(args, n_bubbles, info):
             "batch_bubbles": int(n_bubbles), "db_kmers": (info or {}).get("N"),
             "step": "lookup-A (readCov of entrance + branch unitigs) + SequenceAlignment per bubble + lookup-B (site k-mers of the branching bubbles)",
             "l2": "flushed between timed steps (256 MiB memset); KMC index (>2 GB) exceeds L2",
-            "kmc_index": "partitioned by bin % n_gpus, queries routed by NCCL all-to-all" if getattr(args, "sharded_db", False)
-                         else "replicated on every GPU"}
+            "kmc_index": ("hash index partitioned by mix(key) % n_gpus; " +
+                          ("other partitions mapped through CUDA IPC, buckets loaded over NVLink inside the lookup kernel"
+                           if getattr(args, "peer_active", False) else "queries routed by NCCL all-to-all"))
+                         if getattr(args, "sharded_db", False) else "replicated on every GPU"}
 
 
 def main():
@@ -213,6 +215,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--region-rank", type=int, default=None,
                     help="diagnostics: take the batch another rank would take (its region of the genome) on this GPU")
+    ap.add_argument("--no-peer-lookup", action="store_true",
+                    help="with --sharded-db: keep the route / NCCL all-to-all / scatter path instead of mapping the other partitions "
+                         "through CUDA IPC and loading their buckets over NVLink")
     ap.add_argument("--sharded-db", action="store_true",
                     help="partition the KMC index across the ranks (bin % world) and route queries with an NCCL all-to-all "
                          "instead of replicating it (BASELINE config 3 variant)")
@@ -254,9 +259,12 @@ def main():
         from ploidyfrost_b200 import sharded
         db = capi.KmcDb(ctx, prefix, part=rank, n_parts=world)
         sh = sharded.ShardedKmcDb(db)
+        peer = (not args.no_peer_lookup) and sharded.attach_peers(db, dev)
     else:
         db = capi.KmcDb(ctx, prefix)
+        peer = False
     barrier()
+    args.peer_active = bool(peer)
     t_setup = time.perf_counter() - t_setup
 
     # ---- device-resident batch ----
@@ -288,7 +296,7 @@ def main():
     def step_device(ev=None):
         if ev:
             ev[0].record(stream)
-        if args.sharded_db:
+        if args.sharded_db and not peer:
             sh.lookup(d_lb, d_lo, d_wo, n_win, mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up, stream=stream)
         else:
             db.lookup_dev(d_lb.data_ptr(), len(lb), d_lo.data_ptr(), d_wo.data_ptr(), n_lseq, n_win, capi.LOOKUP_CANONICAL, args.low,
@@ -348,7 +356,7 @@ def main():
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        if args.sharded_db:   # no host-pointer form of the partitioned lookup: copy in, route/exchange/lookup, copy the cov records out
+        if args.sharded_db and not peer:   # no host-pointer form of the partitioned lookup: copy in, route/exchange/lookup, copy the cov records out
             with torch.cuda.stream(stream):
                 e_lb = h_lb[0].to(dev, non_blocking=True)
                 e_lo = h_lo[0].to(dev, non_blocking=True).view(torch.int64)
@@ -362,7 +370,7 @@ def main():
         t1 = time.perf_counter()
         msa = ctx.align(h_ab[1], h_ao[1], h_bo[1], copy=False)   # views of the pinned result arena (C-ABI ownership rule)
         sites = db.site_cov(args.low, args.up, skip_np, copy=False) if do_sites else None   # views, like the alignment result
-        if not args.sharded_db:
+        if not args.sharded_db or peer:
             db.wait()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0

@@ -140,6 +140,15 @@ int pf_kmc_open_part(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_
  * bin / prefix partition of the verbatim image (PF_KMC_INDEX_VERBATIM forces it) when the database fails the verification.
  * All ranks of a job must use the same layout (they route by the same owner function). */
 int pf_kmc_open_part_ex(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, uint32_t flags, pf_kmc **db);
+/*
+ * Peer-memory form (one process per GPU of one NVLink / NVSwitch box): every rank exports its slice of the hash index as a
+ * 128-byte blob (CUDA IPC handle + table geometry), the ranks exchange the blobs by any transport, and pf_kmc_attach_peers
+ * maps the other slices.  After that the ordinary calls on the partition handle -- pf_kmc_lookup_dev, pf_kmc_counts, pf_kmc_cov,
+ * pf_kmc_cov_async -- answer EVERY query in one kernel: the owner of a key is mix(key) % n_parts and its bucket is loaded from
+ * the owner's HBM over NVLink (one 32-byte read per lookup); there is no route / all-to-all / scatter step.
+ */
+int pf_kmc_export_ipc(pf_kmc *db, void *blob128);
+int pf_kmc_attach_peers(pf_kmc *db, const void *blobs, uint32_t n_parts);
 /* records held by this index (== total_kmers unless partitioned) */
 uint64_t pf_kmc_local_kmers(const pf_kmc *db);
 /* d_send_keys: u64[n_windows], d_send_idx: u32[n_windows] (device, caller-allocated).  On return h_send_off[0..n_parts]

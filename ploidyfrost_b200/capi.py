@@ -23,7 +23,7 @@ LOOKUP_CANONICAL, LOOKUP_FWD_THEN_RC, LOOKUP_FWD = 0, 1, 2
 # every symbol include/pf_gpu.h declares (tests check that the library exports all of them)
 EXPORTS = ["pf_init", "pf_shutdown", "pf_last_error", "pf_version", "pf_launch_count", "pf_sync", "pf_kmc_open",
            "pf_kmc_close", "pf_kmc_info", "pf_kmc_set_min_count", "pf_kmc_set_max_count", "pf_kmc_reset_min_max",
-           "pf_kmc_device_bytes", "pf_kmc_open_ex", "pf_kmc_index_kind", "pf_kmc_build_status", "pf_kmc_open_part", "pf_kmc_open_part_ex", "pf_kmc_local_kmers", "pf_kmc_route_dev", "pf_kmc_lookup_keys_dev",
+           "pf_kmc_device_bytes", "pf_kmc_open_ex", "pf_kmc_index_kind", "pf_kmc_build_status", "pf_kmc_open_part", "pf_kmc_open_part_ex", "pf_kmc_export_ipc", "pf_kmc_attach_peers", "pf_kmc_local_kmers", "pf_kmc_route_dev", "pf_kmc_lookup_keys_dev",
            "pf_kmc_scatter_dev", "pf_kmc_counts", "pf_kmc_cov", "pf_kmc_cov_async", "pf_kmc_wait", "pf_site_cov", "pf_site_cov_dev", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
            "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_heavy_queued", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32"]
 
@@ -90,6 +90,8 @@ def load():
     L.pf_site_cov_dev.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pf_kmc_open_part.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.pf_kmc_open_part_ex.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.pf_kmc_export_ipc.argtypes = [C.c_void_p, C.c_void_p]
+    L.pf_kmc_attach_peers.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.pf_kmc_local_kmers.argtypes = [C.c_void_p]
     L.pf_kmc_local_kmers.restype = C.c_uint64
     L.pf_kmc_route_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int,
@@ -292,6 +294,16 @@ class KmcDb:
     @property
     def device_bytes(self) -> int:
         return int(self.lib.pf_kmc_device_bytes(self.h))
+
+    def export_ipc(self) -> np.ndarray:
+        blob = np.zeros(128, np.uint8)
+        _check(self.lib.pf_kmc_export_ipc(self.h, blob.ctypes.data), "pf_kmc_export_ipc")
+        return blob
+
+    def attach_peers(self, blobs: np.ndarray):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8)
+        assert blobs.size == 128 * self.n_parts
+        _check(self.lib.pf_kmc_attach_peers(self.h, blobs.ctypes.data, self.n_parts), "pf_kmc_attach_peers")
 
     @property
     def build_status(self) -> int:

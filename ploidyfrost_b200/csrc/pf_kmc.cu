@@ -713,7 +713,11 @@ struct pf_kmc {
     pfkmc::HashView hview{};
     void *d_hash = nullptr;
     uint32_t build_status = 0;
-    uint64_t hash_inserted = 0;   // keys in the hash index (== total_kmers unless this handle is one partition)
+    uint64_t hash_inserted = 0;
+    // peer-memory form of a partitioned index: the slices of the other partitions mapped through CUDA IPC
+    const unsigned long long *peer_tab[pfkmc::PF_MAX_PEERS] = {nullptr};
+    void *peer_mapped[pfkmc::PF_MAX_PEERS] = {nullptr};
+    bool peers_attached = false;   // keys in the hash index (== total_kmers unless this handle is one partition)
     pf::DevBuf tile_seq;   // per-call scratch of the hash lookup (grow-only)
     pf::DevBuf site_status, site_ncls, site_cov, site_skip, site_map;   // pf_site_cov outputs (grow-only)
     pf::PinnedBuf h_site[5];
@@ -1051,6 +1055,7 @@ int pf_kmc_close(pf_kmc *db) {
     }
     cudaFree(db->d_lut); cudaFree(db->d_sigmap); cudaFree(db->d_norm);
     cudaFree(db->d_rec); cudaFree(db->d_suf); cudaFree(db->d_cnt); cudaFree(db->d_hash);
+    for (auto &m : db->peer_mapped) if (m) cudaIpcCloseMemHandle(m);
     db->tile_seq.release();
     db->site_status.release(); db->site_ncls.release(); db->site_cov.release(); db->site_skip.release(); db->site_map.release();
     for (auto &b : db->h_site) b.release();
@@ -1103,7 +1108,7 @@ int pf_kmc_lookup_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const v
     if (!db) { pf::set_error("pf_kmc_lookup_dev: null database"); return PF_E_INVALID; }
     if (mode < PF_LOOKUP_CANONICAL || mode > PF_LOOKUP_FWD) { pf::set_error("pf_kmc_lookup_dev: bad mode %d", mode); return PF_E_INVALID; }
     if (n_windows >= (1ull << 32)) { pf::set_error("pf_kmc_lookup_dev: more than 2^32-1 windows in one call; split the batch"); return PF_E_INVALID; }
-    if (db->view.n_parts > 1) { pf::set_error("pf_kmc_lookup_dev: this index holds one partition of the database; use pf_kmc_route_dev / pf_kmc_lookup_keys_dev"); return PF_E_INVALID; }
+    if (db->view.n_parts > 1 && !db->peers_attached) { pf::set_error("pf_kmc_lookup_dev: this index holds one partition of the database; use pf_kmc_route_dev / pf_kmc_lookup_keys_dev, or attach the other partitions (pf_kmc_attach_peers)"); return PF_E_INVALID; }
     pf_ctx *ctx = db->ctx;
     PF_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
@@ -1128,12 +1133,15 @@ int pf_kmc_lookup_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const v
         ctx->launches++;
         static int per_sm = 0;
         if (!per_sm) {
-            PF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pfkmc::kmc_hash_lookup_kernel<false>, pfkmc::HL_THREADS, 0));
+            PF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pfkmc::kmc_hash_lookup_kernel<0>, pfkmc::HL_THREADS, 0));
             if (per_sm < 1) per_sm = 1;
         }
         const unsigned hgrid = (unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)ctx->sm_count * per_sm);
-        a.n_parts = 1; a.route_keys = nullptr; a.route_owner = nullptr;
-        pfkmc::kmc_hash_lookup_kernel<false><<<hgrid, pfkmc::HL_THREADS, 0, st>>>(a);
+        a.n_parts = db->view.n_parts; a.route_keys = nullptr; a.route_owner = nullptr;
+        a.peer_lookup = db->peers_attached ? 1u : 0u;
+        for (int i = 0; i < pfkmc::PF_MAX_PEERS; i++) a.peer_tab[i] = db->peer_tab[i];
+        if (db->peers_attached) pfkmc::kmc_hash_lookup_kernel<2><<<hgrid, pfkmc::HL_THREADS, 0, st>>>(a);
+        else pfkmc::kmc_hash_lookup_kernel<0><<<hgrid, pfkmc::HL_THREADS, 0, st>>>(a);
         ctx->launches++;
         PF_CUDA_TRY(cudaGetLastError());
         return PF_OK;
@@ -1187,9 +1195,11 @@ int pf_kmc_route_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const vo
         if ((rc = db->tile_seq.reserve((a.n_tiles + 1) * 4))) return rc;
         a.tile_seq = db->tile_seq.as<uint32_t>();
         a.n_parts = P; a.route_keys = R->keys.as<unsigned long long>(); a.route_owner = R->owner.as<uint8_t>();
+        a.peer_lookup = 0;
+        for (int i = 0; i < pfkmc::PF_MAX_PEERS; i++) a.peer_tab[i] = nullptr;
         pfkmc::tile_seq_kernel<<<(unsigned)((a.n_tiles + 1 + 255) / 256), 256, 0, st>>>(a.seq_off, n_seq, a.n_tiles, db->tile_seq.as<uint32_t>());
         const unsigned hgrid = (unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)ctx->sm_count * 3);
-        pfkmc::kmc_hash_lookup_kernel<true><<<hgrid, pfkmc::HL_THREADS, 0, st>>>(a);
+        pfkmc::kmc_hash_lookup_kernel<1><<<hgrid, pfkmc::HL_THREADS, 0, st>>>(a);
         ctx->launches++;
     } else {
     const uint64_t n_tiles = (n_bases + LK_TILE - 1) / LK_TILE;
@@ -1264,6 +1274,56 @@ int pf_kmc_scatter_dev(pf_kmc *db, const void *d_send_idx, uint64_t n_sent, cons
         ctx->launches++;
     }
     PF_CUDA_TRY(cudaGetLastError());
+    return PF_OK;
+}
+
+// ---- peer-memory form of the partitioned index ---------------------------------------------------------------------------
+struct PeerBlob {   // 128 bytes exchanged between the ranks (any transport)
+    cudaIpcMemHandle_t handle;       // 64 bytes
+    uint32_t bucket_bits, rem_bits, cbits, kbits, part, n_parts, hash_on, pad;
+    uint8_t reserved[32];
+};
+static_assert(sizeof(PeerBlob) == 128, "PeerBlob layout");
+
+int pf_kmc_export_ipc(pf_kmc *db, void *blob128) {
+    if (!db || !blob128) { pf::set_error("pf_kmc_export_ipc: null argument"); return PF_E_INVALID; }
+    if (!db->hash_on || !db->d_hash) { pf::set_error("pf_kmc_export_ipc: only a hash-index partition can be shared"); return PF_E_UNSUPPORTED; }
+    PF_CUDA_TRY(cudaSetDevice(db->ctx->device));
+    PeerBlob b;
+    memset(&b, 0, sizeof(b));
+    PF_CUDA_TRY(cudaIpcGetMemHandle(&b.handle, db->d_hash));
+    b.bucket_bits = db->hview.bucket_bits; b.rem_bits = db->hview.rem_bits; b.cbits = db->hview.cbits; b.kbits = db->hview.kbits;
+    b.part = db->view.part; b.n_parts = db->view.n_parts; b.hash_on = 1;
+    memcpy(blob128, &b, sizeof(b));
+    return PF_OK;
+}
+
+int pf_kmc_attach_peers(pf_kmc *db, const void *blobs, uint32_t n_parts) {
+    if (!db || !blobs) { pf::set_error("pf_kmc_attach_peers: null argument"); return PF_E_INVALID; }
+    if (!db->hash_on || n_parts != db->view.n_parts || n_parts > (uint32_t)pfkmc::PF_MAX_PEERS) {
+        pf::set_error("pf_kmc_attach_peers: needs a hash-index partition and one blob per partition (<= %d)", pfkmc::PF_MAX_PEERS);
+        return PF_E_INVALID;
+    }
+    PF_CUDA_TRY(cudaSetDevice(db->ctx->device));
+    const PeerBlob *B = (const PeerBlob *)blobs;
+    for (uint32_t r = 0; r < n_parts; r++) {
+        if (!B[r].hash_on || B[r].part != r || B[r].n_parts != n_parts || B[r].bucket_bits != db->hview.bucket_bits ||
+            B[r].rem_bits != db->hview.rem_bits || B[r].cbits != db->hview.cbits) {
+            pf::set_error("pf_kmc_attach_peers: partition %u has a different table geometry", r);
+            return PF_E_INVALID;
+        }
+        if (r == db->view.part) { db->peer_tab[r] = (const unsigned long long *)db->d_hash; continue; }
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, B[r].handle, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            pf::set_error("pf_kmc_attach_peers: cudaIpcOpenMemHandle for partition %u failed: %s", r, cudaGetErrorString(e));
+            cudaGetLastError();
+            return PF_E_CUDA;
+        }
+        db->peer_mapped[r] = p;
+        db->peer_tab[r] = (const unsigned long long *)p;
+    }
+    db->peers_attached = true;
     return PF_OK;
 }
 
@@ -1348,7 +1408,7 @@ static int kmc_host_call(pf_kmc *db, const char *bases, const uint64_t *seq_off,
     pf_ctx *ctx = db->ctx;
     PF_CUDA_TRY(cudaSetDevice(ctx->device));
     if (n_seq == 0) return PF_OK;
-    if (db->view.n_parts > 1) { pf::set_error("pf_kmc_counts/cov: this index holds one partition of the database; use the route / lookup_keys / scatter calls"); return PF_E_INVALID; }
+    if (db->view.n_parts > 1 && !db->peers_attached) { pf::set_error("pf_kmc_counts/cov: this index holds one partition of the database; use the route / lookup_keys / scatter calls or pf_kmc_attach_peers"); return PF_E_INVALID; }
     if (!db->k_stream) PF_CUDA_TRY(cudaStreamCreateWithFlags(&db->k_stream, cudaStreamNonBlocking));
     PF_CUDA_TRY(cudaStreamSynchronize(db->k_stream));   // an earlier asynchronous call still owns the staging buffers
     const uint64_t n_bases = seq_off[n_seq] - seq_off[0];

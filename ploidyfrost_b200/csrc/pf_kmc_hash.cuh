@@ -68,7 +68,8 @@ __device__ __forceinline__ uint64_t revcomp2(uint64_t v, uint32_t k) {
 }
 
 // Search for the key whose mixed value is h, the home bucket's four slots already in v[].
-__device__ __forceinline__ bool hash_resolve(const HashView &hv, uint64_t h, unsigned long long v[4], uint32_t &cnt) {
+__device__ __forceinline__ bool hash_resolve(const HashView &hv, const unsigned long long *tab, uint64_t h, unsigned long long v[4],
+                                             uint32_t &cnt) {
     const uint64_t nb_mask = (1ull << hv.bucket_bits) - 1;
     const uint64_t home = h >> hv.rem_bits;
     const uint64_t rem = hv.rem_bits ? (h & ((1ull << hv.rem_bits) - 1)) : 0ull;
@@ -82,16 +83,20 @@ __device__ __forceinline__ bool hash_resolve(const HashView &hv, uint64_t h, uns
             open |= v[s] == H_EMPTY;
         }
         if (open || d == H_MAX_DIST) return false;
-        ld_bucket(hv.tab + 4 * ((home + d + 1) & nb_mask), v);
+        ld_bucket(tab + 4 * ((home + d + 1) & nb_mask), v);
     }
 }
+__device__ __forceinline__ bool hash_resolve(const HashView &hv, uint64_t h, unsigned long long v[4], uint32_t &cnt) {
+    return hash_resolve(hv, hv.tab, h, v, cnt);
+}
 
-__device__ __forceinline__ bool hash_find(const HashView &hv, uint64_t key, uint32_t &cnt) {
+__device__ __forceinline__ bool hash_find(const HashView &hv, const unsigned long long *tab, uint64_t key, uint32_t &cnt) {
     const uint64_t h = hash_mix(key, hv.kbits);
     unsigned long long v[4];
-    ld_bucket(hv.tab + 4 * (h >> hv.rem_bits), v);
-    return hash_resolve(hv, h, v, cnt);
+    ld_bucket(tab + 4 * (h >> hv.rem_bits), v);
+    return hash_resolve(hv, tab, h, v, cnt);
 }
+__device__ __forceinline__ bool hash_find(const HashView &hv, uint64_t key, uint32_t &cnt) { return hash_find(hv, hv.tab, key, cnt); }
 
 // Insert (build time).  Returns false when the key would sit more than H_MAX_DIST buckets from home.
 __device__ __forceinline__ bool hash_insert(const HashView &hv, uint64_t key, uint64_t counter) {
@@ -115,7 +120,8 @@ constexpr int HL_THREADS = 256;
 constexpr int HL_PPT = 8;                          // window starts per thread
 constexpr int HL_TILE = HL_THREADS * HL_PPT;       // 2048 base positions per tile
 constexpr int HL_WORDS = HL_TILE / 16 + 3;         // 16 bases per packed word + 48 bases of halo (k-1+7 <= 38)
-constexpr int HL_NSEQ = 512;                       // sequence ends staged per tile (more than that: per-thread search)
+constexpr int HL_NSEQ = 512;
+constexpr int PF_MAX_PEERS = 16;                       // sequence ends staged per tile (more than that: per-thread search)
 
 struct HashLookupArgs {
     HashView hv;
@@ -133,7 +139,9 @@ struct HashLookupArgs {
     uint8_t *found;
     pf_cov_t *cov;
     uint64_t n_tiles;
-    uint32_t n_parts;                      // ROUTE instantiation: partitions of the index
+    const unsigned long long *peer_tab[PF_MAX_PEERS];   // peer-memory form: the slice of every partition (own slice included), else unused
+    uint32_t peer_lookup;                  // 1: every lookup loads the owner's bucket through peer_tab (NVLink), n_parts partitions
+    uint32_t n_parts;                      // ROUTE instantiation / peer lookups: partitions of the index
     unsigned long long *route_keys;        // ROUTE: key of every live window ...
     uint8_t *route_owner;                  // ... and the partition that owns it (windows that are not looked up keep 0xFF)
     const uint32_t *tile_seq;   // [n_tiles + 1] sequence containing the first base of each tile (tile_seq_kernel)
@@ -171,10 +179,12 @@ struct CovRun {   // readCov partials of one (thread, sequence) run  (CDBG.cpp:2
 // window starts, takes its first k-mer from three packed words, rolls the forward and reverse-complement values from
 // base to base in registers, and keeps four bucket loads in flight at a time.  The readCov reductions are accumulated
 // per (thread, sequence) run and leave the warp as one set of atomics per (warp, sequence).
-// ROUTE = true (partitioned index): nothing is looked up here -- the key of every live window and the partition that owns it
+// MODE 1 = ROUTE (partitioned index): nothing is looked up here -- the key of every live window and the partition that owns it
 // are written out for the exchange (pf_kmc_route_dev).
-template <bool ROUTE>
+// MODE 2 (peer-memory form): like 0, but the bucket of a key is loaded from the slice of the partition that owns it.
+template <int MODE>
 __global__ void __launch_bounds__(HL_THREADS, 3) kmc_hash_lookup_kernel(const HashLookupArgs a) {
+    constexpr bool ROUTE = MODE == 1, PEER = MODE == 2;
     __shared__ uint32_t s_pk[HL_WORDS];
     __shared__ uint32_t s_bad[HL_WORDS];
     __shared__ uint32_t s_end[HL_NSEQ];   // end of the tile's sequences relative to the tile start (saturated)
@@ -302,7 +312,11 @@ __global__ void __launch_bounds__(HL_THREADS, 3) kmc_hash_lookup_kernel(const Ha
                     hk[u] = hash_mix(key, a.hv.kbits);
                     if (ROUTE) {
                         if (st[u] == 2) { a.route_keys[wi[u]] = key; a.route_owner[wi[u]] = (uint8_t)(hk[u] % a.n_parts); }
-                    } else if (st[u] == 2) ld_bucket(a.hv.tab + 4 * (hk[u] >> a.hv.rem_bits), bk[u]);
+                    } else if (st[u] == 2) {
+                        // peer-memory form: the bucket lives in the slice of the partition that owns the key (a load over NVLink)
+                        const unsigned long long *tab = PEER ? a.peer_tab[hk[u] % a.n_parts] : a.hv.tab;
+                        ld_bucket(tab + 4 * (hk[u] >> a.hv.rem_bits), bk[u]);
+                    }
                     const uint64_t c = rest >> 62;                           // roll to the next window
                     rest <<= 2;
                     fwd = ((fwd << 2) | c) & kmask;
@@ -315,10 +329,12 @@ __global__ void __launch_bounds__(HL_THREADS, 3) kmc_hash_lookup_kernel(const Ha
                     uint32_t cnt = 0;
                     bool ok = false;
                     if (st[u] == 2) {
-                        ok = hash_resolve(a.hv, hk[u], bk[u], cnt);
+                        const unsigned long long *tab = PEER ? a.peer_tab[hk[u] % a.n_parts] : a.hv.tab;
+                        ok = hash_resolve(a.hv, tab, hk[u], bk[u], cnt);
                         ok = ok && cnt >= a.min_count && (uint64_t)cnt <= a.max_count;            // kmc_file.cpp:1459
                         if (!ok && a.mode == PF_LOOKUP_FWD_THEN_RC) {                             // CDBG.cpp:38-43
-                            ok = hash_find(a.hv, alt[u], cnt);
+                            const unsigned long long *tab2 = PEER ? a.peer_tab[hash_mix(alt[u], a.hv.kbits) % a.n_parts] : a.hv.tab;
+                            ok = hash_find(a.hv, tab2, alt[u], cnt);
                             ok = ok && cnt >= a.min_count && (uint64_t)cnt <= a.max_count;
                         }
                         if (!ok) cnt = 0;

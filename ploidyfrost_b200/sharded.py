@@ -47,6 +47,32 @@ def exchange_back(reply: torch.Tensor, recv_counts, send_counts, group=None):
     return out
 
 
+def attach_peers(db, device, group=None) -> bool:
+    """Peer-memory form: every rank exports its slice of the hash index (CUDA IPC handle), the blobs are all-gathered and the
+    other slices are mapped (pf_kmc_attach_peers).  After that db.lookup_dev / db.cov answer every query in ONE kernel by
+    loading the owner's bucket over NVLink.  Returns False (and leaves the exchange path in place) when the partition is not a
+    hash slice or the mapping is refused."""
+    from . import capi
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1 or db.index_kind != "hash":
+        return False
+    world = dist.get_world_size(group)
+    ok = 1
+    try:
+        mine = torch.from_numpy(db.export_ipc()).to(device)
+    except capi.PfError:
+        mine, ok = torch.zeros(128, dtype=torch.uint8, device=device), 0
+    blobs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(blobs, mine, group=group)
+    if ok:
+        try:
+            db.attach_peers(torch.cat(blobs).cpu().numpy())
+        except capi.PfError:
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # all ranks or none
+    return bool(flag.item())
+
+
 class ShardedKmcDb:
     """One rank's view of a partitioned KMC database.  `db` is a capi.KmcDb opened with (part=rank, n_parts=world)."""
 

@@ -105,8 +105,19 @@ def _nccl_worker(rank, world, port, prefix, seqs, k, outdir):
         bases, off, wo, d_b, d_o, d_w = _dev_batch(mine, k, dev)
         cnt, fnd, cov = sh.lookup(d_b, d_o, d_w, int(wo[-1]), mode=0, low=1, up=3)
         torch.cuda.synchronize()
+        # peer-memory form: map the other partition through CUDA IPC, then the ordinary host-pointer calls answer everything
+        peer = sharded.attach_peers(db, dev)
+        p_cnt = p_fnd = np.zeros(0)
+        p_cov = np.zeros(0, np.uint8)
+        if peer:
+            for mode in (0, 1, 2):
+                pc, pf = db.counts(bases, off, mode=mode)
+                if mode == 0:
+                    p_cnt, p_fnd = pc, pf
+                    p_cov = db.cov(bases, off, mode=0, low=1, up=3).view(np.uint8)
+                np.savez(os.path.join(outdir, f"peer{rank}_m{mode}.npz"), cnt=pc, fnd=pf)
         np.savez(os.path.join(outdir, f"r{rank}.npz"), cnt=cnt.cpu().numpy().view(np.uint32), fnd=fnd.cpu().numpy(),
-                 cov=cov.cpu().numpy(), sent=sh.last_sent, recv=sh.last_received)
+                 cov=cov.cpu().numpy(), sent=sh.last_sent, recv=sh.last_received, peer=int(peer), p_cnt=p_cnt, p_fnd=p_fnd, p_cov=p_cov)
         dist.barrier()
         db.close()
         ctx.close()
@@ -133,5 +144,12 @@ def test_two_gpu_sharded_lookup_nccl(gpu_ctx, tmp_path):
             assert np.array_equal(z["cnt"], ec) and np.array_equal(z["fnd"], ef)
             assert np.array_equal(z["cov"].view(capi.COV_DTYPE), full.cov(bases, off, mode=0, low=1, up=3))
             assert int(z["sent"]) > 0 and int(z["recv"]) > 0
+            assert int(z["peer"]) == 1, "CUDA IPC mapping of the other partition was refused"
+            assert np.array_equal(z["p_cnt"], ec) and np.array_equal(z["p_fnd"], ef)
+            assert np.array_equal(z["p_cov"].view(capi.COV_DTYPE), full.cov(bases, off, mode=0, low=1, up=3))
+            for mode in (1, 2):
+                zz = np.load(os.path.join(str(tmp_path), f"peer{r}_m{mode}.npz"))
+                mc, mf = full.counts(bases, off, mode=mode)
+                assert np.array_equal(zz["cnt"], mc) and np.array_equal(zz["fnd"], mf), mode
     finally:
         full.close()

@@ -282,7 +282,7 @@ def main():
     d_bo = torch.from_numpy(bb.bubble_off.astype(np.int32)).to(dev)
     skip_np = np.ascontiguousarray(bb.bubble_type.astype(np.uint8))        # strict bubbles: class coverage = sum of branch means, no site k-mers
     d_skip = torch.from_numpy(skip_np).to(dev)
-    do_sites = not args.sharded_db                                          # lookup phase B needs the whole index on this GPU
+    do_sites = (not args.sharded_db) or peer                                # lookup phase B needs every k-mer reachable from this GPU
     seq_len = np.diff(bb.seq_off)
     max_len, max_rows = int(seq_len.max()), int(np.diff(bb.bubble_off).max())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

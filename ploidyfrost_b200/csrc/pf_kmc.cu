@@ -530,11 +530,14 @@ struct SiteArgs {
     unsigned long long *site_cov;
     const uint32_t *site_bubble;
     uint64_t n_sites;
+    const unsigned long long *peer_tab[pfkmc::PF_MAX_PEERS];   // peer-memory form of a partitioned index (else unused)
+    uint32_t peer_lookup, n_parts;
 };
 
 __device__ __forceinline__ bool site_lookup_one(const SiteArgs &a, uint64_t key, uint32_t &cnt) {
     if (a.hash_on) {
-        const bool ok = pfkmc::hash_find(a.hv, key, cnt);
+        const unsigned long long *tab = a.peer_lookup ? a.peer_tab[pfkmc::hash_owner(key, a.hv.kbits, a.n_parts)] : a.hv.tab;
+        const bool ok = pfkmc::hash_find(a.hv, tab, key, cnt);
         return ok && cnt >= a.db.min_count && (uint64_t)cnt <= a.db.max_count;
     }
     uint32_t bin = 0;
@@ -1330,7 +1333,7 @@ int pf_kmc_attach_peers(pf_kmc *db, const void *blobs, uint32_t n_parts) {
 // device-resident form: d_skip is a device pointer (or NULL); results stay in the handle's device buffers, `out_dev` gets DEVICE pointers
 int pf_site_cov_dev(pf_kmc *db, uint32_t low, uint32_t up, const void *d_skip, pf_site_batch_t *out_dev, void *cuda_stream) {
     if (!db) { pf::set_error("pf_site_cov_dev: null database"); return PF_E_INVALID; }
-    if (db->view.n_parts > 1) { pf::set_error("pf_site_cov: this index holds one partition of the database"); return PF_E_INVALID; }
+    if (db->view.n_parts > 1 && !db->peers_attached) { pf::set_error("pf_site_cov: this index holds one partition of the database (attach the others with pf_kmc_attach_peers)"); return PF_E_INVALID; }
     pf_ctx *ctx = db->ctx;
     PF_CUDA_TRY(cudaSetDevice(ctx->device));
     pf_msa_batch_t m;
@@ -1348,6 +1351,8 @@ int pf_site_cov_dev(pf_kmc *db, uint32_t low, uint32_t up, const void *d_skip, p
     a.n = n; a.status = m.status; a.n_rows = m.n_rows; a.aln_len = m.aln_len; a.rows_off = m.rows_off; a.rows = m.rows;
     a.var_off = m.var_off; a.var_col = m.var_col; a.var_kind = m.var_kind; a.cls_off = m.cls_off; a.cls = m.cls;
     a.skip = (const uint8_t *)d_skip; a.low = low; a.up = up;
+    a.peer_lookup = db->peers_attached ? 1u : 0u; a.n_parts = db->view.n_parts;
+    for (int i = 0; i < pfkmc::PF_MAX_PEERS; i++) a.peer_tab[i] = db->peer_tab[i];
     a.site_status = db->site_status.as<uint8_t>(); a.site_ncls = db->site_ncls.as<uint8_t>();
     a.site_cov = db->site_cov.as<unsigned long long>();
     if ((rc = db->site_map.reserve(n_var * 4 + 16))) return rc;

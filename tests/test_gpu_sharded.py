@@ -116,6 +116,17 @@ def _nccl_worker(rank, world, port, prefix, seqs, k, outdir):
                     p_cnt, p_fnd = pc, pf
                     p_cov = db.cov(bases, off, mode=0, low=1, up=3).view(np.uint8)
                 np.savez(os.path.join(outdir, f"peer{rank}_m{mode}.npz"), cnt=pc, fnd=pf)
+            # lookup phase B through the peers: the end-to-end fixture of the reference, index split over the two GPUs
+            from tests import e2e_rows
+            meta, eb, _, _ = e2e_rows.load_fixture()
+            edb = capi.KmcDb(ctx, os.path.join(e2e_rows.E2E, "db"), part=rank, n_parts=world)
+            assert sharded.attach_peers(edb, dev)
+            hook, _ = e2e_rows.device_site_cov_hook(edb, meta, eb)
+            n_rows, _ = e2e_rows.check_against_reference(lambda *f: ctx.align(*f),
+                                                         lambda b, o: edb.cov(b, o, mode=capi.LOOKUP_FWD_THEN_RC, low=2, up=1000), None, hook)
+            assert n_rows == 493
+            dist.barrier()
+            edb.close()
         np.savez(os.path.join(outdir, f"r{rank}.npz"), cnt=cnt.cpu().numpy().view(np.uint32), fnd=fnd.cpu().numpy(),
                  cov=cov.cpu().numpy(), sent=sh.last_sent, recv=sh.last_received, peer=int(peer), p_cnt=p_cnt, p_fnd=p_fnd, p_cov=p_cov)
         dist.barrier()

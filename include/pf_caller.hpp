@@ -116,8 +116,6 @@ class BubbleCaller {
         pf_site_batch_t sc;
         if (pf_site_cov(db_, lower_, upper_, skip.data(), &sc) != PF_OK) return fail(pf_last_error());
         // ---- rows ----
-        static const char *kNames[4] = {"bi", "tri", "tetra", "penta"};
-        (void)kNames;
         for (size_t q = 0; q < kept.size(); q++) {
             const Kept &kb = kept[q];
             const Bubble &b = batch[kb.src];
@@ -141,14 +139,12 @@ class BubbleCaller {
             const size_t n_ilen = (size_t)(m.ilen_off[q + 1] - m.ilen_off[q]);
             size_t indel = 0;
             for (size_t i = 0; i < n_var; i++) {
-                const uint32_t col = m.var_col[v0 + i];
                 const bool is_indel = m.var_kind[v0 + i] == 1;
                 size_t var_distance;                                               // :2312-2330
                 auto gap_to = [&](size_t a, size_t c) { return (size_t)(m.var_col[v0 + c] - m.var_col[v0 + a] - 1); };
                 if (i == 0) var_distance = n_var > 1 ? std::min(gap_to(0, 1), b.entrance_size) : std::min(b.entrance_size, b.exit_size);
                 else if (i == n_var - 1) var_distance = std::min(gap_to(i - 1, i), b.exit_size);
                 else var_distance = std::min(gap_to(i - 1, i), gap_to(i, i + 1));
-                (void)col;
                 unsigned maxnum = 0;
                 for (uint32_t r = 0; r < nr; r++) maxnum = std::max<unsigned>(maxnum, cls[i * nr + r]);
                 std::vector<double> tc(maxnum, 0.0);

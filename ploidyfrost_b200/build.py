@@ -22,7 +22,7 @@ def _stale() -> bool:
         return True
     t = os.path.getmtime(LIB)
     inc = os.path.join(ROOT, "include")
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(inc, f) for f in os.listdir(inc)]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(inc, f) for f in ("pf_gpu.h", "pf_types.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((mhz, rs))
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def summary(self):
         if not self.samples:
@@ -82,7 +82,7 @@ class ClockSampler(threading.Thread):
         sm = sorted(s[0] for s in self.samples)
         reasons = [n for n, bit in self.REASONS.items() if any(s[1] & bit for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples),
-                "source": "NVML (nvmlDeviceGetClockInfo / CurrentClocksEventReasons), 50 ms period, timed region + e2e loop"}
+                "source": "NVML (nvmlDeviceGetClockInfo / CurrentClocksEventReasons), 10 ms period, timed region + e2e loop"}
 
 
 def make_workload(args, rank, world, need_db_files, db_dir, device=None):

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE.  Regenerates the rows PloidyFrost writes for the bubbles it aligned (coverage / frequency files, `-t 1`
 dialect) from: the bubbles' raw branch strings, a SequenceAlignment implementation, a KMC lookup implementation.  The logic is a
 restatement of the reference's per-bubble caller -- strict bubbles CDBG.cpp:1186-1330 (= :1998-2189), branching bubbles
-:1440-1660 (= :2190-2575), site k-mers SURVEY.md Appendix C -- used to pin the oracle AND the CUDA path against the unmodified
+:1440-1660 (= :2190-2575); the per-site pieces (site k-mers, class coverages, VarDis) live in oracle/caller.py -- used to pin the oracle AND the CUDA path against the unmodified
 reference's own output files (tests/golden/e2e, made by tests/golden/make_golden_e2e.py)."""
 from __future__ import annotations
 
@@ -11,14 +11,10 @@ import os
 import numpy as np
 
 from oracle.bindings import flatten_bubbles, flatten_seqs, msa_bubble
+from oracle.caller import class_coverage, fmt, site_kmers, site_outcome, var_distance  # noqa: F401  (the CPU restatement)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 E2E = os.path.join(HERE, "golden", "e2e")
-
-
-def fmt(x: float) -> str:
-    """ostream << double at default precision == printf %g (6 significant digits)."""
-    return "%g" % x
 
 
 def parse_alignseq(path):
@@ -43,71 +39,6 @@ def parse_cov_files(d):
     return rows
 
 
-def site_kmers(rows, c, k, is_indel, n_indel_before):
-    """The k-mer each row contributes at variable column c (CDBG.cpp:2338-2388 indel sites, :2433-2472 SNP sites)."""
-    n = len(rows)
-    if is_indel:
-        cur = [c] * n
-        ext = [""] * n
-        while True:                                       # :2338-2357: extend every row by its next base until they differ
-            chars = set()
-            for r in range(n):
-                while rows[r][cur[r]] == "-":
-                    cur[r] += 1
-                ch = rows[r][cur[r]]
-                cur[r] += 1
-                ext[r] += ch
-                chars.add(ch)
-            if len(chars) > 1:
-                break
-        out = []
-        for r in range(n):
-            e = len(ext[r])
-            if n_indel_before == 0:                       # :2358-2365
-                start = c - k + e
-                assert start >= 0, "substr with a negative start throws in the reference"
-                out.append(rows[r][start:start + k - e] + ext[r])
-            else:                                         # :2366-2388
-                t = rows[r][:c].replace("-", "")
-                if len(t) < k - e:
-                    s = t + ext[r]
-                    x = cur[r]
-                    while len(s) < k:
-                        if rows[r][x] != "-":
-                            s += rows[r][x]
-                        x += 1
-                    out.append(s)
-                else:
-                    out.append(t[len(t) - (k - e):] + ext[r])
-        return out
-    if n_indel_before > 0:                                # :2433-2465
-        out = []
-        for r in range(n):
-            t = rows[r][:c + 1].replace("-", "")
-            if len(t) < k:
-                s = t
-                x = c + 1
-                while len(s) < k:
-                    if rows[r][x] != "-":
-                        s += rows[r][x]
-                    x += 1
-                out.append(s)
-            else:
-                out.append(t[len(t) - k:])
-        return out
-    assert c - k + 1 >= 0
-    return [rows[r][c - k + 1:c + 1] for r in range(n)]    # :2469-2472
-
-
-def var_distance(i, var_site, ent_size, exit_size):
-    """CDBG.cpp:2312-2330 (same in the strict path)."""
-    if i == 0:
-        return min(var_site[1] - var_site[0] - 1, ent_size) if len(var_site) > 1 else min(ent_size, exit_size)
-    if i == len(var_site) - 1:
-        return min(var_site[i] - var_site[i - 1] - 1, exit_size)
-    return min(var_site[i] - var_site[i - 1] - 1, var_site[i + 1] - var_site[i] - 1)
-
-
 def branching_site_plan(bubbles, aligned, k):
     """Every variable column of every branching bubble with its site k-mers: [(bubble index, site index, column, is_indel,
     indel sites seen so far incl. this one, offset into the k-mer list)], [k-mer strings]."""
@@ -124,26 +55,6 @@ def branching_site_plan(bubbles, aligned, k):
             plan.append((bi, i, c, is_ind, n_ind, len(kmers)))
             kmers.extend(km)
     return plan, kmers
-
-
-def class_coverage(part, kmers, k0, counts, found, low, up):
-    """Coverage per allele class of one site (CDBG.cpp:2393-2418): distinct k-mers per class in std::set order; returns None when
-    the site is dropped."""
-    sets = [dict() for _ in range(max(part))]
-    for j, cl in enumerate(part):
-        sets[cl - 1].setdefault(kmers[k0 + j], k0 + j)
-    tc = []
-    for st in sets:
-        acc = 0.0
-        for s in sorted(st):
-            idx = st[s]
-            assert found[idx], f"k-mer {s} missing: the reference exits here (CDBG.cpp:54)"
-            cval = int(counts[idx])
-            if not (low < cval < up):
-                return None
-            acc += float(cval)
-        tc.append(acc)
-    return tc
 
 
 def regenerate(bubbles, unitig_len, k, low, up, align_fn, cov_fn, kmer_count_fn, site_cov_fn=None):
@@ -304,20 +215,3 @@ def run_reference_config0(workdir, genome=200000, depth=30, read_len=150, k=25, 
     return out, os.path.join(workdir, "db")
 
 
-def site_outcome(part, kmers, k0, counts, found, low, up):
-    """(status, class coverages) of one site in the reference's iteration order (classes ascending, distinct k-mers of a class in
-    std::set order): 0 ok, 1 dropped at the first counter outside (low, up), 2 a missing k-mer reached first (the reference exits)."""
-    sets = [dict() for _ in range(max(part))]
-    for j, cl in enumerate(part):
-        sets[cl - 1].setdefault(kmers[k0 + j], k0 + j)
-    tc = [0] * len(sets)
-    for q, st in enumerate(sets):
-        for s in sorted(st):
-            idx = st[s]
-            if not found[idx]:
-                return 2, tc
-            cval = int(counts[idx])
-            if not (low < cval < up):
-                return 1, tc
-            tc[q] += cval
-    return 0, tc

@@ -38,6 +38,7 @@ struct CallerFiles {   // what the reference appends to its streams (Appendix D 
     std::string allele_frequency;    // P_allele_frequency.txt
     size_t alleles[4] = {0, 0, 0, 0};
     size_t bubbles_called = 0;
+    std::vector<unsigned char> called;   // appended per input bubble: 1 = it was aligned and got a VarId
 };
 
 class BubbleCaller {
@@ -52,6 +53,8 @@ class BubbleCaller {
     // the program (a k-mer of a branch or of a site is not in the database, CDBG.cpp:52-56) or on a device error; error() says which.
     bool call(const std::vector<Bubble> &batch, size_t &var_id, CallerFiles &out) {
         err_.clear();
+        const size_t called_base = out.called.size();
+        out.called.resize(called_base + batch.size(), 0);
         // ---- lookup-A: readCov of every branch of the strict bubbles (CDBG.cpp:66-120) ----
         std::string lbases;
         std::vector<uint64_t> loff(1, 0);
@@ -124,6 +127,7 @@ class BubbleCaller {
             if (nr == 0) continue;                                                 // str_vec came back empty (:2051, :2273)
             const size_t var_count = var_id++;
             out.bubbles_called++;
+            out.called[called_base + kb.src] = 1;
             const char *rows = m.rows + m.rows_off[q];
             for (uint32_t r = 0; r < nr; r++) {
                 std::ostringstream ln;
@@ -165,11 +169,11 @@ class BubbleCaller {
                 for (double c : tc) { cov_info << c << "\t"; fre_info << c / sum << "\n"; }
                 const uint32_t il = is_indel ? (indel - 1 < n_ilen ? ilen[indel - 1] : 0u) : 0u;
                 cov_info << (b.strict ? 1 : 0) << "\t" << il << "\t" << var_count << "\t" << n_var << "\t" << var_distance << "\t\n";
-                if (maxnum >= 2 && maxnum <= 5) {                                  // switch (maxnum), :2126-2147
+                out.allele_frequency += fre_info.str();                            // -t 1: every site in site order (:1318, :1630)
+                if (maxnum >= 2 && maxnum <= 5) {                                  // switch (maxnum), :1319-1340 / :2126-2147
                     out.alleles[maxnum - 2]++;
                     out.cov[maxnum - 2] += cov_info.str();
                     out.fre[maxnum - 2] += fre_info.str();
-                    out.allele_frequency += fre_info.str();                        // -t 1: every site in site order (:1318, :1630)
                 }
             }
         }

@@ -48,6 +48,12 @@ class BubbleCaller {
 
     const std::string &error() const { return err_; }
 
+    // false (default): the `-t 1` files (CDBG::ploidyEstimation_ptr).  true: the `-t N` files (ploidyEstimation_multithread_ptr):
+    // P_allele_frequency.txt holds, per bubble, the frequencies of its 2-allele sites, then 3-, then 4- (and 5- for strict bubbles)
+    // and nothing for sites with more classes (CDBG.cpp:2162, :2550); start `var_id` at 0 there (fetch_add, :2056).  The bubbles
+    // come out in the order they went in -- one of the schedules the reference's worker threads can produce.
+    void set_thread_dialect(bool multithread) { mt_ = multithread; }
+
     // Calls one batch.  `var_id` is the reference's running variant counter (var_count_all; start it at 1 for the `-t 1` files)
     // and advances by one for every bubble whose alignment is not empty.  Returns false where the reference would have ended
     // the program (a k-mer of a branch or of a site is not in the database, CDBG.cpp:52-56) or on a device error; error() says which.
@@ -142,6 +148,7 @@ class BubbleCaller {
             const uint32_t *ilen = m.ilen + m.ilen_off[q];
             const size_t n_ilen = (size_t)(m.ilen_off[q + 1] - m.ilen_off[q]);
             size_t indel = 0;
+            std::string grouped_fre[4];
             for (size_t i = 0; i < n_var; i++) {
                 const bool is_indel = m.var_kind[v0 + i] == 1;
                 size_t var_distance;                                               // :2312-2330
@@ -169,12 +176,17 @@ class BubbleCaller {
                 for (double c : tc) { cov_info << c << "\t"; fre_info << c / sum << "\n"; }
                 const uint32_t il = is_indel ? (indel - 1 < n_ilen ? ilen[indel - 1] : 0u) : 0u;
                 cov_info << (b.strict ? 1 : 0) << "\t" << il << "\t" << var_count << "\t" << n_var << "\t" << var_distance << "\t\n";
-                out.allele_frequency += fre_info.str();                            // -t 1: every site in site order (:1318, :1630)
+                if (!mt_) out.allele_frequency += fre_info.str();                  // -t 1: every site in site order (:1318, :1630)
                 if (maxnum >= 2 && maxnum <= 5) {                                  // switch (maxnum), :1319-1340 / :2126-2147
                     out.alleles[maxnum - 2]++;
                     out.cov[maxnum - 2] += cov_info.str();
                     out.fre[maxnum - 2] += fre_info.str();
+                    if (mt_) grouped_fre[maxnum - 2] += fre_info.str();
                 }
+            }
+            if (mt_) {                                                             // -t N: grouped per bubble (:2162 strict, :2550 branching)
+                out.allele_frequency += grouped_fre[0] + grouped_fre[1] + grouped_fre[2];
+                if (b.strict) out.allele_frequency += grouped_fre[3];
             }
         }
         return true;
@@ -186,6 +198,7 @@ class BubbleCaller {
     pf_kmc *db_;
     double M_, D_, G_;
     unsigned lower_, upper_;
+    bool mt_ = false;
     std::string err_;
 };
 

@@ -48,7 +48,18 @@ void write_text(const string &path, const string &text) {
 
 }  // namespace
 
+// The `-t N` entry (CDBG.hpp:33, CDBG.cpp:1872): the device takes the place of the worker threads, so the walk is the same
+// single pass; what changes is the dialect of the files (0-based ids, P_allele_frequency grouped per bubble).  The reference's
+// own `-t N` files are schedule-dependent in row order and ids; ours are one legal schedule, always the same.
+static bool g_thread_dialect = false;
+
+void CDBG::ploidyEstimation_multithread_ptr(const string &outpre, const int &lower, const int &upper, const size_t &thr) {
+    g_thread_dialect = thr > 1;
+    ploidyEstimation_ptr(outpre, lower, upper);
+}
+
 void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const int &upper) {
+    const bool thread_dialect = g_thread_dialect;
     const clock_t start_clock = clock();
     const double start_time = time(NULL);
     cout << "CDBG::PloidyEstimation():  Analyzing superbubbles to generate sites' information" << endl;
@@ -138,8 +149,9 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
     if (pf_init(0, &ctx) != PF_OK) { cout << "CDBG::PloidyEstimation(): " << pf_last_error() << endl; exit(EXIT_FAILURE); }
     if (pf_kmc_open(ctx, prefix.c_str(), &db) != PF_OK) { cout << "CDBG::PloidyEstimation(): " << pf_last_error() << endl; exit(EXIT_FAILURE); }
     pfdropin::BubbleCaller caller(ctx, db, match, mismatch, gap, (unsigned)lower, (unsigned)upper);
+    caller.set_thread_dialect(thread_dialect);
     pfdropin::CallerFiles files;
-    size_t var_id = 1;
+    size_t var_id = thread_dialect ? 0 : 1;
     const size_t kBatch = 1u << 18;
     for (size_t at = 0; at < bubbles.size(); at += kBatch) {
         const vector<pfdropin::Bubble> part(bubbles.begin() + at, bubbles.begin() + min(bubbles.size(), at + kBatch));

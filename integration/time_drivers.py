@@ -1,0 +1,63 @@
+"""Whole-program timing of the reference's driver against the same binary with the per-superbubble analysis bound to libpfgpu.so
+(integration/Makefile), BASELINE configs[0]: synthetic diploid 1 Mbp, 30x 150 bp reads, k = 25.  Both binaries load the same graph
+and find the same superbubbles with the reference's own code; only the estimation phase differs.  Wall clock of the whole program
+and the phase's own `Cpu time` line are reported; the output files of every run are compared (bytes for -t 1).
+Usage: python integration/time_drivers.py [genome_bp] [out.json]"""
+import filecmp
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tests import e2e_rows  # noqa: E402  (dataset generator shared with the tests)
+
+
+def run(binary, cwd, threads):
+    t0 = time.perf_counter()
+    r = subprocess.run([binary, "-g", "dbg.gfa", "-d", "db", "-t", str(threads), "-l", "2", "-u", "1000", "-o", "P"], cwd=cwd,
+                       capture_output=True, text=True, check=True)
+    wall = time.perf_counter() - t0
+    m = re.search(r"PloidyEstimation\(\):\s+Cpu time : ([0-9.e+-]+)s", r.stdout)
+    return {"wall_s": round(wall, 3), "estimation_cpu_s": float(m.group(1)) if m else None}
+
+
+def main():
+    genome = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+    out_json = sys.argv[2] if len(sys.argv) > 2 else None
+    pf, _ = e2e_rows.reference_binaries()
+    gpu = os.path.join(ROOT, "oracle", "_ref", "PloidyFrost_gpu")
+    cores = os.cpu_count()
+    with tempfile.TemporaryDirectory() as tmp:
+        ref_dir = os.path.join(tmp, "ref")
+        os.mkdir(ref_dir)
+        e2e_rows.run_reference_config0(ref_dir, genome=genome)       # writes reads, graph, database; runs the reference once (-t 1)
+        res = {"genome_bp": genome, "host_cores": cores, "runs": {}}
+        golden = os.path.join(tmp, "golden")
+        shutil.copytree(os.path.join(ref_dir, "PloidyFrost_output"), golden)
+        for name, binary, threads in (("reference -t 1", pf, 1), (f"reference -t {cores}", pf, cores), ("gpu -t 1", gpu, 1),
+                                      ("gpu -t 1 (second run)", gpu, 1)):
+            d = os.path.join(tmp, "run")
+            shutil.rmtree(d, ignore_errors=True)
+            os.mkdir(d)
+            for f in ("dbg.gfa", "db.kmc_pre", "db.kmc_suf"):
+                shutil.copy(os.path.join(ref_dir, f), d)
+            res["runs"][name] = run(binary, d, threads)
+            if threads == 1:
+                same = all(filecmp.cmp(os.path.join(golden, n), os.path.join(d, "PloidyFrost_output", n), shallow=False)
+                           for n in os.listdir(golden) if n.startswith("P_"))
+                res["runs"][name]["files_identical_to_reference_t1"] = same
+        n_bubbles = len({ln.split("\t")[0] for ln in open(os.path.join(golden, "P_alignseq.txt"))})
+        res["bubbles_called"] = n_bubbles
+    print(json.dumps(res))
+    if out_json:
+        json.dump(res, open(out_json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

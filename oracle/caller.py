@@ -114,3 +114,19 @@ def site_outcome(part, kmers, k0, counts, found, low, up):
                 return 1, tc
             tc[q] += cval
     return 0, tc
+
+
+def coloured_read_cov(counts, found, low, up):
+    """CCDBG::readCov(s, low, up, colour) / readCovUni (CCDBG.cpp:89-124, :125-160) over the per-window answers of colour's
+    database looked up 'as written, else reverse complement' (IsKmer / reverse / CheckKmer, :99-103): the windows are read in order;
+    the first one that is absent, or whose count is not strictly inside (low, up), ends the read with (0, False) -- unlike the
+    single-sample form (CDBG.cpp:52-56) a missing k-mer does not end the program here, the exit() after the return is dead code
+    (:117).  Otherwise (sum / #windows, True).  Both-strands databases only (:95)."""
+    total = 0.0
+    for c, f in zip(counts, found):
+        if not f:
+            return 0.0, False
+        if not (low < int(c) < up):
+            return 0.0, False
+        total += float(int(c))
+    return total / len(counts), True

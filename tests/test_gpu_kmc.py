@@ -1,4 +1,6 @@
 """-m gpu: the CUDA KMC index + lookup kernel (through the C ABI) against the oracle, bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -258,3 +260,56 @@ def test_async_cov_beside_an_alignment(gpu_ctx, oracle, tmp_path):
         assert np.array_equal(a, want[100:])
     finally:
         db.close()
+
+
+def test_per_colour_lookups_config3_shape(gpu_ctx, ref, tmp_path):
+    """BASELINE configs[3] at lookup level: 8 samples = 8 KMC databases open side by side on one context (CCDBG.cpp:44-84), every
+    branch string read against every colour's database with that colour's own cut-offs (CCDBG::readCov, CCDBG.cpp:89-124).
+    Expected: the coloured rule (oracle/caller.py) over the per-k-mer answers of the UNMODIFIED CKMCFile."""
+    from oracle.caller import coloured_read_cov
+    from ploidyfrost_b200 import capi
+    from ploidyfrost_b200.synth import kmcdb
+    k, n_col = 25, 8
+    rng = np.random.default_rng(83)
+    base = gen.rand_seq(rng, 30000)
+    shapes = [(0x200, 9, 2), (0, 5, 1), (0x200, 5, 4), (0, 9, 2), (0x200, 1, 2), (0, 5, 4), (0x200, 9, 1), (0, 1, 2)]
+    cutoff, prefixes, genomes = [], [], []
+    for ci, (ver, p, C) in enumerate(shapes):
+        g = gen.mutate(rng, base, 150, 20)                       # every sample has its own SNPs / indels
+        depth = 3 + 2 * ci
+        reads = [g] * depth + [g[a:a + 4000] for a in rng.integers(0, len(g) - 4000, 6)]
+        u, c = kmcdb.count_canonical_kmers(reads, k)
+        prefix = os.path.join(str(tmp_path), f"colour{ci}")
+        kmcdb.write_kmc_db(prefix, u, np.minimum(c, 255 if C == 1 else 60000).astype(np.uint64), k, version=ver, lut_prefix_len=p,
+                           counter_size=C, n_bins=64, sig_len=9)
+        prefixes.append(prefix); genomes.append(g)
+        cutoff.append((depth - 1, depth + 3))                    # -C file: one (lower, upper) per colour
+    seqs = []
+    for g in genomes:                                            # branch strings of every sample, some foreign to the others
+        seqs += [s for s in gen.query_sequences(rng, g, 250, k=k, p_mut=0.1, p_n=0.02, p_short=0.0) if len(s) >= k]
+    bases, off = flatten_seqs(seqs)
+    dbs = [capi.KmcDb(gpu_ctx, p) for p in prefixes]
+    n_ok = n_bad = 0
+    try:
+        for ci in range(n_col):
+            low, up = cutoff[ci]
+            hr = ref.kmc_open(prefixes[ci])
+            cr, fr = ref.kmc_counts(hr, bases, off, k, mode=1, use_read_api=False, n_threads=4)
+            ref.kmc_close(hr)
+            cov = dbs[ci].cov(bases, off, mode=capi.LOOKUP_FWD_THEN_RC, low=low, up=up)
+            w0 = 0
+            for si, s in enumerate(seqs):
+                n = len(s) - k + 1
+                want = coloured_read_cov(cr[w0:w0 + n], fr[w0:w0 + n], low, up)
+                w0 += n
+                r = cov[si]
+                ok = r["first_missing"] < 0 and r["first_outside"] < 0
+                # the first failure, whichever kind, ends the read; on success every window was found and counted
+                got = (float(r["sum"]) / float(r["n_kmers"]), True) if ok else (0.0, False)
+                assert got == want, (ci, si)
+                n_ok += ok; n_bad += not ok
+            assert w0 == len(cr)
+    finally:
+        for d in dbs:
+            d.close()
+    assert n_ok > 100 and n_bad > 1000

@@ -11,6 +11,8 @@
 // output file byte for byte.
 #include <unistd.h>
 
+#include <chrono>
+
 #include <cstdio>
 #include <cstdlib>
 #include <ctime>
@@ -18,6 +20,7 @@
 #include <iostream>
 #include <stack>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "CDBG.hpp"        // the reference's class (Bifrost graph, MyUnitig marks)
@@ -29,15 +32,54 @@ namespace {
 
 // The reference opens the KMC database in CDBG's constructor and does not keep its name; a maintainer would store it in the
 // class.  From outside the class the name is taken from the command line (`-d <prefix>`).
-string kmc_prefix_of_this_process() {
+string option_of_this_process(const string &flag) {
     ifstream f("/proc/self/cmdline", ios::binary);
     vector<string> args;
     string cur;
     char c;
     while (f.get(c)) { if (c == '\0') { args.push_back(cur); cur.clear(); } else cur += c; }
     for (size_t i = 0; i + 1 < args.size(); i++)
-        if (args[i] == "-d") return args[i + 1];
+        if (args[i] == flag) return args[i + 1];
     return "";
+}
+string kmc_prefix_of_this_process() { return option_of_this_process("-d"); }
+
+// Creating the CUDA context takes 0.6 - 2 s and staging the database scales with its size; the reference spends at least as
+// long loading the graph and finding the superbubbles before the estimation phase starts.  So both are started on a second
+// thread when the program starts (static initialiser, only for command lines that name a graph and a database) and the
+// estimation phase joins it.
+struct DeviceWarmup {
+    thread worker;
+    pf_ctx *ctx = nullptr;
+    pf_kmc *db = nullptr;
+    string error;
+
+    void open_now(const string &prefix) {
+        if (pf_init(0, &ctx) != PF_OK) { error = pf_last_error(); ctx = nullptr; return; }
+        if (pf_kmc_open(ctx, prefix.c_str(), &db) != PF_OK) { error = pf_last_error(); db = nullptr; }
+    }
+    DeviceWarmup() {
+        const string prefix = kmc_prefix_of_this_process();
+        if (!prefix.empty() && !option_of_this_process("-g").empty()) worker = thread([this, prefix] { open_now(prefix); });
+    }
+    void ready(const string &prefix) {               // called by the estimation phase
+        if (worker.joinable()) worker.join();
+        else if (!ctx && error.empty()) open_now(prefix);
+    }
+    void release() {
+        if (db) pf_kmc_close(db);
+        if (ctx) pf_shutdown(ctx);
+        db = nullptr; ctx = nullptr;
+    }
+    ~DeviceWarmup() {
+        if (worker.joinable()) worker.join();
+        release();
+    }
+};
+DeviceWarmup g_device;
+
+double seconds_since(const chrono::steady_clock::time_point &t0) {
+    return chrono::duration<double>(chrono::steady_clock::now() - t0).count();
 }
 
 void write_text(const string &path, const string &text) {
@@ -66,6 +108,7 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
     if (access("PloidyFrost_output", 0)) { if (system("mkdir ./PloidyFrost_output")) {} }
 
     // ---- the walk: which bubbles, in which order, with which marks ----
+    auto t_phase = chrono::steady_clock::now();
     vector<pfdropin::Bubble> bubbles;
     vector<string> entrance_seq;
     size_t nb_unitig_processed = 0;
@@ -143,11 +186,14 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
     }
 
     // ---- the device: lookups, alignment, site k-mers for all bubbles, in batches ----
-    pf_ctx *ctx = nullptr;
-    pf_kmc *db = nullptr;
-    const string prefix = kmc_prefix_of_this_process();
-    if (pf_init(0, &ctx) != PF_OK) { cout << "CDBG::PloidyEstimation(): " << pf_last_error() << endl; exit(EXIT_FAILURE); }
-    if (pf_kmc_open(ctx, prefix.c_str(), &db) != PF_OK) { cout << "CDBG::PloidyEstimation(): " << pf_last_error() << endl; exit(EXIT_FAILURE); }
+    const double t_walk = seconds_since(t_phase);
+    t_phase = chrono::steady_clock::now();
+    g_device.ready(kmc_prefix_of_this_process());
+    if (!g_device.error.empty() || !g_device.db) { cout << "CDBG::PloidyEstimation(): " << g_device.error << endl; exit(EXIT_FAILURE); }
+    pf_ctx *ctx = g_device.ctx;
+    pf_kmc *db = g_device.db;
+    const double t_open = seconds_since(t_phase);
+    t_phase = chrono::steady_clock::now();
     pfdropin::BubbleCaller caller(ctx, db, match, mismatch, gap, (unsigned)lower, (unsigned)upper);
     caller.set_thread_dialect(thread_dialect);
     pfdropin::CallerFiles files;
@@ -173,8 +219,8 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
             for (const pf_cov_t &c : cov) { coreCov += (size_t)((double)c.sum / (double)c.n_kmers); coreNum++; }
         }
     }
-    pf_kmc_close(db);
-    pf_shutdown(ctx);
+    const double t_calls = seconds_since(t_phase);
+    g_device.release();
 
     // ---- the files ----
     const string dir = "PloidyFrost_output/" + outpre;
@@ -188,6 +234,8 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
     const time_t end_time = time(NULL);
     cout << "CDBG::PloidyEstimation():  Cpu time : " << (double)(clock() - start_clock) / CLOCKS_PER_SEC << "s" << endl;
     cout << "CDBG::PloidyEstimation():  Real time : " << (double)difftime(end_time, start_time) << "s" << endl;
+    cout << "CDBG::PloidyEstimation():  GPU path : " << bubbles.size() << " bubbles, graph walk " << t_walk << "s, waited for device + database "
+         << t_open << "s, lookups + alignment + rows " << t_calls << "s" << endl;
     cout << "CDBG::PloidyEstimation(): Alleles in SuperBubbles  :\t"
          << "2 :" << files.alleles[0] << "\t" << "3 :" << files.alleles[1] << "\t" << "4 :" << files.alleles[2] << "\t" << "5 :" << files.alleles[3] << endl;
     const int avg = coreNum ? (int)(coreCov / coreNum) : 0;

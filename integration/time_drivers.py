@@ -24,7 +24,12 @@ def run(binary, cwd, threads):
                        capture_output=True, text=True, check=True)
     wall = time.perf_counter() - t0
     m = re.search(r"PloidyEstimation\(\):\s+Cpu time : ([0-9.e+-]+)s", r.stdout)
-    return {"wall_s": round(wall, 3), "estimation_cpu_s": float(m.group(1)) if m else None}
+    out = {"wall_s": round(wall, 3), "estimation_cpu_s": float(m.group(1)) if m else None}
+    g = re.search(r"GPU path : (\d+) bubbles, graph walk ([0-9.e+-]+)s, waited for device \+ database ([0-9.e+-]+)s, lookups \+ alignment \+ rows ([0-9.e+-]+)s",
+                  r.stdout)
+    if g:
+        out.update(bubbles=int(g.group(1)), walk_s=float(g.group(2)), open_s=float(g.group(3)), calls_s=float(g.group(4)))
+    return out
 
 
 def main():

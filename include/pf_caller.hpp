@@ -11,8 +11,8 @@
 #define PF_CALLER_HPP
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
-#include <sstream>
 #include <string>
 #include <vector>
 
@@ -57,16 +57,18 @@ class BubbleCaller {
     // Calls one batch.  `var_id` is the reference's running variant counter (var_count_all; start it at 1 for the `-t 1` files)
     // and advances by one for every bubble whose alignment is not empty.  Returns false where the reference would have ended
     // the program (a k-mer of a branch or of a site is not in the database, CDBG.cpp:52-56) or on a device error; error() says which.
-    bool call(const std::vector<Bubble> &batch, size_t &var_id, CallerFiles &out) {
+    bool call(const std::vector<Bubble> &batch, size_t &var_id, CallerFiles &out) { return call(batch.data(), batch.size(), var_id, out); }
+
+    bool call(const Bubble *batch, size_t n_batch, size_t &var_id, CallerFiles &out) {
         err_.clear();
         const size_t called_base = out.called.size();
-        out.called.resize(called_base + batch.size(), 0);
+        out.called.resize(called_base + n_batch, 0);
         // ---- lookup-A: readCov of every branch of the strict bubbles (CDBG.cpp:66-120) ----
         std::string lbases;
         std::vector<uint64_t> loff(1, 0);
-        for (const Bubble &b : batch)
-            if (b.strict)
-                for (const std::string &s : b.branches) { lbases += s; loff.push_back(lbases.size()); }
+        for (size_t bi = 0; bi < n_batch; bi++)
+            if (batch[bi].strict)
+                for (const std::string &s : batch[bi].branches) { lbases += s; loff.push_back(lbases.size()); }
         std::vector<pf_cov_t> cov(loff.size() - 1);
         if (!cov.empty() && pf_kmc_cov(db_, lbases.data(), loff.data(), (uint32_t)cov.size(), PF_LOOKUP_FWD_THEN_RC, 0, 0xFFFFFFFFu,
                                        cov.data()) != PF_OK)
@@ -79,7 +81,7 @@ class BubbleCaller {
         std::vector<uint32_t> boff(1, 0);
         std::vector<uint8_t> skip;
         size_t ci = 0;
-        for (size_t bi = 0; bi < batch.size(); bi++) {
+        for (size_t bi = 0; bi < n_batch; bi++) {
             const Bubble &b = batch[bi];
             Kept kb;
             kb.src = bi; kb.sum = 0;
@@ -135,10 +137,10 @@ class BubbleCaller {
             out.bubbles_called++;
             out.called[called_base + kb.src] = 1;
             const char *rows = m.rows + m.rows_off[q];
+            char head[96];
+            const int head_len = std::snprintf(head, sizeof head, "%zu\t%d\t%u\t%u\t", var_count, b.strict ? 1 : 0, b.entrance_id, b.exit_id);
             for (uint32_t r = 0; r < nr; r++) {
-                std::ostringstream ln;
-                ln << var_count << "\t" << (b.strict ? 1 : 0) << "\t" << b.entrance_id << "\t" << b.exit_id << "\t";
-                out.alignseq += ln.str();
+                out.alignseq.append(head, (size_t)head_len);
                 out.alignseq.append(rows + (size_t)r * L, L);
                 out.alignseq += "\n";
             }
@@ -148,7 +150,7 @@ class BubbleCaller {
             const uint32_t *ilen = m.ilen + m.ilen_off[q];
             const size_t n_ilen = (size_t)(m.ilen_off[q + 1] - m.ilen_off[q]);
             size_t indel = 0;
-            std::string grouped_fre[4];
+            std::string grouped_fre[4], cov_info, fre_info;
             for (size_t i = 0; i < n_var; i++) {
                 const bool is_indel = m.var_kind[v0 + i] == 1;
                 size_t var_distance;                                               // :2312-2330
@@ -172,16 +174,22 @@ class BubbleCaller {
                     const uint64_t *cv = sc.cov + sc.cov_off[q] + i * nr;
                     for (unsigned c = 0; c < maxnum; c++) { tc[c] = (double)cv[c]; sum += tc[c]; }
                 }
-                std::ostringstream cov_info, fre_info;
-                for (double c : tc) { cov_info << c << "\t"; fre_info << c / sum << "\n"; }
+                cov_info.clear();
+                fre_info.clear();
+                for (double c : tc) {                                              // `stream << double`: precision 6, general format == %g
+                    put_double(cov_info, c); cov_info += '\t';
+                    put_double(fre_info, c / sum); fre_info += '\n';
+                }
                 const uint32_t il = is_indel ? (indel - 1 < n_ilen ? ilen[indel - 1] : 0u) : 0u;
-                cov_info << (b.strict ? 1 : 0) << "\t" << il << "\t" << var_count << "\t" << n_var << "\t" << var_distance << "\t\n";
-                if (!mt_) out.allele_frequency += fre_info.str();                  // -t 1: every site in site order (:1318, :1630)
+                char tail[128];
+                const int tail_len = std::snprintf(tail, sizeof tail, "%d\t%u\t%zu\t%zu\t%zu\t\n", b.strict ? 1 : 0, il, var_count, n_var, var_distance);
+                cov_info.append(tail, (size_t)tail_len);
+                if (!mt_) out.allele_frequency += fre_info;                        // -t 1: every site in site order (:1318, :1630)
                 if (maxnum >= 2 && maxnum <= 5) {                                  // switch (maxnum), :1319-1340 / :2126-2147
                     out.alleles[maxnum - 2]++;
-                    out.cov[maxnum - 2] += cov_info.str();
-                    out.fre[maxnum - 2] += fre_info.str();
-                    if (mt_) grouped_fre[maxnum - 2] += fre_info.str();
+                    out.cov[maxnum - 2] += cov_info;
+                    out.fre[maxnum - 2] += fre_info;
+                    if (mt_) grouped_fre[maxnum - 2] += fre_info;
                 }
             }
             if (mt_) {                                                             // -t N: grouped per bubble (:2162 strict, :2550 branching)
@@ -193,6 +201,10 @@ class BubbleCaller {
     }
 
   private:
+    static void put_double(std::string &to, double v) {
+        char buf[40];
+        to.append(buf, (size_t)std::snprintf(buf, sizeof buf, "%g", v));
+    }
     bool fail(const std::string &why) { err_ = why; return false; }
     pf_ctx *ctx_;
     pf_kmc *db_;

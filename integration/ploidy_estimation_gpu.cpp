@@ -200,8 +200,7 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
     size_t var_id = thread_dialect ? 0 : 1;
     const size_t kBatch = 1u << 18;
     for (size_t at = 0; at < bubbles.size(); at += kBatch) {
-        const vector<pfdropin::Bubble> part(bubbles.begin() + at, bubbles.begin() + min(bubbles.size(), at + kBatch));
-        if (!caller.call(part, var_id, files)) { cout << "CDBG::readCov():" << caller.error() << endl; exit(EXIT_FAILURE); }
+        if (!caller.call(bubbles.data() + at, min(bubbles.size() - at, kBatch), var_id, files)) { cout << "CDBG::readCov():" << caller.error() << endl; exit(EXIT_FAILURE); }
     }
     // mean coverage of the entrances of the called bubbles (only printed, CDBG.cpp:1186, :1703)
     size_t coreNum = 0, coreCov = 0;

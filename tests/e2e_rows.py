@@ -215,3 +215,31 @@ def run_reference_config0(workdir, genome=200000, depth=30, read_len=150, k=25, 
     return out, os.path.join(workdir, "db")
 
 
+# ---- the `-t N` files, schedule-independent ------------------------------------------------------------------------------------
+def unitig_seq(d):
+    return {ln.split("\t")[0]: ln.rstrip("\n").split("\t")[1] for ln in open(os.path.join(d, "P_Unitig_Id.txt"))}
+
+
+def thread_dialect_view(d):
+    """The `-t N` files as the schedule-independent things they are (row order, VarIds and unitig ids depend on
+    the thread schedule): coverage rows without the VarId column, frequency lines, aligned bubbles keyed by the entrance / exit
+    unitig SEQUENCES -- all as sorted multisets."""
+    useq = unitig_seq(d)
+    view = {}
+    for a in ("bi", "tri", "tetra", "penta"):
+        rows = []
+        for ln in open(os.path.join(d, f"P_{a}cov.txt")):
+            p = ln.rstrip("\n").split("\t")
+            del p[-4]                                    # ... type, indelLen, VarId, VarNum, VarDis, ''
+            rows.append("\t".join(p))
+        view[a + "cov"] = sorted(rows)
+        view[a + "fre"] = sorted(open(os.path.join(d, f"P_{a}fre.txt")).read().split("\n"))
+    view["allfre"] = sorted(open(os.path.join(d, "P_allele_frequency.txt")).read().split("\n"))
+    groups, ids = {}, []
+    for ln in open(os.path.join(d, "P_alignseq.txt")):
+        p = ln.rstrip("\n").split("\t")
+        if p[0] not in groups:
+            ids.append(int(p[0]))
+        groups.setdefault(p[0], []).append((p[1], useq[p[2]], useq[p[3]], p[4]))
+    view["alignseq"] = sorted(tuple(g) for g in groups.values())
+    return view, ids

@@ -90,3 +90,29 @@ def test_small_capacity_reports_overflow_not_wrong_answers(oracle, hostemu):
         assert flagged > 0
     finally:
         hostemu.pfemu_set_limits(16, 64, 64, 0, 0)
+
+
+def test_bound_reference_binary_has_no_cpu_path(tmp_path):
+    """oracle/_ref/PloidyFrost_gpu (integration/Makefile) on a machine without a GPU: the estimation phase stops with pf_init's
+    error and a non-zero exit code -- it does not fall back to the reference's CPU code that is still linked into the binary."""
+    import shutil
+    import subprocess
+    import torch
+    from tests import e2e_rows
+    gpu_bin = os.path.join(ROOT, "oracle", "_ref", "PloidyFrost_gpu")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    if e2e_rows.reference_binaries() is None or not os.path.exists(gpu_bin):
+        pytest.skip("oracle/_ref/PloidyFrost_gpu not built (make -C integration)")
+    ref_dir = tmp_path / "ref"
+    run_dir = tmp_path / "gpu"
+    ref_dir.mkdir(); run_dir.mkdir()
+    e2e_rows.run_reference_config0(str(ref_dir), genome=40000)
+    for name in ("dbg.gfa", "db.kmc_pre", "db.kmc_suf"):
+        shutil.copy(ref_dir / name, run_dir / name)
+    for threads in ("1", "4"):
+        r = subprocess.run([gpu_bin, "-g", "dbg.gfa", "-d", "db", "-t", threads, "-l", "2", "-u", "1000", "-o", "P"], cwd=run_dir,
+                           capture_output=True, text=True)
+        assert r.returncode != 0
+        assert "no CPU fallback" in r.stdout
+        assert not os.path.exists(run_dir / "PloidyFrost_output" / "P_bicov.txt")

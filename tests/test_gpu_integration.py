@@ -38,35 +38,6 @@ def test_patched_reference_binary_writes_identical_files(tmp_path, hap, genome, 
     assert os.path.getsize(got / "P_bicov.txt") > 10000
 
 
-def _unitig_seq(d):
-    return {ln.split("\t")[0]: ln.rstrip("\n").split("\t")[1] for ln in open(os.path.join(d, "P_Unitig_Id.txt"))}
-
-
-def _thread_dialect_view(d):
-    """The `-t N` files as the schedule-independent things they are (row order, VarIds and unitig ids depend on
-    the thread schedule): coverage rows without the VarId column, frequency lines, aligned bubbles keyed by the entrance / exit
-    unitig SEQUENCES -- all as sorted multisets."""
-    useq = _unitig_seq(d)
-    view = {}
-    for a in ("bi", "tri", "tetra", "penta"):
-        rows = []
-        for ln in open(os.path.join(d, f"P_{a}cov.txt")):
-            p = ln.rstrip("\n").split("\t")
-            del p[-4]                                    # ... type, indelLen, VarId, VarNum, VarDis, ''
-            rows.append("\t".join(p))
-        view[a + "cov"] = sorted(rows)
-        view[a + "fre"] = sorted(open(os.path.join(d, f"P_{a}fre.txt")).read().split("\n"))
-    view["allfre"] = sorted(open(os.path.join(d, "P_allele_frequency.txt")).read().split("\n"))
-    groups, ids = {}, []
-    for ln in open(os.path.join(d, "P_alignseq.txt")):
-        p = ln.rstrip("\n").split("\t")
-        if p[0] not in groups:
-            ids.append(int(p[0]))
-        groups.setdefault(p[0], []).append((p[1], useq[p[2]], useq[p[3]], p[4]))
-    view["alignseq"] = sorted(tuple(g) for g in groups.values())
-    return view, ids
-
-
 def test_patched_reference_binary_thread_dialect(tmp_path):
     """`-t 4`: the reference's worker threads against ours (the device); files equal as multisets, ours with ids 0..n-1 in order."""
     if e2e_rows.reference_binaries() is None or not os.path.exists(GPU_BIN):
@@ -80,8 +51,8 @@ def test_patched_reference_binary_thread_dialect(tmp_path):
     r = subprocess.run([GPU_BIN, "-g", "dbg.gfa", "-d", "db", "-t", "4", "-l", "2", "-u", "1000", "-o", "P"], cwd=gpu_dir,
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    want, _ = _thread_dialect_view(out)
-    got, ids = _thread_dialect_view(str(gpu_dir / "PloidyFrost_output"))
+    want, _ = e2e_rows.thread_dialect_view(out)
+    got, ids = e2e_rows.thread_dialect_view(str(gpu_dir / "PloidyFrost_output"))
     assert ids == list(range(len(ids))) and len(ids) > 1000
     for key in want:
         assert got[key] == want[key], f"{key}: differs from the unmodified reference's -t 4 run as a multiset"

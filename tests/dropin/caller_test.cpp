@@ -1,6 +1,6 @@
 // tests/dropin/caller_test.cpp -- TEST: include/pf_caller.hpp (the batched per-bubble caller over the C ABI) fed with the bubbles
 // the unmodified reference aligned in tests/golden/e2e (their raw branch strings, entrance / exit ids and sizes) must write the
-// reference's own files.  usage: caller_test <fixture dir> <out dir> <lower> <upper>; tests/test_gpu_dropin.py builds it with g++
+// reference's own files.  usage: caller_test <fixture dir> <out dir> <lower> <upper> [mt]; `mt` = the `-t N` dialect.  tests/test_gpu_dropin.py builds it with g++
 // against libpfgpu.so, runs it and compares the files byte for byte.
 #include <cstdio>
 #include <cstdlib>
@@ -60,8 +60,10 @@ int main(int argc, char **argv) {
     if (pf_init(0, &ctx) != PF_OK) { fprintf(stderr, "pf_init: %s\n", pf_last_error()); return 1; }
     if (pf_kmc_open(ctx, (fx + "/db").c_str(), &db) != PF_OK) { fprintf(stderr, "pf_kmc_open: %s\n", pf_last_error()); return 1; }
     pfdropin::BubbleCaller caller(ctx, db, 2, -1, -3, lower, upper);
+    const bool mt = argc > 5 && std::string(argv[5]) == "mt";
+    caller.set_thread_dialect(mt);
     pfdropin::CallerFiles out;
-    size_t var_id = 1;
+    size_t var_id = mt ? 0 : 1;
     // two calls: the caller is batched, the files must not depend on where the batches are cut
     std::vector<pfdropin::Bubble> first(batch.begin(), batch.begin() + batch.size() / 3), second(batch.begin() + batch.size() / 3, batch.end());
     if (!caller.call(first, var_id, out) || !caller.call(second, var_id, out)) { fprintf(stderr, "caller: %s\n", caller.error().c_str()); return 1; }

@@ -4,6 +4,7 @@ oracle.  No CUDA compute is called here."""
 import ctypes as C
 import re
 import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -116,3 +117,76 @@ def test_bound_reference_binary_has_no_cpu_path(tmp_path):
         assert r.returncode != 0
         assert "no CPU fallback" in r.stdout
         assert not os.path.exists(run_dir / "PloidyFrost_output" / "P_bicov.txt")
+
+
+def _build_caller_over_oracle(tmp_path):
+    exe = os.path.join(str(tmp_path), "caller_over_oracle")
+    orc = os.path.join(ROOT, "oracle")
+    if not os.path.exists(os.path.join(orc, "libpforacle.so")):
+        subprocess.run(["make", "-C", orc, "oracle"], check=True, capture_output=True)
+    subprocess.run(["g++", "-O1", "-std=c++14", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "dropin", "caller_test.cpp"),
+                    os.path.join(ROOT, "tests", "dropin", "abi_over_oracle.cpp"), "-o", exe, "-L", orc, "-lpforacle", "-Wl,-rpath," + orc,
+                    "-lpthread"], check=True)
+    return exe
+
+
+def test_batched_caller_host_logic_writes_the_reference_files(tmp_path):
+    """The HOST side of include/pf_caller.hpp (gating, ordering, strict-bubble arithmetic, VarDis, row text) with the device calls
+    played by the CPU oracle (tests/dropin/abi_over_oracle.cpp, test infrastructure): fed with the bubbles of tests/golden/e2e it
+    writes the unmodified reference's `-t 1` files byte for byte; in the `-t N` dialect the same rows with 0-based ids and
+    P_allele_frequency grouped per bubble (CDBG.cpp:2056, :2162, :2550)."""
+    import filecmp
+    from collections import Counter
+    exe = _build_caller_over_oracle(tmp_path)
+    fx = os.path.join(ROOT, "tests", "golden", "e2e")
+    names = ["P_alignseq.txt"] + [f"P_{a}{w}.txt" for a in ("bi", "tri", "tetra", "penta") for w in ("cov", "fre")]   # the fixture's files
+    one = tmp_path / "t1"
+    one.mkdir()
+    r = subprocess.run([exe, fx, str(one), "2", "1000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for n in names:
+        assert filecmp.cmp(os.path.join(fx, n), one / n, shallow=False), n
+    # P_allele_frequency.txt is not in the fixture (tests/test_gpu_integration.py compares it with a live reference run): -t 1
+    # writes every site, so it holds at least the lines of the four frequency files
+    fre_lines = Counter(ln for a in ("bi", "tri", "tetra", "penta") for ln in open(one / f"P_{a}fre.txt"))
+    assert not (fre_lines - Counter(open(one / "P_allele_frequency.txt")))
+    mt = tmp_path / "mt"
+    mt.mkdir()
+    r = subprocess.run([exe, fx, str(mt), "2", "1000", "mt"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+    def shift_id(line, col):
+        p = line.split("\t")
+        p[col] = str(int(p[col]) - 1)
+        return "\t".join(p)
+    assert [shift_id(ln, 0) for ln in open(one / "P_alignseq.txt")] == list(open(mt / "P_alignseq.txt"))
+    for a in ("bi", "tri", "tetra", "penta"):
+        assert [shift_id(ln, -4) for ln in open(one / f"P_{a}cov.txt")] == list(open(mt / f"P_{a}cov.txt"))
+        assert filecmp.cmp(one / f"P_{a}fre.txt", mt / f"P_{a}fre.txt", shallow=False)
+    all_mt = list(open(mt / "P_allele_frequency.txt"))
+    assert not (Counter(all_mt) - Counter(open(one / "P_allele_frequency.txt")))
+    n_fre = sum(len(list(open(mt / f"P_{a}fre.txt"))) for a in ("bi", "tri", "tetra"))
+    assert n_fre <= len(all_mt) <= n_fre + len(list(open(mt / "P_pentafre.txt")))
+
+
+def test_batched_caller_host_logic_on_a_live_reference_run(tmp_path):
+    """Same stand-in, bubbles of a fresh run of the unmodified reference (tetraploid, indel-rich: 3-8 branches per bubble): all ten
+    files of the `-t 1` run, P_allele_frequency.txt included, byte for byte."""
+    import filecmp
+    import shutil
+    from tests import e2e_rows
+    if e2e_rows.reference_binaries() is None:
+        pytest.skip("oracle/_ref/PloidyFrost not built (make -C oracle ref_full)")
+    out, dbp = e2e_rows.run_reference_config0(str(tmp_path), genome=200000, haplotypes=4, p_indel=0.003, depth=60)
+    for ext in (".kmc_pre", ".kmc_suf"):
+        shutil.copy(dbp + ext, os.path.join(out, "db" + ext))
+    exe = _build_caller_over_oracle(tmp_path)
+    got = tmp_path / "got"
+    got.mkdir()
+    r = subprocess.run([exe, out, str(got), "2", "1000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    names = sorted(os.listdir(got))
+    assert len(names) == 10
+    for n in names:
+        assert filecmp.cmp(os.path.join(out, n), got / n, shallow=False), n
+    assert os.path.getsize(got / "P_bicov.txt") > 10000

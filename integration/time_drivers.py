@@ -2,7 +2,7 @@
 (integration/Makefile), BASELINE configs[0]: synthetic diploid 1 Mbp, 30x 150 bp reads, k = 25.  Both binaries load the same graph
 and find the same superbubbles with the reference's own code; only the estimation phase differs.  Wall clock of the whole program
 and the phase's own `Cpu time` line are reported; the output files of every run are compared (bytes for -t 1).
-Usage: python integration/time_drivers.py [genome_bp] [out.json]"""
+Usage: [PF_DRIVER_RUNS=ref1,refN,gpu1,gpu1b,gpuN] python integration/time_drivers.py [genome_bp] [out.json]"""
 import filecmp
 import json
 import os
@@ -45,8 +45,10 @@ def main():
         res = {"genome_bp": genome, "host_cores": cores, "runs": {}}
         golden = os.path.join(tmp, "golden")
         shutil.copytree(os.path.join(ref_dir, "PloidyFrost_output"), golden)
-        for name, binary, threads in (("reference -t 1", pf, 1), (f"reference -t {cores}", pf, cores), ("gpu -t 1", gpu, 1),
-                                      ("gpu -t 1 (second run)", gpu, 1)):
+        plan = {"ref1": ("reference -t 1", pf, 1), "refN": (f"reference -t {cores}", pf, cores), "gpu1": ("gpu -t 1", gpu, 1),
+                "gpu1b": ("gpu -t 1 (second run)", gpu, 1), "gpuN": (f"gpu -t {cores}", gpu, cores)}
+        for key in os.environ.get("PF_DRIVER_RUNS", "ref1,refN,gpu1,gpu1b,gpuN").split(","):
+            name, binary, threads = plan[key]
             d = os.path.join(tmp, "run")
             shutil.rmtree(d, ignore_errors=True)
             os.mkdir(d)

@@ -169,21 +169,24 @@ def test_batched_caller_host_logic_writes_the_reference_files(tmp_path):
     assert n_fre <= len(all_mt) <= n_fre + len(list(open(mt / "P_pentafre.txt")))
 
 
-def test_batched_caller_host_logic_on_a_live_reference_run(tmp_path):
-    """Same stand-in, bubbles of a fresh run of the unmodified reference (tetraploid, indel-rich: 3-8 branches per bubble): all ten
-    files of the `-t 1` run, P_allele_frequency.txt included, byte for byte."""
+@pytest.mark.parametrize("kw", [dict(haplotypes=4, p_indel=0.003, depth=60),                               # 3-8 branches per bubble
+                                dict(haplotypes=4, p_indel=0.003, depth=60, low=10, up=40),              # tight gate: dropped sites
+                                dict(haplotypes=2, p_indel=0.01, p_snp=0.03, depth=30, low=2, up=25)])   # variant-dense, low ceiling
+def test_batched_caller_host_logic_on_a_live_reference_run(tmp_path, kw):
+    """Same stand-in, bubbles of a fresh run of the unmodified reference: all ten files of the `-t 1` run, P_allele_frequency.txt
+    included, byte for byte -- also under gates (-l / -u) that make the reference skip sites."""
     import filecmp
     import shutil
     from tests import e2e_rows
     if e2e_rows.reference_binaries() is None:
         pytest.skip("oracle/_ref/PloidyFrost not built (make -C oracle ref_full)")
-    out, dbp = e2e_rows.run_reference_config0(str(tmp_path), genome=200000, haplotypes=4, p_indel=0.003, depth=60)
+    out, dbp = e2e_rows.run_reference_config0(str(tmp_path), genome=200000, **kw)
     for ext in (".kmc_pre", ".kmc_suf"):
         shutil.copy(dbp + ext, os.path.join(out, "db" + ext))
     exe = _build_caller_over_oracle(tmp_path)
     got = tmp_path / "got"
     got.mkdir()
-    r = subprocess.run([exe, out, str(got), "2", "1000"], capture_output=True, text=True)
+    r = subprocess.run([exe, out, str(got), str(kw.get("low", 2)), str(kw.get("up", 1000))], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     names = sorted(os.listdir(got))
     assert len(names) == 10

@@ -17,17 +17,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GPU_BIN = os.path.join(ROOT, "oracle", "_ref", "PloidyFrost_gpu")
 
 
-@pytest.mark.parametrize("hap,genome,p_indel,p_snp", [(2, 300000, 0.001, 0.01), (4, 300000, 0.003, 0.01)])
-def test_patched_reference_binary_writes_identical_files(tmp_path, hap, genome, p_indel, p_snp):
+@pytest.mark.parametrize("hap,genome,p_indel,p_snp,low,up", [(2, 300000, 0.001, 0.01, 2, 1000), (4, 300000, 0.003, 0.01, 2, 1000),
+                                                             (4, 300000, 0.003, 0.01, 10, 40)])   # tight gate: dropped bubbles and sites
+def test_patched_reference_binary_writes_identical_files(tmp_path, hap, genome, p_indel, p_snp, low, up):
     if e2e_rows.reference_binaries() is None or not os.path.exists(GPU_BIN):
         pytest.skip("oracle/_ref/PloidyFrost_gpu not built (make -C integration in the dev container)")
     ref_dir = tmp_path / "ref"
     gpu_dir = tmp_path / "gpu"
     ref_dir.mkdir(); gpu_dir.mkdir()
-    out, dbp = e2e_rows.run_reference_config0(str(ref_dir), genome=genome, haplotypes=hap, p_indel=p_indel, p_snp=p_snp, depth=15 * hap)
+    out, dbp = e2e_rows.run_reference_config0(str(ref_dir), genome=genome, haplotypes=hap, p_indel=p_indel, p_snp=p_snp, depth=15 * hap,
+                                              low=low, up=up)
     for name in ("dbg.gfa", "db.kmc_pre", "db.kmc_suf"):
         shutil.copy(ref_dir / name, gpu_dir / name)
-    r = subprocess.run([GPU_BIN, "-g", "dbg.gfa", "-d", "db", "-t", "1", "-l", "2", "-u", "1000", "-o", "P"], cwd=gpu_dir,
+    r = subprocess.run([GPU_BIN, "-g", "dbg.gfa", "-d", "db", "-t", "1", "-l", str(low), "-u", str(up), "-o", "P"], cwd=gpu_dir,
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     got = gpu_dir / "PloidyFrost_output"

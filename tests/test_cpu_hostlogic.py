@@ -193,3 +193,55 @@ def test_batched_caller_host_logic_on_a_live_reference_run(tmp_path, kw):
     for n in names:
         assert filecmp.cmp(os.path.join(out, n), got / n, shallow=False), n
     assert os.path.getsize(got / "P_bicov.txt") > 10000
+
+
+def _hostcheck_binary():
+    """oracle/_ref/PloidyFrost_hostcheck: integration/ploidy_estimation_gpu.cpp inside the unmodified reference, linked against the
+    oracle stand-in instead of libpfgpu.so (integration/Makefile `hostcheck`; dev container only, it needs the reference's objects)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "PloidyFrost_hostcheck")
+    if not os.path.exists(exe) and os.path.isdir("/root/reference/src"):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "integration"), "hostcheck"], check=False, capture_output=True)
+    return exe if os.path.exists(exe) else None
+
+
+@pytest.mark.parametrize("kw", [dict(haplotypes=2, p_indel=0.001, depth=30),                              # BASELINE configs[0], scaled
+                                dict(haplotypes=4, p_indel=0.003, depth=60, low=10, up=40),              # a third of the bubbles gated out
+                                dict(haplotypes=2, p_indel=0.01, p_snp=0.03, depth=30, low=2, up=25)])
+def test_bound_reference_binary_walk_and_host_logic(tmp_path, kw):
+    """The reference-side binding end to end on the CPU: same binary as PloidyFrost_gpu except that the device calls are played by
+    the oracle.  Its graph walk (which bubbles, which order, ids, sizes, branch strings, sort keys), the caller's host logic and the
+    writers must reproduce every file of the unmodified binary byte for byte, and its closing statistics."""
+    import filecmp
+    import shutil
+    from tests import e2e_rows
+    hc = _hostcheck_binary()
+    if e2e_rows.reference_binaries() is None or hc is None:
+        pytest.skip("oracle/_ref/PloidyFrost_hostcheck not built (make -C integration hostcheck, dev container)")
+    ref_dir, run_dir = tmp_path / "ref", tmp_path / "hc"
+    ref_dir.mkdir(); run_dir.mkdir()
+    low, up = kw.get("low", 2), kw.get("up", 1000)
+    out, _ = e2e_rows.run_reference_config0(str(ref_dir), genome=200000, **kw)
+    for name in ("dbg.gfa", "db.kmc_pre", "db.kmc_suf"):
+        shutil.copy(ref_dir / name, run_dir / name)
+    cmd = ["-g", "dbg.gfa", "-d", "db", "-t", "1", "-l", str(low), "-u", str(up), "-o", "P"]
+    r = subprocess.run([hc] + cmd, cwd=run_dir, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    names = sorted(n for n in os.listdir(out) if n.startswith("P_"))
+    assert len(names) == 12
+    for n in names:
+        assert filecmp.cmp(os.path.join(out, n), run_dir / "PloidyFrost_output" / n, shallow=False), n
+    ref_stdout = subprocess.run([e2e_rows.reference_binaries()[0]] + cmd, cwd=ref_dir, capture_output=True, text=True).stdout
+
+    def closing(text):
+        return [ln for ln in text.split("\n") if "Alleles in SuperBubbles" in ln or "Average Coverage" in ln]
+    assert closing(r.stdout) == closing(ref_stdout) and len(closing(r.stdout)) == 2
+    # -t 4: the reference's worker threads against the binding's single pass, as multisets (ids and order are schedule-dependent)
+    cmd[5] = "4"
+    subprocess.run([e2e_rows.reference_binaries()[0]] + cmd, cwd=ref_dir, check=True, capture_output=True)
+    r = subprocess.run([hc] + cmd, cwd=run_dir, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    want, _ = e2e_rows.thread_dialect_view(out)
+    got, ids = e2e_rows.thread_dialect_view(str(run_dir / "PloidyFrost_output"))
+    assert ids == list(range(len(ids)))
+    for key in want:
+        assert got[key] == want[key], key

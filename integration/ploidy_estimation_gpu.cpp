@@ -94,9 +94,11 @@ void write_text(const string &path, const string &text) {
 // single pass; what changes is the dialect of the files (0-based ids, P_allele_frequency grouped per bubble).  The reference's
 // own `-t N` files are schedule-dependent in row order and ids; ours are one legal schedule, always the same.
 static bool g_thread_dialect = false;
+static unsigned g_host_threads = 1;   // -t N: the threads format the rows of a batch (BubbleCaller::set_host_threads)
 
 void CDBG::ploidyEstimation_multithread_ptr(const string &outpre, const int &lower, const int &upper, const size_t &thr) {
     g_thread_dialect = thr > 1;
+    g_host_threads = (unsigned)thr;
     ploidyEstimation_ptr(outpre, lower, upper);
 }
 
@@ -196,6 +198,7 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
     t_phase = chrono::steady_clock::now();
     pfdropin::BubbleCaller caller(ctx, db, match, mismatch, gap, (unsigned)lower, (unsigned)upper);
     caller.set_thread_dialect(thread_dialect);
+    caller.set_host_threads(g_host_threads);
     pfdropin::CallerFiles files;
     size_t var_id = thread_dialect ? 0 : 1;
     const size_t kBatch = 1u << 18;

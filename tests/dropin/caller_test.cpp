@@ -1,6 +1,6 @@
 // tests/dropin/caller_test.cpp -- TEST: include/pf_caller.hpp (the batched per-bubble caller over the C ABI) fed with the bubbles
 // the unmodified reference aligned in tests/golden/e2e (their raw branch strings, entrance / exit ids and sizes) must write the
-// reference's own files.  usage: caller_test <fixture dir> <out dir> <lower> <upper> [mt]; `mt` = the `-t N` dialect.  tests/test_gpu_dropin.py builds it with g++
+// reference's own files.  usage: caller_test <fixture dir> <out dir> <lower> <upper> [mt|t1] [host threads]; `mt` = the `-t N` dialect.  tests/test_gpu_dropin.py builds it with g++
 // against libpfgpu.so, runs it and compares the files byte for byte.
 #include <cstdio>
 #include <cstdlib>
@@ -62,6 +62,7 @@ int main(int argc, char **argv) {
     pfdropin::BubbleCaller caller(ctx, db, 2, -1, -3, lower, upper);
     const bool mt = argc > 5 && std::string(argv[5]) == "mt";
     caller.set_thread_dialect(mt);
+    if (argc > 6) caller.set_host_threads((unsigned)atoi(argv[6]));
     pfdropin::CallerFiles out;
     size_t var_id = mt ? 0 : 1;
     // two calls: the caller is batched, the files must not depend on where the batches are cut

@@ -192,6 +192,13 @@ def test_batched_caller_host_logic_on_a_live_reference_run(tmp_path, kw):
     assert len(names) == 10
     for n in names:
         assert filecmp.cmp(os.path.join(out, n), got / n, shallow=False), n
+    # the rows formatted by 5 host threads (contiguous ranges joined in order): the same bytes
+    got5 = tmp_path / "got5"
+    got5.mkdir()
+    r = subprocess.run([exe, out, str(got5), str(kw.get("low", 2)), str(kw.get("up", 1000)), "t1", "5"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for n in names:
+        assert filecmp.cmp(got / n, got5 / n, shallow=False), n
     assert os.path.getsize(got / "P_bicov.txt") > 10000
 
 

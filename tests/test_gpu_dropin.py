@@ -22,7 +22,7 @@ def build_caller_test(outdir):
     exe = os.path.join(str(outdir), "caller_test")
     pkg = os.path.join(ROOT, "ploidyfrost_b200")
     subprocess.run(["g++", "-O1", "-std=c++14", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "dropin", "caller_test.cpp"),
-                    "-o", exe, "-L", pkg, "-lpfgpu", "-Wl,-rpath," + pkg], check=True)
+                    "-o", exe, "-L", pkg, "-lpfgpu", "-Wl,-rpath," + pkg, "-pthread"], check=True)
     return exe
 
 

@@ -180,7 +180,7 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
                     }
                 }
             }
-            bubbles.push_back(b);
+            bubbles.push_back(std::move(b));
             entrance_seq.push_back(u.referenceUnitigToString());
             if (u.strand) ud->set_plus_visited(); else ud->set_minus_visited();
             if (exit_uni.strand) exit_uni.getData()->set_minus_visited(); else exit_uni.getData()->set_plus_visited();

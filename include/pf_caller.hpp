@@ -59,7 +59,8 @@ class BubbleCaller {
 
     // Calls one batch.  `var_id` is the reference's running variant counter (var_count_all; start it at 1 for the `-t 1` files)
     // and advances by one for every bubble whose alignment is not empty.  Returns false where the reference would have ended
-    // the program (a k-mer of a branch or of a site is not in the database, CDBG.cpp:52-56) or on a device error; error() says which.
+    // the program (a k-mer of a branch or of a site is not in the database, CDBG.cpp:52-56) or on a device error; error() says which,
+    // no text of the failed batch is appended to `out` (its `called` flags and `var_id` are not meaningful then).
     bool call(const std::vector<Bubble> &batch, size_t &var_id, CallerFiles &out) { return call(batch.data(), batch.size(), var_id, out); }
 
     bool call(const Bubble *batch, size_t n_batch, size_t &var_id, CallerFiles &out) {

@@ -1,23 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- PloidyFrost per-superbubble hot path on B200 (see DESIGN.md "Measurement").
 
-A "step" is one pass of the hot path over one batch of synthetic superbubbles of BASELINE.json configs[1]
-(tetraploid, k=25, default scoring): phase-A k-mer coverage lookups (entrance unitig + every branch,
-CDBG::readCov) followed by SeqAlign::SequenceAlignment of every bubble's branches.
+A "step" is one pass of the hot path over one batch of synthetic superbubbles of a BASELINE.json config: lookup phase A
+(CDBG::readCov of the entrance unitig and of every branch), SeqAlign::SequenceAlignment of every bubble's branches, lookup
+phase B (site k-mers of the branching bubbles, pf_site_cov).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one process per GPU under torchrun)
-  python bench.py --impl reference ...                           the reference's own CPU code (oracle/_ref)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C]      our arm (one process per GPU under torchrun)
+  python bench.py --impl reference ...                                   the reference's own CPU code (oracle/_ref)
 
-`value` = bubbles/s with the batch resident in HBM (CUDA events, max over ranks); `e2e` = the same through the
-host-pointer C ABI (pf_kmc_cov_async + pf_align + pf_site_cov + pf_kmc_wait) from pinned host buffers, copies inside the
-timed region.
+--config 2 (default, the headline): BASELINE configs[2], synthetic hexaploid 1 Gbp -- 3 subgenomes x 333 Mbp, 10 % diverged,
+             2 haplotypes each, 90x-equivalent KMC2 database (~1.2 G distinct 25-mers, 2^30-bucket hash index, 34 GB)
+--config 1: configs[1], synthetic tetraploid 100 Mbp, 60x (the round-1 headline)
+--config 4: configs[4], indel-heavy stress: branches log-uniform 50 bp .. 5 kbp, >= 1 long indel per bubble
+
+`value` = bubbles/s with the batch resident in HBM (CUDA events, max over ranks); `e2e` = the same through the host-pointer
+C ABI (pf_kmc_cov_async | pf_align | pf_site_cov | pf_kmc_wait) from pinned host buffers, copies inside the timed region;
+`parity` = the results of the timed batch diffed against the unmodified reference (oracle/_ref) on a sample of that batch --
+any mismatch makes the run exit non-zero.  At N > 1 the same run also times the KMC index PARTITIONED across the GPUs
+(peer-memory lookups and NCCL all-to-all routing) on the same batch and checks it against the replicated index (`sharded`).
 """
 from __future__ import annotations
 
 import argparse
+import fcntl
 import json
 import os
-import subprocess
+import shutil
 import sys
 import threading
 import time
@@ -28,8 +36,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 K = 25
-SEED = 20261017 + 1            # seed = 20261017 + config index
-BUBBLES_PER_MBP = 14000        # measured density of the generator at these rates (only used to size regions)
+SEED0 = 20261017               # seed = 20261017 + config index
+SUB_DIVERGENCE = 0.0527        # per-subgenome substitution rate from the root: 10 % between two subgenomes
 
 
 def env_int(name, default):
@@ -85,35 +93,161 @@ class ClockSampler(threading.Thread):
                 "source": "NVML (nvmlDeviceGetClockInfo / CurrentClocksEventReasons), 10 ms period, timed region + e2e loop"}
 
 
-def make_workload(args, rank, world, need_db_files, db_dir, device=None):
-    from ploidyfrost_b200.synth import workload as wl
-    G = int(args.genome_mbp * 1e6)
-    w = wl.Workload(SEED, G, 4, p_snp=0.01, p_indel=0.001, n_threads=min(16, os.cpu_count() or 8))
-    region = int(args.batch / BUBBLES_PER_MBP * 1e6 * 1.15) + 200000
-    region = min(region, G)
-    r0 = (rank * region) % max(1, G - region + 1)
-    bb = w.bubbles(K, r0, r0 + region, args.batch)
-    prefix = os.path.join(db_dir, "db")
-    info = None
-    if need_db_files:
-        haps = [w.haplotype(i) for i in range(4)]
-        lam = 15.0 * 126.0 / 150.0           # 60x over 4 haplotype copies, k-mer coverage = depth*(L-k+1)/L
-        if device is not None:
-            info = wl.write_db_torch(prefix, haps, K, lam, SEED, device=device, version=0x200, lut_prefix_len=9, sig_len=9,
-                                     n_bins=512)
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------------
+class Config:
+    """One BASELINE.json config: how its genome is made of subgenomes / haplotypes, and the defaults that go with it."""
+
+    def __init__(self, idx, genome_mbp):
+        self.idx = idx
+        self.seed = SEED0 + idx
+        if idx == 2:      # hexaploid: 3 subgenomes, 2 haplotypes each; 90x over 6 haplotype copies
+            self.genome_mbp = genome_mbp or 1000.0
+            self.n_sub, self.n_hap = 3, 2
+            self.batch, self.ref_sample, self.cpu_sample = 1048576, 262144, 524288
+            self.bubbles_per_mbp = 12600
+            self.name = (f"configs[2]: synthetic hexaploid {self.genome_mbp:g} Mbp (3 subgenomes x {self.genome_mbp / 3:.4g} Mbp, 10% diverged, "
+                         f"2 haplotypes each, 1% SNP, 0.1% indel), 90x-equivalent KMC2 db (k=25, p=9, sig 9, 512 bins), -z 8, M/D/G = 2/-1/-3")
+        elif idx == 1:    # tetraploid: one genome, 4 haplotypes; 60x over 4 copies
+            self.genome_mbp = genome_mbp or 100.0
+            self.n_sub, self.n_hap = 1, 4
+            self.batch, self.ref_sample, self.cpu_sample = 262144, 65536, 131072
+            self.bubbles_per_mbp = 14000
+            self.name = (f"configs[1]: synthetic tetraploid {self.genome_mbp:g} Mbp (4 haplotypes, 1% SNP, 0.1% indel), "
+                         f"60x-equivalent KMC2 db (k=25, p=9, sig 9, 512 bins), -z 8, M/D/G = 2/-1/-3")
+        elif idx == 4:    # indel-heavy stress
+            self.genome_mbp = 0.0
+            self.n_sub, self.n_hap = 0, 0
+            self.batch, self.ref_sample, self.cpu_sample = 2048, 32, 48
+            self.bubbles_per_mbp = 0
+            self.name = ("configs[4]: indel-heavy stress, 2-4 branches per bubble, branch lengths log-uniform 50 bp .. 5 kbp, >= 1 long "
+                         "indel (5-40 % of the branch) per branch pair, KMC2 db of the batch's own k-mers, M/D/G = 2/-1/-3")
         else:
-            info, _, _ = wl.write_db_numpy(prefix, haps, K, lam, SEED, version=0x200, lut_prefix_len=9, sig_len=9,
-                                           n_bins=512 if G > 5e6 else 64)
-        del haps
-    w.close()
-    return bb, prefix, info
+            raise SystemExit(f"bench.py: --config {idx} is not a bench workload (1, 2 or 4)")
+        self.lam = 15.0 * 126.0 / 150.0    # 15x per haplotype copy; k-mer coverage = depth * (L - k + 1) / L
+        self.sub_len = int(self.genome_mbp * 1e6 / max(self.n_sub, 1))
+
+    def sub_seed(self, s):
+        return self.seed * 1000003 + s
+
+    def root_seed(self):
+        return (self.seed * 7919 + 17) if self.n_sub > 1 else 0
+
+
+def cache_dir(need_bytes):
+    """Where the synthetic database lives between the arms / runs of one box: RAM disk when it has room, else /tmp."""
+    env = os.environ.get("PF_BENCH_CACHE")
+    if env:
+        os.makedirs(env, exist_ok=True)
+        return env
+    for base in ("/dev/shm", "/tmp"):
+        try:
+            if os.path.isdir(base) and shutil.disk_usage(base).free > need_bytes * 1.25 + (2 << 30):
+                d = os.path.join(base, "pfbench_cache")
+                os.makedirs(d, exist_ok=True)
+                return d
+        except OSError:
+            pass
+    d = "/tmp/pfbench_cache"
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def make_bubbles(cfg, args, region_rank):
+    """The batch of rank `region_rank`: bubbles of its own stretch of every subgenome (generated on its own: the synthetic
+    genome is keyed by absolute position, so the stretch carries the whole genome's bases and variants)."""
+    from ploidyfrost_b200.synth import workload as wl
+    nt = min(16, os.cpu_count() or 8)
+    if cfg.idx == 4:
+        w = wl.Workload(cfg.seed, 1000, 1, n_threads=1)
+        bb = w.long_bubbles(cfg.seed * 31 + region_rank, K, args.batch, 50, 5000, 4)
+        w.close()
+        return bb
+    per_sub = (args.batch + cfg.n_sub - 1) // cfg.n_sub
+    margin = 6000
+    region = int(per_sub / cfg.bubbles_per_mbp * 1e6 * 1.15) + 200000 + 2 * margin
+    region = min(region, cfg.sub_len)
+    parts = []
+    for s in range(cfg.n_sub):
+        r0 = (region_rank * region) % max(1, cfg.sub_len - region + 1)
+        w = wl.Workload(cfg.sub_seed(s), region, cfg.n_hap, p_snp=0.01, p_indel=0.001, n_threads=nt, root_seed=cfg.root_seed(),
+                        divergence=SUB_DIVERGENCE if cfg.n_sub > 1 else 0.0, offset=r0)
+        want = per_sub if s + 1 < cfg.n_sub else args.batch - per_sub * (cfg.n_sub - 1)
+        parts.append(w.bubbles(K, margin, region - margin, want))
+        w.close()
+    return wl.BubbleBatch.concat(parts)
+
+
+def ensure_db(cfg, args, device, bb=None, tag=""):
+    """The KMC database of the config: built once per box (GPU sort/unique with torch -- data tooling -- or numpy for small
+    cases) under an exclusive lock, then reused by every arm / rank / run.  Returns (prefix, info)."""
+    from ploidyfrost_b200.synth import workload as wl
+    est = int(cfg.genome_mbp * 1e6 * 1.3 * 6 + (1 << 30) + (1 << 28)) if cfg.idx != 4 else 1 << 30
+    d = cache_dir(est)
+    name = f"c{cfg.idx}_g{cfg.genome_mbp:g}_s{cfg.seed}{tag}" if cfg.idx != 4 else f"c4_b{args.batch}_s{cfg.seed}{tag}"
+    prefix = os.path.join(d, name)
+    meta = prefix + ".json"
+    with open(prefix + ".lock", "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        if os.path.exists(meta):
+            return prefix, json.load(open(meta))
+        t0 = time.perf_counter()
+        tmp = prefix + ".tmp"
+        if cfg.idx == 4:
+            seqs = [bb.bases[int(bb.seq_off[i]):int(bb.seq_off[i + 1])] for i in range(bb.n_seq)]
+            seqs += [bb.ent_bases[int(bb.ent_off[i]):int(bb.ent_off[i + 1])] for i in range(bb.n_bubbles)]
+            info, _, _ = wl.write_db_numpy(tmp, seqs, K, cfg.lam, cfg.seed, version=0x200, lut_prefix_len=9, sig_len=9, n_bins=64)
+        else:
+            nt = min(32, os.cpu_count() or 8)
+            groups = []
+            for s in range(cfg.n_sub):
+                w = wl.Workload(cfg.sub_seed(s), cfg.sub_len, cfg.n_hap, p_snp=0.01, p_indel=0.001, n_threads=nt, root_seed=cfg.root_seed(),
+                                divergence=SUB_DIVERGENCE if cfg.n_sub > 1 else 0.0)
+                groups.append([w.haplotype(i) for i in range(cfg.n_hap)])
+                w.close()
+            if device is not None:
+                info = wl.write_db_torch(tmp, groups, K, cfg.lam, cfg.seed, device=device, version=0x200, lut_prefix_len=9, sig_len=9,
+                                         n_bins=512)
+            else:
+                flat = [h for g in groups for h in g]
+                info, _, _ = wl.write_db_numpy(tmp, flat, K, cfg.lam, cfg.seed, version=0x200, lut_prefix_len=9, sig_len=9,
+                                               n_bins=512 if cfg.genome_mbp > 5 else 64)
+            del groups
+        info["build_s"] = round(time.perf_counter() - t0, 1)
+        os.replace(tmp + ".kmc_pre", prefix + ".kmc_pre")
+        os.replace(tmp + ".kmc_suf", prefix + ".kmc_suf")
+        json.dump(info, open(meta, "w"))
+        return prefix, info
+
+
+def workload_config(cfg, args, n_bubbles, info, extra=None):
+    c = {"workload": cfg.name, "batch_bubbles": int(n_bubbles), "db_kmers": (info or {}).get("N"),
+         "step": "lookup-A (readCov of entrance + branch unitigs) + SequenceAlignment per bubble + lookup-B (site k-mers of the branching bubbles)",
+         "l2": "flushed between timed steps (256 MiB memset); the KMC index exceeds L2" if cfg.idx != 4 else
+               "flushed between timed steps (256 MiB memset); flag matrices of the long pairs exceed L2",
+         "kmc_index": "replicated on every GPU"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU legs: the unmodified reference (oracle/_ref), all host threads
+# ---------------------------------------------------------------------------------------------------------------------
+def open_checker():
+    from oracle.bindings import Checker
+    try:
+        return Checker("ref"), "reference"
+    except Exception:
+        return Checker("oracle"), "port"
 
 
 def site_kmer_proxy(msa, strict, k):
-    """CPU legs only: the lookup-B workload of an alignment result as a flat k-mer batch -- for every variable column of every
-    branching bubble and every row, the k characters ending at the column (the reference's site k-mer when no indel precedes the
-    site, CDBG.cpp:2469-2472); windows that touch a gap or start before the row are left out.  A proxy for the reference's own
-    string handling (which cannot be driven without its Bifrost graph): same number and kind of database lookups."""
+    """The lookup-B workload of an alignment result as a flat k-mer batch: for every variable column of every branching bubble and
+    every row, the k characters ending at the column (the reference's site k-mer when no indel precedes the site,
+    CDBG.cpp:2469-2472); windows that touch a gap or start before the row are left out.  Stands in for the reference's own
+    string handling in the TIMED reference legs (same number and kind of database lookups)."""
     nv = np.diff(msa["var_off"]).astype(np.int64)
     b_of_site = np.repeat(np.arange(len(nv)), nv)
     keep = strict[b_of_site] == 0
@@ -127,24 +261,19 @@ def site_kmer_proxy(msa, strict, k):
     c = col[site_of_row]
     ok = c - k + 1 >= 0
     start = (msa["rows_off"].astype(np.int64)[b] + r * L + c - k + 1)[ok]
+    if len(start) == 0:
+        return np.zeros(0, np.uint8), np.zeros(1, np.uint64)
     win = msa["rows"][start[:, None] + np.arange(k)[None, :]]
     win = win[~(win == ord("-")).any(axis=1)]
     return np.ascontiguousarray(win.reshape(-1)), (np.arange(len(win) + 1, dtype=np.uint64) * k)
 
 
-def reference_arm(args, rank, world):
-    """The reference's own CPU implementation (unmodified SeqAlign + KMC API in oracle/_ref, driven by
+def reference_arm(args, cfg, rank):
+    """`--impl reference`: the reference's own CPU implementation (unmodified SeqAlign + KMC API in oracle/_ref, driven by
     oracle/ref_shim.cpp with PloidyFrost's readCov call pattern), all host threads, bounded sample per step."""
     if rank != 0:
         return
-    import tempfile
-    from oracle.bindings import Checker
-    try:
-        ref = Checker("ref")
-        kind = "reference"
-    except Exception:
-        ref = Checker("oracle")
-        kind = "port"
+    ref, kind = open_checker()
     cores = os.cpu_count() or 1
     device = None
     try:
@@ -153,34 +282,34 @@ def reference_arm(args, rank, world):
             device = "cuda:0"
     except Exception:
         pass
-    with tempfile.TemporaryDirectory(prefix="pfbench_ref_") as d:
-        bb, prefix, info = make_workload(args, 0, 1, True, d, device)
-        sample = bb.slice(0, min(bb.n_bubbles, args.ref_sample))
-        lb, lo = sample.lookup_sequences()
-        h = ref.kmc_open(prefix)
-        times = []
-        n_lookups = int(np.maximum(np.diff(lo).astype(np.int64) - K + 1, 0).sum())
-        n_site_kmers = 0
-        for it in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            ref.kmc_cov(h, lb, lo, mode=1, low=args.low, up=args.up, n_threads=cores)
-            msa = ref.align(sample.bases, sample.seq_off, sample.bubble_off, n_threads=cores)
-            t1 = time.perf_counter()
-            sb, so = site_kmer_proxy(msa, sample.bubble_type, K)       # untimed: stands in for the reference's string handling
-            t2 = time.perf_counter()
-            if len(so) > 1:
-                ref.kmc_counts(h, sb, so, K, mode=1, n_threads=cores)  # lookup-B
-            n_site_kmers = len(so) - 1
-            dt = (time.perf_counter() - t2) + (t1 - t0)
-            if it >= args.warmup:
-                times.append(dt)
-        ref.kmc_close(h)
+    bb = make_bubbles(cfg, args, 0)
+    prefix, info = ensure_db(cfg, args, device, bb)
+    sample = bb.slice(0, min(bb.n_bubbles, args.ref_sample))
+    lb, lo = sample.lookup_sequences()
+    h = ref.kmc_open(prefix)
+    times = []
+    n_lookups = int(np.maximum(np.diff(lo).astype(np.int64) - K + 1, 0).sum())
+    n_site_kmers = 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        ref.kmc_cov(h, lb, lo, mode=1, low=args.low, up=args.up, n_threads=cores)
+        msa = ref.align(sample.bases, sample.seq_off, sample.bubble_off, n_threads=cores)
+        t1 = time.perf_counter()
+        sb, so = site_kmer_proxy(msa, sample.bubble_type, K)       # untimed: stands in for the reference's string handling
+        t2 = time.perf_counter()
+        if len(so) > 1:
+            ref.kmc_counts(h, sb, so, K, mode=1, n_threads=cores)  # lookup-B
+        n_site_kmers = len(so) - 1
+        dt = (time.perf_counter() - t2) + (t1 - t0)
+        if it >= args.warmup:
+            times.append(dt)
+    ref.kmc_close(h)
     ms = 1e3 * sum(times) / len(times)
     val = sample.n_bubbles / (ms * 1e-3)
     line = {"impl": "reference", "metric": "superbubble variants/sec", "value": val, "unit": "bubbles/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": workload_config(args, sample.n_bubbles, info),
+            "config": workload_config(cfg, args, args.batch, info, {"sample_bubbles_per_step": sample.n_bubbles}),
             "kmc_lookups_per_s": n_lookups / (ms * 1e-3),
             "cpu_baseline": {"value": val, "unit": "bubbles/s", "cores": cores, "kind": kind,
                              "sample": f"{sample.n_bubbles} bubbles ({n_lookups} k-mer lookups + {n_site_kmers} site k-mer lookups) of the same batch per step"},
@@ -188,44 +317,105 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, n_bubbles, info):
-    return {"workload": f"configs[1]: synthetic tetraploid {args.genome_mbp:g} Mbp (4 haplotypes, 1% SNP, 0.1% indel), "
-                        f"60x-equivalent KMC2 db (k=25, p=9, sig 9, 512 bins), -z 8, M/D/G = 2/-1/-3",
-            "batch_bubbles": int(n_bubbles), "db_kmers": (info or {}).get("N"),
-            "step": "lookup-A (readCov of entrance + branch unitigs) + SequenceAlignment per bubble + lookup-B (site k-mers of the branching bubbles)",
-            "l2": "flushed between timed steps (256 MiB memset); KMC index (>2 GB) exceeds L2",
-            "kmc_index": ("hash index partitioned by mix(key) % n_gpus; " +
-                          ("other partitions mapped through CUDA IPC, buckets loaded over NVLink inside the lookup kernel"
-                           if getattr(args, "peer_active", False) else "queries routed by NCCL all-to-all"))
-                         if getattr(args, "sharded_db", False) else "replicated on every GPU"}
+def slice_msa(m, nb):
+    """first nb bubbles of a pf_msa_batch_t dump"""
+    out = {"n_bubbles": nb}
+    for key in ("status", "n_rows", "aln_len"):
+        out[key] = m[key][:nb]
+    for name, arrs in (("rows", ("rows",)), ("var", ("var_col", "var_kind")), ("cls", ("cls",)), ("ilen", ("ilen",))):
+        off = m[name + "_off"][:nb + 1]
+        out[name + "_off"] = off
+        for a in arrs:
+            out[a] = m[a][:int(off[-1])]
+    return out
 
 
+def cpu_baseline_and_parity(args, cfg, bb, prefix, n_sample, gpu_cov, gpu_msa, gpu_sites, skip_np, timed=True):
+    """oracle/_ref (the unmodified reference) on this box's host cores, on the first n_sample bubbles of the timed batch, same
+    database: its time is `cpu_baseline`, its results are what the CUDA path's results of those bubbles are diffed against."""
+    from oracle import parity
+    ref, kind = open_checker()
+    cores = os.cpu_count() or 1
+    S = min(bb.n_bubbles, n_sample)
+    sample = bb.slice(0, S)
+    lb, lo = sample.lookup_sequences()
+    n_lookups = int(np.maximum(np.diff(lo).astype(np.int64) - K + 1, 0).sum())
+    h = ref.kmc_open(prefix)
+    t0 = time.perf_counter()
+    cov_ref = ref.kmc_cov(h, lb, lo, mode=1, low=args.low, up=args.up, n_threads=cores)
+    t1 = time.perf_counter()
+    msa_ref = ref.align(sample.bases, sample.seq_off, sample.bubble_off, n_threads=cores)
+    t2 = time.perf_counter()
+    t_site = [0.0, 0]
+
+    def lookup(b, o):   # lookup-B of the reference: 'as written, else reverse complement' per site k-mer
+        ta = time.perf_counter()
+        r = ref.kmc_counts(h, b, o, K, mode=1, use_read_api=False, n_threads=cores)
+        t_site[0] += time.perf_counter() - ta
+        t_site[1] += len(o) - 1
+        return r
+
+    # ---- parity of the timed batch ----
+    nseq_s = int(sample.bubble_off[-1])
+    g_cov = np.concatenate([gpu_cov[:S], gpu_cov[bb.n_bubbles:bb.n_bubbles + nseq_s]])
+    cov_bad = parity.compare_cov(g_cov, cov_ref)
+    g_msa = slice_msa(gpu_msa, S)
+    msa_bad = int(parity.compare_msa(g_msa, msa_ref).sum())
+    site_bad, n_checked = 0, 0
+    if gpu_sites is not None:
+        checked, st, ncls, cv = parity.expected_site_cov(msa_ref, skip_np[:S], K, args.low, args.up, lookup, max_general=args.parity_general_sites)
+        ns, nc = int(msa_ref["var_off"][-1]), int(msa_ref["cls_off"][-1])
+        g_sites = {"status": gpu_sites["status"][:ns], "n_class": gpu_sites["n_class"][:ns], "cov": gpu_sites["cov"][:nc]}
+        site_bad = parity.compare_site_cov(g_sites, msa_ref, checked, st, ncls, cv) if msa_bad == 0 else -1
+        n_checked = int(checked.sum())
+    ref.kmc_close(h)
+    par = {"against": "oracle/_ref (unmodified SeqAlign + CKMCFile)" if kind == "reference" else "oracle port",
+           "bubbles": int(S), "cov_records": int(len(cov_ref)), "cov_mismatches": int(cov_bad),
+           "msa_bubbles_all_fields": int(S), "msa_mismatches": int(msa_bad),
+           "site_columns_checked": n_checked, "site_mismatches": int(site_bad),
+           "mismatches": int(cov_bad + msa_bad + max(site_bad, 0) + (1 if site_bad < 0 else 0))}
+    total = (t2 - t0) + t_site[0]
+    base = {"value": S / total, "unit": "bubbles/s", "cores": cores, "kind": kind,
+            "sample": f"{S} bubbles / {n_lookups} k-mer lookups + {t_site[1]} site k-mer lookups of the same batch, one pass, same KMC db",
+            "kmc_lookups_per_s": n_lookups / max(t1 - t0, 1e-9), "align_bubbles_per_s": S / max(t2 - t1, 1e-9),
+            "site_kmer_lookups_per_s": t_site[1] / max(t_site[0], 1e-9), "seconds": round(total, 2)}
+    return (base if timed else None), par
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--genome-mbp", type=float, default=100.0)
-    ap.add_argument("--batch", type=int, default=262144, help="bubbles per step per GPU")
-    ap.add_argument("--ref-sample", type=int, default=65536, help="bubbles per step of the CPU reference arm")
-    ap.add_argument("--cpu-sample", type=int, default=131072, help="bubbles of the cpu_baseline leg")
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json configs index: 2 hexaploid 1 Gbp (headline), 1 tetraploid 100 Mbp, 4 indel-heavy")
+    ap.add_argument("--genome-mbp", type=float, default=None, help="override the genome size of the config (smaller test runs)")
+    ap.add_argument("--batch", type=int, default=None, help="bubbles per step per GPU")
+    ap.add_argument("--ref-sample", type=int, default=None, help="bubbles per step of the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=None, help="bubbles of the cpu_baseline / parity leg")
+    ap.add_argument("--parity-general-sites", type=int, default=4000,
+                    help="parity: variable columns behind an indel site checked through the pure-Python restatement (all others are checked vectorised)")
     ap.add_argument("--low", type=int, default=2)
     ap.add_argument("--up", type=int, default=1000)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg AND the parity block (profiling runs)")
+    ap.add_argument("--no-sharded-legs", action="store_true", help="N > 1: skip the partitioned-index legs")
     ap.add_argument("--region-rank", type=int, default=None,
                     help="diagnostics: take the batch another rank would take (its region of the genome) on this GPU")
     ap.add_argument("--no-peer-lookup", action="store_true",
                     help="with --sharded-db: keep the route / NCCL all-to-all / scatter path instead of mapping the other partitions "
                          "through CUDA IPC and loading their buckets over NVLink")
     ap.add_argument("--sharded-db", action="store_true",
-                    help="partition the KMC index across the ranks (bin % world) and route queries with an NCCL all-to-all "
-                         "instead of replicating it (BASELINE config 3 variant)")
+                    help="ONLY the partitioned KMC index (no replicated copy): for databases beyond one GPU's HBM")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    cfg = Config(args.config, args.genome_mbp)
+    args.batch = args.batch or cfg.batch
+    args.ref_sample = args.ref_sample or cfg.ref_sample
+    args.cpu_sample = args.cpu_sample or cfg.cpu_sample
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
-        reference_arm(args, rank, world)
+        reference_arm(args, cfg, rank)
         return
 
     import torch
@@ -245,17 +435,21 @@ def main():
             dist.barrier()
 
     t_setup = time.perf_counter()
-    db_dir = f"/tmp/pfbench_{os.environ.get('MASTER_PORT', 'solo')}_{args.genome_mbp:g}"
-    os.makedirs(db_dir, exist_ok=True)
-    bb, prefix, info = make_workload(args, rank if args.region_rank is None else args.region_rank, world, rank == 0, db_dir, str(dev))
-    if world > 1:
-        obj = [info]
+    bb = make_bubbles(cfg, args, rank if args.region_rank is None else args.region_rank)
+    t_bubbles = time.perf_counter() - t_setup
+    prefix = info = None
+    if rank == 0 or cfg.idx == 4:
+        prefix, info = ensure_db(cfg, args, str(dev), bb, tag=f"_r{rank}" if cfg.idx == 4 and world > 1 else "")
+    if world > 1 and cfg.idx != 4:
+        obj = [prefix, info]
         dist.broadcast_object_list(obj, src=0)
-        info = obj[0]
+        prefix, info = obj
     barrier()
     torch.cuda.empty_cache()
+    t_open = time.perf_counter()
     ctx = capi.Context(local_rank)
-    if args.sharded_db:
+    sharded_only = bool(args.sharded_db and world > 1)
+    if sharded_only:
         from ploidyfrost_b200 import sharded
         db = capi.KmcDb(ctx, prefix, part=rank, n_parts=world)
         sh = sharded.ShardedKmcDb(db)
@@ -263,8 +457,11 @@ def main():
     else:
         db = capi.KmcDb(ctx, prefix)
         peer = False
+    if cfg.idx != 4 and not sharded_only and db.index_kind != "hash":
+        raise SystemExit(f"bench.py: the headline workload must run on the hash index, pf_kmc_open kept '{db.index_kind}' "
+                         f"(build status {db.build_status:#x}): a silent layout fallback is a failed run")
     barrier()
-    args.peer_active = bool(peer)
+    t_open = time.perf_counter() - t_open
     t_setup = time.perf_counter() - t_setup
 
     # ---- device-resident batch ----
@@ -282,7 +479,7 @@ def main():
     d_bo = torch.from_numpy(bb.bubble_off.astype(np.int32)).to(dev)
     skip_np = np.ascontiguousarray(bb.bubble_type.astype(np.uint8))        # strict bubbles: class coverage = sum of branch means, no site k-mers
     d_skip = torch.from_numpy(skip_np).to(dev)
-    do_sites = (not args.sharded_db) or peer                                # lookup phase B needs every k-mer reachable from this GPU
+    do_sites = (not sharded_only) or peer                                   # lookup phase B needs every k-mer reachable from this GPU
     seq_len = np.diff(bb.seq_off)
     max_len, max_rows = int(seq_len.max()), int(np.diff(bb.bubble_off).max())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -293,28 +490,42 @@ def main():
     assert sptr != 0
     torch.cuda.synchronize()
 
-    def step_device(ev=None):
+    def step_device(ev=None, kdb=None, route=None, cov_t=None):
+        kdb = kdb or db
+        cov_t = cov_t if cov_t is not None else d_cov
         if ev:
             ev[0].record(stream)
-        if args.sharded_db and not peer:
-            sh.lookup(d_lb, d_lo, d_wo, n_win, mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up, stream=stream)
+        if route is not None:
+            _, _, c = route.lookup(d_lb, d_lo, d_wo, n_win, mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up, stream=stream)
+            cov_t[:n_lseq * 24].copy_(c[:n_lseq * 24])
         else:
-            db.lookup_dev(d_lb.data_ptr(), len(lb), d_lo.data_ptr(), d_wo.data_ptr(), n_lseq, n_win, capi.LOOKUP_CANONICAL, args.low,
-                          args.up, None, None, d_cov.data_ptr(), sptr)
+            kdb.lookup_dev(d_lb.data_ptr(), len(lb), d_lo.data_ptr(), d_wo.data_ptr(), n_lseq, n_win, capi.LOOKUP_CANONICAL, args.low,
+                           args.up, None, None, cov_t.data_ptr(), sptr)
         if ev:
             ev[1].record(stream)
         ctx.align_dev(d_ab.data_ptr(), len(bb.bases), d_ao.data_ptr(), bb.n_seq, d_bo.data_ptr(), bb.n_bubbles, max_len, max_rows,
                       stream=sptr)
         if ev:
             ev[2].record(stream)
-        if do_sites:
-            db.site_cov_dev(args.low, args.up, d_skip.data_ptr(), sptr)
+        if route is None and (kdb is not db or do_sites):
+            kdb.site_cov_dev(args.low, args.up, d_skip.data_ptr(), sptr)
         if ev:
             ev[3].record(stream)
 
+    def timed_loop(**kw):
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+        with torch.cuda.stream(stream):
+            for it in range(args.steps):
+                flush.fill_(it & 0xFF)
+                step_device(evs[it], **kw)
+        torch.cuda.synchronize()
+        seg = lambda a, b: sum(e[a].elapsed_time(e[b]) for e in evs) / len(evs)
+        return seg(0, 3), seg(0, 1), seg(1, 2), seg(2, 3)
+
+    main_route = sh if (sharded_only and not peer) else None
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 1)):
-            step_device()
+            step_device(route=main_route)
     torch.cuda.synchronize()
     cells = ctx.last_cells
     retry = ctx.last_retry_count
@@ -325,38 +536,27 @@ def main():
     barrier()
     torch.cuda.synchronize()
     launches0 = ctx.launches
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    with torch.cuda.stream(stream):
-        for it in range(args.steps):
-            flush.fill_(it & 0xFF)
-            step_device(evs[it])
-    torch.cuda.synchronize()
+    ms_step, ms_lookup, ms_align, ms_site = timed_loop(route=main_route)
     barrier()
     launches = ctx.launches - launches0
-    t_lookup = [e[0].elapsed_time(e[1]) for e in evs]
-    t_align = [e[1].elapsed_time(e[2]) for e in evs]
-    t_site = [e[2].elapsed_time(e[3]) for e in evs]
-    t_step = [e[0].elapsed_time(e[3]) for e in evs]
-    ms_step = sum(t_step) / len(t_step)
 
     # ---- e2e: host-pointer C ABI from pinned host buffers ----
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t, t.numpy()
 
-    keep = []
     h_lb, h_lo, h_ab, h_ao, h_bo, h_wo = [pinned(x) for x in (lb, lo, bb.bases, bb.seq_off, bb.bubble_off, wo)]
-    keep += [h_lb, h_lo, h_ab, h_ao, h_bo, h_wo]
     e2e_times = []
     e2e_cov_times = []
     cov_pinned = torch.empty(n_lseq * 24, dtype=torch.uint8).pin_memory()
     cov_out = cov_pinned.numpy().view(capi.COV_DTYPE)
     d2h_bytes = 0
+    msa = sites = cov = None
     for it in range(2 + args.steps):
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        if args.sharded_db and not peer:   # no host-pointer form of the partitioned lookup: copy in, route/exchange/lookup, copy the cov records out
+        if main_route is not None:   # no host-pointer form of the routed lookup: copy in, route/exchange/lookup, copy the cov records out
             with torch.cuda.stream(stream):
                 e_lb = h_lb[0].to(dev, non_blocking=True)
                 e_lo = h_lo[0].to(dev, non_blocking=True).view(torch.int64)
@@ -370,7 +570,7 @@ def main():
         t1 = time.perf_counter()
         msa = ctx.align(h_ab[1], h_ao[1], h_bo[1], copy=False)   # views of the pinned result arena (C-ABI ownership rule)
         sites = db.site_cov(args.low, args.up, skip_np, copy=False) if do_sites else None   # views, like the alignment result
-        if not args.sharded_db or peer:
+        if main_route is None:
             db.wait()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -387,14 +587,68 @@ def main():
     site_hist = np.bincount(sites["status"], minlength=5).tolist() if sites is not None else None
     n_sites = int(len(sites["status"])) if sites is not None else 0
     n_ok = int((msa["status"] == 0).sum())
+    status_hist = {int(k): int(v) for k, v in zip(*np.unique(msa["status"], return_counts=True))}
+
+    # ---- N > 1: the same batch through the KMC index PARTITIONED across the GPUs, checked against the replicated index ----
+    shard_res = None
+    if world > 1 and not sharded_only and not args.no_sharded_legs and cfg.idx != 4:
+        from ploidyfrost_b200 import sharded
+        shard_res = {"n_parts": world, "partition": "hash index sliced by mix(key) % n_gpus"}
+        rep_cov = d_cov.clone()
+        rep_sites = {k_: v.copy() for k_, v in sites.items()}
+        t0 = time.perf_counter()
+        dbp = capi.KmcDb(ctx, prefix, part=rank, n_parts=world)
+        barrier()
+        shard_res["open_s"] = round(time.perf_counter() - t0, 2)
+        shard_res["index_bytes_per_gpu"] = dbp.device_bytes
+        shard_res["index_kind"] = dbp.index_kind
+        d_cov2 = torch.empty_like(d_cov)
+        shp = sharded.ShardedKmcDb(dbp)
+        with torch.cuda.stream(stream):        # (a) route -> NCCL all-to-all -> lookup at the owner -> all-to-all -> scatter
+            step_device(kdb=dbp, route=shp, cov_t=d_cov2)
+        torch.cuda.synchronize()
+        barrier()
+        r_step, r_lookup, _, _ = timed_loop(kdb=dbp, route=shp, cov_t=d_cov2)
+        eq_route = bool(torch.equal(d_cov2, rep_cov))
+        shard_res["nccl_route"] = {"ms_lookup": r_lookup, "equal_to_replicated": eq_route, "keys_sent_per_step": shp.last_sent}
+        barrier()
+        eq_peer = eq_sites = None
+        if sharded.attach_peers(dbp, dev):     # (b) the other slices mapped through CUDA IPC: one kernel, buckets loaded over NVLink
+            d_cov2.zero_()
+            with torch.cuda.stream(stream):
+                step_device(kdb=dbp, cov_t=d_cov2)
+            torch.cuda.synchronize()
+            barrier()
+            p_step, p_lookup, p_align, p_site = timed_loop(kdb=dbp, cov_t=d_cov2)
+            eq_peer = bool(torch.equal(d_cov2, rep_cov))
+            psites = dbp.site_cov(args.low, args.up, skip_np, copy=False)
+            eq_sites = all(np.array_equal(psites[k_], rep_sites[k_]) for k_ in rep_sites)
+            shard_res["peer_memory"] = {"ms_step": p_step, "ms_lookup": p_lookup, "ms_site_cov": p_site, "equal_to_replicated": eq_peer,
+                                        "site_cov_equal_to_replicated": bool(eq_sites)}
+        else:
+            shard_res["peer_memory"] = None
+        barrier()
+        flags = torch.tensor([int(eq_route), int(eq_peer is not False), int(eq_sites is not False)], dtype=torch.int32, device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        shard_res["all_ranks_equal"] = bool(flags.min().item())
+        tt = torch.tensor([r_lookup, shard_res["peer_memory"]["ms_lookup"] if shard_res["peer_memory"] else 0.0,
+                           shard_res["peer_memory"]["ms_step"] if shard_res["peer_memory"] else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        shard_res["nccl_route"]["ms_lookup"] = float(tt[0])
+        if shard_res["peer_memory"]:
+            shard_res["peer_memory"]["ms_lookup"] = float(tt[1])
+            shard_res["peer_memory"]["ms_step"] = float(tt[2])
+        dbp.close()
 
     # ---- reduce over ranks (max time, summed work) ----
-    sys.stderr.write(f"[rank {rank}] step {ms_step:.2f} ms (lookup {sum(t_lookup) / len(t_lookup):.2f}, align {sum(t_align) / len(t_align):.2f}, sites {sum(t_site) / len(t_site):.2f}), "
-                     f"e2e {ms_e2e:.2f} ms; tiers {ctx.last_tier_counts} heavy-queued {heavy_q}; batch {bb.stats()}\n")
+    sys.stderr.write(f"[rank {rank}] step {ms_step:.2f} ms (lookup {ms_lookup:.2f}, align {ms_align:.2f}, sites {ms_site:.2f}), "
+                     f"e2e {ms_e2e:.2f} ms; tiers {ctx.last_tier_counts} heavy-queued {heavy_q}; setup {t_setup:.1f}s "
+                     f"(bubbles {t_bubbles:.1f}s, open {t_open:.1f}s); batch {bb.stats()}\n")
     from ploidyfrost_b200 import shard
     (ms_step, ms_e2e, ms_lookup, ms_align, ms_site), (tot_bubbles, tot_win, tot_cells) = shard.reduce_step(
-        [ms_step, ms_e2e, sum(t_lookup) / len(t_lookup), sum(t_align) / len(t_align), sum(t_site) / len(t_site)], [bb.n_bubbles, n_win, cells], device=dev)
+        [ms_step, ms_e2e, ms_lookup, ms_align, ms_site], [bb.n_bubbles, n_win, cells], device=dev)
 
+    rc = 0
     if rank == 0:
         peaks = {}
         try:
@@ -402,37 +656,48 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         gather_gbs = ctx.bench_random_gather(4 << 30)
         int32_gops = ctx.bench_int32()
-        # measured DRAM traffic per launch (ncu, profiles/r01_traffic.json) -- only valid for the workload it was captured on
+        # DRAM traffic per launch comes from an ncu capture of THIS workload (profiles/r02_traffic.json); it is not measured in the run
         traffic = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(f"config{cfg.idx}", {})
         except Exception:
             pass
-        default_wl = args.batch == 262144 and args.genome_mbp == 100.0 and not args.sharded_db
-        t_lookup = traffic.get("kmc_hash_lookup_kernel", {}).get("bytes") if default_wl and db.index_kind == "hash" else None
-        t_align = traffic.get("align_pipeline", {}).get("bytes") if default_wl else None
+        default_wl = args.batch == cfg.batch and args.genome_mbp is None and not sharded_only
+        tr_lookup = traffic.get("kmc_hash_lookup_kernel") if default_wl and db.index_kind == "hash" else None
+        tr_align = traffic.get("align_pipeline") if default_wl else None
         lookups_s = (tot_win / world) / (ms_lookup * 1e-3)       # per GPU, for the per-kernel roofline
         cells_s = (tot_cells / world) / (ms_align * 1e-3)
         roof_lookup = {"kernel": "kmc_hash_lookup_kernel" if db.index_kind == "hash" else "kmc_lookup_kernel", "bound": "hbm",
                        "achieved": lookups_s * 64 / 1e9, "peak": hbm_peak,
-                       "unit": "GB/s", "frac": lookups_s * 64 / 1e9 / hbm_peak, "traffic": t_lookup, "peak_source": peak_src,
+                       "unit": "GB/s", "frac": lookups_s * 64 / 1e9 / hbm_peak,
+                       "traffic": (tr_lookup or {}).get("bytes"), "traffic_source": (tr_lookup or {}).get("source"),
+                       "peak_source": peak_src,
                        "algorithmic_bytes_per_lookup": 64, "lookups_per_launch": tot_win / world, "ms": ms_lookup,
-                       "random_sector_gather_gbs": gather_gbs, "index": db.index_kind,
-                       "index_bytes": db.device_bytes, "frac_of_random_gather": lookups_s * 64 / 1e9 / gather_gbs}
-        roof_align = {"kernel": "alignment pipeline: msa_lane_kernel (branches <= 96) + msa_group_kernel<2/2/4/32> (<= 128 / 192 / 256 / longer), concurrent streams",
+                       "random_sector_gather_gbs": gather_gbs, "index": db.index_kind, "index_bytes": db.device_bytes,
+                       "sectors_per_lookup_design": 1,
+                       "frac_of_random_sector_rate": lookups_s * 32 / 1e9 / gather_gbs}
+        roof_align = {"kernel": "alignment pipeline (msa_lane_kernel / msa_group_kernel / msa_cta_kernel by size class, concurrent streams)",
                       "bound": "int32", "achieved": cells_s * 18 / 1e9, "peak": int32_gops,
-                      "unit": "Gop/s", "frac": cells_s * 18 / 1e9 / int32_gops, "traffic": t_align,
-                      "peak_source": "measured in this run (pf_bench_int32: IADD/IMNMX/LOP mix)", "int32_ops_per_cell": 18,
-                      "cells_per_launch": tot_cells / world, "ms": ms_align}
+                      "unit": "Gop/s", "frac": cells_s * 18 / 1e9 / int32_gops,
+                      "traffic": (tr_align or {}).get("bytes"), "traffic_source": (tr_align or {}).get("source"),
+                      "peak_source": "measured in this run (pf_bench_int32: IADD/IMNMX/LOP mix); MEASURED_PEAKS.json has no INT32 entry",
+                      "int32_ops_per_cell": 18, "cells_per_launch": tot_cells / world, "ms": ms_align}
         dominant = roof_align if ms_align >= ms_lookup else roof_lookup
+        extra = {}
+        if sharded_only:
+            extra["kmc_index"] = ("hash index partitioned by mix(key) % n_gpus; " +
+                                  ("other partitions mapped through CUDA IPC, buckets loaded over NVLink inside the lookup kernel" if peer
+                                   else "queries routed by NCCL all-to-all"))
         line = {"metric": "superbubble variants/sec", "value": tot_bubbles / (ms_step * 1e-3), "unit": "bubbles/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": workload_config(args, bb.n_bubbles, info),
-                "kmc_lookups_per_s": tot_win / (ms_step * 1e-3), "kmc_lookups_per_s_kernel": tot_win / (ms_lookup * 1e-3),
+                "config": workload_config(cfg, args, bb.n_bubbles, info, extra),
+                "kmc_lookups": {"metric": "KMC k-mer lookups/sec", "value": tot_win / (ms_lookup * 1e-3), "unit": "lookups/s",
+                                "lookups_per_step": tot_win, "ms_lookup_kernel": ms_lookup,
+                                "per_step_rate": tot_win / (ms_step * 1e-3)},
                 "dp_cells_per_s_kernel": tot_cells / (ms_align * 1e-3),
                 "ms_lookup_kernel": ms_lookup, "ms_align_pipeline": ms_align, "ms_site_cov_kernel": ms_site,
                 "site_columns_per_step": n_sites, "site_status_hist(ok,dropped,missing,undefined,skipped)": site_hist,
@@ -443,53 +708,36 @@ def main():
                         "calls": "pf_kmc_cov_async | pf_align | pf_site_cov | pf_kmc_wait"},
                 "gpu_launches": int(launches),
                 "roofline": dominant, "roofline_lookup": roof_lookup, "roofline_align": roof_align,
-                "bubbles_ok": n_ok, "tier2_retries": int(retry), "heavy_queued": int(heavy_q), "setup_s": round(t_setup, 1),
+                "bubbles_ok": n_ok, "bubble_status_hist": status_hist, "tier2_retries": int(retry), "heavy_queued": int(heavy_q),
+                "setup_s": round(t_setup, 1), "db_open_s": round(t_open, 2), "db_build_s": (info or {}).get("build_s"),
                 "batch_stats": bb.stats()}
-        if not args.no_cpu_baseline and world >= 1:
-            line["cpu_baseline"] = cpu_baseline(args, bb, prefix)
+        if shard_res is not None:
+            line["sharded"] = shard_res
+            if not shard_res.get("all_ranks_equal", True):
+                rc = 3
+        if not args.no_cpu_baseline:
+            n_par = args.cpu_sample if world == 1 else min(args.cpu_sample, 32768)
+            base, par = cpu_baseline_and_parity(args, cfg, bb, prefix, n_par, cov, msa, sites, skip_np, timed=(world == 1))
+            if base is not None:
+                line["cpu_baseline"] = base
+            line["parity"] = par
+            if par["mismatches"]:
+                rc = 2
+        else:
+            line["parity"] = None
         print(json.dumps(line), flush=True)
-        for ext in (".kmc_pre", ".kmc_suf"):
-            try:
-                os.remove(prefix + ext)
-            except OSError:
-                pass
+        if rc:
+            sys.stderr.write(f"bench.py: PARITY FAILURE (rc {rc}): {json.dumps(line.get('parity'))} {json.dumps(line.get('sharded'))}\n")
     db.close()
     ctx.close()
     if world > 1:
+        code = torch.tensor([rc], dtype=torch.int32, device=dev)
+        dist.all_reduce(code, op=dist.ReduceOp.MAX)
+        rc = int(code.item())
         dist.barrier()
         dist.destroy_process_group()
-
-
-def cpu_baseline(args, bb, prefix):
-    """oracle/_ref (the unmodified reference) on this box's host cores, bounded sample of the same batch, same database."""
-    from oracle.bindings import Checker
-    try:
-        ref = Checker("ref")
-        kind = "reference"
-    except Exception:
-        ref = Checker("oracle")
-        kind = "port"
-    cores = os.cpu_count() or 1
-    sample = bb.slice(0, min(bb.n_bubbles, args.cpu_sample))
-    lb, lo = sample.lookup_sequences()
-    n_lookups = int(np.maximum(np.diff(lo).astype(np.int64) - K + 1, 0).sum())
-    h = ref.kmc_open(prefix)
-    t0 = time.perf_counter()
-    ref.kmc_cov(h, lb, lo, mode=1, low=args.low, up=args.up, n_threads=cores)
-    t1 = time.perf_counter()
-    msa = ref.align(sample.bases, sample.seq_off, sample.bubble_off, n_threads=cores)
-    t2 = time.perf_counter()
-    sb, so = site_kmer_proxy(msa, sample.bubble_type, K)               # untimed: stands in for the reference's string handling
-    t3 = time.perf_counter()
-    if len(so) > 1:
-        ref.kmc_counts(h, sb, so, K, mode=1, n_threads=cores)          # lookup-B
-    t4 = time.perf_counter()
-    ref.kmc_close(h)
-    total = (t2 - t0) + (t4 - t3)
-    return {"value": sample.n_bubbles / total, "unit": "bubbles/s", "cores": cores, "kind": kind,
-            "sample": f"{sample.n_bubbles} bubbles / {n_lookups} k-mer lookups + {len(so) - 1} site k-mer lookups of the same batch, one pass, same KMC db",
-            "kmc_lookups_per_s": n_lookups / (t1 - t0), "align_bubbles_per_s": sample.n_bubbles / (t2 - t1),
-            "site_kmer_lookups_per_s": (len(so) - 1) / max(t4 - t3, 1e-9), "seconds": round(total, 2)}
+    if rc:
+        sys.exit(rc)
 
 
 if __name__ == "__main__":

@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libpfgpu.so")
-SOURCES = ["pf_api.cu", "pf_kmc.cu", "pf_align.cu", "pf_pipeline.cu"]
+SOURCES = ["pf_api.cu", "pf_kmc.cu", "pf_align.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -82,15 +82,40 @@ class ShardedKmcDb:
         self.k = db.k
         self.last_sent = 0
         self.last_received = 0
+        self._stream = None   # the stream lookup() runs on when the caller gives none (never torch's default stream)
 
     def lookup(self, d_bases: torch.Tensor, d_seq_off: torch.Tensor, d_win_off: torch.Tensor, n_windows: int, mode=0, low=0,
                up=0xFFFFFFFF, want_cov=True, stream=None):
         """Device tensors in (uint8 bases -- may be padded past the last sequence --, int64 offsets), device tensors
         out: (counts int32-as-u32, found uint8, cov bytes)."""
         dev = d_bases.device
+        # The C calls and the NCCL exchanges must share ONE explicit stream: handle 0 (torch's legacy default stream) means "the
+        # context's own non-blocking stream" to the C ABI, which NCCL's collectives (ordered on torch's current stream) would not
+        # order against.  So the body always runs under a non-default torch stream; when the caller did not supply one, ours is
+        # ordered after the caller's current stream (the inputs) and the caller's stream after ours (the outputs).
+        own = stream is None or stream.cuda_stream == 0
+        if own:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(dev)
+            stream = self._stream
+            stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream):
+            out = self._lookup_on(stream, d_bases, d_seq_off, d_win_off, n_windows, mode, low, up, want_cov)
+        if own:
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_stream(stream)
+            for t in (d_bases, d_seq_off, d_win_off):   # allocated on the caller's stream, read on ours
+                t.record_stream(stream)
+            for t in out:                                # allocated on ours, read on the caller's
+                if t is not None:
+                    t.record_stream(cur)
+        return out
+
+    def _lookup_on(self, stream, d_bases, d_seq_off, d_win_off, n_windows, mode, low, up, want_cov):
+        dev = d_bases.device
         n_seq = d_seq_off.numel() - 1
-        sptr = stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
-        sptr = sptr or None
+        sptr = stream.cuda_stream
+        assert sptr != 0
         send_keys = torch.empty(max(n_windows, 1), dtype=torch.int64, device=dev)
         send_idx = torch.empty(max(n_windows, 1), dtype=torch.int32, device=dev)
         off = self.db.route_dev(d_bases.data_ptr(), d_bases.numel(), d_seq_off.data_ptr(), d_win_off.data_ptr(), n_seq, n_windows, mode,

@@ -12,6 +12,7 @@
 // the exit unitig (CDBG.cpp:2226).  A cluster whose paths share no inner k-mer is a strict bubble (each
 // branch is one unitig, CDBG.cpp:1998-2050), otherwise a branching one (:2190-2273).
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -47,8 +48,10 @@ struct Hap {
 
 const char ALPHA[4] = {'A', 'C', 'G', 'T'};
 
+// `offset`: absolute coordinate of anc[0] -- events are keyed by absolute position, so a region generated on its own carries the
+// same variants as the same stretch of the whole genome (away from the region's `margin`s, where no event is placed).
 void make_haplotype(uint64_t seed, uint32_t hap_id, const std::vector<uint8_t> &anc, double p_snp, double p_indel,
-                    double p_long, uint32_t long_min, uint32_t long_max, Hap &h) {
+                    double p_long, uint32_t long_min, uint32_t long_max, Hap &h, uint64_t offset = 0) {
     const uint64_t n = anc.size();
     h.seq.clear();
     h.seq.reserve(n + n / 64);
@@ -57,7 +60,7 @@ void make_haplotype(uint64_t seed, uint32_t hap_id, const std::vector<uint8_t> &
     const uint64_t key = splitmix64(seed ^ (0xA5A5A5A5ull * (hap_id + 1)));
     const uint64_t margin = 64;
     while (a < n) {
-        const uint64_t r0 = splitmix64(key ^ (a * 0x9E3779B97F4A7C15ull));
+        const uint64_t r0 = splitmix64(key ^ ((a + offset) * 0x9E3779B97F4A7C15ull));
         const double u = u01(r0);
         const bool inner = a > margin && a + margin + long_max + 16 < n;
         if (inner && u < p_snp) {
@@ -146,13 +149,24 @@ struct Workload {
 
 extern "C" {
 
-void *pfs_create(uint64_t seed, uint64_t genome_len, uint32_t n_hap, double p_snp, double p_indel, double p_long,
-                 uint32_t long_min, uint32_t long_max, int n_threads) {
+// root_seed != 0: the ancestor is a SUBGENOME ancestor -- the i.i.d. root genome of `root_seed` with every base substituted
+// with probability `divergence` (BASELINE configs[2]: 3 subgenomes, 10 % diverged); root_seed == 0: the ancestor is i.i.d.
+// offset: the generated stretch is [offset, offset + genome_len) of the (conceptual) whole genome.
+void *pfs_create_sub(uint64_t seed, uint64_t genome_len, uint32_t n_hap, double p_snp, double p_indel, double p_long,
+                     uint32_t long_min, uint32_t long_max, int n_threads, uint64_t root_seed, double divergence, uint64_t offset) {
     Workload *w = new Workload();
     w->anc.resize(genome_len);
-    const uint64_t gkey = splitmix64(seed);
+    const uint64_t gkey = splitmix64(root_seed ? root_seed : seed), skey = splitmix64(seed ^ 0x5B5B5B5B5B5B5B5Bull);
     auto fill = [&](uint64_t b, uint64_t e) {
-        for (uint64_t i = b; i < e; i++) w->anc[i] = (uint8_t)ALPHA[splitmix64(gkey ^ (i * 0xD6E8FEB86659FD93ull)) & 3];
+        for (uint64_t ii = b; ii < e; ii++) {
+            const uint64_t i = ii + offset;
+            uint32_t c = (uint32_t)(splitmix64(gkey ^ (i * 0xD6E8FEB86659FD93ull)) & 3);
+            if (root_seed) {
+                const uint64_t r = splitmix64(skey ^ (i * 0x9E3779B97F4A7C15ull));
+                if (u01(r) < divergence) c = (c + 1 + (uint32_t)(splitmix64(r) % 3)) & 3;
+            }
+            w->anc[ii] = (uint8_t)ALPHA[c];
+        }
     };
     n_threads = std::max(1, n_threads);
     {
@@ -168,13 +182,18 @@ void *pfs_create(uint64_t seed, uint64_t genome_len, uint32_t n_hap, double p_sn
     {
         std::vector<std::thread> th;
         for (uint32_t h = 0; h < n_hap; h++)
-            th.emplace_back([=] { make_haplotype(seed, h, w->anc, p_snp, p_indel, p_long, long_min, long_max, w->haps[h]); });
+            th.emplace_back([=] { make_haplotype(seed, h, w->anc, p_snp, p_indel, p_long, long_min, long_max, w->haps[h], offset); });
         for (auto &t : th) t.join();
     }
     return w;
 }
 
 void pfs_destroy(void *h) { delete (Workload *)h; }
+
+void *pfs_create(uint64_t seed, uint64_t genome_len, uint32_t n_hap, double p_snp, double p_indel, double p_long,
+                 uint32_t long_min, uint32_t long_max, int n_threads) {
+    return pfs_create_sub(seed, genome_len, n_hap, p_snp, p_indel, p_long, long_min, long_max, n_threads, 0, 0.0, 0);
+}
 
 uint64_t pfs_hap_len(void *h, uint32_t hap) { return ((Workload *)h)->haps[hap].seq.size(); }
 const uint8_t *pfs_hap_ptr(void *h, uint32_t hap) { return ((Workload *)h)->haps[hap].seq.data(); }
@@ -241,6 +260,60 @@ uint64_t pfs_make_bubbles(void *hh, uint32_t k, uint64_t r0, uint64_t r1, uint64
         i = j;
     }
     return nb;
+}
+
+// BASELINE configs[4] (indel-heavy stress): n bubbles of 2..max_rows branches; the first branch has a length log-uniform in
+// [min_len, max_len]; every other branch is a copy with 1 % substitutions, 0.1 % short indels and at least one long indel
+// (an insertion or deletion of 5 .. 40 % of the branch, capped so the result stays within [k, max_len]).  Branches are
+// ordered like the reference's branching bubbles (sort_branching).  The ancestor / haplotypes of `hh` are not used.
+uint64_t pfs_make_long_bubbles(void *hh, uint64_t seed, uint32_t k, uint64_t n_bubbles, uint32_t min_len, uint32_t max_len,
+                               uint32_t max_rows) {
+    Workload *w = (Workload *)hh;
+    w->bases.clear(); w->seq_off.assign(1, 0); w->bubble_off.assign(1, 0); w->bubble_type.clear();
+    w->ent_size.clear(); w->exit_size.clear(); w->ent_bases.clear(); w->ent_off.assign(1, 0);
+    const double lmin = std::log((double)min_len), lmax = std::log((double)max_len);
+    for (uint64_t b = 0; b < n_bubbles; b++) {
+        uint64_t r = splitmix64(seed ^ (b * 0xD1B54A32D192ED03ull));
+        auto next = [&]() { return r = splitmix64(r); };
+        const uint32_t L = (uint32_t)std::min<double>(max_len, std::max<double>(min_len, std::exp(lmin + (lmax - lmin) * u01(next()))));
+        const uint32_t nr = 2 + (uint32_t)(next() % (uint64_t)(max_rows - 1));
+        std::string first(L, 'A');
+        for (auto &c : first) c = ALPHA[next() & 3];
+        std::vector<std::string> seqs{first};
+        for (uint32_t q = 1; q < nr; q++) {
+            std::string s;
+            s.reserve(L + L / 2);
+            const uint32_t ilen = std::max<uint32_t>(10, (uint32_t)(L * (0.05 + 0.35 * u01(next()))));
+            const bool ins = (next() & 1) && L + ilen <= max_len;
+            const bool can_del = L > ilen + 2 * k;
+            const uint32_t at = k + (uint32_t)(next() % (uint64_t)std::max<int64_t>(1, (int64_t)L - 2 * k - (ins ? 0 : ilen)));
+            for (uint32_t i = 0; i < L; i++) {
+                if (i == at && ins) for (uint32_t t = 0; t < ilen; t++) s.push_back(ALPHA[next() & 3]);
+                if (!ins && can_del && i >= at && i < at + ilen) continue;
+                const double u = u01(next());
+                if (u < 0.01) { const char c = first[i]; const uint32_t ix = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3; s.push_back(ALPHA[(ix + 1 + next() % 3) & 3]); }
+                else if (u < 0.0105) { s.push_back(first[i]); for (uint32_t t = 0, n = 1 + next() % 5; t < n; t++) s.push_back(ALPHA[next() & 3]); }
+                else if (u < 0.011) { i += (uint32_t)(next() % 5); }
+                else s.push_back(first[i]);
+            }
+            if (s.size() > max_len) s.resize(max_len);
+            if (s.size() < k) s = first.substr(0, std::max<uint32_t>(k, L / 2));
+            if (std::find(seqs.begin(), seqs.end(), s) == seqs.end()) seqs.push_back(s);
+        }
+        if (seqs.size() < 2) { std::string s = first; s[s.size() / 2] = s[s.size() / 2] == 'A' ? 'C' : 'A'; seqs.push_back(s); }
+        sort_branching(seqs, 0, (int)seqs.size() - 1);
+        for (auto &s : seqs) {
+            w->bases.insert(w->bases.end(), s.begin(), s.end());
+            w->seq_off.push_back(w->bases.size());
+        }
+        w->bubble_off.push_back((uint32_t)(w->seq_off.size() - 1));
+        w->bubble_type.push_back(0);
+        for (uint32_t i = 0; i < 100; i++) w->ent_bases.push_back(ALPHA[next() & 3]);
+        w->ent_off.push_back(w->ent_bases.size());
+        w->ent_size.push_back(100);
+        w->exit_size.push_back(100);
+    }
+    return n_bubbles;
 }
 
 uint64_t pfs_n_seq(void *h) { return ((Workload *)h)->seq_off.size() - 1; }

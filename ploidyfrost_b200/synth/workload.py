@@ -35,6 +35,11 @@ def _load():
         L.pfs_create.restype = C.c_void_p
         L.pfs_create.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_uint32,
                                  C.c_uint32, C.c_int]
+        L.pfs_create_sub.restype = C.c_void_p
+        L.pfs_create_sub.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_uint32,
+                                     C.c_uint32, C.c_int, C.c_uint64, C.c_double, C.c_uint64]
+        L.pfs_make_long_bubbles.restype = C.c_uint64
+        L.pfs_make_long_bubbles.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
         L.pfs_destroy.argtypes = [C.c_void_p]
         L.pfs_hap_len.restype = C.c_uint64
         L.pfs_hap_len.argtypes = [C.c_void_p, C.c_uint32]
@@ -83,6 +88,24 @@ class BubbleBatch:
         off = np.concatenate([self.ent_off, self.seq_off[1:] + self.ent_off[-1]]).astype(np.uint64)
         return bases, off
 
+    @staticmethod
+    def concat(parts):
+        """one batch out of several (bubbles of different subgenomes / regions), in the order given"""
+        parts = [p for p in parts if p.n_bubbles]
+        if len(parts) == 1:
+            return parts[0]
+
+        def cat_off(arrs, dtype):
+            out, base = [np.zeros(1, dtype)], 0
+            for a in arrs:
+                out.append((a[1:].astype(np.uint64) + np.uint64(base)).astype(dtype))
+                base += int(a[-1])
+            return np.concatenate(out)
+        return BubbleBatch(np.concatenate([p.bases for p in parts]), cat_off([p.seq_off for p in parts], np.uint64),
+                           cat_off([p.bubble_off for p in parts], np.uint32), np.concatenate([p.bubble_type for p in parts]),
+                           np.concatenate([p.ent_bases for p in parts]), cat_off([p.ent_off for p in parts], np.uint64),
+                           np.concatenate([p.ent_size for p in parts]), np.concatenate([p.exit_size for p in parts]))
+
     def slice(self, b0, b1):
         s0, s1 = int(self.bubble_off[b0]), int(self.bubble_off[b1])
         c0, c1 = int(self.seq_off[s0]), int(self.seq_off[s1])
@@ -118,9 +141,13 @@ class BubbleBatch:
 
 class Workload:
     def __init__(self, seed, genome_len, n_hap, p_snp=0.01, p_indel=0.001, p_long=0.0, long_min=100, long_max=5000,
-                 n_threads=8):
+                 n_threads=8, root_seed=0, divergence=0.0, offset=0):
+        """root_seed != 0: a subgenome -- the ancestor is the root genome of `root_seed` with `divergence` substitutions.
+        offset: generate only the stretch [offset, offset + genome_len) of the whole genome (same bases, same variants away
+        from the first / last ~6 kbp of the stretch)."""
         self.L = _load()
-        self.h = self.L.pfs_create(seed, genome_len, n_hap, p_snp, p_indel, p_long, long_min, long_max, n_threads)
+        self.h = self.L.pfs_create_sub(seed, genome_len, n_hap, p_snp, p_indel, p_long, long_min, long_max, n_threads,
+                                       root_seed, divergence, offset)
         self.n_hap = n_hap
         self.genome_len = genome_len
 
@@ -135,8 +162,16 @@ class Workload:
     def ancestor(self) -> np.ndarray:
         return _arr(self.L.pfs_anc_ptr(self.h), self.genome_len, np.uint8)
 
+    def long_bubbles(self, seed, k, n_bubbles, min_len=50, max_len=5000, max_rows=4) -> BubbleBatch:
+        """BASELINE configs[4]: branch lengths log-uniform in [min_len, max_len], >= 1 long indel per bubble"""
+        self.L.pfs_make_long_bubbles(self.h, seed, k, n_bubbles, min_len, max_len, max_rows)
+        return self._batch(n_bubbles)
+
     def bubbles(self, k, r0, r1, max_bubbles=1 << 62) -> BubbleBatch:
         nb = self.L.pfs_make_bubbles(self.h, k, r0, r1, max_bubbles)
+        return self._batch(nb)
+
+    def _batch(self, nb) -> BubbleBatch:
         ns = self.L.pfs_n_seq(self.h)
         h = self.h
         return BubbleBatch(_arr(self.L.pfs_bases(h), self.L.pfs_n_bases(h), np.uint8),
@@ -157,30 +192,53 @@ def write_db_numpy(prefix, haps, k, lam_per_copy, seed, **kw):
     return info, u, cnt
 
 
+def _canonical_kmers_torch(h, k, dev, code):
+    import torch
+    c = code[torch.from_numpy(h).to(dev).long()]
+    n = c.numel() - k + 1
+    fwd = torch.zeros(n, dtype=torch.int64, device=dev)
+    rc = torch.zeros(n, dtype=torch.int64, device=dev)
+    for i in range(k):
+        fwd = (fwd << 2) | c[i:i + n]
+        rc = rc | ((3 - c[i:i + n]) << (2 * i))
+    return torch.minimum(fwd, rc)
+
+
 def write_db_torch(prefix, haps, k, lam_per_copy, seed, device="cuda", version=0x200, lut_prefix_len=9, sig_len=9,
                    n_bins=512, counter_size=2, min_count=1, max_count=10000):
-    """Large cases: the same database built with torch on the GPU (sort/unique of ~4e8 packed k-mers)."""
+    """Large cases: the same database built with torch on the GPU (sort/unique of the packed canonical k-mers).
+    `haps` is a list of haplotypes, or a list of GROUPS of haplotypes (subgenomes): every group is de-duplicated on its own
+    and the groups are merged afterwards, so that no single sort sees more than one group's k-mers (configs[2]: 3 groups of
+    2 x 333 Mbp, 1.2 G distinct k-mers)."""
     import torch
     dev = torch.device(device)
     code = torch.full((256,), 0, dtype=torch.int64, device=dev)
     for i, c in enumerate(b"ACGT"):
         code[c] = i
-    mask = (1 << (2 * k)) - 1
-    parts = []
-    for h in haps:
-        c = code[torch.from_numpy(h).to(dev).long()]
-        n = c.numel() - k + 1
-        fwd = torch.zeros(n, dtype=torch.int64, device=dev)
-        rc = torch.zeros(n, dtype=torch.int64, device=dev)
-        for i in range(k):
-            fwd = (fwd << 2) | c[i:i + n]
-            rc = rc | ((3 - c[i:i + n]) << (2 * i))
-        parts.append(torch.minimum(fwd, rc))
-        del c, fwd, rc
-    allk = torch.cat(parts)
-    del parts
-    u, mult = torch.unique(allk, sorted=True, return_counts=True)
-    del allk
+    groups = haps if isinstance(haps[0], (list, tuple)) else [haps]
+    us, ms = [], []
+    for grp in groups:
+        allk = torch.cat([_canonical_kmers_torch(h, k, dev, code) for h in grp])
+        u, mult = torch.unique(allk, sorted=True, return_counts=True)
+        del allk
+        us.append(u)
+        ms.append(mult)
+    if len(us) == 1:
+        u, mult = us[0], ms[0]
+    else:   # merge the groups: k-mers shared between subgenomes add their multiplicities
+        keys, mm = torch.cat(us), torch.cat(ms)
+        del us, ms
+        keys, order = torch.sort(keys)
+        mm = mm[order]
+        del order
+        first = torch.ones(keys.numel(), dtype=torch.bool, device=dev)
+        first[1:] = keys[1:] != keys[:-1]
+        seg = torch.cumsum(first, 0) - 1
+        u = keys[first]
+        del keys
+        mult = torch.zeros(u.numel(), dtype=torch.int64, device=dev).index_add_(0, seg, mm)
+        del seg, mm, first
+    us = ms = None
     g = torch.Generator(device=dev)
     g.manual_seed(int(seed))
     cnt = torch.poisson(mult.double() * lam_per_copy, generator=g).clamp_(1, 10000).long()
@@ -197,6 +255,7 @@ def write_db_torch(prefix, haps, k, lam_per_copy, seed, device="cuda", version=0
         for i in range(k - sig_len + 1):
             v = norm[(u >> (2 * (k - sig_len - i))) & smask]
             sig = v if sig is None else torch.minimum(sig, v)
+        del v
         smap_np = kmcdb.default_signature_map(sig_len, n_bins)
         bins = torch.from_numpy(smap_np.astype(np.int64)).to(dev)[sig]
         del sig
@@ -210,19 +269,25 @@ def write_db_torch(prefix, haps, k, lam_per_copy, seed, device="cuda", version=0
     u, cnt, slot = u[order], cnt[order], slot[order]
     del order
     lut = torch.searchsorted(slot, torch.arange(n_bins * (1 << (2 * p)), device=dev, dtype=torch.int64))
-    suf = u & ((1 << (2 * (k - p))) - 1)
-    rec = torch.empty((N, S + counter_size), dtype=torch.uint8, device=dev)
-    for j in range(S):
-        rec[:, j] = ((suf >> (8 * (S - 1 - j))) & 0xFF).to(torch.uint8)
-    for b in range(counter_size):
-        rec[:, S + b] = ((cnt >> (8 * b)) & 0xFF).to(torch.uint8)
-    rec_np = rec.cpu().numpy()
+    del slot
     lut_np = lut.cpu().numpy().astype(np.uint64)
-    del rec, lut, suf
-    with open(prefix + ".kmc_suf", "wb") as f:
+    del lut
+    suf = u & ((1 << (2 * (k - p))) - 1)
+    del u
+    with open(prefix + ".kmc_suf", "wb") as f:   # records in chunks: the host never holds more than one chunk
         f.write(b"KMCS")
-        rec_np.tofile(f)
+        step = 1 << 26
+        for a in range(0, N, step):
+            b = min(N, a + step)
+            rec = torch.empty((b - a, S + counter_size), dtype=torch.uint8, device=dev)
+            for j in range(S):
+                rec[:, j] = ((suf[a:b] >> (8 * (S - 1 - j))) & 0xFF).to(torch.uint8)
+            for q in range(counter_size):
+                rec[:, S + q] = ((cnt[a:b] >> (8 * q)) & 0xFF).to(torch.uint8)
+            rec.cpu().numpy().tofile(f)
+            del rec
         f.write(b"KMCS")
+    del suf, cnt
     with open(prefix + ".kmc_pre", "wb") as f:
         f.write(b"KMCP")
         lut_np.tofile(f)
@@ -237,4 +302,5 @@ def write_db_torch(prefix, haps, k, lam_per_copy, seed, device="cuda", version=0
         f.write(hdr)
         f.write(np.uint32(len(hdr)).tobytes())
         f.write(b"KMCP")
+    torch.cuda.empty_cache() if dev.type == "cuda" else None
     return dict(k=k, p=p, S=S, C=counter_size, N=int(N), version=version, n_bins=n_bins, sig_len=sig_len)

@@ -328,6 +328,7 @@ struct GroupExec {
     bool pf;             // flag bytes in HBM (prefetch ahead of the DFS) or in shared memory (heavy kernel)
     unsigned long long cells;
     __device__ __forceinline__ bool prefetch_flags() const { return pf; }
+    __device__ __forceinline__ uint32_t prefetch_cells() const { return 6; }
     // Everything outside the fill runs redundantly on all G lanes (identical loads, decisions and stores), so every lane
     // "is" the leader; the kernel uses g == 0 where something must happen once (queue, counters).
     __device__ __forceinline__ bool leader() const { return true; }
@@ -353,7 +354,7 @@ struct GroupExec {
         for (uint32_t p0 = 0; p0 < depth; p0 += G) {
             const uint32_t p = p0 + g;
             const bool live = p < depth;
-            const uint8_t m = live ? mv[depth - 1 - p] : (uint8_t)MV_NONE;
+            const uint8_t m = live ? (uint8_t)(mv[depth - 1 - p] & 3) : (uint8_t)MV_NONE;
             const bool use_a = live && m != MV_L, use_b = live && m != MV_U;
             const uint32_t ma = group_bits(__ballot_sync(gmask, use_a)), mb = group_bits(__ballot_sync(gmask, use_b));
             const uint8_t a = use_a ? row[ia + __popc(ma & ltm)] : (uint8_t)'-';
@@ -389,7 +390,7 @@ struct GroupExec {
         for (uint32_t p0 = 0; p0 < depth; p0 += G) {
             const uint32_t p = p0 + g;
             const bool live = p < depth;
-            const bool use = live && mv[depth - 1 - p] != gap_move;
+            const bool use = live && (mv[depth - 1 - p] & 3) != gap_move;
             const uint32_t mu = group_bits(__ballot_sync(gmask, use));
             if (live) dst[p] = use ? src[ia + __popc(mu & ltm)] : (uint8_t)'-';
             ia += __popc(mu);

@@ -175,7 +175,7 @@ PF_HD PairKey analyze_moves(const Scoring &sc, const CBV row, const CBV B, const
         const uint32_t cnt = t0 < PF_CH ? t0 : PF_CH;
         uint8_t m[PF_CH], a[PF_CH], b[PF_CH];
 #pragma unroll
-        for (uint32_t q = 0; q < PF_CH; q++) m[q] = q < cnt ? mv[t0 - 1 - q] : (uint8_t)MV_NONE;
+        for (uint32_t q = 0; q < PF_CH; q++) m[q] = q < cnt ? (uint8_t)(mv[t0 - 1 - q] & 3) : (uint8_t)MV_NONE;
         uint32_t ia_q = ia, jb_q = jb;
 #pragma unroll
         for (uint32_t q = 0; q < PF_CH; q++) {
@@ -207,17 +207,26 @@ struct TbResult {
     uint64_t steps;
 };
 
-// traceback (SeqAlign.cpp:306-478).  flags: diagonal-major bytes written by the fill.
+// traceback (SeqAlign.cpp:306-478).  flags: the 3 base bits per cell written by the fill.
 // Kept alignments go to ext_mv[a*mv_stride ..] with lengths ext_len[a].
+//
+// How the reference's two matrices map onto this DFS: `matrix` (by value, permanently pruned) is the flag byte in memory, and the
+// only writes to it are the prunes.  `matrix_temp` (which directions of a cell were tried already, reset when the search leaves
+// the cell, :432) is NOT stored per cell: a cell on the current path is on it exactly once (every move lowers i + j), the
+// directions are tried in the fixed order Left, Up, Diag (:356, :393, :425), so "tried" at the cell the search returns to is
+// "everything up to the move that was taken from it" -- a function of the stack entry.  The stack entry (one byte of `mv`) is
+// move | base_flags << 2: the base flags of a cell cannot change while it is on the stack (pruning only touches the current
+// cell), so backtracking needs no flag load at all -- it walks the stack, whose top eight entries live in a register.
+// Readers of a move string mask the entry with 3.
 template <bool DIAG, class X>
 PF_HDN inline TbResult traceback(X &x, const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n,
                                  const Scoring &sc, const BV mv, const BV ext_mv, const WV ext_len,
                                  uint32_t mv_stride, uint32_t k_aln, uint64_t step_limit, uint32_t pitch_n) {
     TbResult r;
     r.n_aln = 0; r.status = PF_BUBBLE_OK; r.steps = 0;
-    // The loop below is ONE dependent chain per step (flag byte -> decision -> next cell), i.e. pure latency on a GPU lane, so it
+    // The forward walk is ONE dependent chain per step (flag byte -> decision -> next cell), i.e. pure latency on a GPU lane, so it
     // is kept to as few instructions as the semantics allow: the cell index moves by a constant per move instead of being
-    // recomputed, (0,0) is cell 0 in both layouts, the last two moves live in registers, counters are 32 bit.
+    // recomputed, (0,0) is cell 0 in both layouts, counters are 32 bit.
     // indel1 / indel2 (size_t in the reference, :312-315) may wrap below zero; a 32-bit counter orders against the small caps
     // exactly like the 64-bit one as long as fewer than 2^31 moves are on the stack.
     const uint32_t dL = DIAG ? m + 1 : 1u;                     // cell(i, j) - cell(i, j-1)
@@ -230,11 +239,14 @@ PF_HDN inline TbResult traceback(X &x, const BV flags, const CBV A, uint32_t m, 
     PairKey last;
     last.score = 0; last.n_pos = 0; last.n_indel = 0;
     const bool pf = x.prefetch_flags();
-    const uint32_t pf_min = 6 * dD;                            // six cells up the diagonal: the path of a good alignment
-    uint32_t lastmv = MV_NONE, prevmv = MV_NONE;               // mv[depth-1], mv[depth-2]
+    const uint32_t pf_min = x.prefetch_cells() * dD;           // that many cells up the diagonal: the path of a good alignment
+    uint64_t win = 0;                                          // stack entries depth-1 (low byte) .. depth-8
+    uint32_t nwin = 0;                                         // valid entries in win; >= min(depth, 2) between steps
+    uint32_t c = (uint32_t)flags[cell] & 7u;                   // base flags of the current cell
+    uint32_t tried = 0;                                        // directions already searched from the current cell
     for (;;) {
         if (++steps > budget) { r.status = PF_BUBBLE_STEP_LIMIT; r.steps = steps; return r; }
-        if (pf && cell >= pf_min) prefetch_byte(&flags[cell - pf_min]);
+        const uint32_t lastmv = depth ? (uint32_t)win & 3u : (uint32_t)MV_NONE;
         if (cell == 0 && open_a <= cap_a && open_b <= cap_b) {          // :322-355
             const PairKey cand = x.analyze(sc, A, B, cbv(mv), depth);
             bool keep = true;
@@ -253,43 +265,50 @@ PF_HDN inline TbResult traceback(X &x, const BV flags, const CBV A, uint32_t m, 
                 cap_b = open_b;
             }
         }
-        const uint32_t c = flags[cell];
-        const uint32_t w = c & 7u & ~(c >> 4);                          // still-untried directions of this cell
+        const uint32_t w = c & ~tried;                                  // still-untried directions of this cell
+        uint32_t move;
         if (w & F_LEFT) {                                               // :356-392
             bool take;
             if (open_a < cap_a) { if (lastmv != MV_L) ++open_a; take = true; }
             else if (open_a == cap_a) take = (lastmv == MV_L);
             else take = false;
-            if (!take) { flags[cell] = (uint8_t)(c & ~(uint32_t)F_LEFT); continue; }   // permanent prune of the base matrix
-            flags[cell] = (uint8_t)(c | (F_LEFT << 4));
-            mv[depth++] = MV_L;
-            prevmv = lastmv; lastmv = MV_L;
-            cell -= dL;
+            if (!take) { c &= ~(uint32_t)F_LEFT; flags[cell] = (uint8_t)c; continue; }   // permanent prune of the base matrix
+            move = MV_L;
         } else if (w & F_UP) {                                          // :393-424
             bool take;
             if (open_b < cap_b) { if (depth == 0 || lastmv == MV_U) ++open_b; take = true; }  // sic (:397)
             else if (open_b == cap_b) take = (lastmv == MV_U);
             else take = false;
-            if (!take) { flags[cell] = (uint8_t)(c & ~(uint32_t)F_UP); continue; }
-            flags[cell] = (uint8_t)(c | (F_UP << 4));
-            mv[depth++] = MV_U;
-            prevmv = lastmv; lastmv = MV_U;
-            cell -= dU;
+            if (!take) { c &= ~(uint32_t)F_UP; flags[cell] = (uint8_t)c; continue; }
+            move = MV_U;
         } else if (w & F_DIAG) {                                        // :425-431
-            flags[cell] = (uint8_t)(c | (F_DIAG << 4));
-            mv[depth++] = MV_D;
-            prevmv = lastmv; lastmv = MV_D;
-            cell -= dD;
-        } else {                                                        // :432-474
+            move = MV_D;
+        } else {                                                        // :432-474: leave the cell, back to where the search came from
             if (depth == 0) break;
-            flags[cell] = (uint8_t)(c & 7u);                            // matrix_temp[p] = matrix[p]
-            if (lastmv == MV_L) { if (prevmv != MV_L) --open_a; cell += dL; }
-            else if (lastmv == MV_U) { if (prevmv != MV_U) --open_b; cell += dU; }   // may wrap below zero, as in the reference
-            else cell += dD;
-            depth--;
-            lastmv = prevmv;
-            prevmv = depth >= 2 ? (uint32_t)mv[depth - 2] : (uint32_t)MV_NONE;
+            const uint32_t e = (uint32_t)win & 0xFFu;
+            const uint32_t pm = e & 3u;                                 // the move that led here
+            const uint32_t prevmv = depth >= 2 ? (uint32_t)(win >> 8) & 3u : (uint32_t)MV_NONE;
+            if (pm == MV_L) { if (prevmv != MV_L) --open_a; cell += dL; tried = F_LEFT; }
+            else if (pm == MV_U) { if (prevmv != MV_U) --open_b; cell += dU; tried = F_LEFT | F_UP; }   // may wrap below zero, as in the reference
+            else { cell += dD; tried = F_LEFT | F_UP | F_DIAG; }
+            c = e >> 2;
+            win >>= 8; nwin--; depth--;
+            if (nwin < 2 && depth > nwin) {                             // refill the register window: independent loads, one latency
+                nwin = depth < 8 ? depth : 8;
+                win = 0;
+#pragma unroll
+                for (uint32_t q = 0; q < 8; q++) if (q < nwin) win |= (uint64_t)mv[depth - 1 - q] << (8 * q);
+            }
+            continue;
         }
+        const uint32_t e = move | (c << 2);
+        mv[depth++] = (uint8_t)e;
+        win = (win << 8) | e;
+        nwin = nwin < 8 ? nwin + 1 : 8;
+        cell -= move == MV_L ? dL : (move == MV_U ? dU : dD);
+        if (pf && cell >= pf_min) prefetch_byte(&flags[cell - pf_min]);
+        c = (uint32_t)flags[cell] & 7u;
+        tried = 0;
     }
     r.steps = steps;
     return r;
@@ -303,7 +322,7 @@ PF_HD void project_moves(const CBV src, const CBV mv, uint32_t depth, const BV d
         const uint32_t cnt = t0 < PF_CH ? t0 : PF_CH;
         uint8_t m[PF_CH], v[PF_CH];
 #pragma unroll
-        for (uint32_t q = 0; q < PF_CH; q++) m[q] = q < cnt ? mv[t0 - 1 - q] : gap_move;
+        for (uint32_t q = 0; q < PF_CH; q++) m[q] = q < cnt ? (uint8_t)(mv[t0 - 1 - q] & 3) : gap_move;
         uint32_t ia_q = ia;
 #pragma unroll
         for (uint32_t q = 0; q < PF_CH; q++) {
@@ -611,6 +630,7 @@ PF_HD SlotLayout slot_layout(uint32_t n_seq, uint64_t sum_len, const Limits &l) 
 // the group kernel overrides them with versions that spread the loop over the lanes of the group.
 struct SerialHelpers {
     PF_HD bool prefetch_flags() const { return false; }
+    PF_HD uint32_t prefetch_cells() const { return 6; }
     PF_HD PairKey analyze(const Scoring &sc, const CBV row, const CBV B, const CBV mv, uint32_t depth) const { return analyze_moves(sc, row, B, mv, depth); }
     PF_HD void copy(const CBV src, const BV dst, uint32_t n) const { copy_bytes(src, dst, n); }
     PF_HD void project(const CBV src, const CBV mv, uint32_t depth, const BV dst, uint8_t gap_move) const { project_moves(src, mv, depth, dst, gap_move); }

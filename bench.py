@@ -357,7 +357,8 @@ def cpu_baseline_and_parity(args, cfg, bb, prefix, n_sample, gpu_cov, gpu_msa, g
 
     # ---- parity of the timed batch ----
     nseq_s = int(sample.bubble_off[-1])
-    g_cov = np.concatenate([gpu_cov[:S], gpu_cov[bb.n_bubbles:bb.n_bubbles + nseq_s]])
+    # gpu_cov: the records of exactly these sequences (a sub-batch call), or of the whole batch (entrances first, then branches)
+    g_cov = gpu_cov if len(gpu_cov) == S + nseq_s else np.concatenate([gpu_cov[:S], gpu_cov[bb.n_bubbles:bb.n_bubbles + nseq_s]])
     cov_bad = parity.compare_cov(g_cov, cov_ref)
     g_msa = slice_msa(gpu_msa, S)
     msa_bad = int(parity.compare_msa(g_msa, msa_ref).sum())
@@ -400,6 +401,9 @@ def main():
     ap.add_argument("--up", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg AND the parity block (profiling runs)")
     ap.add_argument("--no-sharded-legs", action="store_true", help="N > 1: skip the partitioned-index legs")
+    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads of the e2e leg (one pf_ctx + shared index handle each)")
+    ap.add_argument("--e2e-sweep", default="", help="also time the e2e leg with these host thread counts, e.g. 1,2,8")
+    ap.add_argument("--e2e-chunks", type=int, default=2, help="sub-batches per host thread and step in the e2e leg")
     ap.add_argument("--region-rank", type=int, default=None,
                     help="diagnostics: take the batch another rank would take (its region of the genome) on this GPU")
     ap.add_argument("--no-peer-lookup", action="store_true",
@@ -541,53 +545,121 @@ def main():
     launches = ctx.launches - launches0
 
     # ---- e2e: host-pointer C ABI from pinned host buffers ----
+    # The batch is handed over the way a multi-threaded host hands it over (the reference walks the graph with -t N threads,
+    # CDBG.cpp:1929-1945): T host threads, each with its own pf_ctx and a shared handle on the one index (pf_kmc_share), each
+    # pushing its share of the step as sub-batches through pf_kmc_cov_async | pf_align | pf_site_cov | pf_kmc_wait.  The copy-in
+    # of one thread's sub-batch overlaps the kernels and the copy-out of another's.  T = 1 is the single-threaded caller.
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t, t.numpy()
 
-    h_lb, h_lo, h_ab, h_ao, h_bo, h_wo = [pinned(x) for x in (lb, lo, bb.bases, bb.seq_off, bb.bubble_off, wo)]
-    e2e_times = []
-    e2e_cov_times = []
-    cov_pinned = torch.empty(n_lseq * 24, dtype=torch.uint8).pin_memory()
-    cov_out = cov_pinned.numpy().view(capi.COV_DTYPE)
-    d2h_bytes = 0
-    msa = sites = cov = None
-    for it in range(2 + args.steps):
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
+    h_wo = pinned(wo)
+    workers_all = [(ctx, db)]
+
+    def run_chunk(wctx, wdb, ch, keep=False):
         if main_route is not None:   # no host-pointer form of the routed lookup: copy in, route/exchange/lookup, copy the cov records out
             with torch.cuda.stream(stream):
-                e_lb = h_lb[0].to(dev, non_blocking=True)
-                e_lo = h_lo[0].to(dev, non_blocking=True).view(torch.int64)
+                e_lb = ch["lb"][0].to(dev, non_blocking=True)
+                e_lo = ch["lo"][0].to(dev, non_blocking=True).view(torch.int64)
                 e_wo = h_wo[0].to(dev, non_blocking=True).view(torch.int64)
                 _, _, e_cov = sh.lookup(e_lb, e_lo, e_wo, n_win, mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up, stream=stream)
-                cov_pinned.copy_(e_cov[:n_lseq * 24], non_blocking=True)
+                ch["cov_t"].copy_(e_cov[:n_lseq * 24], non_blocking=True)
             stream.synchronize()
-            cov = cov_out
+            cv = ch["cov"]
         else:   # lookup-A runs on the handle's own stream beside the alignment (pf_kmc_cov_async ... pf_kmc_wait)
-            cov = db.cov_async(h_lb[1], h_lo[1], cov_out, mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up)
-        t1 = time.perf_counter()
-        msa = ctx.align(h_ab[1], h_ao[1], h_bo[1], copy=False)   # views of the pinned result arena (C-ABI ownership rule)
-        sites = db.site_cov(args.low, args.up, skip_np, copy=False) if do_sites else None   # views, like the alignment result
+            cv = wdb.cov_async(ch["lb"][1], ch["lo"][1], ch["cov"], mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up)
+        m = wctx.align(ch["ab"][1], ch["ao"][1], ch["bo"][1], copy=keep)   # copy=False: views of the pinned result arena (C-ABI ownership rule)
+        st = wdb.site_cov(args.low, args.up, ch["skip"], copy=keep) if do_sites else None
         if main_route is None:
-            db.wait()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if it >= 2:
-            e2e_times.append(dt)
-            e2e_cov_times.append(t1 - t0)
-        d2h_bytes = cov.nbytes + sum(v.nbytes for v in msa.values() if isinstance(v, np.ndarray))
-        if sites is not None:
-            d2h_bytes += sum(v.nbytes for v in sites.values())
+            wdb.wait()
+        nb = cv.nbytes + sum(v.nbytes for v in m.values() if isinstance(v, np.ndarray))
+        if st is not None:
+            nb += sum(v.nbytes for v in st.values())
+        return cv, m, st, nb
+
+    def e2e_leg(T_req):
+        """-> (ms per step, h2d bytes, d2h bytes, threads, sub-batches) of the e2e leg with T_req host threads"""
+        T_e2e = 1 if main_route is not None else max(1, T_req)
+        n_chunks = T_e2e * max(1, args.e2e_chunks) if T_e2e > 1 else 1
+        chunks = []
+        for c in range(n_chunks):
+            b0, b1 = bb.n_bubbles * c // n_chunks, bb.n_bubbles * (c + 1) // n_chunks
+            sub = bb if n_chunks == 1 else bb.slice(b0, b1)
+            clb, clo = (lb, lo) if n_chunks == 1 else sub.lookup_sequences()
+            ch = {"lb": pinned(clb), "lo": pinned(clo), "ab": pinned(sub.bases), "ao": pinned(sub.seq_off), "bo": pinned(sub.bubble_off),
+                  "skip": np.ascontiguousarray(sub.bubble_type.astype(np.uint8)), "n": sub.n_bubbles}
+            cp = torch.empty((len(clo) - 1) * 24, dtype=torch.uint8).pin_memory()
+            ch["cov_t"], ch["cov"] = cp, cp.numpy().view(capi.COV_DTYPE)
+            ch["h2d"] = clb.nbytes + clo.nbytes + sub.bases.nbytes + sub.seq_off.nbytes + sub.bubble_off.nbytes + (ch["skip"].nbytes if do_sites else 0)
+            chunks.append(ch)
+        while len(workers_all) < T_e2e:
+            c2 = capi.Context(local_rank)
+            workers_all.append((c2, capi.KmcDb(c2, prefix, share_of=db)))
+        workers = workers_all[:T_e2e]
+        d2h_acc = [0] * T_e2e
+
+        def worker_step(t):
+            wctx, wdb = workers[t]
+            tot = 0
+            for c in range(t, n_chunks, T_e2e):
+                tot += run_chunk(wctx, wdb, chunks[c])[3]
+            d2h_acc[t] = tot
+
+        e2e_times = []
+        for it in range(2 + args.steps):
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if T_e2e == 1:
+                worker_step(0)
+            else:
+                th = [threading.Thread(target=worker_step, args=(t,)) for t in range(T_e2e)]
+                for x_ in th:
+                    x_.start()
+                for x_ in th:
+                    x_.join()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if it >= 2:
+                e2e_times.append(dt)
+        return 1e3 * sum(e2e_times) / len(e2e_times), sum(ch["h2d"] for ch in chunks), sum(d2h_acc), T_e2e, n_chunks, chunks
+
+    e2e_sweep = {}
+    for T_s in [int(x) for x in args.e2e_sweep.split(",") if x]:
+        e2e_sweep[T_s] = e2e_leg(T_s)[0]
+    ms_e2e, h2d_bytes, d2h_bytes, T_e2e, n_chunks, chunks = e2e_leg(args.e2e_threads)
+    # the results the parity block diffs: one more (untimed) pass of the first bubbles of the batch through the same calls, copied out
+    n_keep = min(bb.n_bubbles, args.cpu_sample if world == 1 else min(args.cpu_sample, 32768))
+    if n_chunks == 1 and n_keep == bb.n_bubbles:
+        cov, msa, sites, _ = run_chunk(ctx, db, chunks[0], keep=True)
+        cov = cov.copy()
+    else:
+        sub = bb.slice(0, n_keep)
+        klb, klo = sub.lookup_sequences()
+        kch = {"lb": pinned(klb), "lo": pinned(klo), "ab": pinned(sub.bases), "ao": pinned(sub.seq_off), "bo": pinned(sub.bubble_off),
+               "skip": np.ascontiguousarray(sub.bubble_type.astype(np.uint8))}
+        kp = torch.empty((len(klo) - 1) * 24, dtype=torch.uint8).pin_memory()
+        kch["cov_t"], kch["cov"] = kp, kp.numpy().view(capi.COV_DTYPE)
+        if main_route is None:
+            cov, msa, sites, _ = run_chunk(ctx, db, kch, keep=True)
+            cov = cov.copy()
+        else:
+            cov, msa, sites = None, None, None
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    ms_e2e = 1e3 * sum(e2e_times) / len(e2e_times)
-    h2d_bytes = lb.nbytes + lo.nbytes + wo.nbytes + bb.bases.nbytes + bb.seq_off.nbytes + bb.bubble_off.nbytes + (skip_np.nbytes if do_sites else 0)
-    site_hist = np.bincount(sites["status"], minlength=5).tolist() if sites is not None else None
-    n_sites = int(len(sites["status"])) if sites is not None else 0
-    n_ok = int((msa["status"] == 0).sum())
-    status_hist = {int(k): int(v) for k, v in zip(*np.unique(msa["status"], return_counts=True))}
+    # whole-batch status / site histograms: one untimed single call over the full batch (views)
+    if main_route is not None:
+        fm = fs = None
+    elif n_chunks == 1:
+        _, fm, fs, _ = run_chunk(ctx, db, chunks[0])
+    else:
+        _, fm, fs, _ = run_chunk(ctx, db, {"lb": pinned(lb), "lo": pinned(lo), "ab": pinned(bb.bases), "ao": pinned(bb.seq_off), "bo": pinned(bb.bubble_off),
+                                           "skip": skip_np, "cov": torch.empty(n_lseq * 24, dtype=torch.uint8).pin_memory().numpy().view(capi.COV_DTYPE)})
+    site_hist = np.bincount(fs["status"], minlength=5).tolist() if fs is not None else None
+    n_sites = int(len(fs["status"])) if fs is not None else 0
+    n_ok = int((fm["status"] == 0).sum()) if fm is not None else -1
+    status_hist = {int(k): int(v) for k, v in zip(*np.unique(fm["status"], return_counts=True))} if fm is not None else None
+    full_sites = {k_: v.copy() for k_, v in fs.items()} if fs is not None else None
 
     # ---- N > 1: the same batch through the KMC index PARTITIONED across the GPUs, checked against the replicated index ----
     shard_res = None
@@ -595,7 +667,7 @@ def main():
         from ploidyfrost_b200 import sharded
         shard_res = {"n_parts": world, "partition": "hash index sliced by mix(key) % n_gpus"}
         rep_cov = d_cov.clone()
-        rep_sites = {k_: v.copy() for k_, v in sites.items()}
+        rep_sites = full_sites
         t0 = time.perf_counter()
         dbp = capi.KmcDb(ctx, prefix, part=rank, n_parts=world)
         barrier()
@@ -704,8 +776,9 @@ def main():
                 "clocks": sampler.summary(),
                 "e2e": {"value": tot_bubbles / (ms_e2e * 1e-3), "unit": "bubbles/s", "h2d_bytes_per_step": int(h2d_bytes),
                         "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e,
-                        "ms_pf_kmc_cov_async_enqueue": 1e3 * sum(e2e_cov_times) / len(e2e_cov_times),
-                        "calls": "pf_kmc_cov_async | pf_align | pf_site_cov | pf_kmc_wait"},
+                        "host_threads": T_e2e, "sub_batches_per_step": n_chunks,
+                        "ms_per_step_by_host_threads": {str(k_): v for k_, v in e2e_sweep.items()} or None,
+                        "calls": "pf_kmc_cov_async | pf_align | pf_site_cov | pf_kmc_wait per sub-batch; one pf_ctx + pf_kmc_share handle per host thread"},
                 "gpu_launches": int(launches),
                 "roofline": dominant, "roofline_lookup": roof_lookup, "roofline_align": roof_align,
                 "bubbles_ok": n_ok, "bubble_status_hist": status_hist, "tier2_retries": int(retry), "heavy_queued": int(heavy_q),
@@ -715,9 +788,8 @@ def main():
             line["sharded"] = shard_res
             if not shard_res.get("all_ranks_equal", True):
                 rc = 3
-        if not args.no_cpu_baseline:
-            n_par = args.cpu_sample if world == 1 else min(args.cpu_sample, 32768)
-            base, par = cpu_baseline_and_parity(args, cfg, bb, prefix, n_par, cov, msa, sites, skip_np, timed=(world == 1))
+        if not args.no_cpu_baseline and cov is not None:
+            base, par = cpu_baseline_and_parity(args, cfg, bb, prefix, n_keep, cov, msa, sites, skip_np, timed=(world == 1))
             if base is not None:
                 line["cpu_baseline"] = base
             line["parity"] = par
@@ -728,6 +800,9 @@ def main():
         print(json.dumps(line), flush=True)
         if rc:
             sys.stderr.write(f"bench.py: PARITY FAILURE (rc {rc}): {json.dumps(line.get('parity'))} {json.dumps(line.get('sharded'))}\n")
+    for wc, wd in workers_all[1:]:
+        wd.close()
+        wc.close()
     db.close()
     ctx.close()
     if world > 1:

@@ -213,11 +213,22 @@ int pf_site_cov(pf_kmc *db, uint32_t low, uint32_t up, const uint8_t *skip, pf_s
 /* device-resident form: `d_skip` is a device pointer (or NULL), `out_dev` (may be NULL) receives DEVICE pointers; asynchronous on the stream */
 int pf_site_cov_dev(pf_kmc *db, uint32_t low, uint32_t up, const void *d_skip, pf_site_batch_t *out_dev, void *cuda_stream);
 
+/*
+ * pf_kmc_share -- a second handle on the same HBM-resident index for ANOTHER pf_ctx of the same device.  The reference keeps
+ * one CKMCFile per CDBG and walks the graph with N threads (CDBG.cpp:1929-1945); here every host thread owns its own context -- stream,
+ * staging, result arena -- and a shared handle, so the copy-in of one thread's batch overlaps the kernels and the copy-out of
+ * another's.  Close the shared handle before the handle it was taken from.
+ */
+int pf_kmc_share(pf_kmc *db, pf_ctx *ctx, pf_kmc **out);
+
 /* ---- roofline denominators measured on this device (bench.py reports them next to the kernels) ------- */
 /* random 32-byte-sector gather rate over a `bytes`-sized table (GB/s of sectors touched) */
 int pf_bench_random_gather(pf_ctx *ctx, uint64_t bytes, double *gb_per_s);
 /* sustained INT32 ALU rate of an IADD3/VIMNMX/LOP3 mix (Gop/s, counting one op per lane-instruction) */
 int pf_bench_int32(pf_ctx *ctx, double *gop_per_s);
+/* diagnostics: random-access ceiling -- accesses of `width` (16 / 32 / 64) bytes, `ilp` (4 / 8 / 16) in flight per thread,
+ * `ctas_per_sm` 256-thread CTAs per SM, over a power-of-two table of <= `bytes`; G accesses per second */
+int pf_bench_gather_sweep(pf_ctx *ctx, uint64_t bytes, uint32_t width, uint32_t ilp, uint32_t ctas_per_sm, double *g_access_per_s);
 
 #ifdef __cplusplus
 }

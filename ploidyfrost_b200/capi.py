@@ -25,7 +25,7 @@ EXPORTS = ["pf_init", "pf_shutdown", "pf_last_error", "pf_version", "pf_launch_c
            "pf_kmc_close", "pf_kmc_info", "pf_kmc_set_min_count", "pf_kmc_set_max_count", "pf_kmc_reset_min_max",
            "pf_kmc_device_bytes", "pf_kmc_open_ex", "pf_kmc_index_kind", "pf_kmc_build_status", "pf_kmc_open_part", "pf_kmc_open_part_ex", "pf_kmc_export_ipc", "pf_kmc_attach_peers", "pf_kmc_local_kmers", "pf_kmc_route_dev", "pf_kmc_lookup_keys_dev",
            "pf_kmc_scatter_dev", "pf_kmc_counts", "pf_kmc_cov", "pf_kmc_cov_async", "pf_kmc_wait", "pf_site_cov", "pf_site_cov_dev", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
-           "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_heavy_queued", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32"]
+           "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_heavy_queued", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32", "pf_kmc_share", "pf_bench_gather_sweep"]
 
 
 class SiteBatch(C.Structure):
@@ -127,6 +127,8 @@ def load():
     L.pf_align_last_cells.restype = C.c_uint64
     L.pf_bench_random_gather.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]
     L.pf_bench_int32.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.pf_bench_gather_sweep.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
+    L.pf_kmc_share.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     _lib = L
     return L
 
@@ -225,8 +227,8 @@ class Context:
 
     @property
     def last_tier_counts(self) -> list:
-        a = (C.c_uint32 * 8)()
-        _check(self.lib.pf_align_last_tier_counts(self.h, a, 8), "pf_align_last_tier_counts")
+        a = (C.c_uint32 * 9)()
+        _check(self.lib.pf_align_last_tier_counts(self.h, a, 9), "pf_align_last_tier_counts")
         return list(a)
 
     @property
@@ -236,6 +238,11 @@ class Context:
     def bench_random_gather(self, nbytes: int) -> float:
         v = C.c_double()
         _check(self.lib.pf_bench_random_gather(self.h, nbytes, C.byref(v)), "pf_bench_random_gather")
+        return v.value
+
+    def bench_gather_sweep(self, nbytes: int, width: int, ilp: int, ctas_per_sm: int) -> float:
+        v = C.c_double()
+        _check(self.lib.pf_bench_gather_sweep(self.h, nbytes, width, ilp, ctas_per_sm, C.byref(v)), "pf_bench_gather_sweep")
         return v.value
 
     def bench_int32(self) -> float:
@@ -250,14 +257,18 @@ INDEX_AUTO, INDEX_VERBATIM, INDEX_HASH = 0, 1, 2
 class KmcDb:
     """pf_kmc: HBM-resident KMC index (CKMCFile opened for random access)."""
 
-    def __init__(self, ctx: Context, prefix: str, part: int = 0, n_parts: int = 1, index: str = "auto"):
+    def __init__(self, ctx: Context, prefix: str, part: int = 0, n_parts: int = 1, index: str = "auto", share_of: "KmcDb" = None):
         """n_parts > 1: load only partition `part` of the database (pf_kmc_open_part); such an index answers
-        route_dev / lookup_keys_dev / scatter_dev, not counts / cov."""
+        route_dev / lookup_keys_dev / scatter_dev, not counts / cov.
+        share_of: do not open anything -- a second handle on `share_of`'s index for the context `ctx` (pf_kmc_share)."""
         self.ctx = ctx
         self.lib = ctx.lib
         self.part, self.n_parts = part, n_parts
         h = C.c_void_p()
-        if n_parts == 1 and index == "verbatim":
+        if share_of is not None:
+            self.part, self.n_parts = share_of.part, share_of.n_parts
+            _check(self.lib.pf_kmc_share(share_of.h, ctx.h, C.byref(h)), "pf_kmc_share")
+        elif n_parts == 1 and index == "verbatim":
             _check(self.lib.pf_kmc_open_ex(ctx.h, prefix.encode(), INDEX_VERBATIM, C.byref(h)), "pf_kmc_open_ex")
         elif n_parts == 1:
             _check(self.lib.pf_kmc_open(ctx.h, prefix.encode(), C.byref(h)), "pf_kmc_open")

@@ -46,10 +46,12 @@ constexpr uint32_t FULL = 0xffffffffu;
 
 // size classes of the lane kernel: longest branch of the bubble <= LANE_NMAX[c]
 constexpr int N_LANE_CLASSES = 5;
-constexpr int CLS_BIG = N_LANE_CLASSES;        // first pass of the warp kernel
-constexpr int CLS_RETRY_SMEM = N_LANE_CLASSES + 1;  // re-run, warp kernel with the flag bytes in shared memory (long DFS searches)
-constexpr int CLS_RETRY = N_LANE_CLASSES + 2;       // re-run, warp kernel with the large limits
-constexpr int N_TIERS = N_LANE_CLASSES + 3;
+constexpr int CLS_BIG = N_LANE_CLASSES;        // longest branch 257 .. BIG_SPLIT: one warp per bubble
+constexpr int CLS_HUGE = N_LANE_CLASSES + 1;   // longer branches: one CTA per bubble (msa_cta_kernel)
+constexpr int CLS_RETRY_SMEM = N_LANE_CLASSES + 2;  // re-run, warp kernel with the flag bytes in shared memory (long DFS searches)
+constexpr int CLS_RETRY = N_LANE_CLASSES + 3;       // re-run with the large limits
+constexpr int N_TIERS = N_LANE_CLASSES + 4;
+constexpr uint32_t BIG_SPLIT = 1536;           // up to here every score of the default scoring fits the s16x2 fill of a warp
 // traceback iterations a lane / group may spend on one bubble before it is handed to the heavy queue (bench workload: median 250,
 // p99.9 1 500, p99.99 2 000, a handful per 262 144 bubbles at 3 000 .. 32 000; sweep in profiles/r01_summary.md section 7)
 constexpr uint32_t LANE_STEP_LIMIT = 2048;
@@ -104,7 +106,7 @@ __device__ __forceinline__ void warp_fill(uint8_t *__restrict__ flags, const CBV
 
 template <bool INTEGRAL>
 struct WarpExec : SerialHelpers {
-    static constexpr bool kDiagFlags = true;
+    static constexpr int kLayout = LAYOUT_DIAG;
     uint32_t lane;
     unsigned long long cells;
     __device__ __forceinline__ bool leader() const { return lane == 0; }
@@ -161,7 +163,7 @@ struct S16Step {
 
 template <int VARIANT>
 struct LaneExec : SerialHelpers {
-    static constexpr bool kDiagFlags = false;
+    static constexpr int kLayout = LAYOUT_ROW;
     static constexpr bool INTEGRAL = VARIANT != LANE_FP64;
     int32_t *rowbuf;     // 4 bytes per column: packed score*8+flags (scalar fills) or (U, D) as two int16 (s16x2 fill)
     uint8_t *bs;
@@ -318,7 +320,7 @@ struct LaneExec : SerialHelpers {
 // the G x NB lanes of a step hit 32 different banks.
 template <int G>
 struct GroupExec {
-    static constexpr bool kDiagFlags = false;
+    static constexpr int kLayout = LAYOUT_ROW;
     static constexpr uint32_t NB = 32 / G;
     uint32_t g;          // lane within the group
     uint32_t gmask;      // the group's lanes
@@ -329,6 +331,9 @@ struct GroupExec {
     unsigned long long cells;
     __device__ __forceinline__ bool prefetch_flags() const { return pf; }
     __device__ __forceinline__ uint32_t prefetch_cells() const { return 6; }
+    __device__ __forceinline__ uint32_t skew_T() const { return 1; }
+    __device__ __forceinline__ uint32_t skew_w(uint32_t) const { return 1; }
+    __device__ __forceinline__ void prefetch_ahead(const BV, uint32_t, uint32_t, uint32_t, uint32_t) const {}
     // Everything outside the fill runs redundantly on all G lanes (identical loads, decisions and stores), so every lane
     // "is" the leader; the kernel uses g == 0 where something must happen once (queue, counters).
     __device__ __forceinline__ bool leader() const { return true; }
@@ -542,8 +547,118 @@ struct MsaArgs {
     uint32_t *hq;              // heavy queue (see msa_heavy_kernel); nullptr = none
     uint32_t lane_pitch;       // lane kernel: 1 = one flag row pitch per launch (lanes at the same cell share a sector)
     uint32_t warp_dequeue;     // group kernel: 1 = the warp's groups start their bubbles together, 0 = every group on its own
+    uint32_t lane_contig;      // lane / group kernels: per-lane contiguous arrays for the sequential phases (carve_work_area)
     Limits lim;
     Scoring sc;
+};
+
+
+// ---- T lanes per bubble: the CTA-wide fill for long branches -----------------------------------------------------------------
+// Branches of kilobases (BASELINE configs[4]: up to 5 kbp, 25 M cells per pair) are too long for a warp: one pair is a
+// serial job of tens of milliseconds, and beyond ~1.8 kbp the scores leave int16, so the s16x2 fill does not apply.  Here one
+// CTA of T = 256 lanes works on one bubble.  The DP row is cut into T column strips of w = ceil((n + 1) / T) columns; lane l fills
+// its strip of row t + 1 - l at time step t (an anti-diagonal wavefront over (row, strip)), INT32, with the carried values of the
+// s16x2 design (U = S + [Up], D = S + [Diag], L = S + [Left], so a cell is three adds, a max3 and three add-max).  Bands in shared
+// memory: the (U, D) pairs of the latest row of every column ([q * T + l]: conflict-free), the B characters, and a double-buffered
+// hand-over row through which lane l - 1 passes (L, D) of its last column to lane l; one __syncthreads per time step.  Flag bytes
+// go to HBM in the skewed layout (LAYOUT_SKEW): the lanes of a warp store 32 consecutive bytes.  Everything sequential
+// (traceback DFS, MSA filter, site calling) runs on warp 0 with the 32-lane cooperative helpers of the group kernel, while the
+// DFS's flag reads are covered by a 32-cell prefetch fan up the diagonal (one lane per cell).
+constexpr int CTA_THREADS = 256;
+struct CtaExec {
+    static constexpr int kLayout = LAYOUT_SKEW;
+    static constexpr uint32_t T = CTA_THREADS;
+    uint32_t tid, lane, warp;
+    int2 *rb;            // [w_max * T]
+    int2 *hand;          // [2 * T]
+    uint8_t *bs;         // [w_max * T]
+    uint32_t *bc;        // broadcast word
+    GroupExec<32> h;     // warp 0's helpers
+    unsigned long long cells;
+    __device__ __forceinline__ bool leader() const { return warp == 0; }
+    __device__ __forceinline__ uint32_t bcast(uint32_t v) const { __syncthreads(); if (tid == 0) *bc = v; __syncthreads(); return *(volatile uint32_t *)bc; }
+    __device__ __forceinline__ int bcast_i(int v) const { return (int)bcast((uint32_t)v); }
+    __device__ __forceinline__ uint32_t bcast_ld(const uint32_t *p) const { __syncthreads(); return *(const volatile uint32_t *)p; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void note_steps(uint64_t) const {}
+    __device__ __forceinline__ uint32_t pitch_n(uint32_t n) const { return n; }
+    __device__ __forceinline__ bool prefetch_flags() const { return true; }
+    __device__ __forceinline__ uint32_t prefetch_cells() const { return 6; }
+    __device__ __forceinline__ uint32_t skew_T() const { return T; }
+    __device__ __forceinline__ uint32_t skew_w(uint32_t n) const { return (n + T) / T; }
+    // lane g asks for the cell g + 1 steps up the diagonal of the DFS's position (the path of a good alignment)
+    __device__ __forceinline__ void prefetch_ahead(const BV flags, uint32_t cell, uint32_t q, uint32_t w, uint32_t) const {
+        const uint32_t k = lane + 1;
+        uint32_t back = k * w * T;                       // k rows up
+        if (q >= k) back += k * T;                       // k columns left inside the strip
+        else {
+            const uint32_t nb = (k - q + w - 1) / w;     // strips crossed
+            back += nb * w * T + nb;                     // one row of the skew and one lane per strip
+            back -= (nb * w - k) * T;                    // q' - q = nb * w - k columns to the right inside the new strip
+        }
+        if (back <= cell) prefetch_byte(flags.p + (cell - back));
+    }
+    __device__ __forceinline__ PairKey analyze(const Scoring &sc, const CBV row, const CBV B, const CBV mv, uint32_t depth) const { return h.analyze(sc, row, B, mv, depth); }
+    __device__ __forceinline__ void copy(const CBV src, const BV dst, uint32_t n) const { h.copy(src, dst, n); }
+    __device__ __forceinline__ void project(const CBV src, const CBV mv, uint32_t depth, const BV dst, uint8_t gap_move) const { h.project(src, mv, depth, dst, gap_move); }
+
+    __device__ __forceinline__ void fill(const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n, const Scoring &sc, int32_t *) {
+        __syncthreads();                                                     // warp 0 is done with the previous matrix
+        const uint32_t w = (n + T) / T;                                      // strip width = ceil((n + 1) / T)
+        const uint32_t l = tid, j0 = l * w;                                  // my columns j0 .. j1 (column 0 = the border)
+        const uint32_t j1 = min(j0 + w - 1, n);
+        const bool have = j0 <= n;
+        const uint32_t nl = n / w + 1;                                       // lanes that own a column
+        if (tid == 0) cells += (unsigned long long)m * n;
+        uint8_t *F = flags.p;
+        const int G = sc.iG, Mv = sc.iM, Dv = sc.iD;
+        if (have)
+            for (uint32_t j = j0; j <= j1; j++) {                            // row 0 carries only Left (:492-496)
+                const uint32_t q = j - j0;
+                if (j) bs[q * T + l] = B[j - 1];
+                rb[q * T + l] = make_int2(G * (int)j, G * (int)j);
+                F[((uint64_t)l * w + q) * T + l] = j ? (uint8_t)F_LEFT : (uint8_t)0;
+            }
+        int prevD = G * ((int)j0 - 1);                                       // D(0, j0 - 1); unused by lane 0
+        __syncthreads();
+        const uint32_t steps = m + nl - 1;
+        for (uint32_t t = 0; t < steps; t++) {
+            const uint32_t i = t + 1 - l;                                    // my row at this time step
+            if (have && t + 1 > l && i <= m) {
+                const uint8_t a = A[i - 1];
+                const bool blk = i != m && A[i] == '-';                      // the profile rule (:528-532)
+                const int sub_ne = a == '-' ? G : Dv, Grow = blk ? -(1 << 28) : G;
+                uint8_t *Fr = F + ((uint64_t)(i + l) * w) * T + l;
+                int curL, curD, dgD;
+                uint32_t q = 0;
+                if (l == 0) {                                                // the border column (:486-491): Up only
+                    curL = curD = G * (int)i;
+                    dgD = G * ((int)i - 1);
+                    Fr[0] = (uint8_t)F_UP;
+                    q = 1;
+                } else {
+                    const int2 hv = hand[((t - 1) & 1) * T + l - 1];         // (L, D) of (i, j0 - 1)
+                    curL = hv.x; curD = hv.y;
+                    dgD = prevD;                                             // D(i - 1, j0 - 1)
+                    prevD = hv.y;
+                }
+                const uint32_t qn = j1 - j0 + 1;
+#pragma unroll 2
+                for (; q < qn; q++) {
+                    const int2 up = rb[q * T + l];
+                    const uint8_t b = bs[q * T + l];
+                    const int t_up = up.x + G, t_dg = dgD + (a == b ? Mv : sub_ne), t_lf = curL + Grow;
+                    const int best = __vimax3_s32(t_up, t_dg, t_lf);
+                    const int nU = __viaddmax_s32(t_up, 1, best), nD = __viaddmax_s32(t_dg, 1, best), nL = __viaddmax_s32(t_lf, 1, best);
+                    Fr[(uint64_t)q * T] = (uint8_t)((nU - best) + 2 * (nD - best) + 4 * (nL - best));
+                    rb[q * T + l] = make_int2(nU, nD);
+                    dgD = up.y; curL = nL; curD = nD;
+                }
+                hand[(t & 1) * T + l] = make_int2(curL, curD);
+            }
+            __syncthreads();
+        }
+    }
 };
 
 // ---- bubbles whose co-optimal DFS explodes ------------------------------------------------------------------------------
@@ -700,7 +815,7 @@ __global__ void __launch_bounds__(LANE_BLOCK, PF_LANE_MINB) msa_lane_kernel(cons
     x.bs = smem + (size_t)wib * per_warp + 32 * 4 * (nmax + 1) + lane;
     x.pitch = a.lane_pitch ? nmax + 1 : 0;
     x.cells = 0;
-    const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim, 32, lane);
+    const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim, 32, lane, a.lane_contig != 0);
     for (;;) {
         uint32_t g = 0;
         if (lane == 0) g = atomicAdd(a.counter, 1u);
@@ -726,6 +841,39 @@ __global__ void __launch_bounds__(LANE_BLOCK, PF_LANE_MINB) msa_lane_kernel(cons
     if (lane == 0 && c) atomicAdd(a.stat_cells, c);
 }
 
+
+__host__ __device__ constexpr uint32_t cta_smem_bytes(uint32_t nmax) {
+    return (((nmax + CTA_THREADS) / CTA_THREADS) * CTA_THREADS) * 9u + 2u * CTA_THREADS * 8u + 32u;   // rb + bs, hand, broadcast word
+}
+
+// One CTA per bubble (CtaExec); work items are taken biggest first.
+__global__ void __launch_bounds__(CTA_THREADS) msa_cta_kernel(const MsaArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t wmax = (a.lim.max_blen + CTA_THREADS) / CTA_THREADS;
+    CtaExec x;
+    x.tid = threadIdx.x; x.lane = threadIdx.x & 31; x.warp = threadIdx.x >> 5;
+    x.rb = (int2 *)smem;
+    x.hand = x.rb + (size_t)wmax * CTA_THREADS;
+    x.bs = (uint8_t *)(x.hand + 2 * CTA_THREADS);
+    x.bc = (uint32_t *)(x.bs + (size_t)wmax * CTA_THREADS);
+    x.h.g = x.lane; x.h.gmask = FULL; x.h.rb = nullptr; x.h.bs = nullptr; x.h.pn = 0; x.h.pf = true; x.h.cells = 0;
+    x.cells = 0;
+    const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)blockIdx.x * a.ws_stride, a.lim);
+    for (;;) {
+        uint32_t q = 0;
+        if (threadIdx.x == 0) q = atomicAdd(a.counter, 1u);
+        q = x.bcast(q);
+        if (q >= a.n_items) break;
+        const uint32_t w = a.first + (a.n_items - 1 - q);
+        const uint32_t b = a.order[w];
+        const uint32_t s0 = a.bubble_off[b], ns = a.bubble_off[b + 1] - s0;
+        uint8_t *slot = a.slot_base + a.slot_off[w];
+        msa_run(x, a.bases, a.seq_off, s0, ns, ws, a.lim, a.sc, slot);
+        if (threadIdx.x == 0) { a.slot_ptr[b] = (uint64_t)(uintptr_t)slot; a.tier[b] = a.tier_id; }
+    }
+    if (threadIdx.x == 0 && x.cells) atomicAdd(a.stat_cells, x.cells);
+}
+
 constexpr int GROUP_BLOCK = 64;
 __host__ __device__ constexpr uint32_t group_smem_per_warp(uint32_t nmax, uint32_t nb) {
     return (nb * 4 * (nmax + 2) + nb * (nmax + 2) + 15) / 16 * 16;           // score rows + B characters (index 1..nmax)
@@ -748,7 +896,7 @@ __global__ void __launch_bounds__(GROUP_BLOCK, PF_GROUP_MINB) msa_group_kernel(c
     x.pn = nmax;
     x.pf = true;
     x.cells = 0;
-    const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim, NB, bi);
+    const WorkArea ws = carve_work_area(a.ws_base + (uint64_t)warp * a.ws_stride, a.lim, NB, bi, a.lane_contig != 0);
     if (a.warp_dequeue) {
         // The warp pulls NB neighbouring bubbles of the size-sorted list at a time and its groups start them together: alike
         // bubbles stay in the same phase (fill with fill, traceback with traceback), i.e. little SIMT divergence between
@@ -800,7 +948,7 @@ struct TierTable {
 };
 
 __global__ void plan_kernel(const uint64_t *__restrict__ seq_off, const uint32_t *__restrict__ bubble_off, uint32_t n,
-                            uint32_t *keys, uint32_t *ids) {
+                            uint32_t big_split, uint32_t *keys, uint32_t *ids) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n) return;
     const uint32_t s0 = bubble_off[b], ns = bubble_off[b + 1] - s0;
@@ -809,7 +957,7 @@ __global__ void plan_kernel(const uint64_t *__restrict__ seq_off, const uint32_t
         const uint64_t l = seq_off[s0 + s + 1] - seq_off[s0 + s];
         mx = l > mx ? l : mx;
     }
-    uint32_t cls = CLS_BIG;
+    uint32_t cls = mx <= big_split ? CLS_BIG : CLS_HUGE;
     if (ns <= LANE_MAX_ROWS) {
 #pragma unroll
         for (int c = N_LANE_CLASSES - 1; c >= 0; c--)
@@ -820,11 +968,11 @@ __global__ void plan_kernel(const uint64_t *__restrict__ seq_off, const uint32_t
     ids[b] = b;
 }
 
-// bounds[c] = first sorted work item of class c (c = 0 .. CLS_BIG), bounds[CLS_BIG + 1] = n
+// bounds[c] = first sorted work item of class c (c = 0 .. CLS_HUGE), bounds[CLS_HUGE + 1] = n
 __global__ void class_bounds_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t *bounds) {
     const uint32_t c = threadIdx.x;
-    if (c > CLS_BIG + 1) return;
-    if (c == CLS_BIG + 1) { bounds[c] = n; return; }
+    if (c > CLS_HUGE + 1) return;
+    if (c == CLS_HUGE + 1) { bounds[c] = n; return; }
     uint32_t lo = 0, hi = n;
     const uint32_t want = c << 28;
     while (lo < hi) {
@@ -958,8 +1106,10 @@ struct pf_align_state {
     uint32_t last_class_count[N_TIERS] = {0};
     int lane_blocks_per_sm[3][N_LANE_CLASSES];   // [variant][class]; variants: LANE_FP64, LANE_I32, LANE_S16X2
     bool lane_attr_done = false;
-    cudaStream_t aux[N_LANE_CLASSES + 1] = {nullptr};   // the size classes run concurrently
-    cudaEvent_t ev_fork = nullptr, ev_join[N_LANE_CLASSES + 1] = {nullptr};
+    cudaStream_t aux[N_LANE_CLASSES + 2] = {nullptr};   // the size classes run concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join[N_LANE_CLASSES + 2] = {nullptr};
+    pf::DevBuf ws_cta[2];                              // work areas of the CTA kernel (first pass, re-run)
+    bool cta_attr_done = false;
     pf::DevBuf ws_cls[N_LANE_CLASSES];
     pf::DevBuf hq, heavy_pool, heavy_ws;               // heavy queue, its slot pool and work areas
     cudaStream_t heavy_stream = nullptr;
@@ -973,6 +1123,7 @@ struct pf_align_state {
 void pf_align_state_free(pf_align_state *s) {
     if (!s) return;
     for (auto &b : s->ws_cls) b.release();
+    for (auto &b : s->ws_cta) b.release();
     s->hq.release(); s->heavy_pool.release(); s->heavy_ws.release();
     if (s->heavy_stream) cudaStreamDestroy(s->heavy_stream);
     if (s->ev_heavy) cudaEventDestroy(s->ev_heavy);
@@ -1054,6 +1205,8 @@ void fill_args(MsaArgs &a, pf_align_state *st, int slot_pool, const Limits &lim,
     a.warp_dequeue = (uint32_t)wd;
     static const int lp = getenv("PF_LANE_PITCH") ? atoi(getenv("PF_LANE_PITCH")) : 1;
     a.lane_pitch = (uint32_t)lp;
+    static const int lc = getenv("PF_LANE_CONTIG") ? atoi(getenv("PF_LANE_CONTIG")) : 0;
+    a.lane_contig = (uint32_t)lc;
 }
 
 // one launch of the warp-per-bubble kernel over work items [first, first + n_items) of `d_order`
@@ -1146,6 +1299,50 @@ int launch_group_tier(pf_ctx *ctx, pf_align_state *st, pf::DevBuf &pool, const L
     return PF_OK;
 }
 
+
+// one launch of the CTA-per-bubble kernel over work items [first, first + n_items) of `d_order`
+int launch_cta_tier(pf_ctx *ctx, pf_align_state *st, pf::DevBuf &pool, int slot_pool, const Limits &lim, const Scoring &sc, const uint8_t *d_bases,
+                    const uint64_t *d_seq_off, const uint32_t *d_bubble_off, const uint32_t *d_order, uint32_t first, uint32_t n_items,
+                    int tier_id, uint32_t *counter, cudaStream_t s) {
+    const uint64_t ws_bytes = align_up(work_area_bytes(lim), 256);
+    const size_t smem = cta_smem_bytes(lim.max_blen);
+    if (smem > 200 * 1024) { pf::set_error("CTA kernel: %u-base branches do not fit shared memory", lim.max_blen); return PF_E_INVALID; }
+    if (!st->cta_attr_done) {
+        PF_CUDA_TRY(cudaFuncSetAttribute(msa_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        st->cta_attr_done = true;
+    }
+    int per_sm = 0;
+    PF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msa_cta_kernel, CTA_THREADS, smem));
+    uint64_t ctas = (uint64_t)ctx->sm_count * std::max(1, per_sm);
+    ctas = std::min<uint64_t>(ctas, std::max<uint64_t>(1, WS_BUDGET / ws_bytes));
+    ctas = std::min<uint64_t>(ctas, (uint64_t)n_items);
+    int rc;
+    if ((rc = pool.reserve(ctas * ws_bytes))) return rc;
+    MsaArgs a;
+    fill_args(a, st, slot_pool, lim, sc, d_bases, d_seq_off, d_bubble_off, d_order, first, n_items, tier_id, counter);
+    a.ws_base = pool.as<uint8_t>(); a.ws_stride = ws_bytes;
+    msa_cta_kernel<<<(unsigned)ctas, CTA_THREADS, smem, s>>>(a);
+    ctx->launches++;
+    PF_CUDA_TRY(cudaGetLastError());
+    return PF_OK;
+}
+
+// limits of the CTA kernel: generous from the start (a re-run of a multi-kilobase bubble would cost as much as the pass itself);
+// max_alen is capped so that the skewed flag area stays below 2^32 bytes (32-bit cell indices in the traceback)
+Limits cta_limits(uint32_t max_blen, uint32_t max_rows, uint32_t alen_factor) {
+    Limits l;
+    l.max_rows = std::min<uint32_t>(std::max<uint32_t>(max_rows, 2), 64);
+    l.max_blen = std::max<uint32_t>(max_blen, 1);
+    l.diag_flags = LAYOUT_SKEW; l.pad_ = CTA_THREADS;
+    uint64_t alen = (uint64_t)l.max_blen * alen_factor + 64;
+    const uint64_t wT = (uint64_t)((l.max_blen + CTA_THREADS) / CTA_THREADS) * CTA_THREADS;
+    const uint64_t cap = (0xFFFFFFFFull / wT) - CTA_THREADS - 2;
+    l.max_alen = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(alen, cap), 1u << 20);
+    l.k_cand = 64; l.k_aln = 64; l.max_var = l.max_alen;
+    l.step_limit = 2000000000ull;
+    return l;
+}
+
 struct DevResult {
     uint64_t tot_rows, tot_var, tot_cls, tot_ilen;
 };
@@ -1196,9 +1393,14 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
     }
     TierTable tt;
     for (int c = 0; c < N_LANE_CLASSES; c++) tt.lim[c] = lane_limits(c);
-    Limits &big = tt.lim[CLS_BIG];        // warp kernel, first pass: work area sized from the batch's longest branch
+    // Branches beyond BIG_SPLIT go to the CTA kernel (integral scoring; the FP64 add+truncate scoring keeps the warp kernel for
+    // every long bubble).  PF_BIG_SPLIT overrides the split (diagnostics, A/B runs).
+    static const uint32_t split_env = getenv("PF_BIG_SPLIT") ? (uint32_t)strtoul(getenv("PF_BIG_SPLIT"), nullptr, 10) : 0;
+    const bool use_cta = sc.integral && cta_smem_bytes(max_len) <= 200 * 1024;
+    const uint32_t big_split = use_cta ? (split_env ? split_env : BIG_SPLIT) : 0xFFFFFFFFu;
+    Limits &big = tt.lim[CLS_BIG];        // one warp per bubble, first pass: work area sized from the longest branch of the class
     big.max_rows = std::min<uint32_t>(std::max<uint32_t>(max_rows, 2), 8);
-    big.max_blen = std::max<uint32_t>(max_len, 1);
+    big.max_blen = std::max<uint32_t>(std::min<uint32_t>(max_len, big_split), 1);
     big.max_alen = big.max_blen + std::min<uint32_t>(64, big.max_blen);
     big.k_cand = 8; big.k_aln = 8; big.max_var = 48;
     big.step_limit = 200000000ull; big.diag_flags = 1; big.pad_ = 0;
@@ -1213,17 +1415,21 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
     heavy.max_alen = heavy.max_blen + 64;
     heavy.k_cand = 64; heavy.k_aln = 64; heavy.max_var = heavy.max_alen;
     heavy.step_limit = 2000000000ull; heavy.diag_flags = 1; heavy.pad_ = 0;
-    Limits &huge = tt.lim[CLS_RETRY];     // warp kernel, second pass: generous
-    huge.max_rows = std::min<uint32_t>(std::max<uint32_t>(max_rows, 2), 64);
-    huge.max_blen = big.max_blen;
-    huge.max_alen = (uint32_t)std::min<uint64_t>((uint64_t)huge.max_blen * std::min<uint32_t>(huge.max_rows, 4) + 64, 1u << 20);
-    huge.k_cand = 64; huge.k_aln = 64; huge.max_var = huge.max_alen;
-    huge.step_limit = 2000000000ull; huge.diag_flags = 1; huge.pad_ = 0;
+    tt.lim[CLS_HUGE] = cta_limits(max_len, max_rows, 2);   // CTA kernel, first pass
+    Limits &huge = tt.lim[CLS_RETRY];     // second pass: generous (CTA kernel when the scoring is integral, else the warp kernel)
+    if (use_cta) huge = cta_limits(max_len, max_rows, std::min<uint32_t>(std::max<uint32_t>(max_rows, 2), 4));
+    else {
+        huge.max_rows = std::min<uint32_t>(std::max<uint32_t>(max_rows, 2), 64);
+        huge.max_blen = std::max<uint32_t>(max_len, 1);
+        huge.max_alen = (uint32_t)std::min<uint64_t>((uint64_t)huge.max_blen * std::min<uint32_t>(huge.max_rows, 4) + 64, 1u << 20);
+        huge.k_cand = 64; huge.k_aln = 64; huge.max_var = huge.max_alen;
+        huge.step_limit = 2000000000ull; huge.diag_flags = 1; huge.pad_ = 0;
+    }
 
     // ---- plan: class + sort ----
     uint32_t *k0 = st->keys[0].as<uint32_t>(), *k1 = st->keys[1].as<uint32_t>();
     uint32_t *i0 = st->ids[0].as<uint32_t>(), *i1 = st->ids[1].as<uint32_t>();
-    plan_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_seq_off, d_bubble_off, n, k0, i0);
+    plan_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_seq_off, d_bubble_off, n, big_split, k0, i0);
     {
         size_t tmp = 0;
         PF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k0, k1, i0, i1, (int)n, 0, 32, s));
@@ -1240,7 +1446,7 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
     uint64_t *h_total = st->h_scalars.as<uint64_t>();
     uint32_t *h_bounds = (uint32_t *)(st->h_scalars.as<uint8_t>() + 256);
     PF_CUDA_TRY(cudaMemcpyAsync(h_total, st->slot_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));
-    PF_CUDA_TRY(cudaMemcpyAsync(h_bounds, d_bounds, (CLS_BIG + 2) * 4, cudaMemcpyDeviceToHost, s));
+    PF_CUDA_TRY(cudaMemcpyAsync(h_bounds, d_bounds, (CLS_HUGE + 2) * 4, cudaMemcpyDeviceToHost, s));
     PF_CUDA_TRY(cudaMemsetAsync(st->counter.p, 0, 256, s));   // work queues [0..15], stat_cells at byte 128
     PF_CUDA_TRY(cudaStreamSynchronize(s));
     if ((rc = st->slots[0].reserve(*h_total + 64))) return rc;
@@ -1280,6 +1486,18 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
     }
     // ---- first pass: every non-empty size class on its own stream (they overlap; heaviest first) ----
     PF_CUDA_TRY(cudaEventRecord(st->ev_fork, s));
+    {
+        const uint32_t cnt = h_bounds[CLS_HUGE + 1] - h_bounds[CLS_HUGE];
+        st->last_class_count[CLS_HUGE] = cnt;
+        if (cnt) {
+            cudaStream_t as = st->aux[N_LANE_CLASSES + 1];
+            PF_CUDA_TRY(cudaStreamWaitEvent(as, st->ev_fork, 0));
+            if ((rc = launch_cta_tier(ctx, st, st->ws_cta[0], 0, tt.lim[CLS_HUGE], sc, d_bases, d_seq_off, d_bubble_off, d_order, h_bounds[CLS_HUGE], cnt,
+                                      CLS_HUGE, st->counter.as<uint32_t>() + CLS_HUGE, as))) return rc;
+            PF_CUDA_TRY(cudaEventRecord(st->ev_join[N_LANE_CLASSES + 1], as));
+            PF_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_join[N_LANE_CLASSES + 1], 0));
+        }
+    }
     {
         const uint32_t cnt = h_bounds[CLS_BIG + 1] - h_bounds[CLS_BIG];
         st->last_class_count[CLS_BIG] = cnt;
@@ -1373,6 +1591,8 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         if ((rc = st->slots[1 + pass].reserve(*h_total + 64))) return rc;
         if (pass == 0) rc = launch_warp_smem_tier(ctx, st, 1, heavy, sc, d_bases, d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), nr, tier,
                                                   st->counter.as<uint32_t>() + tier, s);
+        else if (use_cta) rc = launch_cta_tier(ctx, st, st->ws_cta[1], 2, huge, sc, d_bases, d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), 0, nr, tier,
+                                               st->counter.as<uint32_t>() + tier, s);
         else rc = launch_warp_tier(ctx, st, 2, huge, sc, d_bases, d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), 0, nr, tier,
                                    st->counter.as<uint32_t>() + tier, s);
         if (rc) return rc;

@@ -80,6 +80,15 @@ template <bool DIAG>
 PF_HD uint32_t flag_index(uint32_t i, uint32_t j, uint32_t m, uint32_t n) {
     return DIAG ? (i + j) * (m + 1) + i : i * (n + 1) + j;
 }
+// Layouts of the flag bytes (X::kLayout): 0 row-major with a pitch, 1 diagonal-major, 2 SKEWED for the CTA-wide fill:
+// T lanes own w-column strips (lane l: columns l*w .. l*w+w-1, column 0 = the border) and lane l is at row t - l at time step t,
+// so the byte of cell (i, j) lives at ((i + j/w) * w + j%w) * T + j/w -- the lanes of a warp store 32 consecutive bytes per
+// column of their strips.  (0,0) is byte 0 in every layout.
+enum { LAYOUT_ROW = 0, LAYOUT_DIAG = 1, LAYOUT_SKEW = 2 };
+PF_HD uint64_t skew_index(uint32_t i, uint32_t j, uint32_t w, uint32_t T) {
+    const uint32_t l = j / w, q = j - l * w;
+    return ((uint64_t)(i + l) * w + q) * T + l;
+}
 
 struct Scoring {   // SeqAlign(double&,double&,double&), SeqAlign.hpp:10
     double M, D, G;
@@ -218,7 +227,7 @@ struct TbResult {
 // move | base_flags << 2: the base flags of a cell cannot change while it is on the stack (pruning only touches the current
 // cell), so backtracking needs no flag load at all -- it walks the stack, whose top eight entries live in a register.
 // Readers of a move string mask the entry with 3.
-template <bool DIAG, class X>
+template <int LAYOUT, class X>
 PF_HDN inline TbResult traceback(X &x, const BV flags, const CBV A, uint32_t m, const CBV B, uint32_t n,
                                  const Scoring &sc, const BV mv, const BV ext_mv, const WV ext_len,
                                  uint32_t mv_stride, uint32_t k_aln, uint64_t step_limit, uint32_t pitch_n) {
@@ -229,10 +238,15 @@ PF_HDN inline TbResult traceback(X &x, const BV flags, const CBV A, uint32_t m, 
     // recomputed, (0,0) is cell 0 in both layouts, counters are 32 bit.
     // indel1 / indel2 (size_t in the reference, :312-315) may wrap below zero; a 32-bit counter orders against the small caps
     // exactly like the 64-bit one as long as fewer than 2^31 moves are on the stack.
-    const uint32_t dL = DIAG ? m + 1 : 1u;                     // cell(i, j) - cell(i, j-1)
-    const uint32_t dU = DIAG ? m + 2 : pitch_n + 1;            // cell(i, j) - cell(i-1, j)
+    constexpr bool DIAG = LAYOUT == LAYOUT_DIAG, SKEW = LAYOUT == LAYOUT_SKEW;
+    // skewed layout: a Left move inside a strip is -T, across a strip boundary -(T+1) (q = column inside the strip is tracked)
+    const uint32_t sk_T = SKEW ? x.skew_T() : 0u, sk_w = SKEW ? x.skew_w(n) : 1u;
+    // (cell indices are 32 bit: the launchers keep every flag area below 2^32 bytes)
+    const uint32_t dL = SKEW ? sk_T : (DIAG ? m + 1 : 1u);                      // cell(i, j) - cell(i, j-1)
+    const uint32_t dU = SKEW ? sk_w * sk_T : (DIAG ? m + 2 : pitch_n + 1);      // cell(i, j) - cell(i-1, j)
     const uint32_t dD = dL + dU;                               // cell(i, j) - cell(i-1, j-1)
-    uint32_t cell = flag_index<DIAG>(m, n, m, pitch_n);
+    uint32_t cell = SKEW ? (uint32_t)skew_index(m, n, sk_w, sk_T) : flag_index<DIAG>(m, n, m, pitch_n);
+    uint32_t sk_q = SKEW ? n % sk_w : 0u;
     uint32_t depth = 0, steps = 0;
     const uint32_t budget = step_limit > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)step_limit;
     uint32_t open_a = 0, open_b = 0, cap_a = 5, cap_b = 5;     // indel1, indel2, indel1_max, indel2_max
@@ -291,6 +305,7 @@ PF_HDN inline TbResult traceback(X &x, const BV flags, const CBV A, uint32_t m, 
             if (pm == MV_L) { if (prevmv != MV_L) --open_a; cell += dL; tried = F_LEFT; }
             else if (pm == MV_U) { if (prevmv != MV_U) --open_b; cell += dU; tried = F_LEFT | F_UP; }   // may wrap below zero, as in the reference
             else { cell += dD; tried = F_LEFT | F_UP | F_DIAG; }
+            if (SKEW && pm != MV_U) { if (++sk_q == sk_w) { sk_q = 0; cell += 1; } }   // back over a strip boundary
             c = e >> 2;
             win >>= 8; nwin--; depth--;
             if (nwin < 2 && depth > nwin) {                             // refill the register window: independent loads, one latency
@@ -306,7 +321,9 @@ PF_HDN inline TbResult traceback(X &x, const BV flags, const CBV A, uint32_t m, 
         win = (win << 8) | e;
         nwin = nwin < 8 ? nwin + 1 : 8;
         cell -= move == MV_L ? dL : (move == MV_U ? dU : dD);
-        if (pf && cell >= pf_min) prefetch_byte(&flags[cell - pf_min]);
+        if (SKEW && move != MV_U) { if (sk_q == 0) { sk_q = sk_w - 1; cell -= 1; } else --sk_q; }
+        if (SKEW) x.prefetch_ahead(flags, cell, sk_q, sk_w, sk_T);
+        else if (pf && cell >= pf_min) prefetch_byte(&flags[cell - pf_min]);
         c = (uint32_t)flags[cell] & 7u;
         tried = 0;
     }
@@ -551,11 +568,15 @@ struct Limits {          // uniform for one launch
     uint32_t k_aln;      // co-optimal pairwise alignments kept by one traceback (<= 64)
     uint32_t max_var;    // variable columns per output slot
     uint64_t step_limit; // traceback iterations per bubble (summed over its pairwise alignments)
-    uint32_t diag_flags; // 1: flag bytes stored diagonal-major (generic warp kernel), 0: row-major (lane kernel, host)
-    uint32_t pad_;
+    uint32_t diag_flags; // layout of the flag bytes: LAYOUT_ROW (lane / group kernels, host), LAYOUT_DIAG (generic warp kernel), LAYOUT_SKEW (CTA kernel)
+    uint32_t pad_;       // LAYOUT_SKEW: T = lanes of the CTA-wide fill
 };
 
 PF_HD uint64_t flag_area_cells(const Limits &l) {
+    if (l.diag_flags == LAYOUT_SKEW) {
+        const uint64_t T = l.pad_ ? l.pad_ : 1, w = (l.max_blen + T) / T;      // ceil((max_blen + 1) / T)
+        return (uint64_t)(l.max_alen + T + 1) * w * T;
+    }
     return l.diag_flags ? (uint64_t)(l.max_alen + l.max_blen + 1) * (l.max_alen + 1) : (uint64_t)(l.max_alen + 1) * (l.max_blen + 1);
 }
 
@@ -587,15 +608,25 @@ PF_HD uint64_t work_area_bytes(const Limits &l, uint32_t lanes = 1) {
 }
 
 // lanes == 1: contiguous private area.  lanes == 32: element t of lane L's array sits at array_base + t*32 + L.
-PF_HD WorkArea carve_work_area(uint8_t *base, const Limits &l, uint32_t lanes = 1, uint32_t lane = 0) {
+// contig (lanes > 1): only the flag bytes are interleaved (the fill's lock-step stores coalesce); the arrays of the sequential
+// phases -- move strings, kept alignments, candidate MSAs -- are contiguous per lane, so a lane streaming through its own array
+// stays inside one 32-byte sector for 32 elements (L1) instead of touching a new sector per element.
+PF_HD WorkArea carve_work_area(uint8_t *base, const Limits &l, uint32_t lanes = 1, uint32_t lane = 0, bool contig = false) {
     WorkArea w;
     uint8_t *p = base;
+    const uint32_t st = contig ? 1u : lanes;
+    uint64_t sz;
     w.flags = bv(p + lane, lanes); p += lanes * align_up(flag_area_cells(l), 16);
-    w.mv = bv(p + lane, lanes); p += lanes * align_up(l.max_alen + l.max_blen, 16);
-    w.ext_mv = bv(p + lane, lanes); p += lanes * align_up((uint64_t)l.k_aln * (l.max_alen + l.max_blen), 16);
-    w.ext_len = wv((uint32_t *)p + lane, lanes); p += lanes * align_up((uint64_t)l.k_aln * 4, 16);
-    for (int i = 0; i < 2; i++) { w.cand[i] = bv(p + lane, lanes); p += lanes * align_up((uint64_t)l.k_cand * l.max_rows * l.max_alen, 16); }
-    for (int i = 0; i < 2; i++) { w.cand_len[i] = wv((uint32_t *)p + lane, lanes); p += lanes * align_up((uint64_t)l.k_cand * 4, 16); }
+    sz = align_up(l.max_alen + l.max_blen, 16);
+    w.mv = bv(p + (contig ? lane * sz : lane), st); p += lanes * sz;
+    sz = align_up((uint64_t)l.k_aln * (l.max_alen + l.max_blen), 16);
+    w.ext_mv = bv(p + (contig ? lane * sz : lane), st); p += lanes * sz;
+    sz = align_up((uint64_t)l.k_aln * 4, 16);
+    w.ext_len = wv((uint32_t *)p + (contig ? lane * (sz / 4) : lane), st); p += lanes * sz;
+    sz = align_up((uint64_t)l.k_cand * l.max_rows * l.max_alen, 16);
+    for (int i = 0; i < 2; i++) { w.cand[i] = bv(p + (contig ? lane * sz : lane), st); p += lanes * sz; }
+    sz = align_up((uint64_t)l.k_cand * 4, 16);
+    for (int i = 0; i < 2; i++) { w.cand_len[i] = wv((uint32_t *)p + (contig ? lane * (sz / 4) : lane), st); p += lanes * sz; }
     w.brow = (int32_t *)p;
     return w;
 }
@@ -631,6 +662,9 @@ PF_HD SlotLayout slot_layout(uint32_t n_seq, uint64_t sum_len, const Limits &l) 
 struct SerialHelpers {
     PF_HD bool prefetch_flags() const { return false; }
     PF_HD uint32_t prefetch_cells() const { return 6; }
+    PF_HD uint32_t skew_T() const { return 1; }
+    PF_HD uint32_t skew_w(uint32_t) const { return 1; }
+    PF_HD void prefetch_ahead(const BV, uint32_t, uint32_t, uint32_t, uint32_t) const {}
     PF_HD PairKey analyze(const Scoring &sc, const CBV row, const CBV B, const CBV mv, uint32_t depth) const { return analyze_moves(sc, row, B, mv, depth); }
     PF_HD void copy(const CBV src, const BV dst, uint32_t n) const { copy_bytes(src, dst, n); }
     PF_HD void project(const CBV src, const CBV mv, uint32_t depth, const BV dst, uint8_t gap_move) const { project_moves(src, mv, depth, dst, gap_move); }
@@ -646,7 +680,7 @@ struct SerialHelpers {
 //     everywhere: same loads, same decisions, same stores to the same addresses -- no extra time under SIMT), which lets
 //     the O(L) helpers (analyze / copy / project) use the G lanes instead of one;
 //   * tests/hostemu: a single CPU thread.
-// X::kDiagFlags selects the flag-byte layout the policy's fill writes.
+// X::kLayout selects the flag-byte layout the policy's fill writes.
 template <class X>
 PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, uint32_t s0, uint32_t ns,
                            const WorkArea &ws, const Limits &lim, const Scoring &sc, uint8_t *slot) {
@@ -676,7 +710,7 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
             if (m > lim.max_alen) { status = PF_BUBBLE_TOO_LONG; break; }
             x.fill(ws.flags, A, m, B, n, sc, ws.brow);
             if (x.leader()) {
-                const TbResult tb = traceback<X::kDiagFlags>(x, ws.flags, A, m, B, n, sc, ws.mv, ws.ext_mv, ws.ext_len, mv_stride,
+                const TbResult tb = traceback<X::kLayout>(x, ws.flags, A, m, B, n, sc, ws.mv, ws.ext_mv, ws.ext_len, mv_stride,
                                                              lim.k_aln, steps_left, x.pitch_n(n));
                 steps_left -= tb.steps < steps_left ? tb.steps : steps_left;
                 x.note_steps(tb.steps);

@@ -1,5 +1,6 @@
 // pf_api.cu -- context lifetime, error channel and buffer helpers of libpfgpu.so.
 #include "pf_common.cuh"
+#include <algorithm>
 
 #include <cstring>
 
@@ -138,6 +139,36 @@ __global__ void gather_bench_kernel(const uint4 *__restrict__ table, uint64_t n_
     if (acc == 0x12345678u) *sink = acc;
 }
 
+// The ceiling of a one-sector-per-lookup index: every thread keeps ILP independent random loads of WIDTH bytes (32 = one sector,
+// 64 = two adjacent sectors, 16 = half a sector) in flight against a table of 2^bits units, addresses from a xorshift stream
+// (shift + mask: no division), L1 no-allocate like the lookup kernel's bucket loads.
+template <int WIDTH, int ILP>
+__global__ void __launch_bounds__(256) gather_sweep_kernel(const unsigned long long *__restrict__ table, uint32_t unit_bits, uint32_t iters,
+                                                           unsigned long long *sink) {
+    uint64_t x = ((uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) + 1) * 0x9E3779B97F4A7C15ull;
+    const uint64_t mask = (1ull << unit_bits) - 1;
+    unsigned long long acc = 0;
+    for (uint32_t it = 0; it < iters; it++) {
+        unsigned long long v[ILP][WIDTH / 8];
+#pragma unroll
+        for (int u = 0; u < ILP; u++) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            const unsigned long long *p = table + ((x >> 11) & mask) * (WIDTH / 8);
+            if (WIDTH == 16) asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(v[u][0]), "=l"(v[u][1]) : "l"(p));
+            else {
+                asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[u][0]), "=l"(v[u][1]), "=l"(v[u][2]), "=l"(v[u][3]) : "l"(p));
+                if (WIDTH == 64)
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[u][4]), "=l"(v[u][5]), "=l"(v[u][6]), "=l"(v[u][7]) : "l"(p + 4));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; u++)
+#pragma unroll
+            for (int q = 0; q < WIDTH / 8; q++) acc += v[u][q];
+    }
+    if (acc == 0x123456789ull) *sink = acc;
+}
+
 __global__ void int32_bench_kernel(uint32_t iters, int *sink) {
     int a = threadIdx.x, b = blockIdx.x, c = 7, d = 3;
     for (uint32_t it = 0; it < iters; it++) {
@@ -178,6 +209,48 @@ int pf_bench_random_gather(pf_ctx *ctx, uint64_t bytes, double *gb_per_s) {
     float ms = 0;
     PF_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
     *gb_per_s = (double)blocks * threads * iters * 8 * 32.0 / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(tab); cudaFree(sink);
+    return PF_OK;
+}
+
+// diagnostics: random-access ceiling.  width 16 / 32 / 64 bytes per access, ilp 4 / 8 / 16 loads in flight per thread,
+// ctas_per_sm resident 256-thread CTAs; returns accesses per second (G/s).
+int pf_bench_gather_sweep(pf_ctx *ctx, uint64_t bytes, uint32_t width, uint32_t ilp, uint32_t ctas_per_sm, double *g_access_per_s) {
+    if (!ctx || !g_access_per_s || bytes < (1u << 20)) { pf::set_error("pf_bench_gather_sweep: bad argument"); return PF_E_INVALID; }
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint32_t bits = 0;
+    while ((2ull << bits) * width <= bytes) bits++;
+    const uint64_t tab_bytes = (1ull << bits) * width;
+    void *tab = nullptr, *sink = nullptr;
+    PF_CUDA_TRY(cudaMalloc(&tab, tab_bytes));
+    PF_CUDA_TRY(cudaMalloc(&sink, 8));
+    PF_CUDA_TRY(cudaMemsetAsync(tab, 1, tab_bytes, ctx->stream));
+    const unsigned blocks = ctx->sm_count * std::max(1u, ctas_per_sm), threads = 256;
+    const uint32_t iters = 256 / ilp * 4;
+    auto launch = [&](uint32_t it) {
+        const unsigned long long *t = (const unsigned long long *)tab;
+        unsigned long long *sk = (unsigned long long *)sink;
+#define PF_GS(W, I) gather_sweep_kernel<W, I><<<blocks, threads, 0, ctx->stream>>>(t, bits, it, sk)
+        if (width == 16) { if (ilp <= 4) PF_GS(16, 4); else if (ilp <= 8) PF_GS(16, 8); else PF_GS(16, 16); }
+        else if (width == 64) { if (ilp <= 4) PF_GS(64, 4); else if (ilp <= 8) PF_GS(64, 8); else PF_GS(64, 16); }
+        else { if (ilp <= 4) PF_GS(32, 4); else if (ilp <= 8) PF_GS(32, 8); else PF_GS(32, 16); }
+#undef PF_GS
+    };
+    const uint32_t ilp_eff = ilp <= 4 ? 4 : ilp <= 8 ? 8 : 16;
+    cudaEvent_t e0, e1;
+    PF_CUDA_TRY(cudaEventCreate(&e0));
+    PF_CUDA_TRY(cudaEventCreate(&e1));
+    launch(4);
+    PF_CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+    launch(iters);
+    PF_CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+    PF_CUDA_TRY(cudaEventSynchronize(e1));
+    PF_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 2;
+    float ms = 0;
+    PF_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    *g_access_per_s = (double)blocks * threads * iters * ilp_eff / (ms * 1e-3) / 1e9;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(tab); cudaFree(sink);
     return PF_OK;

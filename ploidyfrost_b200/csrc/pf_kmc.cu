@@ -721,6 +721,7 @@ struct pf_kmc {
     const unsigned long long *peer_tab[pfkmc::PF_MAX_PEERS] = {nullptr};
     void *peer_mapped[pfkmc::PF_MAX_PEERS] = {nullptr};
     bool peers_attached = false;   // keys in the hash index (== total_kmers unless this handle is one partition)
+    bool borrowed = false;         // pf_kmc_share: the index memory belongs to another handle, only the per-call buffers are ours
     pf::DevBuf tile_seq;   // per-call scratch of the hash lookup (grow-only)
     pf::DevBuf site_status, site_ncls, site_cov, site_skip, site_map;   // pf_site_cov outputs (grow-only)
     pf::PinnedBuf h_site[5];
@@ -1056,9 +1057,11 @@ int pf_kmc_close(pf_kmc *db) {
         db->route->h_bounds.release();
         delete db->route;
     }
-    cudaFree(db->d_lut); cudaFree(db->d_sigmap); cudaFree(db->d_norm);
-    cudaFree(db->d_rec); cudaFree(db->d_suf); cudaFree(db->d_cnt); cudaFree(db->d_hash);
-    for (auto &m : db->peer_mapped) if (m) cudaIpcCloseMemHandle(m);
+    if (!db->borrowed) {
+        cudaFree(db->d_lut); cudaFree(db->d_sigmap); cudaFree(db->d_norm);
+        cudaFree(db->d_rec); cudaFree(db->d_suf); cudaFree(db->d_cnt); cudaFree(db->d_hash);
+        for (auto &m : db->peer_mapped) if (m) cudaIpcCloseMemHandle(m);
+    }
     db->tile_seq.release();
     db->site_status.release(); db->site_ncls.release(); db->site_cov.release(); db->site_skip.release(); db->site_map.release();
     for (auto &b : db->h_site) b.release();
@@ -1067,6 +1070,28 @@ int pf_kmc_close(pf_kmc *db) {
     for (auto &b : db->k_in) b.release();
     for (auto &b : db->k_out) b.release();
     delete db;
+    return PF_OK;
+}
+
+// A second handle on the SAME index for another context of the same device (one pf_ctx per host thread: every thread drives
+// its own batches through its own stream and buffers while the HBM-resident index exists once).  The borrowed handle must be
+// closed before the handle it was taken from.
+int pf_kmc_share(pf_kmc *db, pf_ctx *ctx, pf_kmc **out) {
+    if (!db || !ctx || !out) { pf::set_error("pf_kmc_share: null argument"); return PF_E_INVALID; }
+    *out = nullptr;
+    if (ctx->device != db->ctx->device) { pf::set_error("pf_kmc_share: the context is on another device than the index"); return PF_E_INVALID; }
+    pf_kmc *h = new pf_kmc();
+    h->ctx = ctx;
+    h->info = db->info; h->orig_min = db->orig_min; h->orig_max = db->orig_max;
+    h->view = db->view;
+    h->d_lut = db->d_lut; h->d_sigmap = db->d_sigmap; h->d_norm = db->d_norm; h->d_rec = db->d_rec; h->d_suf = db->d_suf; h->d_cnt = db->d_cnt;
+    h->device_bytes = db->device_bytes; h->local_kmers = db->local_kmers;
+    h->hash_on = db->hash_on; h->canonical_ok = db->canonical_ok; h->hview = db->hview; h->d_hash = db->d_hash;
+    h->build_status = db->build_status; h->hash_inserted = db->hash_inserted;
+    for (int i = 0; i < pfkmc::PF_MAX_PEERS; i++) h->peer_tab[i] = db->peer_tab[i];
+    h->peers_attached = db->peers_attached;
+    h->borrowed = true;
+    *out = h;
     return PF_OK;
 }
 

@@ -16,9 +16,17 @@ using namespace pfalign;
 
 namespace {
 
-template <bool DIAG>
+uint32_t g_skew_T = 8;   // lanes of the emulated CTA-wide fill (LAYOUT_SKEW)
+
+template <int LAYOUT>
 struct HostExec : SerialHelpers {
-    static constexpr bool kDiagFlags = DIAG;
+    static constexpr int kLayout = LAYOUT;
+    static constexpr bool DIAG = LAYOUT == LAYOUT_DIAG;
+    uint32_t skew_T() const { return g_skew_T; }
+    uint32_t skew_w(uint32_t n) const { return (n + g_skew_T) / g_skew_T; }
+    uint64_t fidx(uint32_t i, uint32_t j, uint32_t m, uint32_t n) const {
+        return LAYOUT == LAYOUT_SKEW ? skew_index(i, j, skew_w(n), g_skew_T) : (uint64_t)flag_index<DIAG>(i, j, m, n);
+    }
     std::vector<int> rowbuf;
     bool leader() const { return true; }
     uint32_t bcast(uint32_t v) const { return v; }
@@ -32,15 +40,15 @@ struct HostExec : SerialHelpers {
         rowbuf.assign(2 * (size_t)(n + 1), 0);
         int *prev = rowbuf.data(), *cur = rowbuf.data() + n + 1;
         flags[0] = 0;
-        for (uint32_t j = 1; j <= n; j++) { prev[j] = pack_sf(border_score(sc, j), F_LEFT); flags[flag_index<DIAG>(0, j, m, n)] = F_LEFT; }
+        for (uint32_t j = 1; j <= n; j++) { prev[j] = pack_sf(border_score(sc, j), F_LEFT); flags[fidx(0, j, m, n)] = F_LEFT; }
         prev[0] = pack_sf(0, 0);
         for (uint32_t i = 1; i <= m; i++) {
             cur[0] = pack_sf(border_score(sc, i), F_UP);
-            flags[flag_index<DIAG>(i, 0, m, n)] = F_UP;
+            flags[fidx(i, 0, m, n)] = F_UP;
             const bool block_left = (i != m) && A[i] == '-';
             for (uint32_t j = 1; j <= n; j++) {
                 cur[j] = nw_cell(sc, prev[j], prev[j - 1], cur[j - 1], A[i - 1], B[j - 1], block_left);
-                flags[flag_index<DIAG>(i, j, m, n)] = (uint8_t)unpack_f(cur[j]);
+                flags[fidx(i, j, m, n)] = (uint8_t)unpack_f(cur[j]);
             }
             std::swap(prev, cur);
         }
@@ -57,7 +65,11 @@ std::vector<uint64_t> g_steps;   // traceback iterations per bubble of the last 
 extern "C" {
 
 // diag = 1: diagonal-major flag bytes (msa_warp_kernel); lanes = 32: lane-interleaved work area (msa_lane_kernel)
-void pfemu_set_layout(uint32_t diag, uint32_t lanes, uint32_t lane) { g_lim.diag_flags = diag; g_lanes = lanes; g_lane = lane; }
+// diag = 2: the skewed layout of msa_cta_kernel with `lane` emulated lanes (work area contiguous)
+void pfemu_set_layout(uint32_t diag, uint32_t lanes, uint32_t lane) {
+    g_lim.diag_flags = diag; g_lanes = lanes; g_lane = lane;
+    if (diag == LAYOUT_SKEW) { g_skew_T = lane ? lane : 8; g_lim.pad_ = g_skew_T; g_lanes = 1; g_lane = 0; }
+}
 
 void pfemu_set_limits(uint32_t max_rows, uint32_t k_cand, uint32_t k_aln, uint32_t max_alen, uint32_t max_var) {
     g_lim.max_rows = max_rows; g_lim.k_cand = k_cand; g_lim.k_aln = k_aln; g_lim.max_alen = max_alen; g_lim.max_var = max_var;
@@ -72,8 +84,9 @@ void *pfemu_align(double M, double D, double G, const char *bases, const uint64_
     const Scoring sc = make_scoring(M, D, G);
     std::atomic<uint32_t> next(0);
     auto worker = [&]() {
-        HostExec<true> xd;
-        HostExec<false> xr;
+        HostExec<LAYOUT_DIAG> xd;
+        HostExec<LAYOUT_ROW> xr;
+        HostExec<LAYOUT_SKEW> xs;
         std::vector<uint8_t> wbuf, slot;
         for (;;) {
             const uint32_t b = next.fetch_add(1);
@@ -93,10 +106,11 @@ void *pfemu_align(double M, double D, double G, const char *bases, const uint64_
             const WorkArea ws = carve_work_area(wbuf.data(), lim, g_lanes, g_lanes > 1 ? (b + g_lane) % g_lanes : 0);
             const SlotLayout lay = slot_layout(ns, sum, lim);
             slot.assign(lay.bytes + 64, 0);
-            xd.steps = xr.steps = 0;
-            if (lim.diag_flags) msa_run(xd, (const uint8_t *)bases, seq_off, s0, ns, ws, lim, sc, slot.data());
+            xd.steps = xr.steps = xs.steps = 0;
+            if (lim.diag_flags == LAYOUT_SKEW) msa_run(xs, (const uint8_t *)bases, seq_off, s0, ns, ws, lim, sc, slot.data());
+            else if (lim.diag_flags) msa_run(xd, (const uint8_t *)bases, seq_off, s0, ns, ws, lim, sc, slot.data());
             else msa_run(xr, (const uint8_t *)bases, seq_off, s0, ns, ws, lim, sc, slot.data());
-            g_steps[b] = xd.steps + xr.steps;
+            g_steps[b] = xd.steps + xr.steps + xs.steps;
             const SlotHdr *h = (const SlotHdr *)slot.data();
             status[b] = h->status;
             pforacle::MsaResult &r = res[b];

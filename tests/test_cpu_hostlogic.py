@@ -63,10 +63,11 @@ def test_device_state_machines_on_host_match_oracle(oracle, hostemu, seed, kw, s
     a = oracle.align_bubbles(bubbles, n_threads=8, **sc)
     try:
         # (diagonal-major flags, contiguous area) = msa_warp_kernel; (row-major, lane-interleaved) = msa_lane_kernel
-        for diag, lanes in ((1, 1), (0, 1), (0, 32)):
-            hostemu.pfemu_set_layout(diag, lanes, seed)
+        # (2, 1, T) = the skewed layout of msa_cta_kernel with T emulated lanes
+        for diag, lanes, arg in ((1, 1, seed), (0, 1, seed), (0, 32, seed), (2, 1, 7), (2, 1, 64)):
+            hostemu.pfemu_set_layout(diag, lanes, arg)
             b = _emu_align(hostemu, bubbles, **sc)
-            assert_msa_equal(a, b, bubbles, f"seed {seed} diag={diag} lanes={lanes}")
+            assert_msa_equal(a, b, bubbles, f"seed {seed} diag={diag} lanes={lanes} arg={arg}")
     finally:
         hostemu.pfemu_set_layout(0, 1, 0)
 

@@ -33,6 +33,43 @@ struct Bubble {
     std::vector<std::string> sort_keys;
 };
 
+// A batch of bubbles as flat arrays -- what a host that cares about its own speed hands over (no std::string per branch).
+// Branch s of the batch is bases[seq_off[s] .. seq_off[s+1]); bubble b owns branches bubble_off[b] .. bubble_off[b+1].
+struct FlatBatch {
+    std::string bases;
+    std::vector<uint64_t> seq_off{0};
+    std::vector<uint32_t> bubble_off{0};
+    std::vector<uint8_t> fwd;                  // per branch, strict bubbles only: 1 = the string is the unitig's forward strand
+                                               // (referenceUnitigToString() == the string), 0 = its reverse complement
+    std::vector<uint8_t> strict;               // per bubble
+    std::vector<uint32_t> entrance_id, exit_id;
+    std::vector<uint64_t> entrance_size, exit_size;
+    size_t n_bubbles() const { return bubble_off.size() - 1; }
+    size_t n_seq() const { return seq_off.size() - 1; }
+    void clear() {
+        bases.clear(); seq_off.assign(1, 0); bubble_off.assign(1, 0); fwd.clear(); strict.clear();
+        entrance_id.clear(); exit_id.clear(); entrance_size.clear(); exit_size.clear();
+    }
+    void add_branch(const char *p, size_t n, bool forward) { bases.append(p, n); seq_off.push_back(bases.size()); fwd.push_back(forward ? 1 : 0); }
+    void end_bubble(bool is_strict, unsigned ent_id, unsigned ex_id, size_t ent_size, size_t ex_size) {
+        bubble_off.push_back((uint32_t)n_seq()); strict.push_back(is_strict ? 1 : 0);
+        entrance_id.push_back(ent_id); exit_id.push_back(ex_id); entrance_size.push_back(ent_size); exit_size.push_back(ex_size);
+    }
+    void append(const FlatBatch &o) {          // batches built by several threads are joined in order
+        const uint64_t b0 = bases.size();
+        const uint32_t s0 = (uint32_t)n_seq();
+        bases += o.bases;
+        for (size_t i = 1; i < o.seq_off.size(); i++) seq_off.push_back(o.seq_off[i] + b0);
+        for (size_t i = 1; i < o.bubble_off.size(); i++) bubble_off.push_back(o.bubble_off[i] + s0);
+        fwd.insert(fwd.end(), o.fwd.begin(), o.fwd.end());
+        strict.insert(strict.end(), o.strict.begin(), o.strict.end());
+        entrance_id.insert(entrance_id.end(), o.entrance_id.begin(), o.entrance_id.end());
+        exit_id.insert(exit_id.end(), o.exit_id.begin(), o.exit_id.end());
+        entrance_size.insert(entrance_size.end(), o.entrance_size.begin(), o.entrance_size.end());
+        exit_size.insert(exit_size.end(), o.exit_size.begin(), o.exit_size.end());
+    }
+};
+
 struct CallerFiles {   // what the reference appends to its streams (Appendix D of SURVEY.md), `-t 1` dialect
     std::string alignseq;            // P_alignseq.txt
     std::string cov[4], fre[4];      // P_{bi,tri,tetra,penta}{cov,fre}.txt
@@ -63,93 +100,133 @@ class BubbleCaller {
     // no text of the failed batch is appended to `out` (its `called` flags and `var_id` are not meaningful then).
     bool call(const std::vector<Bubble> &batch, size_t &var_id, CallerFiles &out) { return call(batch.data(), batch.size(), var_id, out); }
 
+    // the std::string form: flattened and handed to the flat form below
     bool call(const Bubble *batch, size_t n_batch, size_t &var_id, CallerFiles &out) {
-        err_.clear();
-        const size_t called_base = out.called.size();
-        out.called.resize(called_base + n_batch, 0);
-        // ---- lookup-A: readCov of every branch of the strict bubbles (CDBG.cpp:66-120) ----
-        std::string lbases;
-        std::vector<uint64_t> loff(1, 0);
-        for (size_t bi = 0; bi < n_batch; bi++)
-            if (batch[bi].strict)
-                for (const std::string &s : batch[bi].branches) { lbases += s; loff.push_back(lbases.size()); }
-        std::vector<pf_cov_t> cov(loff.size() - 1);
-        if (!cov.empty() && pf_kmc_cov(db_, lbases.data(), loff.data(), (uint32_t)cov.size(), PF_LOOKUP_FWD_THEN_RC, 0, 0xFFFFFFFFu,
-                                       cov.data()) != PF_OK)
-            return fail(pf_last_error());
-        // ---- gate + order the branches; build the alignment batch ----
-        struct Kept { size_t src; std::vector<size_t> order; std::vector<double> means; double sum; };
-        std::vector<Kept> kept;
-        std::string abases;
-        std::vector<uint64_t> aoff(1, 0);
-        std::vector<uint32_t> boff(1, 0);
-        std::vector<uint8_t> skip;
-        size_t ci = 0;
+        FlatBatch fb;
+        size_t total = 0;
+        for (size_t bi = 0; bi < n_batch; bi++) for (const std::string &s : batch[bi].branches) total += s.size();
+        fb.bases.reserve(total);
+        std::vector<std::string> keys;             // explicit sort keys of strict bubbles (referenceUnitigToString), else empty
+        bool any_keys = false;
         for (size_t bi = 0; bi < n_batch; bi++) {
             const Bubble &b = batch[bi];
-            Kept kb;
-            kb.src = bi; kb.sum = 0;
-            const size_t n = b.branches.size();
-            if (b.strict) {
+            const bool has_keys = b.strict && b.sort_keys.size() == b.branches.size();
+            for (size_t j = 0; j < b.branches.size(); j++) {
+                fb.add_branch(b.branches[j].data(), b.branches[j].size(), true);
+                keys.push_back(has_keys ? b.sort_keys[j] : std::string());
+                any_keys |= has_keys;
+            }
+            fb.end_bubble(b.strict, b.entrance_id, b.exit_id, b.entrance_size, b.exit_size);
+        }
+        explicit_keys_ = any_keys ? &keys : nullptr;
+        const bool ok = call(fb, var_id, out);
+        explicit_keys_ = nullptr;
+        return ok;
+    }
+
+    // Calls one flat batch (see FlatBatch).
+    bool call(const FlatBatch &fb, size_t &var_id, CallerFiles &out) {
+        err_.clear();
+        const size_t n_batch = fb.n_bubbles(), n_seq = fb.n_seq();
+        const size_t called_base = out.called.size();
+        out.called.resize(called_base + n_batch, 0);
+        if (n_batch == 0) return true;
+        auto fail_batch = [&](const std::string &why) { out.called.resize(called_base); return fail(why); };
+        const char *B = fb.bases.data();
+        auto seq_ptr = [&](size_t s) { return B + fb.seq_off[s]; };
+        auto seq_len = [&](size_t s) { return (size_t)(fb.seq_off[s + 1] - fb.seq_off[s]); };
+        // ---- lookup-A: readCov of every branch string (CDBG.cpp:66-120).  The reference reads the branches of STRICT bubbles only;
+        //      the records of the other bubbles' paths come back with the same call and are not looked at. ----
+        bool any_strict = false;
+        for (size_t bi = 0; bi < n_batch && !any_strict; bi++) any_strict = fb.strict[bi] != 0;
+        cov_.resize(n_seq);
+        if (any_strict && n_seq && pf_kmc_cov(db_, B, fb.seq_off.data(), (uint32_t)n_seq, PF_LOOKUP_FWD_THEN_RC, 0, 0xFFFFFFFFu, cov_.data()) != PF_OK)
+            return fail_batch(pf_last_error());
+        // ---- gate + order the branches; build the alignment batch ----
+        k_src_.clear(); k_first_.assign(1, 0); k_sum_.clear(); sorted_seq_.clear(); sorted_mean_.clear();
+        abases_.clear(); aoff_.assign(1, 0); boff_.assign(1, 0); skip_.clear();
+        abases_.reserve(fb.bases.size());
+        std::vector<double> mean_tmp;
+        std::vector<uint32_t> ord;
+        std::string key_x, key_y;
+        for (size_t bi = 0; bi < n_batch; bi++) {
+            const size_t s0 = fb.bubble_off[bi], n = fb.bubble_off[bi + 1] - s0;
+            const bool strict = fb.strict[bi] != 0;
+            double sum = 0;
+            mean_tmp.assign(n, 0.0);
+            if (strict) {
                 bool ok = true;
-                for (size_t j = 0; j < n; j++, ci++) {
-                    const pf_cov_t &c = cov[ci];
-                    if (!ok) continue;                                             // the reference stopped reading at the first failure (:2027-2031)
-                    if (c.first_missing >= 0) return fail("a k-mer of a branch unitig is not in the database: the reference exits here (CDBG.cpp:94)");
-                    if (c.min > lower_ && c.min < upper_) {                       // :2021 (min count of the branch inside the thresholds)
-                        const double m = (double)c.sum / (double)c.n_kmers;
-                        kb.means.push_back(m);
-                        kb.sum += m;                                               // in successor order (:2024)
-                    } else ok = false;                                             // :2027-2031: the bubble is dropped
+                for (size_t j = 0; j < n && ok; j++) {                               // the reference stops reading at the first failure (:2027-2031)
+                    const pf_cov_t &c = cov_[s0 + j];
+                    if (c.first_missing >= 0) return fail_batch("a k-mer of a branch unitig is not in the database: the reference exits here (CDBG.cpp:94)");
+                    if (c.min > lower_ && c.min < upper_) {                         // :2021 (min count of the branch inside the thresholds)
+                        mean_tmp[j] = (double)c.sum / (double)c.n_kmers;
+                        sum += mean_tmp[j];                                         // in successor order (:2024)
+                    } else ok = false;                                              // :2027-2031: the bubble is dropped
                 }
                 if (!ok || n < 2) continue;
-                kb.order.resize(n);
-                for (size_t j = 0; j < n; j++) kb.order[j] = j;
-                const std::vector<std::string> &keys = b.sort_keys.size() == n ? b.sort_keys : b.branches;
-                std::sort(kb.order.begin(), kb.order.end(), [&](size_t x, size_t y) {          // sortSeq_simple's order (:482-551)
-                    if (kb.means[x] != kb.means[y]) return kb.means[x] > kb.means[y];
-                    return std::strcmp(keys[x].c_str(), keys[y].c_str()) > 0;
+            } else if (n < 2) continue;
+            ord.resize(n);
+            for (size_t j = 0; j < n; j++) ord[j] = (uint32_t)j;
+            if (strict) {
+                std::sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) {      // sortSeq_simple's order (:482-551)
+                    if (mean_tmp[x] != mean_tmp[y]) return mean_tmp[x] > mean_tmp[y];
+                    sort_key(fb, s0 + x, key_x); sort_key(fb, s0 + y, key_y);        // referenceUnitigToString of the two branches
+                    return std::strcmp(key_x.c_str(), key_y.c_str()) > 0;
                 });
             } else {
-                if (n < 2) continue;
-                kb.order.resize(n);
-                for (size_t j = 0; j < n; j++) kb.order[j] = j;
-                std::sort(kb.order.begin(), kb.order.end(), [&](size_t x, size_t y) {          // sortSeq_branching: longer first, then larger
-                    if (b.branches[x].size() != b.branches[y].size()) return b.branches[x].size() > b.branches[y].size();
-                    return b.branches[x] > b.branches[y];
+                std::sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) {      // sortSeq_branching: longer first, then larger
+                    const size_t lx = seq_len(s0 + x), ly = seq_len(s0 + y);
+                    if (lx != ly) return lx > ly;
+                    return std::memcmp(seq_ptr(s0 + x), seq_ptr(s0 + y), lx) > 0;
                 });
             }
-            for (size_t j : kb.order) { abases += b.branches[j]; aoff.push_back(abases.size()); }
-            boff.push_back((uint32_t)(aoff.size() - 1));
-            skip.push_back(b.strict ? 1 : 0);
-            kept.push_back(std::move(kb));
+            for (uint32_t j : ord) {
+                abases_.append(seq_ptr(s0 + j), seq_len(s0 + j));
+                aoff_.push_back(abases_.size());
+                sorted_seq_.push_back((uint32_t)(s0 + j));
+                sorted_mean_.push_back(mean_tmp[j]);
+            }
+            boff_.push_back((uint32_t)(aoff_.size() - 1));
+            skip_.push_back(strict ? 1 : 0);
+            k_src_.push_back((uint32_t)bi);
+            k_first_.push_back((uint32_t)sorted_seq_.size());
+            k_sum_.push_back(sum);
         }
-        if (kept.empty()) return true;
+        const size_t n_kept = k_src_.size();
+        if (n_kept == 0) return true;
         // ---- SequenceAlignment of every kept bubble, then the site k-mers of the branching ones ----
         pf_msa_batch_t m;
-        if (pf_align(ctx_, M_, D_, G_, abases.data(), aoff.data(), boff.data(), (uint32_t)kept.size(), &m) != PF_OK) return fail(pf_last_error());
+        if (pf_align(ctx_, M_, D_, G_, abases_.data(), aoff_.data(), boff_.data(), (uint32_t)n_kept, &m) != PF_OK) return fail_batch(pf_last_error());
         pf_site_batch_t sc;
-        if (pf_site_cov(db_, lower_, upper_, skip.data(), &sc) != PF_OK) return fail(pf_last_error());
+        if (pf_site_cov(db_, lower_, upper_, skip_.data(), &sc) != PF_OK) return fail_batch(pf_last_error());
+        for (size_t q = 0; q < n_kept; q++)
+            if (m.status[q] != PF_BUBBLE_OK)
+                return fail_batch("bubble " + std::to_string(k_src_[q]) + " of the batch does not fit the device limits (pf_msa_batch_t status " + std::to_string(m.status[q]) +
+                                  ": more than 64 co-optimal alignments / candidate MSAs, 64 rows, or an alignment beyond the work area)");
         // ---- ids: the bubbles whose alignment is not empty take consecutive ids in batch order (:2051, :2273) ----
-        std::vector<size_t> ids(kept.size(), 0);
-        for (size_t q = 0; q < kept.size(); q++) {
-            if (m.status[q] != PF_BUBBLE_OK) return fail("a bubble does not fit the device limits (status " + std::to_string(m.status[q]) + ")");
+        std::vector<size_t> ids(n_kept, 0);
+        size_t next_id = var_id, n_called = 0;
+        for (size_t q = 0; q < n_kept; q++) {
             if (m.n_rows[q] == 0) continue;                                        // str_vec came back empty
-            ids[q] = var_id++;
-            out.bubbles_called++;
-            out.called[called_base + kept[q].src] = 1;
+            ids[q] = next_id++;
+            n_called++;
         }
         // ---- rows: contiguous ranges of the kept bubbles, one host thread each, text joined in order ----
         auto emit = [&](size_t q0, size_t q1, CallerFiles &to, std::string &why) -> bool {
+            std::string grouped_fre[4], cov_info, fre_info;
+            std::vector<double> tc;
             for (size_t q = q0; q < q1; q++) {
-                const Kept &kb = kept[q];
-                const Bubble &b = batch[kb.src];
+                const size_t bi = k_src_[q];
+                const bool strict = fb.strict[bi] != 0;
+                const size_t ent_size = (size_t)fb.entrance_size[bi], ex_size = (size_t)fb.exit_size[bi];
+                const double *means = sorted_mean_.data() + k_first_[q];
                 const uint32_t nr = m.n_rows[q], L = m.aln_len[q];
                 if (nr == 0) continue;
                 const size_t var_count = ids[q];
                 const char *rows = m.rows + m.rows_off[q];
                 char head[96];
-                const int head_len = std::snprintf(head, sizeof head, "%zu\t%d\t%u\t%u\t", var_count, b.strict ? 1 : 0, b.entrance_id, b.exit_id);
+                const int head_len = std::snprintf(head, sizeof head, "%zu\t%d\t%u\t%u\t", var_count, strict ? 1 : 0, fb.entrance_id[bi], fb.exit_id[bi]);
                 for (uint32_t r = 0; r < nr; r++) {
                     to.alignseq.append(head, (size_t)head_len);
                     to.alignseq.append(rows + (size_t)r * L, L);
@@ -161,27 +238,31 @@ class BubbleCaller {
                 const uint32_t *ilen = m.ilen + m.ilen_off[q];
                 const size_t n_ilen = (size_t)(m.ilen_off[q + 1] - m.ilen_off[q]);
                 size_t indel = 0;
-                std::string grouped_fre[4], cov_info, fre_info;
+                for (int a = 0; a < 4; a++) grouped_fre[a].clear();
                 for (size_t i = 0; i < n_var; i++) {
                     const bool is_indel = m.var_kind[v0 + i] == 1;
                     size_t var_distance;                                           // :2312-2330
                     auto gap_to = [&](size_t a, size_t c) { return (size_t)(m.var_col[v0 + c] - m.var_col[v0 + a] - 1); };
-                    if (i == 0) var_distance = n_var > 1 ? std::min(gap_to(0, 1), b.entrance_size) : std::min(b.entrance_size, b.exit_size);
-                    else if (i == n_var - 1) var_distance = std::min(gap_to(i - 1, i), b.exit_size);
+                    if (i == 0) var_distance = n_var > 1 ? std::min(gap_to(0, 1), ent_size) : std::min(ent_size, ex_size);
+                    else if (i == n_var - 1) var_distance = std::min(gap_to(i - 1, i), ex_size);
                     else var_distance = std::min(gap_to(i - 1, i), gap_to(i, i + 1));
                     unsigned maxnum = 0;
                     for (uint32_t r = 0; r < nr; r++) maxnum = std::max<unsigned>(maxnum, cls[i * nr + r]);
-                    std::vector<double> tc(maxnum, 0.0);
+                    tc.assign(maxnum, 0.0);
                     double sum = 0;
                     if (is_indel) indel++;                                         // :2390 / strict :2127, before anything can skip the site
-                    if (b.strict) {
-                        for (uint32_t r = 0; r < nr; r++) tc[cls[i * nr + r] - 1] += kb.means[kb.order[r]];   // :2105-2108
-                        sum = kb.sum;
+                    if (strict) {
+                        for (uint32_t r = 0; r < nr; r++) tc[cls[i * nr + r] - 1] += means[r];   // :2105-2108
+                        sum = k_sum_[q];
                     } else {
                         const uint8_t st = sc.status[sc.site_off[q] + i];
                         if (st == PF_SITE_DROPPED) continue;                       // :2415-2418
                         if (st == PF_SITE_MISSING) { why = "a site k-mer is not in the database: the reference exits here (CDBG.cpp:54)"; return false; }
-                        if (st != PF_SITE_OK) { why = "a site k-mer cannot be formed (the reference reads outside the aligned row here)"; return false; }
+                        if (st != PF_SITE_OK) {
+                            why = nr > 16 ? "a branching bubble with more than 16 aligned rows: beyond pf_site_cov's per-site row limit"
+                                          : "a site k-mer cannot be formed (the reference reads outside the aligned row here)";
+                            return false;
+                        }
                         const uint64_t *cv = sc.cov + sc.cov_off[q] + i * nr;
                         for (unsigned c = 0; c < maxnum; c++) { tc[c] = (double)cv[c]; sum += tc[c]; }
                     }
@@ -193,7 +274,7 @@ class BubbleCaller {
                     }
                     const uint32_t il = is_indel ? (indel - 1 < n_ilen ? ilen[indel - 1] : 0u) : 0u;
                     char tail[128];
-                    const int tail_len = std::snprintf(tail, sizeof tail, "%d\t%u\t%zu\t%zu\t%zu\t\n", b.strict ? 1 : 0, il, var_count, n_var, var_distance);
+                    const int tail_len = std::snprintf(tail, sizeof tail, "%d\t%u\t%zu\t%zu\t%zu\t\n", strict ? 1 : 0, il, var_count, n_var, var_distance);
                     cov_info.append(tail, (size_t)tail_len);
                     if (!mt_) to.allele_frequency += fre_info;                     // -t 1: every site in site order (:1318, :1630)
                     if (maxnum >= 2 && maxnum <= 5) {                              // switch (maxnum), :1319-1340 / :2126-2147
@@ -204,25 +285,30 @@ class BubbleCaller {
                     }
                 }
                 if (mt_) {                                                         // -t N: grouped per bubble (:2162 strict, :2550 branching)
-                    to.allele_frequency += grouped_fre[0] + grouped_fre[1] + grouped_fre[2];
-                    if (b.strict) to.allele_frequency += grouped_fre[3];
+                    to.allele_frequency += grouped_fre[0]; to.allele_frequency += grouped_fre[1]; to.allele_frequency += grouped_fre[2];
+                    if (strict) to.allele_frequency += grouped_fre[3];
                 }
             }
             return true;
         };
-        const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads_, kept.size() / 64));
+        const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads_, n_kept / 64));
         std::vector<CallerFiles> part(T);
         std::vector<std::string> why(T);
         std::vector<char> ok(T, 1);
-        if (T == 1) ok[0] = emit(0, kept.size(), part[0], why[0]);
+        if (T == 1) ok[0] = emit(0, n_kept, part[0], why[0]);
         else {
             std::vector<std::thread> workers;
             for (size_t t = 0; t < T; t++)
-                workers.emplace_back([&, t] { ok[t] = emit(kept.size() * t / T, kept.size() * (t + 1) / T, part[t], why[t]); });
+                workers.emplace_back([&, t] { ok[t] = emit(n_kept * t / T, n_kept * (t + 1) / T, part[t], why[t]); });
             for (std::thread &w : workers) w.join();
         }
         for (size_t t = 0; t < T; t++)
-            if (!ok[t]) return fail(why[t]);
+            if (!ok[t]) return fail_batch(why[t]);
+        // ---- commit: only a batch that went through completely changes the caller-visible state ----
+        for (size_t q = 0; q < n_kept; q++)
+            if (m.n_rows[q]) out.called[called_base + k_src_[q]] = 1;
+        out.bubbles_called += n_called;
+        var_id = next_id;
         for (size_t t = 0; t < T; t++) {
             out.alignseq += part[t].alignseq;
             out.allele_frequency += part[t].allele_frequency;
@@ -237,6 +323,27 @@ class BubbleCaller {
         to.append(buf, (size_t)std::snprintf(buf, sizeof buf, "%g", v));
     }
     bool fail(const std::string &why) { err_ = why; return false; }
+    // sort key of a strict bubble's branch: referenceUnitigToString() -- the string itself, or its reverse complement when the
+    // branch was read from the unitig's reverse strand; an explicit key list (the std::string form) takes precedence
+    void sort_key(const FlatBatch &fb, size_t s, std::string &key) const {
+        if (explicit_keys_ && !(*explicit_keys_)[s].empty()) { key = (*explicit_keys_)[s]; return; }
+        const char *p = fb.bases.data() + fb.seq_off[s];
+        const size_t n = (size_t)(fb.seq_off[s + 1] - fb.seq_off[s]);
+        if (fb.fwd[s]) { key.assign(p, n); return; }
+        key.resize(n);
+        for (size_t i = 0; i < n; i++) {
+            const char c = p[n - 1 - i];
+            key[i] = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c == 'a' ? 't' : c == 'c' ? 'g' : c == 'g' ? 'c' : c == 't' ? 'a' : c;
+        }
+    }
+    const std::vector<std::string> *explicit_keys_ = nullptr;
+    std::vector<pf_cov_t> cov_;
+    std::vector<uint32_t> k_src_, k_first_, sorted_seq_;
+    std::vector<double> k_sum_, sorted_mean_;
+    std::string abases_;
+    std::vector<uint64_t> aoff_;
+    std::vector<uint32_t> boff_;
+    std::vector<uint8_t> skip_;
     pf_ctx *ctx_;
     pf_kmc *db_;
     double M_, D_, G_;

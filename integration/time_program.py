@@ -1,0 +1,128 @@
+"""Whole-program timing at scale: the unmodified reference (`oracle/_ref/PloidyFrost -t N`) against the same binary with its
+per-superbubble analysis bound to libpfgpu.so (`oracle/_ref/PloidyFrost_gpu`, integration/Makefile) on a REAL Bifrost graph of a
+synthetic polyploid genome (BASELINE configs[0] / [1] shapes: 1 % SNP, 0.1 % indel, k = 25).
+
+Both binaries load the same graph and find the same superbubbles with the reference's own code; only the estimation phase
+differs.  The graph is built by the reference's own Bifrost from the haplotype sequences (`Bifrost build -r`: the error-free
+read graph at full coverage without simulating 10^8 reads), the KMC database holds the canonical k-mers of the haplotypes with
+Poisson(depth) counters (ploidyfrost_b200/synth, GPU sort/unique with torch -- data tooling).
+
+Reported per run: wall clock of the whole process, the phase's own `Cpu time` / `Real time` lines, the phase time of the GPU
+path, bubbles called; `-t 1` GPU files are compared byte for byte with the reference's `-t 1` files when PF_PROGRAM_CHECK=1
+(costs one more reference run), `-t N` files as schedule-independent multisets (tests/e2e_rows.thread_dialect_view).
+
+Usage: python integration/time_program.py GENOME_BP HAPLOTYPES [out.json]        (needs a GPU; run under gpurun)
+"""
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tests import e2e_rows  # noqa: E402
+
+
+def run(binary, cwd, threads, extra_env=None):
+    env = dict(os.environ)
+    env.update(extra_env or {})
+    t0 = time.perf_counter()
+    r = subprocess.run([binary, "-g", "dbg.gfa", "-d", "db", "-t", str(threads), "-l", "2", "-u", "1000", "-o", "P"], cwd=cwd,
+                       capture_output=True, text=True, env=env)
+    wall = time.perf_counter() - t0
+    if r.returncode != 0:
+        return {"wall_s": round(wall, 3), "rc": r.returncode, "tail": r.stdout[-600:] + r.stderr[-300:]}
+    out = {"wall_s": round(wall, 3)}
+    m = re.search(r"PloidyEstimation\(\):\s+Cpu time : ([0-9.e+-]+)s", r.stdout)
+    if m:
+        out["estimation_cpu_s"] = float(m.group(1))
+    m = re.search(r"PloidyEstimation\(\):\s+Real time : ([0-9.e+-]+)s", r.stdout)
+    if m:
+        out["estimation_real_s_1s_resolution"] = float(m.group(1))
+    g = re.search(r"GPU path : (\d+) bubbles, (\d+) host threads, phase ([0-9.e+-]+)s = waited for device \+ database ([0-9.e+-]+)s, "
+                  r"collecting ([0-9.e+-]+)s, waiting for the device ([0-9.e+-]+)s", r.stdout)
+    if g:
+        out.update(bubbles_walked=int(g.group(1)), host_threads=int(g.group(2)), phase_s=float(g.group(3)), open_wait_s=float(g.group(4)),
+                   collect_s=float(g.group(5)), device_wait_s=float(g.group(6)))
+    # every section of the reference prints "<name>: Real time"; keep them all (1 s resolution) for the phase split
+    out["sections"] = re.findall(r"([A-Za-z:()_ ]+?):?\s+Real time : ([0-9.e+-]+)s", r.stdout)
+    return out
+
+
+def main():
+    genome = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
+    n_hap = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    out_json = sys.argv[3] if len(sys.argv) > 3 else None
+    from ploidyfrost_b200.synth import workload as wl
+    pf, bf = e2e_rows.reference_binaries()
+    gpu = os.path.join(ROOT, "oracle", "_ref", "PloidyFrost_gpu")
+    cores = os.cpu_count()
+    k = 25
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 40 * genome else None
+    with tempfile.TemporaryDirectory(dir=base) as tmp:
+        t0 = time.perf_counter()
+        w = wl.Workload(20261017, genome, n_hap, p_snp=0.01, p_indel=0.001, n_threads=min(16, cores))
+        haps = [w.haplotype(i) for i in range(n_hap)]
+        w.close()
+        with open(os.path.join(tmp, "haps.fa"), "wb") as f:
+            for i, h in enumerate(haps):
+                f.write(b">hap%d\n" % i)
+                f.write(h.tobytes())
+                f.write(b"\n")
+        lam = 60.0 / 4 * 126.0 / 150.0 if n_hap == 4 else 30.0 / n_hap * 126.0 / 150.0
+        info = wl.write_db_torch(os.path.join(tmp, "db"), haps, k, lam, 20261017, device="cuda:0", version=0x200, lut_prefix_len=9, sig_len=9,
+                                 n_bins=512 if genome > 5e6 else 64)
+        del haps
+        t_data = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        subprocess.run([bf, "build", "-r", "haps.fa", "-k", str(k), "-i", "-d", "-o", "dbg", "-t", str(min(cores, 16))], cwd=tmp, check=True,
+                       capture_output=True)
+        t_graph = time.perf_counter() - t0
+        res = {"genome_bp": genome, "haplotypes": n_hap, "k": k, "db_kmers": info["N"], "host_cores": cores, "data_s": round(t_data, 1),
+               "bifrost_build_s": round(t_graph, 1), "runs": {}}
+
+        def fresh(name):
+            d = os.path.join(tmp, name)
+            shutil.rmtree(d, ignore_errors=True)
+            os.mkdir(d)
+            for f in os.listdir(tmp):
+                if f.startswith("dbg.") or f.startswith("db.kmc"):
+                    os.symlink(os.path.join(tmp, f), os.path.join(d, f))
+            return d
+
+        d_refN = fresh("refN")
+        res["runs"][f"reference -t {cores}"] = run(pf, d_refN, cores)
+        d_gpuN = fresh("gpuN")
+        res["runs"][f"gpu -t {cores}"] = run(gpu, d_gpuN, cores)
+        d_gpu1 = fresh("gpu1")
+        res["runs"]["gpu -t 1"] = run(gpu, d_gpu1, 1)
+        try:
+            a = e2e_rows.thread_dialect_view(os.path.join(d_refN, "PloidyFrost_output"))
+            b = e2e_rows.thread_dialect_view(os.path.join(d_gpuN, "PloidyFrost_output"))
+            res["tN_files_equal_as_multisets"] = bool(a == b)
+        except Exception as e:   # noqa: BLE001
+            res["tN_files_equal_as_multisets"] = f"not compared: {e}"
+        if os.environ.get("PF_PROGRAM_CHECK") == "1":
+            import filecmp
+            d_ref1 = fresh("ref1")
+            res["runs"]["reference -t 1"] = run(pf, d_ref1, 1)
+            g1, r1 = os.path.join(d_gpu1, "PloidyFrost_output"), os.path.join(d_ref1, "PloidyFrost_output")
+            res["t1_files_identical"] = all(filecmp.cmp(os.path.join(r1, n), os.path.join(g1, n), shallow=False)
+                                            for n in os.listdir(r1) if n.startswith("P_") and n != "P_Unitig_Id.txt")
+        try:
+            res["bubbles_called"] = len({ln.split("\t")[0] for ln in open(os.path.join(d_gpu1, "PloidyFrost_output", "P_alignseq.txt"))})
+        except OSError:
+            pass
+    print(json.dumps(res))
+    if out_json:
+        json.dump(res, open(out_json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1686,10 +1686,18 @@ int pf_align(pf_ctx *ctx, double M, double D, double G, const char *bases, const
     const uint64_t base0 = seq_off[0], n_bases = seq_off[n_seq] - base0;
     uint32_t max_len = 0, max_rows = 0;
     int rc;
-    if ((rc = ctx->h_stage[0].reserve((uint64_t)(n_seq + 1) * 8))) return rc;   // rebased offsets, pinned
-    uint64_t *off = ctx->h_stage[0].as<uint64_t>();
-    for (uint32_t s = 0; s <= n_seq; s++) off[s] = seq_off[s] - base0;
-    for (uint32_t s = 0; s < n_seq; s++) max_len = std::max<uint32_t>(max_len, (uint32_t)(off[s + 1] - off[s]));
+    const uint64_t *off = seq_off;                          // zero-based offsets are copied to the device as they are
+    if (base0) {                                            // otherwise rebased into pinned staging
+        if ((rc = ctx->h_stage[0].reserve((uint64_t)(n_seq + 1) * 8))) return rc;
+        uint64_t *o = ctx->h_stage[0].as<uint64_t>();
+        for (uint32_t s = 0; s <= n_seq; s++) o[s] = seq_off[s] - base0;
+        off = o;
+    }
+    {
+        uint64_t mx = 0;
+        for (uint32_t s = 0; s < n_seq; s++) { const uint64_t l = off[s + 1] - off[s]; mx = l > mx ? l : mx; }
+        max_len = (uint32_t)std::min<uint64_t>(mx, 0xFFFFFFFFull);
+    }
     for (uint32_t b = 0; b < n_bubbles; b++) max_rows = std::max(max_rows, bubble_off[b + 1] - bubble_off[b]);
     cudaStream_t s = ctx->stream;
     if ((rc = st->in_bases.reserve(n_bases + 16))) return rc;

@@ -402,7 +402,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg AND the parity block (profiling runs)")
     ap.add_argument("--no-sharded-legs", action="store_true", help="N > 1: skip the partitioned-index legs")
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads of the e2e leg (one pf_ctx + shared index handle each)")
-    ap.add_argument("--e2e-sweep", default="", help="also time the e2e leg with these host thread counts, e.g. 1,2,8")
+    ap.add_argument("--e2e-sweep", default="", help="also time the e2e leg with these host thread counts (T) or T x sub-batches per thread (TxC), e.g. 1,2,4x4")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="sub-batches per host thread and step in the e2e leg")
     ap.add_argument("--region-rank", type=int, default=None,
                     help="diagnostics: take the batch another rank would take (its region of the genome) on this GPU")
@@ -577,10 +577,10 @@ def main():
             nb += sum(v.nbytes for v in st.values())
         return cv, m, st, nb
 
-    def e2e_leg(T_req):
-        """-> (ms per step, h2d bytes, d2h bytes, threads, sub-batches) of the e2e leg with T_req host threads"""
+    def e2e_leg(T_req, C_req=None):
+        """-> (ms per step, h2d bytes, d2h bytes, threads, sub-batches) of the e2e leg with T_req host threads, C_req sub-batches each"""
         T_e2e = 1 if main_route is not None else max(1, T_req)
-        n_chunks = T_e2e * max(1, args.e2e_chunks) if T_e2e > 1 else 1
+        n_chunks = T_e2e * max(1, C_req or args.e2e_chunks) if (T_e2e > 1 or C_req) and main_route is None else 1
         chunks = []
         for c in range(n_chunks):
             b0, b1 = bb.n_bubbles * c // n_chunks, bb.n_bubbles * (c + 1) // n_chunks
@@ -625,8 +625,9 @@ def main():
         return 1e3 * sum(e2e_times) / len(e2e_times), sum(ch["h2d"] for ch in chunks), sum(d2h_acc), T_e2e, n_chunks, chunks
 
     e2e_sweep = {}
-    for T_s in [int(x) for x in args.e2e_sweep.split(",") if x]:
-        e2e_sweep[T_s] = e2e_leg(T_s)[0]
+    for spec in [x for x in args.e2e_sweep.split(",") if x]:       # "T" or "TxC": host threads x sub-batches per thread
+        T_s, _, C_s = spec.partition("x")
+        e2e_sweep[spec] = e2e_leg(int(T_s), int(C_s) if C_s else None)[0]
     ms_e2e, h2d_bytes, d2h_bytes, T_e2e, n_chunks, chunks = e2e_leg(args.e2e_threads)
     # the results the parity block diffs: one more (untimed) pass of the first bubbles of the batch through the same calls, copied out
     n_keep = min(bb.n_bubbles, args.cpu_sample if world == 1 else min(args.cpu_sample, 32768))

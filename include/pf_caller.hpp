@@ -11,6 +11,7 @@
 #define PF_CALLER_HPP
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -79,8 +80,14 @@ struct CallerFiles {   // what the reference appends to its streams (Appendix D 
     std::vector<unsigned char> called;   // appended per input bubble: 1 = it was aligned and got a VarId
 };
 
+struct CallerStats {     // where the time of BubbleCaller::call went (seconds, summed over the calls)
+    double lookup_s = 0, gate_s = 0, align_s = 0, site_s = 0, emit_s = 0;
+    size_t calls = 0, bubbles_in = 0, bubbles_aligned = 0;
+};
+
 class BubbleCaller {
   public:
+    const CallerStats &stats() const { return stats_; }
     BubbleCaller(pf_ctx *ctx, pf_kmc *db, double match, double mismatch, double gap, unsigned lower, unsigned upper)
         : ctx_(ctx), db_(db), M_(match), D_(mismatch), G_(gap), lower_(lower), upper_(upper) {}
 
@@ -132,6 +139,13 @@ class BubbleCaller {
         out.called.resize(called_base + n_batch, 0);
         if (n_batch == 0) return true;
         auto fail_batch = [&](const std::string &why) { out.called.resize(called_base); return fail(why); };
+        auto t_mark = std::chrono::steady_clock::now();
+        auto lap = [&](double &acc) {
+            const auto now = std::chrono::steady_clock::now();
+            acc += std::chrono::duration<double>(now - t_mark).count();
+            t_mark = now;
+        };
+        stats_.calls++; stats_.bubbles_in += n_batch;
         const char *B = fb.bases.data();
         auto seq_ptr = [&](size_t s) { return B + fb.seq_off[s]; };
         auto seq_len = [&](size_t s) { return (size_t)(fb.seq_off[s + 1] - fb.seq_off[s]); };
@@ -142,6 +156,7 @@ class BubbleCaller {
         cov_.resize(n_seq);
         if (any_strict && n_seq && pf_kmc_cov(db_, B, fb.seq_off.data(), (uint32_t)n_seq, PF_LOOKUP_FWD_THEN_RC, 0, 0xFFFFFFFFu, cov_.data()) != PF_OK)
             return fail_batch(pf_last_error());
+        lap(stats_.lookup_s);
         // ---- gate + order the branches; build the alignment batch ----
         k_src_.clear(); k_first_.assign(1, 0); k_sum_.clear(); sorted_seq_.clear(); sorted_mean_.clear();
         abases_.clear(); aoff_.assign(1, 0); boff_.assign(1, 0); skip_.clear();
@@ -194,12 +209,16 @@ class BubbleCaller {
             k_sum_.push_back(sum);
         }
         const size_t n_kept = k_src_.size();
+        lap(stats_.gate_s);
         if (n_kept == 0) return true;
+        stats_.bubbles_aligned += n_kept;
         // ---- SequenceAlignment of every kept bubble, then the site k-mers of the branching ones ----
         pf_msa_batch_t m;
         if (pf_align(ctx_, M_, D_, G_, abases_.data(), aoff_.data(), boff_.data(), (uint32_t)n_kept, &m) != PF_OK) return fail_batch(pf_last_error());
+        lap(stats_.align_s);
         pf_site_batch_t sc;
         if (pf_site_cov(db_, lower_, upper_, skip_.data(), &sc) != PF_OK) return fail_batch(pf_last_error());
+        lap(stats_.site_s);
         for (size_t q = 0; q < n_kept; q++)
             if (m.status[q] != PF_BUBBLE_OK)
                 return fail_batch("bubble " + std::to_string(k_src_[q]) + " of the batch does not fit the device limits (pf_msa_batch_t status " + std::to_string(m.status[q]) +
@@ -314,6 +333,7 @@ class BubbleCaller {
             out.allele_frequency += part[t].allele_frequency;
             for (int a = 0; a < 4; a++) { out.cov[a] += part[t].cov[a]; out.fre[a] += part[t].fre[a]; out.alleles[a] += part[t].alleles[a]; }
         }
+        lap(stats_.emit_s);
         return true;
     }
 
@@ -336,6 +356,7 @@ class BubbleCaller {
             key[i] = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c == 'a' ? 't' : c == 'c' ? 'g' : c == 'g' ? 'c' : c == 't' ? 'a' : c;
         }
     }
+    CallerStats stats_;
     const std::vector<std::string> *explicit_keys_ = nullptr;
     std::vector<pf_cov_t> cov_;
     std::vector<uint32_t> k_src_, k_first_, sorted_seq_;

@@ -214,6 +214,13 @@ int pf_site_cov(pf_kmc *db, uint32_t low, uint32_t up, const uint8_t *skip, pf_s
 int pf_site_cov_dev(pf_kmc *db, uint32_t low, uint32_t up, const void *d_skip, pf_site_batch_t *out_dev, void *cuda_stream);
 
 /*
+ * pf_site_kmers -- the site k-mers themselves, no database involved: the coloured caller (CCDBG.cpp:1057-1376) asks the GRAPH
+ * which colours hold each site k-mer (findUnitig, :1127, :1258) before it reads any database, so it needs the strings.  Works on
+ * the last pf_align of the context; `skip` as in pf_site_cov.  `out` views pinned memory of the context, valid until its next call.
+ */
+int pf_site_kmers(pf_ctx *ctx, uint32_t k, const uint8_t *skip, pf_site_kmers_t *out);
+
+/*
  * pf_kmc_share -- a second handle on the same HBM-resident index for ANOTHER pf_ctx of the same device.  The reference keeps
  * one CKMCFile per CDBG and walks the graph with N threads (CDBG.cpp:1929-1945); here every host thread owns its own context -- stream,
  * staging, result arena -- and a shared handle, so the copy-in of one thread's batch overlaps the kernels and the copy-out of

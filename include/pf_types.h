@@ -107,6 +107,19 @@ typedef struct pf_site_batch {
     const uint64_t *cov;      /* class coverage = sum of the counters of the class's distinct site k-mers   */
 } pf_site_batch_t;
 
+/* Site k-mers without lookups (pf_site_kmers): for every variable column of every bubble of the last alignment and every
+ * row, the k-mer the reference forms at that column (CCDBG.cpp:1057-1241 / CDBG.cpp:2295-2509) as a right-aligned 2-bit
+ * value (A=0 C=1 G=2 T=3, first base in the highest bits).  keys of bubble b start at key_off[b]; column j (site_off[b] + j)
+ * owns n_rows[b] consecutive keys.  status: PF_SITE_OK, PF_SITE_UNDEFINED or PF_SITE_SKIPPED per column. */
+typedef struct pf_site_kmers {
+    uint32_t n_bubbles;
+    uint32_t reserved;
+    const uint64_t *site_off; /* [n+1]  == var_off of the alignment                                         */
+    const uint64_t *key_off;  /* [n+1]  == cls_off of the alignment                                         */
+    const uint64_t *keys;     /* one per (variable column, row)                                             */
+    const uint8_t *status;    /* per variable column                                                        */
+} pf_site_kmers_t;
+
 enum {
     PF_SITE_OK = 0,
     PF_SITE_DROPPED = 1,   /* a counter is not inside (low, up): the reference skips the site (CDBG.cpp:2415-2418)            */

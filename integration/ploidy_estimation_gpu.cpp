@@ -299,7 +299,9 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
 
     // the device side of one block; runs on its own thread while the next block is collected
     vector<pf_cov_t> ent_cov;
+    double t_entrance = 0, t_call = 0, t_write = 0;
     auto device_stage = [&](Block &blk) {
+        auto t_s = chrono::steady_clock::now();
         const uint32_t n_ent = (uint32_t)(blk.ent_off.size() - 1);
         ent_cov.resize(n_ent);
         if (n_ent && pf_kmc_cov(db, blk.ent_bases.data(), blk.ent_off.data(), n_ent, PF_LOOKUP_FWD_THEN_RC, 0, 0xFFFFFFFFu, ent_cov.data()) != PF_OK) {
@@ -312,7 +314,9 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
                 cout << "CDBG::readCov():" << revcomp(km) << " kmer can not found ." << endl;
                 exit(EXIT_FAILURE);
             }
+        t_entrance += seconds_since(t_s); t_s = chrono::steady_clock::now();
         if (!caller.call(blk.flat, var_id, files)) { cout << "CDBG::readCov():" << caller.error() << endl; exit(EXIT_FAILURE); }
+        t_call += seconds_since(t_s); t_s = chrono::steady_clock::now();
         for (size_t b = 0; b < blk.flat.n_bubbles(); b++)
             if (files.called[b]) {                      // mean coverage of the entrances of the called bubbles (only printed, CDBG.cpp:1261, :1703)
                 const pf_cov_t &c = ent_cov[blk.bubble_entrance[b]];
@@ -321,6 +325,7 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
             }
         n_bubbles += blk.flat.n_bubbles();
         files_out.append(files);
+        t_write += seconds_since(t_s);
     };
 
     // ---- blocks of unitigs: collect block b + 1 while the device works on block b ----
@@ -369,6 +374,12 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
     cout << "CDBG::PloidyEstimation():  Real time : " << (double)difftime(end_time, start_time) << "s" << endl;
     cout << "CDBG::PloidyEstimation():  GPU path : " << n_bubbles << " bubbles, " << T << " host threads, phase " << seconds_since(t_begin)
          << "s = waited for device + database " << t_open << "s, collecting " << t_collect << "s, waiting for the device " << t_device_wait << "s" << endl;
+    {
+        const pfdropin::CallerStats &cs = caller.stats();
+        cout << "CDBG::PloidyEstimation():  GPU path, device thread : entrance readCov " << t_entrance << "s, BubbleCaller::call " << t_call << "s (branch readCov "
+             << cs.lookup_s << ", gate + order " << cs.gate_s << ", pf_align " << cs.align_s << ", pf_site_cov " << cs.site_s << ", rows " << cs.emit_s
+             << "; " << cs.bubbles_aligned << " of " << cs.bubbles_in << " bubbles aligned in " << cs.calls << " batches), coverage + files " << t_write << "s" << endl;
+    }
     cout << "CDBG::PloidyEstimation(): Alleles in SuperBubbles  :\t"
          << "2 :" << files.alleles[0] << "\t" << "3 :" << files.alleles[1] << "\t" << "4 :" << files.alleles[2] << "\t" << "5 :" << files.alleles[3] << endl;
     const int avg = coreNum ? (int)(coreCov / coreNum) : 0;

@@ -25,7 +25,7 @@ EXPORTS = ["pf_init", "pf_shutdown", "pf_last_error", "pf_version", "pf_launch_c
            "pf_kmc_close", "pf_kmc_info", "pf_kmc_set_min_count", "pf_kmc_set_max_count", "pf_kmc_reset_min_max",
            "pf_kmc_device_bytes", "pf_kmc_open_ex", "pf_kmc_index_kind", "pf_kmc_build_status", "pf_kmc_open_part", "pf_kmc_open_part_ex", "pf_kmc_export_ipc", "pf_kmc_attach_peers", "pf_kmc_local_kmers", "pf_kmc_route_dev", "pf_kmc_lookup_keys_dev",
            "pf_kmc_scatter_dev", "pf_kmc_counts", "pf_kmc_cov", "pf_kmc_cov_async", "pf_kmc_wait", "pf_site_cov", "pf_site_cov_dev", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
-           "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_heavy_queued", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32", "pf_kmc_share", "pf_bench_gather_sweep"]
+           "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_heavy_queued", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32", "pf_kmc_share", "pf_bench_gather_sweep", "pf_site_kmers"]
 
 
 class SiteBatch(C.Structure):
@@ -35,6 +35,11 @@ class SiteBatch(C.Structure):
 
 
 SITE_OK, SITE_DROPPED, SITE_MISSING, SITE_UNDEFINED, SITE_SKIPPED = 0, 1, 2, 3, 4
+
+
+class SiteKmers(C.Structure):
+    _fields_ = [("n_bubbles", C.c_uint32), ("reserved", C.c_uint32), ("site_off", C.POINTER(C.c_uint64)),
+                ("key_off", C.POINTER(C.c_uint64)), ("keys", C.POINTER(C.c_uint64)), ("status", C.POINTER(C.c_uint8))]
 
 
 class KmcInfo(C.Structure):
@@ -129,6 +134,7 @@ def load():
     L.pf_bench_int32.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.pf_bench_gather_sweep.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
     L.pf_kmc_share.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.pf_site_kmers.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(SiteKmers)]
     _lib = L
     return L
 
@@ -216,6 +222,21 @@ class Context:
         _check(self.lib.pf_align_dev(self.h, M, D, G, d_bases, n_bases, d_seq_off, n_seq, d_bubble_off, n_bubbles,
                                      max_len, max_rows, C.byref(mb), stream), "pf_align_dev")
         return mb
+
+    def site_kmers(self, k, skip=None) -> dict:
+        """pf_site_kmers: the site k-mers (2-bit keys) of the last alignment of this context, one per (variable column, row)"""
+        sk = SiteKmers()
+        sp = None
+        if skip is not None:
+            sp = np.ascontiguousarray(skip, dtype=np.uint8)
+        _check(self.lib.pf_site_kmers(self.h, k, sp.ctypes.data if sp is not None else None, C.byref(sk)), "pf_site_kmers")
+        n = sk.n_bubbles
+        site_off = np.ctypeslib.as_array(sk.site_off, shape=(n + 1,)).copy()
+        key_off = np.ctypeslib.as_array(sk.key_off, shape=(n + 1,)).copy()
+        ns, nk = int(site_off[-1]), int(key_off[-1])
+        return {"site_off": site_off, "key_off": key_off,
+                "keys": np.ctypeslib.as_array(sk.keys, shape=(nk,)).copy() if nk else np.zeros(0, np.uint64),
+                "status": np.ctypeslib.as_array(sk.status, shape=(ns,)).copy() if ns else np.zeros(0, np.uint8)}
 
     @property
     def last_retry_count(self) -> int:

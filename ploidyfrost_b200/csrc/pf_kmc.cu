@@ -383,9 +383,13 @@ __global__ void repack_records_kernel(const uint8_t *__restrict__ raw, uint64_t 
 enum { HB_UNSORTED = 1, HB_WRONG_BIN = 2, HB_NOT_CANONICAL = 4, HB_OVERFLOW = 8 };
 // part / n_parts: a partition of the index inserts only the keys it owns (owner = mix(key) % n_parts, pfkmc::hash_owner); every
 // record is still verified.  status[1] (as u64 at status + 2) counts the inserted keys.
+// Chunked form: the thread block range covers records [i0, i0 + n); db.rec / db.suf / db.cnt hold the records from index `base`
+// on (base = i0 - 1 when a carried predecessor record precedes the chunk, else i0); the whole image is (i0, n, base) = (0, N, 0).
 __global__ void kmc_hash_build_kernel(const KmcView db, const pfkmc::HashView hv, uint32_t *__restrict__ status, uint32_t part,
-                                      uint32_t n_parts) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                      uint32_t n_parts, uint64_t i0, uint64_t n, uint64_t base) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint64_t i = i0 + t;
     if (i >= db.N) return;
     if (lut_at(db, 0) > i) return;                     // before the first bucket: no prefix reaches it
     uint64_t lo = 0, hi = db.lut_n - 1;               // lut[lut_n-1] = N+1 > i
@@ -401,12 +405,12 @@ __global__ void kmc_hash_build_kernel(const KmcView db, const pfkmc::HashView hv
     uint64_t rs, c, prev = 0;
     const bool has_prev = i > lut_at(db, slot);
     if (db.packed) {
-        const uint64_t r = db.rec[i];
+        const uint64_t r = db.rec[i - base];
         rs = r >> cbits; c = r & ((1ull << cbits) - 1);
-        if (has_prev) prev = db.rec[i - 1] >> cbits;
+        if (has_prev) prev = db.rec[i - 1 - base] >> cbits;
     } else {
-        rs = db.suf[i]; c = db.cnt[i];
-        if (has_prev) prev = db.suf[i - 1];
+        rs = db.suf[i - base]; c = db.cnt[i - base];
+        if (has_prev) prev = db.suf[i - 1 - base];
     }
     uint32_t st = 0;
     if (has_prev && !(prev < rs)) st |= HB_UNSORTED;
@@ -592,13 +596,52 @@ __device__ __forceinline__ int site_row_kmer(const char *row, uint32_t L, uint32
     return PF_SITE_OK;
 }
 
+// The site k-mer of every row at variable column v of bubble b (CDBG.cpp:2338-2388 indel sites, :2433-2472 SNP sites).
+// Returns PF_SITE_OK or PF_SITE_UNDEFINED (the reference itself would read outside the row / a non-ACGT character).
+__device__ __forceinline__ int site_build_keys(const SiteArgs &a, uint32_t b, uint64_t v, uint32_t n_ind, uint64_t key[SITE_MAX_ROWS]) {
+    const uint32_t nr = a.n_rows[b], L = a.aln_len[b], k = a.db.k;
+    const char *R = a.rows + a.rows_off[b];
+    const uint32_t c = a.var_col[v];
+    const bool is_ind = a.var_kind[v] == 1;
+    int st = PF_SITE_OK;
+    if (is_ind) {
+        uint32_t cur[SITE_MAX_ROWS];
+        uint64_t ext[SITE_MAX_ROWS];
+        for (uint32_t r = 0; r < nr; r++) { cur[r] = c; ext[r] = 0; }
+        uint32_t e = 0;
+        for (;;) {                                            // :2338-2357: one more base per row until the rows differ
+            bool differ = false;
+            uint32_t first = 0;
+            for (uint32_t r = 0; r < nr && st == PF_SITE_OK; r++) {
+                const char *row = R + (uint64_t)r * L;
+                while (cur[r] < L && row[cur[r]] == '-') cur[r]++;
+                if (cur[r] >= L) { st = PF_SITE_UNDEFINED; break; }
+                const uint32_t code = base_code((uint8_t)row[cur[r]]);
+                if (code > 3) { st = PF_SITE_UNDEFINED; break; }
+                cur[r]++;
+                ext[r] = (ext[r] << 2) | code;
+                if (r == 0) first = code; else differ |= code != first;
+            }
+            if (st != PF_SITE_OK) break;
+            e++;
+            if (differ) break;
+            if (e >= k) { st = PF_SITE_UNDEFINED; break; }
+        }
+        for (uint32_t r = 0; r < nr && st == PF_SITE_OK; r++)
+            st = site_row_kmer(R + (uint64_t)r * L, L, k, c, k - e, ext[r], e, cur[r], n_ind == 0, key[r]);
+    } else {
+        for (uint32_t r = 0; r < nr && st == PF_SITE_OK; r++)
+            st = site_row_kmer(R + (uint64_t)r * L, L, k, c + 1, k, 0, 0, c + 1, n_ind == 0, key[r]);
+    }
+    return st;
+}
+
 __global__ void site_cov_kernel(const SiteArgs a) {
     const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= a.n_sites) return;
     const uint32_t b = a.site_bubble[v];
     const uint64_t v0 = a.var_off[b];
-    const uint32_t nr = a.n_rows[b], L = a.aln_len[b], k = a.db.k;
-    const char *R = a.rows + a.rows_off[b];
+    const uint32_t nr = a.n_rows[b], k = a.db.k;
     const uint16_t *C = a.cls + a.cls_off[b];
     unsigned long long *cov_out = a.site_cov + a.cls_off[b];
     const bool skipped = a.skip && a.skip[b];
@@ -606,8 +649,6 @@ __global__ void site_cov_kernel(const SiteArgs a) {
     if (!skipped)
         for (uint64_t u = v0; u < v; u++) n_ind += a.var_kind[u] == 1;     // indel sites before this one (:2390)
     {
-        const uint32_t c = a.var_col[v];
-        const bool is_ind = a.var_kind[v] == 1;
         const uint16_t *cl = C + (v - v0) * nr;
         unsigned long long *cov = cov_out + (v - v0) * nr;
         uint32_t ncls = 0;
@@ -618,35 +659,7 @@ __global__ void site_cov_kernel(const SiteArgs a) {
         if (skipped) st = PF_SITE_SKIPPED;
         else if (nr > SITE_MAX_ROWS || k > 32) st = PF_SITE_UNDEFINED;
         else if (!a.both_strands) st = PF_SITE_OK;               // readCov(string) does nothing on a strand-specific database (CDBG.cpp:34)
-        else if (is_ind) {
-            uint32_t cur[SITE_MAX_ROWS];
-            uint64_t ext[SITE_MAX_ROWS];
-            for (uint32_t r = 0; r < nr; r++) { cur[r] = c; ext[r] = 0; }
-            uint32_t e = 0;
-            for (;;) {                                            // :2338-2357: one more base per row until the rows differ
-                bool differ = false;
-                uint32_t first = 0;
-                for (uint32_t r = 0; r < nr && st == PF_SITE_OK; r++) {
-                    const char *row = R + (uint64_t)r * L;
-                    while (cur[r] < L && row[cur[r]] == '-') cur[r]++;
-                    if (cur[r] >= L) { st = PF_SITE_UNDEFINED; break; }
-                    const uint32_t code = base_code((uint8_t)row[cur[r]]);
-                    if (code > 3) { st = PF_SITE_UNDEFINED; break; }
-                    cur[r]++;
-                    ext[r] = (ext[r] << 2) | code;
-                    if (r == 0) first = code; else differ |= code != first;
-                }
-                if (st != PF_SITE_OK) break;
-                e++;
-                if (differ) break;
-                if (e >= k) { st = PF_SITE_UNDEFINED; break; }
-            }
-            for (uint32_t r = 0; r < nr && st == PF_SITE_OK; r++)
-                st = site_row_kmer(R + (uint64_t)r * L, L, k, c, k - e, ext[r], e, cur[r], n_ind == 0, key[r]);
-        } else {
-            for (uint32_t r = 0; r < nr && st == PF_SITE_OK; r++)
-                st = site_row_kmer(R + (uint64_t)r * L, L, k, c + 1, k, 0, 0, c + 1, n_ind == 0, key[r]);
-        }
+        else st = site_build_keys(a, b, v, n_ind, key);
         if (st == PF_SITE_OK && a.both_strands) {
             for (uint32_t q = 1; q <= ncls && st == PF_SITE_OK; q++) {          // classes in order, strings in std::set order
                 unsigned long long acc = 0;
@@ -671,6 +684,29 @@ __global__ void site_cov_kernel(const SiteArgs a) {
         }
         a.site_status[v] = (uint8_t)st;
     }
+}
+
+// The site k-mers themselves (coloured graphs, CCDBG.cpp:1057-1376: the caller needs the strings -- it asks the graph which colours
+// hold each one before any database is read): key of every (variable column, row) as a right-aligned 2-bit k-mer, one status per column.
+__global__ void site_keys_kernel(const SiteArgs a, unsigned long long *__restrict__ keys) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.n_sites) return;
+    const uint32_t b = a.site_bubble[v];
+    const uint64_t v0 = a.var_off[b];
+    const uint32_t nr = a.n_rows[b];
+    unsigned long long *out = keys + a.cls_off[b] + (v - v0) * nr;
+    const bool skipped = a.skip && a.skip[b];
+    int st;
+    uint64_t key[SITE_MAX_ROWS];
+    if (skipped) st = PF_SITE_SKIPPED;
+    else if (nr > SITE_MAX_ROWS || a.db.k > 32) st = PF_SITE_UNDEFINED;
+    else {
+        uint32_t n_ind = 0;
+        for (uint64_t u = v0; u < v; u++) n_ind += a.var_kind[u] == 1;
+        st = site_build_keys(a, b, v, n_ind, key);
+    }
+    for (uint32_t r = 0; r < nr; r++) out[r] = st == PF_SITE_OK ? key[r] : 0ull;
+    a.site_status[v] = (uint8_t)st;
 }
 
 bool slurp(const std::string &path, std::vector<unsigned char> &buf) {
@@ -739,88 +775,147 @@ struct pf_kmc_route_state {   // scratch of pf_kmc_route_dev (grow-only)
 
 namespace {
 
-// part / n_parts: n_parts == 1 loads the whole database; otherwise only the partition `part`
-// (KMC2: bins with bin % n_parts == part; KMC1: the part-th range of ceil(4^p / n_parts) prefixes).
-// Re-hash the verbatim image into the one-sector index; on success the prefix table and the record arrays are released.
-// Returns PF_OK also when the hash index is not used (database fails the verification, or the slot does not fit).
-int kmc_build_hash(pf_kmc *db, uint32_t part = 0, uint32_t n_parts = 1) {
+// The hash index built WITHOUT staging the database in HBM: the records are streamed from the file through two pinned buffers
+// (64 MB of records each), re-packed, verified and inserted chunk by chunk -- the predecessor of a chunk's first record is
+// carried along for the ascending-suffix check.  Peak HBM = the table + the prefix table + two chunk buffers, so a partition
+// (part / n_parts: only the keys with mix(key) % n_parts == part are inserted) opens a database that is larger than one GPU's
+// memory, and no rank holds the file in host memory.  Leaves db->hash_on false (and everything released) when the database
+// fails the verification or the slot does not fit 63 bits: the caller falls back to the verbatim image.
+int kmc_stream_hash(pf_kmc *db, const std::vector<uint64_t> &lut, const std::vector<uint32_t> &sigmap, const std::vector<uint32_t> &norm,
+                    FILE *suf_f, const char *prefix, uint32_t part, uint32_t n_parts) {
     pf_ctx *ctx = db->ctx;
-    const KmcView &V = db->view;
-    const uint64_t N = V.N;
+    const pf_kmc_info_t &I = db->info;
+    const uint32_t k = I.kmer_length, p = I.lut_prefix_length, C = I.counter_size, S = (k - p) / 4;
+    const uint64_t N = I.total_kmers, R = S + C;
     if (!N) return PF_OK;
-    const uint64_t n_local = n_parts > 1 ? N / n_parts + N / (4 * n_parts) + 1024 : N;   // a partition holds ~N / n_parts keys (+25 % slack)
+    KmcView V{};
+    V.k = k; V.p = p; V.S = S; V.C = C; V.sig_len = I.signature_len; V.is_kmc2 = I.kmc_version == 0x200;
+    V.min_count = I.min_count; V.max_count = I.max_count; V.N = N; V.single_lut = 1ull << (2 * p); V.lut_n = lut.size();
+    V.lut64 = (N + 1 >= (1ull << 32)) ? 1 : 0;
+    V.packed = R <= 8 ? 1 : 0;
+    V.n_parts = 1; V.part = 0; V.prefix_lo = 0; V.prefix_cnt = V.single_lut; V.prefix_per_part = V.single_lut;
+    const uint64_t n_local = n_parts > 1 ? N / n_parts + N / (4 * n_parts) + 1024 : N;
     uint32_t b = 4;
     while (b < 40 && (3ull << b) < 2 * n_local) b++;                        // <= 1.5 keys per 4-slot bucket on average
-    const int need = (int)(2 * V.k + 8 * V.C + pfkmc::H_DIST_BITS) - 63;    // dist + rem + counter must leave the all-ones slot free
+    const int need = (int)(2 * k + 8 * C + pfkmc::H_DIST_BITS) - 63;        // dist + rem + counter must leave the all-ones slot free
     if (need > (int)b) {
-        if (need > 23 || need > 2 * (int)V.k) return PF_OK;                 // would inflate a small table past 256 MB: keep the verbatim index
+        if (need > 23 || need > 2 * (int)k) return PF_OK;
         b = (uint32_t)need;
     }
-    if (b > 2 * V.k) b = 2 * V.k;
-    pfkmc::HashView hv;
-    void *tab = nullptr;
+    if (b > 2 * k) b = 2 * k;
+    cudaStream_t st = ctx->stream;
+    void *d_lut = nullptr, *d_sigmap = nullptr, *d_norm = nullptr, *d_status = nullptr, *tab = nullptr;
+    void *d_raw[2] = {nullptr, nullptr}, *d_rec = nullptr, *d_suf = nullptr, *d_cnt = nullptr;
+    pf::PinnedBuf stage[2];
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    // records per chunk: 64 MB of the file; PF_OPEN_CHUNK_RECORDS overrides it (tests drive the chunk seams with tiny chunks)
+    const char *ch_env = getenv("PF_OPEN_CHUNK_RECORDS");
+    const uint64_t CH_REC = ch_env && atoll(ch_env) > 0 ? (uint64_t)atoll(ch_env) : std::max<uint64_t>(1, (64ull << 20) / R);
+    auto cleanup = [&](bool keep_index) {
+        for (int i = 0; i < 2; i++) { if (done[i]) cudaEventDestroy(done[i]); stage[i].release(); cudaFree(d_raw[i]); }
+        cudaFree(d_rec); cudaFree(d_suf); cudaFree(d_cnt); cudaFree(d_status); cudaFree(d_lut);
+        if (!keep_index) { cudaFree(tab); cudaFree(d_sigmap); cudaFree(d_norm); }
+    };
+#define PF_TRY_CLEAN(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { pf::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); cleanup(false); return PF_E_CUDA; } } while (0)
+    if (V.lut64) {
+        PF_TRY_CLEAN(cudaMalloc(&d_lut, lut.size() * 8));
+        PF_TRY_CLEAN(cudaMemcpyAsync(d_lut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, st));
+        PF_TRY_CLEAN(cudaStreamSynchronize(st));
+    } else {
+        std::vector<uint32_t> l32(lut.size());
+        for (size_t i = 0; i < lut.size(); i++) l32[i] = (uint32_t)lut[i];
+        PF_TRY_CLEAN(cudaMalloc(&d_lut, l32.size() * 4));
+        PF_TRY_CLEAN(cudaMemcpyAsync(d_lut, l32.data(), l32.size() * 4, cudaMemcpyHostToDevice, st));
+        PF_TRY_CLEAN(cudaStreamSynchronize(st));
+    }
+    V.lut = d_lut;
+    if (V.is_kmc2) {
+        PF_TRY_CLEAN(cudaMalloc(&d_sigmap, sigmap.size() * 4));
+        PF_TRY_CLEAN(cudaMemcpyAsync(d_sigmap, sigmap.data(), sigmap.size() * 4, cudaMemcpyHostToDevice, st));
+        PF_TRY_CLEAN(cudaMalloc(&d_norm, norm.size() * 4));
+        PF_TRY_CLEAN(cudaMemcpyAsync(d_norm, norm.data(), norm.size() * 4, cudaMemcpyHostToDevice, st));
+        PF_TRY_CLEAN(cudaStreamSynchronize(st));
+        V.sigmap = (const uint32_t *)d_sigmap; V.norm = (const uint32_t *)d_norm;
+    }
+    for (int i = 0; i < 2; i++) {
+        if (stage[i].reserve(CH_REC * R)) { cleanup(false); return PF_E_NOMEM; }
+        PF_TRY_CLEAN(cudaMalloc(&d_raw[i], CH_REC * R));
+        PF_TRY_CLEAN(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    }
+    if (V.packed) PF_TRY_CLEAN(cudaMalloc(&d_rec, (CH_REC + 1) * 8));
+    else { PF_TRY_CLEAN(cudaMalloc(&d_suf, (CH_REC + 1) * 8)); PF_TRY_CLEAN(cudaMalloc(&d_cnt, (CH_REC + 1) * 4)); }
+    PF_TRY_CLEAN(cudaMalloc(&d_status, 16));
+    V.rec = (const uint64_t *)d_rec; V.suf = (const uint64_t *)d_suf; V.cnt = (const uint32_t *)d_cnt;
+    pfkmc::HashView hv{};
     uint64_t bytes = 0;
-    uint32_t status = 0;
+    uint32_t h_status[4] = {0, 0, 0, 0};
     for (int attempt = 0;; attempt++) {   // a table that overflows (a key more than H_MAX_DIST buckets from home) is rebuilt once, twice as large
-        if (b > 2 * V.k || (2 * V.k - b) + 8 * V.C + pfkmc::H_DIST_BITS > 63) return PF_OK;
-        hv.bucket_bits = b; hv.rem_bits = 2 * V.k - b; hv.cbits = 8 * V.C; hv.kbits = 2 * V.k;
+        if (b > 2 * k || (2 * k - b) + 8 * C + pfkmc::H_DIST_BITS > 63) { cleanup(false); return PF_OK; }
+        hv.bucket_bits = b; hv.rem_bits = 2 * k - b; hv.cbits = 8 * C; hv.kbits = 2 * k;
         bytes = 32ull << b;
         size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < bytes + (256ull << 20)) { cudaGetLastError(); return PF_OK; }
-        void *d_status = nullptr;
-        if (cudaMalloc(&tab, bytes) != cudaSuccess) { cudaGetLastError(); return PF_OK; }
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < bytes + (256ull << 20)) {
+            cudaGetLastError();
+            pf::set_error("%s: the hash index needs %.1f GB of device memory, %.1f GB are free (partition the index: pf_kmc_open_part)", prefix,
+                          bytes / 1e9, free_b / 1e9);
+            cleanup(false);
+            return PF_E_NOMEM;
+        }
+        PF_TRY_CLEAN(cudaMalloc(&tab, bytes));
         hv.tab = (unsigned long long *)tab;
-        cudaStream_t st = ctx->stream;
-        uint32_t h_status[4] = {0, 0, 0, 0};
-        PF_CUDA_TRY(cudaMalloc(&d_status, 16));
-        PF_CUDA_TRY(cudaMemsetAsync(d_status, 0, 16, st));
-        PF_CUDA_TRY(cudaMemsetAsync(tab, 0xFF, bytes, st));
-        kmc_hash_build_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(V, hv, (uint32_t *)d_status, part, n_parts);
-        ctx->launches++;
-        PF_CUDA_TRY(cudaGetLastError());
-        PF_CUDA_TRY(cudaMemcpyAsync(h_status, d_status, 16, cudaMemcpyDeviceToHost, st));
-        PF_CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(d_status);
-        status = h_status[0];
-        db->build_status = status;
-        db->hash_inserted = (uint64_t)h_status[2] | ((uint64_t)h_status[3] << 32);
-        if (!(status & (HB_UNSORTED | HB_WRONG_BIN | HB_OVERFLOW))) break;
+        PF_TRY_CLEAN(cudaMemsetAsync(d_status, 0, 16, st));
+        PF_TRY_CLEAN(cudaMemsetAsync(tab, 0xFF, bytes, st));
+        if (fseeko(suf_f, 4, SEEK_SET) != 0) { pf::set_error("%s.kmc_suf: seek failed", prefix); cleanup(false); return PF_E_IO; }
+        int slot = 0;
+        for (uint64_t i0 = 0; i0 < N; i0 += CH_REC) {
+            const uint64_t n = std::min<uint64_t>(CH_REC, N - i0);
+            cudaEventSynchronize(done[slot]);                              // the copy that last used this staging buffer is over
+            if (fread(stage[slot].p, 1, n * R, suf_f) != n * R) { pf::set_error("%s.kmc_suf: short read", prefix); cleanup(false); return PF_E_IO; }
+            PF_TRY_CLEAN(cudaMemcpyAsync(d_raw[slot], stage[slot].p, n * R, cudaMemcpyHostToDevice, st));
+            PF_TRY_CLEAN(cudaEventRecord(done[slot], st));
+            // slot 0 of the chunk arrays holds the predecessor of the chunk's first record (carried over on the device)
+            if (i0) {
+                if (V.packed) PF_TRY_CLEAN(cudaMemcpyAsync(d_rec, (uint64_t *)d_rec + CH_REC, 8, cudaMemcpyDeviceToDevice, st));
+                else {
+                    PF_TRY_CLEAN(cudaMemcpyAsync(d_suf, (uint64_t *)d_suf + CH_REC, 8, cudaMemcpyDeviceToDevice, st));
+                    PF_TRY_CLEAN(cudaMemcpyAsync(d_cnt, (uint32_t *)d_cnt + CH_REC, 4, cudaMemcpyDeviceToDevice, st));
+                }
+            }
+            repack_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint8_t *)d_raw[slot], n, S, C, (int)V.packed,
+                                                                              V.packed ? (uint64_t *)d_rec + 1 : nullptr,
+                                                                              V.packed ? nullptr : (uint64_t *)d_suf + 1, V.packed ? nullptr : (uint32_t *)d_cnt + 1);
+            kmc_hash_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(V, hv, (uint32_t *)d_status, part, n_parts, i0, n, i0 - 1);
+            ctx->launches += 2;
+            slot ^= 1;
+        }
+        PF_TRY_CLEAN(cudaGetLastError());
+        PF_TRY_CLEAN(cudaMemcpyAsync(h_status, d_status, 16, cudaMemcpyDeviceToHost, st));
+        PF_TRY_CLEAN(cudaStreamSynchronize(st));
+        db->build_status = h_status[0];
+        if (!(h_status[0] & (HB_UNSORTED | HB_WRONG_BIN | HB_OVERFLOW))) break;
         cudaFree(tab);
         tab = nullptr;
-        if ((status & (HB_UNSORTED | HB_WRONG_BIN)) || attempt == 1) return PF_OK;
+        if ((h_status[0] & (HB_UNSORTED | HB_WRONG_BIN)) || attempt == 1) { cleanup(false); return PF_OK; }
         b++;
     }
+#undef PF_TRY_CLEAN
+    db->hash_inserted = (uint64_t)h_status[2] | ((uint64_t)h_status[3] << 32);
     db->hash_on = true;
-    db->canonical_ok = !(status & HB_NOT_CANONICAL);
+    db->canonical_ok = !(h_status[0] & HB_NOT_CANONICAL);
     db->hview = hv;
     db->d_hash = tab;
-    cudaFree(db->d_lut); cudaFree(db->d_rec); cudaFree(db->d_suf); cudaFree(db->d_cnt);
-    db->d_lut = db->d_rec = db->d_suf = db->d_cnt = nullptr;
-    db->view.lut = nullptr; db->view.rec = nullptr; db->view.suf = nullptr; db->view.cnt = nullptr;
+    db->d_sigmap = d_sigmap; db->d_norm = d_norm;
+    V.lut = nullptr; V.rec = nullptr; V.suf = nullptr; V.cnt = nullptr;
+    V.n_parts = n_parts; V.part = part;
+    db->view = V;
+    db->orig_min = I.min_count; db->orig_max = I.max_count;
     db->device_bytes = bytes + (V.is_kmc2 ? ((1ull << (2 * V.sig_len)) * 8 + 4) : 0);
+    db->local_kmers = db->hash_inserted;
+    cleanup(true);
     return PF_OK;
 }
 
 int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, uint32_t flags, pf_kmc **out);
-
-// A partition of the hash index: the whole database is staged once (verbatim image), the keys this partition owns
-// (mix(key) % n_parts == part) are inserted into a table sized for N / n_parts, the image is released.  Falls back to the
-// bin / prefix partition of the verbatim layout when the database fails the verification.
-int kmc_open_hash_part(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, pf_kmc **out) {
-    pf_kmc *db = nullptr;
-    int rc = kmc_open_impl(ctx, prefix, 0, 1, PF_KMC_INDEX_VERBATIM, &db);
-    if (rc) return rc;
-    rc = kmc_build_hash(db, part, n_parts);
-    if (rc) { pf_kmc_close(db); return rc; }
-    if (!db->hash_on) {   // not hashable: the verbatim partition
-        pf_kmc_close(db);
-        return kmc_open_impl(ctx, prefix, part, n_parts, PF_KMC_INDEX_VERBATIM, out);
-    }
-    db->view.n_parts = n_parts; db->view.part = part;
-    db->local_kmers = db->hash_inserted;
-    *out = db;
-    return PF_OK;
-}
 
 int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, uint32_t flags, pf_kmc **out) {
     if (!ctx || !prefix || !out) { pf::set_error("pf_kmc_open: null argument"); return PF_E_INVALID; }
@@ -903,17 +998,33 @@ int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_par
     pre.clear();
     pre.shrink_to_fit();
 
-    std::vector<unsigned char> sufbuf;
-    if (!slurp(base + ".kmc_suf", sufbuf)) { pf::set_error("cannot read %s.kmc_suf", prefix); return PF_E_IO; }
-    if (sufbuf.size() < 8 || memcmp(&sufbuf[0], "KMCS", 4) || memcmp(&sufbuf[sufbuf.size() - 4], "KMCS", 4)) {
-        pf::set_error("%s.kmc_suf: bad KMCS markers", prefix);
-        return PF_E_IO;
+    // .kmc_suf is not read into host memory as a whole: its markers and size are checked here, the records are streamed to
+    // the device further down through two pinned staging buffers (read of chunk i + 1 overlaps the copy of chunk i)
+    const std::string suf_path = base + ".kmc_suf";
+    FILE *suf_f = fopen(suf_path.c_str(), "rb");
+    if (!suf_f) { pf::set_error("cannot read %s.kmc_suf", prefix); return PF_E_IO; }
+    struct FileCloser { FILE *f; ~FileCloser() { if (f) fclose(f); } } suf_closer{suf_f};
+    long long suf_size = -1;
+    {
+        char m0[4] = {0}, m1[4] = {0};
+        if (fseeko(suf_f, 0, SEEK_END) == 0) suf_size = (long long)ftello(suf_f);
+        bool ok = suf_size >= 8;
+        ok = ok && fseeko(suf_f, 0, SEEK_SET) == 0 && fread(m0, 1, 4, suf_f) == 4;
+        ok = ok && fseeko(suf_f, (off_t)(suf_size - 4), SEEK_SET) == 0 && fread(m1, 1, 4, suf_f) == 4;
+        if (!ok || memcmp(m0, "KMCS", 4) || memcmp(m1, "KMCS", 4)) { pf::set_error("%s.kmc_suf: bad KMCS markers", prefix); return PF_E_IO; }
     }
     const uint64_t Nall = I.total_kmers, R = S + C;
-    if (sufbuf.size() - 8 < Nall * R) { pf::set_error("%s.kmc_suf: %zu bytes, expected %llu records of %llu bytes", prefix, sufbuf.size(), (unsigned long long)Nall, (unsigned long long)R); return PF_E_IO; }
+    if ((uint64_t)suf_size - 8 < Nall * R) { pf::set_error("%s.kmc_suf: %lld bytes, expected %llu records of %llu bytes", prefix, suf_size, (unsigned long long)Nall, (unsigned long long)R); return PF_E_IO; }
     for (size_t i = 0; i + 1 < lut.size(); i++)
         if (lut[i] > lut[i + 1] || lut[i] > Nall) { pf::set_error("%s.kmc_pre: prefix table is not monotone", prefix); return PF_E_IO; }
 
+    // ---- default layout: the one-sector hash index, built while the records stream in (no verbatim image in HBM) ----
+    if (!(flags & PF_KMC_INDEX_VERBATIM)) {
+        const int hrc = kmc_stream_hash(db.get(), lut, sigmap, norm, suf_f, prefix, part, n_parts);
+        if (hrc) return hrc;
+        if (db->hash_on) { *out = db.release(); return PF_OK; }
+        // not hashable (fails the verification, or the slot does not fit): the verbatim image below, results are identical
+    }
     // ---- partition: local prefix table (rebased record indices) + the byte ranges of the owned records ----
     KmcView &V = db->view;
     V.n_parts = n_parts; V.part = part; V.prefix_lo = 0; V.prefix_cnt = single;
@@ -981,11 +1092,30 @@ int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_par
     if (N) {
         void *d_raw = nullptr;
         PF_CUDA_TRY(cudaMalloc(&d_raw, N * R));
-        uint64_t at = 0;
-        for (auto &r : ranges) {
-            const uint64_t nb = (r.second - r.first) * R;
-            if (nb) PF_CUDA_TRY(cudaMemcpyAsync((uint8_t *)d_raw + at, &sufbuf[4 + r.first * R], nb, cudaMemcpyHostToDevice, st));
-            at += nb;
+        {
+            const size_t CH = 64u << 20;
+            pf::PinnedBuf stage[2];
+            cudaEvent_t done[2];
+            int rcs = 0;
+            for (int i = 0; i < 2 && !rcs; i++) { rcs = stage[i].reserve(CH); if (!rcs && cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) rcs = PF_E_CUDA; }
+            uint64_t at = 0;
+            int slot = 0;
+            bool io_ok = true;
+            for (auto &r : ranges) {
+                uint64_t left = (r.second - r.first) * R;
+                if (left && fseeko(suf_f, (off_t)(4 + r.first * R), SEEK_SET) != 0) io_ok = false;
+                while (left && io_ok && !rcs) {
+                    const size_t nb = (size_t)std::min<uint64_t>(left, CH);
+                    cudaEventSynchronize(done[slot]);                      // the copy that last used this staging buffer is over
+                    if (fread(stage[slot].p, 1, nb, suf_f) != nb) { io_ok = false; break; }
+                    if (cudaMemcpyAsync((uint8_t *)d_raw + at, stage[slot].p, nb, cudaMemcpyHostToDevice, st) != cudaSuccess) { rcs = PF_E_CUDA; break; }
+                    cudaEventRecord(done[slot], st);
+                    at += nb; left -= nb; slot ^= 1;
+                }
+            }
+            cudaStreamSynchronize(st);
+            for (int i = 0; i < 2; i++) { cudaEventDestroy(done[i]); stage[i].release(); }
+            if (!io_ok || rcs) { cudaFree(d_raw); if (!io_ok) { pf::set_error("%s.kmc_suf: short read", prefix); return PF_E_IO; } return rcs; }
         }
         if (V.packed) {
             PF_CUDA_TRY(cudaMalloc(&db->d_rec, N * 8));
@@ -1007,10 +1137,6 @@ int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_par
     V.rec = (const uint64_t *)db->d_rec; V.suf = (const uint64_t *)db->d_suf; V.cnt = (const uint32_t *)db->d_cnt;
     db->device_bytes = bytes;
     db->local_kmers = N;
-    if (n_parts == 1 && !(flags & PF_KMC_INDEX_VERBATIM)) {
-        const int rc = kmc_build_hash(db.get());
-        if (rc) { pf_kmc_close(db.release()); return rc; }
-    }
     *out = db.release();
     return PF_OK;
 }
@@ -1037,8 +1163,7 @@ int pf_kmc_index_kind(const pf_kmc *db) { return db ? (db->hash_on ? PF_KMC_INDE
 int pf_kmc_open_part_ex(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, uint32_t flags, pf_kmc **out) {
     if (!ctx || !prefix || !out) { pf::set_error("pf_kmc_open_part: null argument"); return PF_E_INVALID; }
     if (n_parts == 0 || part >= n_parts || n_parts > 254) { pf::set_error("pf_kmc_open_part: bad partition %u of %u", part, n_parts); return PF_E_INVALID; }
-    if (n_parts > 1 && !(flags & PF_KMC_INDEX_VERBATIM)) return kmc_open_hash_part(ctx, prefix, part, n_parts, out);
-    return kmc_open_impl(ctx, prefix, part, n_parts, flags | (n_parts > 1 ? (uint32_t)PF_KMC_INDEX_VERBATIM : 0u), out);
+    return kmc_open_impl(ctx, prefix, part, n_parts, flags, out);
 }
 
 int pf_kmc_open_part(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_parts, pf_kmc **out) {
@@ -1427,6 +1552,55 @@ int pf_site_cov(pf_kmc *db, uint32_t low, uint32_t up, const uint8_t *skip, pf_s
     out->n_bubbles = n;
     out->site_off = db->h_site[0].as<uint64_t>(); out->status = db->h_site[1].as<uint8_t>(); out->n_class = db->h_site[2].as<uint8_t>();
     out->cov_off = db->h_site[3].as<uint64_t>(); out->cov = db->h_site[4].as<uint64_t>();
+    return PF_OK;
+}
+
+// pf_site_kmers: the site k-mers of the context's last alignment, without any lookup (see site_keys_kernel).
+int pf_site_kmers(pf_ctx *ctx, uint32_t k, const uint8_t *skip, pf_site_kmers_t *out) {
+    if (!ctx || !out) { pf::set_error("pf_site_kmers: null argument"); return PF_E_INVALID; }
+    if (k < 1 || k > 32) { pf::set_error("pf_site_kmers: k=%u outside 1..32", k); return PF_E_INVALID; }
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    cudaStream_t st = ctx->stream;
+    pf_msa_batch_t m;
+    uint64_t tot[4];
+    if (pf_align_last_dev(ctx, &m, tot) != PF_OK) { pf::set_error("pf_site_kmers: no alignment result on this context (call pf_align first)"); return PF_E_INVALID; }
+    const uint32_t n = m.n_bubbles;
+    const uint64_t n_var = tot[1], n_cls = tot[2], n1 = (uint64_t)n + 1;
+    int rc;
+    pf::DevBuf &d_status = ctx->d_out[0], &d_keys = ctx->d_out[1], &d_map = ctx->d_out[2], &d_skip = ctx->d_in[0];
+    if ((rc = d_status.reserve(n_var + 16))) return rc;
+    if ((rc = d_keys.reserve(n_cls * 8 + 16))) return rc;
+    if ((rc = d_map.reserve(n_var * 4 + 16))) return rc;
+    if (skip) {
+        if ((rc = d_skip.reserve(n + 16))) return rc;
+        PF_CUDA_TRY(cudaMemcpyAsync(d_skip.p, skip, n, cudaMemcpyHostToDevice, st));
+    }
+    SiteArgs a{};
+    a.db.k = k; a.both_strands = 1;
+    a.n = n; a.status = m.status; a.n_rows = m.n_rows; a.aln_len = m.aln_len; a.rows_off = m.rows_off; a.rows = m.rows;
+    a.var_off = m.var_off; a.var_col = m.var_col; a.var_kind = m.var_kind; a.cls_off = m.cls_off; a.cls = m.cls;
+    a.skip = skip ? d_skip.as<uint8_t>() : nullptr;
+    a.site_status = d_status.as<uint8_t>(); a.site_bubble = d_map.as<uint32_t>(); a.n_sites = n_var;
+    if (n_var) {
+        site_map_kernel<<<(n + 255) / 256, 256, 0, st>>>(m.var_off, n, d_map.as<uint32_t>());
+        site_keys_kernel<<<(unsigned)((n_var + 127) / 128), 128, 0, st>>>(a, d_keys.as<unsigned long long>());
+        ctx->launches += 2;
+    }
+    PF_CUDA_TRY(cudaGetLastError());
+    pf::PinnedBuf &h_off = ctx->h_stage[0], &h_rest = ctx->h_stage[1];
+    if ((rc = h_off.reserve(n1 * 16))) return rc;
+    if ((rc = h_rest.reserve(n_cls * 8 + n_var + 32))) return rc;
+    uint64_t *h_site_off = h_off.as<uint64_t>(), *h_key_off = h_site_off + n1;
+    uint64_t *h_keys = h_rest.as<uint64_t>();
+    uint8_t *h_status = (uint8_t *)(h_keys + n_cls);
+    PF_CUDA_TRY(cudaMemcpyAsync(h_site_off, m.var_off, n1 * 8, cudaMemcpyDeviceToHost, st));
+    PF_CUDA_TRY(cudaMemcpyAsync(h_key_off, m.cls_off, n1 * 8, cudaMemcpyDeviceToHost, st));
+    if (n_cls) PF_CUDA_TRY(cudaMemcpyAsync(h_keys, d_keys.p, n_cls * 8, cudaMemcpyDeviceToHost, st));
+    if (n_var) PF_CUDA_TRY(cudaMemcpyAsync(h_status, d_status.p, n_var, cudaMemcpyDeviceToHost, st));
+    PF_CUDA_TRY(cudaStreamSynchronize(st));
+    out->n_bubbles = n;
+    out->site_off = h_site_off; out->key_off = h_key_off; out->keys = h_keys; out->status = h_status;
     return PF_OK;
 }
 

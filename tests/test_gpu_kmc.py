@@ -154,10 +154,14 @@ def _swap_two_records(prefix, k, p, C, first_bucket_of=2):
     open(prefix + ".kmc_suf", "wb").write(bytes(suf))
 
 
-def test_database_the_reference_cannot_search_keeps_the_verbatim_index(gpu_ctx, oracle, tmp_path):
+@pytest.mark.parametrize("chunk", [None, 1, 3])
+def test_database_the_reference_cannot_search_keeps_the_verbatim_index(gpu_ctx, oracle, tmp_path, monkeypatch, chunk):
     """A bucket whose suffixes are not ascending makes BinarySearch's outcome order-dependent: the hash index must
-    refuse it, and the verbatim image must still reproduce whatever the reference's search returns."""
+    refuse it, and the verbatim image must still reproduce whatever the reference's search returns.  chunk: records per
+    chunk of the streaming open -- with 1 the offending pair always straddles a chunk seam (the carried predecessor)."""
     from ploidyfrost_b200 import capi
+    if chunk:
+        monkeypatch.setenv("PF_OPEN_CHUNK_RECORDS", str(chunk))
     k, p, C = 25, 5, 2
     prefix, g, u, c = gen.make_genome_db(tmp_path, seed=21, k=k, version=0, p=p, counter_size=C, genome_len=30000)
     _swap_two_records(prefix, k, p, C, first_bucket_of=3)
@@ -313,3 +317,77 @@ def test_per_colour_lookups_config3_shape(gpu_ctx, ref, tmp_path):
         for d in dbs:
             d.close()
     assert n_ok > 100 and n_bad > 1000
+
+
+@pytest.mark.parametrize("ver,p,C,k,chunk", [(0x200, 5, 2, 25, 1000), (0, 5, 2, 25, 777), (0x200, 9, 3, 25, 1), (0, 4, 4, 31, 4096)])
+def test_streaming_open_chunk_seams(gpu_ctx, oracle, tmp_path, monkeypatch, ver, p, C, k, chunk):
+    """pf_kmc_open streams the records through fixed-size chunks (kmc_stream_hash); with tiny chunks every seam case is hit:
+    the carried predecessor of a chunk's first record (ascending-suffix check), chunks that end inside a prefix bucket, a last
+    chunk that is not full.  Same answers as the oracle, whole database and partitions."""
+    from ploidyfrost_b200 import capi
+    monkeypatch.setenv("PF_OPEN_CHUNK_RECORDS", str(chunk))
+    rng = np.random.default_rng(chunk)
+    prefix, g, u, c = gen.make_genome_db(tmp_path, seed=chunk, k=k, version=ver, p=p, counter_size=C, sig_len=9 if k >= 25 else 7,
+                                         genome_len=30000)
+    ho = oracle.kmc_open(prefix)
+    seqs = gen.query_sequences(rng, g, 2000, k=k) + [g[:2500]]
+    bases, off = flatten_seqs(seqs)
+    co, fo = oracle.kmc_counts(ho, bases, off, k, mode=0, n_threads=4)
+    oracle.kmc_close(ho)
+    db = capi.KmcDb(gpu_ctx, prefix)
+    try:
+        if expect_hash(k, C):
+            assert db.index_kind == "hash" and db.local_kmers == db.info["total_kmers"]
+        cg, fg = db.counts(bases, off, mode=0)
+        assert np.array_equal(co, cg) and np.array_equal(fo, fg)
+    finally:
+        db.close()
+    if expect_hash(k, C):
+        parts = [capi.KmcDb(gpu_ctx, prefix, part=r, n_parts=3) for r in range(3)]
+        try:
+            assert all(d.index_kind == "hash" for d in parts)
+            assert sum(d.local_kmers for d in parts) == parts[0].info["total_kmers"]
+        finally:
+            for d in parts:
+                d.close()
+
+
+def test_shared_handles_on_other_contexts(gpu_ctx, oracle, tmp_path):
+    """pf_kmc_share: one index in HBM, one handle + pf_ctx per host thread; four threads run different batches at the same time
+    and each gets the oracle's answer."""
+    import threading
+    from ploidyfrost_b200 import capi
+    k = 25
+    prefix, g, u, c = gen.make_genome_db(tmp_path, seed=4, k=k, version=0x200, p=9, genome_len=60000)
+    ho = oracle.kmc_open(prefix)
+    db = capi.KmcDb(gpu_ctx, prefix)
+    ctxs = [capi.Context(0) for _ in range(4)]
+    shared = [capi.KmcDb(cx, prefix, share_of=db) for cx in ctxs]
+    assert all(s.device_bytes == db.device_bytes and s.index_kind == db.index_kind for s in shared)
+    batches, want, got = [], [], [None] * 4
+    for t in range(4):
+        rng = np.random.default_rng(100 + t)
+        bases, off = flatten_seqs(gen.query_sequences(rng, g, 4000, k=k))
+        batches.append((bases, off))
+        want.append((oracle.kmc_counts(ho, bases, off, k, mode=1, n_threads=4), oracle.kmc_cov(ho, bases, off, mode=1, low=1, up=3, n_threads=4)))
+    oracle.kmc_close(ho)
+
+    def work(t):
+        for _ in range(5):
+            got[t] = (shared[t].counts(*batches[t], mode=1), shared[t].cov(*batches[t], mode=1, low=1, up=3))
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    try:
+        for t in range(4):
+            assert np.array_equal(want[t][0][0], got[t][0][0]) and np.array_equal(want[t][0][1], got[t][0][1])
+            assert np.array_equal(want[t][1], got[t][1])
+    finally:
+        for s in shared:
+            s.close()
+        for cx in ctxs:
+            cx.close()
+        db.close()

@@ -401,6 +401,9 @@ def main():
     ap.add_argument("--up", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg AND the parity block (profiling runs)")
     ap.add_argument("--no-sharded-legs", action="store_true", help="N > 1: skip the partitioned-index legs")
+    ap.add_argument("--lookup-sms", type=int, default=0,
+                    help="SMs of the partition the lookups run on beside the alignment (pf_lookup_partition); 0 = phases in sequence on one stream")
+    ap.add_argument("--lookup-sms-sweep", default="", help="diagnostics: also time the device step with these partition sizes, e.g. 0,16,24,32,48")
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads of the e2e leg (one pf_ctx + shared index handle each)")
     ap.add_argument("--e2e-sweep", default="", help="also time the e2e leg with these host thread counts (T) or T x sub-batches per thread (TxC), e.g. 1,2,4x4")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="sub-batches per host thread and step in the e2e leg")
@@ -494,14 +497,37 @@ def main():
     assert sptr != 0
     torch.cuda.synchronize()
 
+    # SM partition of the lookups (pf_lookup_partition, a green context): lookup-A runs on its own SMs beside the alignment
+    part = {"ptr": None, "stream": None, "sms": 0}
+
+    def set_partition(n_sm):
+        if n_sm and n_sm >= 8:
+            ptr, granted = ctx.lookup_partition(n_sm)
+            part.update(ptr=ptr, stream=torch.cuda.ExternalStream(ptr, device=dev), sms=granted)
+        else:
+            part.update(ptr=None, stream=None, sms=0)
+
+    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+
     def step_device(ev=None, kdb=None, route=None, cov_t=None):
         kdb = kdb or db
         cov_t = cov_t if cov_t is not None else d_cov
+        side = part["stream"] if (route is None and part["stream"] is not None) else None
         if ev:
             ev[0].record(stream)
         if route is not None:
             _, _, c = route.lookup(d_lb, d_lo, d_wo, n_win, mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up, stream=stream)
             cov_t[:n_lseq * 24].copy_(c[:n_lseq * 24])
+        elif side is not None:      # enqueued FIRST, on its partition: the alignment kernels that follow fill the other SMs
+            ev_fork.record(stream)
+            side.wait_event(ev_fork)
+            if ev:
+                ev[4].record(side)
+            kdb.lookup_dev(d_lb.data_ptr(), len(lb), d_lo.data_ptr(), d_wo.data_ptr(), n_lseq, n_win, capi.LOOKUP_CANONICAL, args.low,
+                           args.up, None, None, cov_t.data_ptr(), part["ptr"])
+            if ev:
+                ev[5].record(side)
+            ev_join.record(side)
         else:
             kdb.lookup_dev(d_lb.data_ptr(), len(lb), d_lo.data_ptr(), d_wo.data_ptr(), n_lseq, n_win, capi.LOOKUP_CANONICAL, args.low,
                            args.up, None, None, cov_t.data_ptr(), sptr)
@@ -513,20 +539,26 @@ def main():
             ev[2].record(stream)
         if route is None and (kdb is not db or do_sites):
             kdb.site_cov_dev(args.low, args.up, d_skip.data_ptr(), sptr)
+        if side is not None:
+            stream.wait_event(ev_join)
         if ev:
             ev[3].record(stream)
 
     def timed_loop(**kw):
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
         with torch.cuda.stream(stream):
             for it in range(args.steps):
                 flush.fill_(it & 0xFF)
                 step_device(evs[it], **kw)
         torch.cuda.synchronize()
         seg = lambda a, b: sum(e[a].elapsed_time(e[b]) for e in evs) / len(evs)
-        return seg(0, 3), seg(0, 1), seg(1, 2), seg(2, 3)
+        concurrent = part["stream"] is not None and kw.get("route") is None
+        return seg(0, 3), (seg(4, 5) if concurrent else seg(0, 1)), seg(1, 2), seg(2, 3)
 
     main_route = sh if (sharded_only and not peer) else None
+    if args.lookup_sms and main_route is None:
+        os.environ["PF_LOOKUP_SMS"] = str(args.lookup_sms)      # the host-pointer calls (pf_kmc_cov_async) use the same partition
+        set_partition(args.lookup_sms)
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 1)):
             step_device(route=main_route)
@@ -543,6 +575,16 @@ def main():
     ms_step, ms_lookup, ms_align, ms_site = timed_loop(route=main_route)
     barrier()
     launches = ctx.launches - launches0
+    part_sweep = {}
+    if args.lookup_sms_sweep and main_route is None:          # diagnostics: the step with other partition sizes (0 = one stream, phases in sequence)
+        for n_s in [int(x) for x in args.lookup_sms_sweep.split(",") if x]:
+            set_partition(n_s)
+            with torch.cuda.stream(stream):
+                step_device()
+            torch.cuda.synchronize()
+            t_ = timed_loop()
+            part_sweep[str(part["sms"] if n_s else 0)] = {"ms_step": t_[0], "ms_lookup": t_[1], "ms_align": t_[2], "ms_site": t_[3]}
+        set_partition(args.lookup_sms)
 
     # ---- e2e: host-pointer C ABI from pinned host buffers ----
     # The batch is handed over the way a multi-threaded host hands it over (the reference walks the graph with -t N threads,
@@ -773,6 +815,10 @@ def main():
                                 "per_step_rate": tot_win / (ms_step * 1e-3)},
                 "dp_cells_per_s_kernel": tot_cells / (ms_align * 1e-3),
                 "ms_lookup_kernel": ms_lookup, "ms_align_pipeline": ms_align, "ms_site_cov_kernel": ms_site,
+                "phase_overlap": ({"lookup_sm_partition": part["sms"], "how": "lookup-A on a green-context stream confined to that many SMs, enqueued before the alignment "
+                                   "pipeline of the same step; ms_lookup_kernel / ms_align_pipeline are their own (overlapping) durations"}
+                                  if part["stream"] is not None else {"lookup_sm_partition": 0, "how": "phases in sequence on one stream"}),
+                "sm_partition_sweep": part_sweep or None,
                 "site_columns_per_step": n_sites, "site_status_hist(ok,dropped,missing,undefined,skipped)": site_hist,
                 "clocks": sampler.summary(),
                 "e2e": {"value": tot_bubbles / (ms_e2e * 1e-3), "unit": "bubbles/s", "h2d_bytes_per_step": int(h2d_bytes),

@@ -228,6 +228,17 @@ int pf_site_kmers(pf_ctx *ctx, uint32_t k, const uint8_t *skip, pf_site_kmers_t 
  */
 int pf_kmc_share(pf_kmc *db, pf_ctx *ctx, pf_kmc **out);
 
+/*
+ * pf_lookup_partition -- a CUDA stream confined to `n_sm` SMs of the context's device (a green context, CUDA 12.4+; n_sm is
+ * rounded by the driver to its partition granularity, pf_lookup_partition_sms reports what was granted).  Pass it as the
+ * stream of pf_kmc_lookup_dev while pf_align_dev of the same step runs on another stream: the random-access-bound lookups
+ * keep to their SMs and the issue-bound alignment kernels fill the others at the same time, instead of each phase leaving the
+ * other's resource idle.  The handle's own stream (pf_kmc_cov_async) uses such a partition when PF_LOOKUP_SMS=<n> is set.
+ * One partition per context; it lives until pf_shutdown.  PF_E_UNSUPPORTED when the driver has no green contexts.
+ */
+int pf_lookup_partition(pf_ctx *ctx, uint32_t n_sm, void **stream_out);
+uint32_t pf_lookup_partition_sms(const pf_ctx *ctx);
+
 /* ---- roofline denominators measured on this device (bench.py reports them next to the kernels) ------- */
 /* random 32-byte-sector gather rate over a `bytes`-sized table (GB/s of sectors touched) */
 int pf_bench_random_gather(pf_ctx *ctx, uint64_t bytes, double *gb_per_s);

@@ -25,7 +25,7 @@ EXPORTS = ["pf_init", "pf_shutdown", "pf_last_error", "pf_version", "pf_launch_c
            "pf_kmc_close", "pf_kmc_info", "pf_kmc_set_min_count", "pf_kmc_set_max_count", "pf_kmc_reset_min_max",
            "pf_kmc_device_bytes", "pf_kmc_open_ex", "pf_kmc_index_kind", "pf_kmc_build_status", "pf_kmc_open_part", "pf_kmc_open_part_ex", "pf_kmc_export_ipc", "pf_kmc_attach_peers", "pf_kmc_local_kmers", "pf_kmc_route_dev", "pf_kmc_lookup_keys_dev",
            "pf_kmc_scatter_dev", "pf_kmc_counts", "pf_kmc_cov", "pf_kmc_cov_async", "pf_kmc_wait", "pf_site_cov", "pf_site_cov_dev", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
-           "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_heavy_queued", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32", "pf_kmc_share", "pf_bench_gather_sweep", "pf_site_kmers"]
+           "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_heavy_queued", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32", "pf_kmc_share", "pf_bench_gather_sweep", "pf_site_kmers", "pf_lookup_partition", "pf_lookup_partition_sms"]
 
 
 class SiteBatch(C.Structure):
@@ -134,6 +134,9 @@ def load():
     L.pf_bench_int32.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.pf_bench_gather_sweep.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
     L.pf_kmc_share.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.pf_lookup_partition.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.pf_lookup_partition_sms.argtypes = [C.c_void_p]
+    L.pf_lookup_partition_sms.restype = C.c_uint32
     L.pf_site_kmers.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(SiteKmers)]
     _lib = L
     return L
@@ -260,6 +263,12 @@ class Context:
         v = C.c_double()
         _check(self.lib.pf_bench_random_gather(self.h, nbytes, C.byref(v)), "pf_bench_random_gather")
         return v.value
+
+    def lookup_partition(self, n_sm: int):
+        """pf_lookup_partition -> (raw CUDA stream handle confined to an SM partition, SMs granted)"""
+        st = C.c_void_p()
+        _check(self.lib.pf_lookup_partition(self.h, n_sm, C.byref(st)), "pf_lookup_partition")
+        return st.value, int(self.lib.pf_lookup_partition_sms(self.h))
 
     def bench_gather_sweep(self, nbytes: int, width: int, ilp: int, ctas_per_sm: int) -> float:
         v = C.c_double()

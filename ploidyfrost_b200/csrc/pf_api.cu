@@ -1,5 +1,6 @@
 // pf_api.cu -- context lifetime, error channel and buffer helpers of libpfgpu.so.
 #include "pf_common.cuh"
+#include <cuda.h>   // driver-API TYPES only (green contexts); the entry points are fetched at run time, libcuda is not linked
 #include <algorithm>
 
 #include <cstring>
@@ -96,11 +97,14 @@ int pf_init(int device, pf_ctx **out) {
     return PF_OK;
 }
 
+static void pf_partition_release(pf_ctx *ctx);
+
 void pf_shutdown(pf_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     pf_align_state_free(ctx->align);
+    pf_partition_release(ctx);
     for (auto &b : ctx->d_in) b.release();
     for (auto &b : ctx->d_out) b.release();
     for (auto &b : ctx->h_stage) b.release();
@@ -109,6 +113,75 @@ void pf_shutdown(pf_ctx *ctx) {
 }
 
 uint64_t pf_launch_count(const pf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- an SM partition for the k-mer lookups -------------------------------------------------------------------------------
+// The lookup kernel is bound by the memory system's random-sector rate, which a fraction of the SMs saturates, while the
+// alignment kernels are bound by instruction issue and want every SM they can get.  Run one after the other they each leave
+// the other's resource idle; run side by side on ordinary streams whichever is launched first fills every SM with its
+// persistent CTAs.  A green context (CUDA 12.4+) gives the lookups a FIXED set of n_sm SMs: their CTAs stay there, and the
+// alignment kernels of the same step fill the rest of the device at the same time.  Driver entry points are resolved through
+// cudaGetDriverEntryPoint, so the library carries no link-time dependency on libcuda.
+static void pf_partition_release(pf_ctx *ctx) {
+    if (ctx->part_stream) { cudaStreamSynchronize(ctx->part_stream); cudaStreamDestroy(ctx->part_stream); ctx->part_stream = nullptr; }
+    if (ctx->part_green) {
+        typedef CUresult (*fn_gdestroy)(CUgreenCtx);
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuGreenCtxDestroy", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && p)
+            ((fn_gdestroy)p)((CUgreenCtx)ctx->part_green);
+        else cudaGetLastError();
+        ctx->part_green = nullptr;
+    }
+    ctx->part_sms = 0;
+}
+
+int pf_lookup_partition(pf_ctx *ctx, uint32_t n_sm, void **stream_out) {
+    if (!ctx || !stream_out) { pf::set_error("pf_lookup_partition: null argument"); return PF_E_INVALID; }
+    *stream_out = nullptr;
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->part_stream && ctx->part_sms == n_sm) { *stream_out = ctx->part_stream; return PF_OK; }
+    pf_partition_release(ctx);                                  // a different size: the old partition goes first
+    if (n_sm < 8 || n_sm + 8 > (uint32_t)ctx->sm_count) { pf::set_error("pf_lookup_partition: %u SMs outside 8 .. %d", n_sm, ctx->sm_count - 8); return PF_E_INVALID; }
+    typedef CUresult (*fn_get_res)(CUdevice, CUdevResource *, CUdevResourceType);
+    typedef CUresult (*fn_split)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int);
+    typedef CUresult (*fn_desc)(CUdevResourceDesc *, CUdevResource *, unsigned int);
+    typedef CUresult (*fn_gctx)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int);
+    typedef CUresult (*fn_gstream)(CUstream *, CUgreenCtx, unsigned int, int);
+    typedef CUresult (*fn_devget)(CUdevice *, int);
+    void *p[6] = {nullptr};
+    const char *names[6] = {"cuDeviceGetDevResource", "cuDevSmResourceSplitByCount", "cuDevResourceGenerateDesc", "cuGreenCtxCreate",
+                            "cuGreenCtxStreamCreate", "cuDeviceGet"};
+    for (int i = 0; i < 6; i++) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint(names[i], &p[i], cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p[i]) {
+            cudaGetLastError();
+            pf::set_error("pf_lookup_partition: the driver does not offer %s (green contexts need CUDA 12.4+)", names[i]);
+            return PF_E_UNSUPPORTED;
+        }
+    }
+    PF_CUDA_TRY(cudaFree(0));                                   // the primary context exists
+    CUdevice dev;
+    CUdevResource sm, part, rest;
+    unsigned int groups = 1;
+    CUdevResourceDesc desc;
+    CUgreenCtx g;
+    CUstream st;
+#define PF_DRV(call, what) do { CUresult _r = (call); if (_r != CUDA_SUCCESS) { pf::set_error("pf_lookup_partition: %s failed (CUresult %d)", what, (int)_r); return PF_E_CUDA; } } while (0)
+    PF_DRV(((fn_devget)p[5])(&dev, ctx->device), "cuDeviceGet");
+    PF_DRV(((fn_get_res)p[0])(dev, &sm, CU_DEV_RESOURCE_TYPE_SM), "cuDeviceGetDevResource");
+    PF_DRV(((fn_split)p[1])(&part, &groups, &sm, &rest, 0, n_sm), "cuDevSmResourceSplitByCount");
+    PF_DRV(((fn_desc)p[2])(&desc, &part, 1), "cuDevResourceGenerateDesc");
+    PF_DRV(((fn_gctx)p[3])(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM), "cuGreenCtxCreate");
+    PF_DRV(((fn_gstream)p[4])(&st, g, CU_STREAM_NON_BLOCKING, 0), "cuGreenCtxStreamCreate");
+#undef PF_DRV
+    ctx->part_stream = (cudaStream_t)st;
+    ctx->part_sms = part.sm.smCount;
+    ctx->part_green = (void *)g;
+    *stream_out = ctx->part_stream;
+    return PF_OK;
+}
+
+uint32_t pf_lookup_partition_sms(const pf_ctx *ctx) { return ctx ? ctx->part_sms : 0; }
 
 int pf_sync(pf_ctx *ctx) {
     if (!ctx) return PF_E_INVALID;

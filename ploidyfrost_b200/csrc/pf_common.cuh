@@ -55,4 +55,8 @@ struct pf_ctx {
     pf::DevBuf d_in[4];
     pf::DevBuf d_out[4];
     pf::PinnedBuf h_stage[2];
+    // SM partition of the lookups (pf_lookup_partition): a green-context stream confined to part_sms SMs
+    cudaStream_t part_stream = nullptr;
+    uint32_t part_sms = 0;
+    void *part_green = nullptr;
 };

@@ -764,6 +764,7 @@ struct pf_kmc {
     uint64_t site_totals[2] = {0, 0};
     // host-pointer calls: the handle's own stream, staging and device buffers
     cudaStream_t k_stream = nullptr;
+    bool k_stream_borrowed = false;   // the context's partition stream (pf_lookup_partition): not ours to destroy
     pf::PinnedBuf k_stage;
     pf::DevBuf k_in[3], k_out[3];   // variable columns, class entries of the last pf_site_cov*
 };
@@ -1190,7 +1191,7 @@ int pf_kmc_close(pf_kmc *db) {
     db->tile_seq.release();
     db->site_status.release(); db->site_ncls.release(); db->site_cov.release(); db->site_skip.release(); db->site_map.release();
     for (auto &b : db->h_site) b.release();
-    if (db->k_stream) { cudaStreamSynchronize(db->k_stream); cudaStreamDestroy(db->k_stream); }
+    if (db->k_stream) { cudaStreamSynchronize(db->k_stream); if (!db->k_stream_borrowed) cudaStreamDestroy(db->k_stream); }
     db->k_stage.release();
     for (auto &b : db->k_in) b.release();
     for (auto &b : db->k_out) b.release();
@@ -1613,7 +1614,14 @@ static int kmc_host_call(pf_kmc *db, const char *bases, const uint64_t *seq_off,
     PF_CUDA_TRY(cudaSetDevice(ctx->device));
     if (n_seq == 0) return PF_OK;
     if (db->view.n_parts > 1 && !db->peers_attached) { pf::set_error("pf_kmc_counts/cov: this index holds one partition of the database; use the route / lookup_keys / scatter calls or pf_kmc_attach_peers"); return PF_E_INVALID; }
-    if (!db->k_stream) PF_CUDA_TRY(cudaStreamCreateWithFlags(&db->k_stream, cudaStreamNonBlocking));
+    if (!db->k_stream) {
+        // PF_LOOKUP_SMS=<n>: the handle's stream is confined to an n-SM partition (pf_lookup_partition), so the lookups of a batch
+        // run beside the alignment kernels of the same context instead of competing with them for every SM
+        static const int part_env = getenv("PF_LOOKUP_SMS") ? atoi(getenv("PF_LOOKUP_SMS")) : 0;
+        void *ps = nullptr;
+        if (part_env >= 8 && pf_lookup_partition(ctx, (uint32_t)part_env, &ps) == PF_OK && ps) { db->k_stream = (cudaStream_t)ps; db->k_stream_borrowed = true; }
+        else PF_CUDA_TRY(cudaStreamCreateWithFlags(&db->k_stream, cudaStreamNonBlocking));
+    }
     PF_CUDA_TRY(cudaStreamSynchronize(db->k_stream));   // an earlier asynchronous call still owns the staging buffers
     const uint64_t n_bases = seq_off[n_seq] - seq_off[0];
     int rc;

@@ -319,7 +319,7 @@ def test_per_colour_lookups_config3_shape(gpu_ctx, ref, tmp_path):
     assert n_ok > 100 and n_bad > 1000
 
 
-@pytest.mark.parametrize("ver,p,C,k,chunk", [(0x200, 5, 2, 25, 1000), (0, 5, 2, 25, 777), (0x200, 9, 3, 25, 1), (0, 4, 4, 31, 4096)])
+@pytest.mark.parametrize("ver,p,C,k,chunk", [(0x200, 5, 2, 25, 1000), (0, 5, 2, 25, 777), (0x200, 9, 3, 25, 1), (0, 3, 4, 31, 4096)])
 def test_streaming_open_chunk_seams(gpu_ctx, oracle, tmp_path, monkeypatch, ver, p, C, k, chunk):
     """pf_kmc_open streams the records through fixed-size chunks (kmc_stream_hash); with tiny chunks every seam case is hit:
     the carried predecessor of a chunk's first record (ascending-suffix check), chunks that end inside a prefix bucket, a last

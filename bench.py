@@ -405,6 +405,8 @@ def main():
                     help="SMs of the partition the lookups run on beside the alignment (pf_lookup_partition); 0 = phases in sequence on one stream")
     ap.add_argument("--lookup-sms-sweep", default="", help="diagnostics: also time the device step with these partition sizes, e.g. 0,16,24,32,48")
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads of the e2e leg (one pf_ctx + shared index handle each)")
+    ap.add_argument("--no-staged-align", action="store_true",
+                    help="e2e leg: send the branches a second time with pf_align instead of aligning the copy the lookup call staged (pf_align_staged)")
     ap.add_argument("--e2e-sweep", default="", help="also time the e2e leg with these host thread counts (T) or T x sub-batches per thread (TxC), e.g. 1,2,4x4")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="sub-batches per host thread and step in the e2e leg")
     ap.add_argument("--region-rank", type=int, default=None,
@@ -610,7 +612,10 @@ def main():
             cv = ch["cov"]
         else:   # lookup-A runs on the handle's own stream beside the alignment (pf_kmc_cov_async ... pf_kmc_wait)
             cv = wdb.cov_async(ch["lb"][1], ch["lo"][1], ch["cov"], mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up)
-        m = wctx.align(ch["ab"][1], ch["ao"][1], ch["bo"][1], copy=keep)   # copy=False: views of the pinned result arena (C-ABI ownership rule)
+        if main_route is None and not args.no_staged_align:   # the branches are in the lookup batch already: aligned where they were staged
+            m = wctx.align_staged(wdb, ch["n"], ch["bo"][1], ch["max_len"], ch["max_rows"], copy=keep)
+        else:
+            m = wctx.align(ch["ab"][1], ch["ao"][1], ch["bo"][1], copy=keep)   # copy=False: views of the pinned result arena (C-ABI ownership rule)
         st = wdb.site_cov(args.low, args.up, ch["skip"], copy=keep) if do_sites else None
         if main_route is None:
             wdb.wait()
@@ -632,7 +637,10 @@ def main():
                   "skip": np.ascontiguousarray(sub.bubble_type.astype(np.uint8)), "n": sub.n_bubbles}
             cp = torch.empty((len(clo) - 1) * 24, dtype=torch.uint8).pin_memory()
             ch["cov_t"], ch["cov"] = cp, cp.numpy().view(capi.COV_DTYPE)
-            ch["h2d"] = clb.nbytes + clo.nbytes + sub.bases.nbytes + sub.seq_off.nbytes + sub.bubble_off.nbytes + (ch["skip"].nbytes if do_sites else 0)
+            ch["max_len"], ch["max_rows"] = int(np.diff(sub.seq_off).max()), int(np.diff(sub.bubble_off).max())
+            staged = main_route is None and not args.no_staged_align
+            ch["h2d"] = (clb.nbytes + clo.nbytes + (0 if staged else sub.bases.nbytes + sub.seq_off.nbytes) + sub.bubble_off.nbytes +
+                         (ch["skip"].nbytes if do_sites else 0))
             chunks.append(ch)
         while len(workers_all) < T_e2e:
             c2 = capi.Context(local_rank)
@@ -680,7 +688,8 @@ def main():
         sub = bb.slice(0, n_keep)
         klb, klo = sub.lookup_sequences()
         kch = {"lb": pinned(klb), "lo": pinned(klo), "ab": pinned(sub.bases), "ao": pinned(sub.seq_off), "bo": pinned(sub.bubble_off),
-               "skip": np.ascontiguousarray(sub.bubble_type.astype(np.uint8))}
+               "skip": np.ascontiguousarray(sub.bubble_type.astype(np.uint8)), "n": sub.n_bubbles,
+               "max_len": int(np.diff(sub.seq_off).max()), "max_rows": int(np.diff(sub.bubble_off).max())}
         kp = torch.empty((len(klo) - 1) * 24, dtype=torch.uint8).pin_memory()
         kch["cov_t"], kch["cov"] = kp, kp.numpy().view(capi.COV_DTYPE)
         if main_route is None:
@@ -697,7 +706,7 @@ def main():
         _, fm, fs, _ = run_chunk(ctx, db, chunks[0])
     else:
         _, fm, fs, _ = run_chunk(ctx, db, {"lb": pinned(lb), "lo": pinned(lo), "ab": pinned(bb.bases), "ao": pinned(bb.seq_off), "bo": pinned(bb.bubble_off),
-                                           "skip": skip_np, "cov": torch.empty(n_lseq * 24, dtype=torch.uint8).pin_memory().numpy().view(capi.COV_DTYPE)})
+                                           "skip": skip_np, "n": bb.n_bubbles, "max_len": max_len, "max_rows": max_rows, "cov": torch.empty(n_lseq * 24, dtype=torch.uint8).pin_memory().numpy().view(capi.COV_DTYPE)})
     site_hist = np.bincount(fs["status"], minlength=5).tolist() if fs is not None else None
     n_sites = int(len(fs["status"])) if fs is not None else 0
     n_ok = int((fm["status"] == 0).sum()) if fm is not None else -1
@@ -825,7 +834,7 @@ def main():
                         "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e,
                         "host_threads": T_e2e, "sub_batches_per_step": n_chunks,
                         "ms_per_step_by_host_threads": {str(k_): v for k_, v in e2e_sweep.items()} or None,
-                        "calls": "pf_kmc_cov_async | pf_align | pf_site_cov | pf_kmc_wait per sub-batch; one pf_ctx + pf_kmc_share handle per host thread"},
+                        "calls": ("pf_kmc_cov_async | " + ("pf_align" if (args.no_staged_align or main_route is not None) else "pf_align_staged") + " | pf_site_cov | pf_kmc_wait per sub-batch; one pf_ctx + pf_kmc_share handle per host thread")},
                 "gpu_launches": int(launches),
                 "roofline": dominant, "roofline_lookup": roof_lookup, "roofline_align": roof_align,
                 "bubbles_ok": n_ok, "bubble_status_hist": status_hist, "tier2_retries": int(retry), "heavy_queued": int(heavy_q),

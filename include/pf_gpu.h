@@ -214,6 +214,17 @@ int pf_site_cov(pf_kmc *db, uint32_t low, uint32_t up, const uint8_t *skip, pf_s
 int pf_site_cov_dev(pf_kmc *db, uint32_t low, uint32_t up, const void *d_skip, pf_site_batch_t *out_dev, void *cuda_stream);
 
 /*
+ * pf_align_staged -- pf_align over branches that are already on the device: the sequences first_seq, first_seq + 1, ... of the
+ * batch that the PRECEDING pf_kmc_cov / pf_kmc_cov_async call on `db` copied there (zero-based offsets).  The reference looks
+ * the branch unitigs up and then aligns the same strings (CDBG.cpp:2016-2036): a host that puts the entrance unitigs first and
+ * the branches after them into ONE lookup batch sends every base once, and only bubble_off (relative to first_seq) travels here.
+ * max_len / max_rows: longest branch and most branches per bubble of the batch (upper bounds are fine).  The staged batch
+ * stays valid until the next host-pointer lookup call on `db`.  Result and ownership as pf_align.
+ */
+int pf_align_staged(pf_ctx *ctx, pf_kmc *db, double M, double D, double G, uint32_t first_seq, const uint32_t *bubble_off,
+                    uint32_t n_bubbles, uint32_t max_len, uint32_t max_rows, pf_msa_batch_t *out);
+
+/*
  * pf_site_kmers -- the site k-mers themselves, no database involved: the coloured caller (CCDBG.cpp:1057-1376) asks the GRAPH
  * which colours hold each site k-mer (findUnitig, :1127, :1258) before it reads any database, so it needs the strings.  Works on
  * the last pf_align of the context; `skip` as in pf_site_cov.  `out` views pinned memory of the context, valid until its next call.

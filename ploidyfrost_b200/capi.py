@@ -25,7 +25,7 @@ EXPORTS = ["pf_init", "pf_shutdown", "pf_last_error", "pf_version", "pf_launch_c
            "pf_kmc_close", "pf_kmc_info", "pf_kmc_set_min_count", "pf_kmc_set_max_count", "pf_kmc_reset_min_max",
            "pf_kmc_device_bytes", "pf_kmc_open_ex", "pf_kmc_index_kind", "pf_kmc_build_status", "pf_kmc_open_part", "pf_kmc_open_part_ex", "pf_kmc_export_ipc", "pf_kmc_attach_peers", "pf_kmc_local_kmers", "pf_kmc_route_dev", "pf_kmc_lookup_keys_dev",
            "pf_kmc_scatter_dev", "pf_kmc_counts", "pf_kmc_cov", "pf_kmc_cov_async", "pf_kmc_wait", "pf_site_cov", "pf_site_cov_dev", "pf_kmc_lookup_dev", "pf_window_offsets", "pf_align",
-           "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_heavy_queued", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32", "pf_kmc_share", "pf_bench_gather_sweep", "pf_site_kmers", "pf_lookup_partition", "pf_lookup_partition_sms"]
+           "pf_align_dev", "pf_align_last_tier_counts", "pf_align_last_retry_count", "pf_align_last_heavy_queued", "pf_align_last_cells", "pf_bench_random_gather", "pf_bench_int32", "pf_kmc_share", "pf_bench_gather_sweep", "pf_site_kmers", "pf_lookup_partition", "pf_lookup_partition_sms", "pf_align_staged"]
 
 
 class SiteBatch(C.Structure):
@@ -121,6 +121,8 @@ def load():
     L.pf_window_offsets.restype = C.c_uint64
     L.pf_align.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                            C.POINTER(MsaBatch)]
+    L.pf_align_staged.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
+                                  C.c_uint32, C.POINTER(MsaBatch)]
     L.pf_align_dev.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_uint64, C.c_void_p,
                                C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(MsaBatch), C.c_void_p]
     L.pf_align_last_retry_count.argtypes = [C.c_void_p]
@@ -217,6 +219,14 @@ class Context:
         mb = MsaBatch()
         _check(self.lib.pf_align(self.h, M, D, G, bases.ctypes.data, seq_off.ctypes.data, bubble_off.ctypes.data,
                                  len(bubble_off) - 1, C.byref(mb)), "pf_align")
+        return msa_to_numpy(mb, copy=copy)
+
+    def align_staged(self, db, first_seq, bubble_off, max_len, max_rows, M=2.0, D=-1.0, G=-3.0, copy=True) -> dict:
+        """pf_align_staged: align the branches the preceding db.cov / db.cov_async call left on the device (sequences first_seq ..)"""
+        bubble_off = np.ascontiguousarray(bubble_off, dtype=np.uint32)
+        mb = MsaBatch()
+        _check(self.lib.pf_align_staged(self.h, db.h, M, D, G, first_seq, bubble_off.ctypes.data, len(bubble_off) - 1, max_len, max_rows,
+                                        C.byref(mb)), "pf_align_staged")
         return msa_to_numpy(mb, copy=copy)
 
     def align_dev(self, d_bases, n_bases, d_seq_off, n_seq, d_bubble_off, n_bubbles, max_len, max_rows, M=2.0, D=-1.0,

@@ -1646,6 +1646,28 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
 
 }  // namespace
 
+
+// device -> pinned host: the compacted arrays of the last align_device call
+static int align_fetch(pf_align_state *st, uint32_t n_bubbles, const DevResult &res, cudaStream_t s, pf_msa_batch_t *out) {
+    int rc;
+    const uint64_t n1 = (uint64_t)n_bubbles + 1;
+    const void *src[12] = {st->status.p, st->n_rows.p, st->aln_len.p, st->off[0].p, st->rows.p, st->off[1].p,
+                           st->var_col.p, st->var_kind.p, st->off[2].p, st->cls.p, st->off[3].p, st->ilen.p};
+    const uint64_t bytes[12] = {(uint64_t)n_bubbles * 4, (uint64_t)n_bubbles * 4, (uint64_t)n_bubbles * 4, n1 * 8, res.tot_rows,
+                                n1 * 8, res.tot_var * 4, res.tot_var, n1 * 8, res.tot_cls * 2, n1 * 8, res.tot_ilen * 4};
+    for (int i = 0; i < 12; i++) {
+        if ((rc = st->h_out[i].reserve(bytes[i] + 16))) return rc;
+        if (bytes[i]) PF_CUDA_TRY(cudaMemcpyAsync(st->h_out[i].p, src[i], bytes[i], cudaMemcpyDeviceToHost, s));
+    }
+    PF_CUDA_TRY(cudaStreamSynchronize(s));
+    out->n_bubbles = n_bubbles;
+    out->status = st->h_out[0].as<int32_t>(); out->n_rows = st->h_out[1].as<uint32_t>(); out->aln_len = st->h_out[2].as<uint32_t>();
+    out->rows_off = st->h_out[3].as<uint64_t>(); out->rows = st->h_out[4].as<char>(); out->var_off = st->h_out[5].as<uint64_t>();
+    out->var_col = st->h_out[6].as<uint32_t>(); out->var_kind = st->h_out[7].as<uint8_t>(); out->cls_off = st->h_out[8].as<uint64_t>();
+    out->cls = st->h_out[9].as<uint16_t>(); out->ilen_off = st->h_out[10].as<uint64_t>(); out->ilen = st->h_out[11].as<uint32_t>();
+    return PF_OK;
+}
+
 extern "C" {
 
 int pf_align_dev(pf_ctx *ctx, double M, double D, double G, const void *d_bases, uint64_t n_bases, const void *d_seq_off,
@@ -1711,23 +1733,41 @@ int pf_align(pf_ctx *ctx, double M, double D, double G, const char *bases, const
     rc = align_device(ctx, sc, st->in_bases.as<uint8_t>(), st->in_seq_off.as<uint64_t>(), n_seq, st->in_bubble_off.as<uint32_t>(),
                       n_bubbles, max_len, max_rows, s, res);
     if (rc) return rc;
-    // device -> pinned host
-    const uint64_t n1 = (uint64_t)n_bubbles + 1;
-    const void *src[12] = {st->status.p, st->n_rows.p, st->aln_len.p, st->off[0].p, st->rows.p, st->off[1].p,
-                           st->var_col.p, st->var_kind.p, st->off[2].p, st->cls.p, st->off[3].p, st->ilen.p};
-    const uint64_t bytes[12] = {(uint64_t)n_bubbles * 4, (uint64_t)n_bubbles * 4, (uint64_t)n_bubbles * 4, n1 * 8, res.tot_rows,
-                                n1 * 8, res.tot_var * 4, res.tot_var, n1 * 8, res.tot_cls * 2, n1 * 8, res.tot_ilen * 4};
-    for (int i = 0; i < 12; i++) {
-        if ((rc = st->h_out[i].reserve(bytes[i] + 16))) return rc;
-        if (bytes[i]) PF_CUDA_TRY(cudaMemcpyAsync(st->h_out[i].p, src[i], bytes[i], cudaMemcpyDeviceToHost, s));
+    return align_fetch(st, n_bubbles, res, s, out);
+}
+
+// SequenceAlignment of branches that are ALREADY on the device: the sequences first_seq .. of the batch the preceding
+// pf_kmc_cov / pf_kmc_cov_async call on `db` staged there (the host looked the branches up anyway, CDBG.cpp:2016-2031; sending
+// them a second time for the alignment would be a third of the step's host-to-device bytes).  Only bubble_off travels.
+int pf_align_staged(pf_ctx *ctx, pf_kmc *db, double M, double D, double G, uint32_t first_seq, const uint32_t *bubble_off, uint32_t n_bubbles,
+                    uint32_t max_len, uint32_t max_rows, pf_msa_batch_t *out) {
+    if (!ctx || !db || !out || !bubble_off) { pf::set_error("pf_align_staged: null argument"); return PF_E_INVALID; }
+    PF_CUDA_TRY(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    if (n_bubbles == 0) return PF_OK;
+    const uint8_t *d_bases = nullptr;
+    const uint64_t *d_off = nullptr;
+    uint32_t n_staged = 0;
+    cudaEvent_t ready;
+    if (pf_kmc_staged_dev(db, &d_bases, &d_off, &n_staged, &ready) != PF_OK) {
+        pf::set_error("pf_align_staged: no staged batch on this handle (call pf_kmc_cov / pf_kmc_cov_async with zero-based offsets first)");
+        return PF_E_INVALID;
     }
-    PF_CUDA_TRY(cudaStreamSynchronize(s));
-    out->n_bubbles = n_bubbles;
-    out->status = st->h_out[0].as<int32_t>(); out->n_rows = st->h_out[1].as<uint32_t>(); out->aln_len = st->h_out[2].as<uint32_t>();
-    out->rows_off = st->h_out[3].as<uint64_t>(); out->rows = st->h_out[4].as<char>(); out->var_off = st->h_out[5].as<uint64_t>();
-    out->var_col = st->h_out[6].as<uint32_t>(); out->var_kind = st->h_out[7].as<uint8_t>(); out->cls_off = st->h_out[8].as<uint64_t>();
-    out->cls = st->h_out[9].as<uint16_t>(); out->ilen_off = st->h_out[10].as<uint64_t>(); out->ilen = st->h_out[11].as<uint32_t>();
-    return PF_OK;
+    if (bubble_off[0] != 0) { pf::set_error("pf_align_staged: bubble_off[0] must be 0"); return PF_E_INVALID; }
+    const uint32_t n_seq = bubble_off[n_bubbles];
+    if ((uint64_t)first_seq + n_seq > n_staged) { pf::set_error("pf_align_staged: sequences %u .. %u are outside the staged batch of %u", first_seq, first_seq + n_seq, n_staged); return PF_E_INVALID; }
+    if (!ctx->align) ctx->align = new pf_align_state();
+    pf_align_state *st = ctx->align;
+    cudaStream_t s = ctx->stream;
+    int rc;
+    if ((rc = st->in_bubble_off.reserve((uint64_t)(n_bubbles + 1) * 4))) return rc;
+    PF_CUDA_TRY(cudaMemcpyAsync(st->in_bubble_off.p, bubble_off, (uint64_t)(n_bubbles + 1) * 4, cudaMemcpyHostToDevice, s));
+    PF_CUDA_TRY(cudaStreamWaitEvent(s, ready, 0));
+    DevResult res;
+    const Scoring sc = make_scoring(M, D, G);
+    rc = align_device(ctx, sc, d_bases, d_off + first_seq, n_seq, st->in_bubble_off.as<uint32_t>(), n_bubbles, max_len, max_rows, s, res);
+    if (rc) return rc;
+    return align_fetch(st, n_bubbles, res, s, out);
 }
 
 // diagnostics: how many bubbles of the last pf_align* call needed the second (large-limit) pass

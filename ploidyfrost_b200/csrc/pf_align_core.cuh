@@ -768,7 +768,8 @@ PF_HDN inline void msa_run(X &x, const uint8_t *bases, const uint64_t *seq_off, 
             const uint64_t Llast = clen[ncand - 1];
             Incumbent inc;
             inc.init();
-            for (uint32_t c = 0; c < ncand; c++) {
+            if (ncand == 1) inc.index = 0;   // a single candidate always replaces the empty incumbent (:158-233): no need to rank it
+            for (uint32_t c = 0; c < ncand && ncand > 1; c++) {
                 MsaKey key;
                 scan_candidate(cbase + c * cand_stride, lim.max_alen, ns, clen[c], Llast, key, false, nullptr, nullptr, nullptr);
                 int p = prefer(key, inc);

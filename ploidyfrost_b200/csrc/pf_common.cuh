@@ -45,6 +45,10 @@ struct pf_align_state;  // defined in pf_align.cu
 // device pointers + totals {row bytes, variable columns, class entries, indel lengths} of the context's last alignment result
 int pf_align_last_dev(pf_ctx *ctx, pf_msa_batch_t *out_dev, uint64_t totals[4]);
 
+struct pf_kmc;
+// device copy of the sequences of the handle's last pf_kmc_cov / pf_kmc_cov_async call (zero-based offsets) + the event after which they are there
+extern "C" int pf_kmc_staged_dev(pf_kmc *db, const uint8_t **bases, const uint64_t **seq_off, uint32_t *n_seq, cudaEvent_t *ready);
+
 struct pf_ctx {
     int device = 0;
     int sm_count = 0;

@@ -764,7 +764,10 @@ struct pf_kmc {
     uint64_t site_totals[2] = {0, 0};
     // host-pointer calls: the handle's own stream, staging and device buffers
     cudaStream_t k_stream = nullptr;
-    bool k_stream_borrowed = false;   // the context's partition stream (pf_lookup_partition): not ours to destroy
+    bool k_stream_borrowed = false;
+    cudaEvent_t k_staged_ev = nullptr;   // recorded when the sequences of the last coverage-only host call are on the device
+    uint32_t k_staged_seq = 0;
+    uint64_t k_staged_bases = 0;   // the context's partition stream (pf_lookup_partition): not ours to destroy
     pf::PinnedBuf k_stage;
     pf::DevBuf k_in[3], k_out[3];   // variable columns, class entries of the last pf_site_cov*
 };
@@ -1193,6 +1196,7 @@ int pf_kmc_close(pf_kmc *db) {
     for (auto &b : db->h_site) b.release();
     if (db->k_stream) { cudaStreamSynchronize(db->k_stream); if (!db->k_stream_borrowed) cudaStreamDestroy(db->k_stream); }
     db->k_stage.release();
+    if (db->k_staged_ev) cudaEventDestroy(db->k_staged_ev);
     for (auto &b : db->k_in) b.release();
     for (auto &b : db->k_out) b.release();
     delete db;
@@ -1556,6 +1560,13 @@ int pf_site_cov(pf_kmc *db, uint32_t low, uint32_t up, const uint8_t *skip, pf_s
     return PF_OK;
 }
 
+// internal (pf_align.cu: pf_align_staged): the sequences the last coverage-only host call left on the device
+int pf_kmc_staged_dev(pf_kmc *db, const uint8_t **bases, const uint64_t **seq_off, uint32_t *n_seq, cudaEvent_t *ready) {
+    if (!db || !db->k_staged_seq || !db->k_staged_ev) return PF_E_INVALID;
+    *bases = db->k_in[0].as<uint8_t>(); *seq_off = db->k_in[1].as<uint64_t>(); *n_seq = db->k_staged_seq; *ready = db->k_staged_ev;
+    return PF_OK;
+}
+
 // pf_site_kmers: the site k-mers of the context's last alignment, without any lookup (see site_keys_kernel).
 int pf_site_kmers(pf_ctx *ctx, uint32_t k, const uint8_t *skip, pf_site_kmers_t *out) {
     if (!ctx || !out) { pf::set_error("pf_site_kmers: null argument"); return PF_E_INVALID; }
@@ -1636,6 +1647,9 @@ static int kmc_host_call(pf_kmc *db, const char *bases, const uint64_t *seq_off,
         if ((rc = db->k_out[2].reserve((uint64_t)n_seq * sizeof(pf_cov_t)))) return rc;
         if (n_bases) PF_CUDA_TRY(cudaMemcpyAsync(db->k_in[0].p, bases, n_bases, cudaMemcpyHostToDevice, st));
         PF_CUDA_TRY(cudaMemcpyAsync(db->k_in[1].p, seq_off, (uint64_t)(n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (!db->k_staged_ev) PF_CUDA_TRY(cudaEventCreateWithFlags(&db->k_staged_ev, cudaEventDisableTiming));
+        PF_CUDA_TRY(cudaEventRecord(db->k_staged_ev, st));      // the batch is on the device: pf_align_staged may read it
+        db->k_staged_seq = n_seq; db->k_staged_bases = n_bases;
         win_len_kernel<<<(n_seq + 1 + 255) / 256, 256, 0, st>>>(db->k_in[1].as<uint64_t>(), n_seq, db->info.kmer_length, db->k_out[1].as<uint64_t>());
         size_t tmp = 0;
         PF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp, db->k_out[1].as<uint64_t>(), db->k_in[2].as<uint64_t>(), (int)(n_seq + 1), st));
@@ -1651,6 +1665,7 @@ static int kmc_host_call(pf_kmc *db, const char *bases, const uint64_t *seq_off,
         if (!async) PF_CUDA_TRY(cudaStreamSynchronize(st));
         return PF_OK;
     }
+    db->k_staged_seq = 0;
     // rebased offsets + window offsets are built straight into pinned staging (one async copy each, no bounce buffer)
     if ((rc = db->k_stage.reserve((uint64_t)(n_seq + 1) * 16))) return rc;
     uint64_t *off = db->k_stage.as<uint64_t>(), *woff = off + (n_seq + 1);

@@ -243,3 +243,59 @@ def thread_dialect_view(d):
         groups.setdefault(p[0], []).append((p[1], useq[p[2]], useq[p[3]], p[4]))
     view["alignseq"] = sorted(tuple(g) for g in groups.values())
     return view, ids
+
+
+# ---- coloured graphs (BASELINE configs[3]; CCDBG.cpp:538 / :2759) --------------------------------------------------------------
+def make_colored_inputs(workdir, genome=120000, n_samples=3, depth=20, read_len=150, k=25, seed=20261017, haplotypes=4, p_snp=0.01,
+                        p_indel=0.002, low=2, up=1000):
+    """n_samples read sets over haplotype subsets of one synthetic polyploid (sample s holds the haplotypes h with (h + s) % 3 != 0,
+    always at least two), `Bifrost build -c` over them (one colour per read file), one KMC database per sample, the database list
+    file `dbs.txt` and the thresholds file `cov.txt` (`low\\tup` per line, Main.cpp:416-447).  Returns the per-sample database prefixes."""
+    import subprocess
+    from ploidyfrost_b200.synth import kmcdb, workload as wl
+    pf, bf = reference_binaries()
+    w = wl.Workload(seed, genome, haplotypes, p_snp=p_snp, p_indel=p_indel, n_threads=2)
+    haps = [bytes(w.haplotype(i)).decode() for i in range(haplotypes)]
+    w.close()
+    rng = np.random.default_rng(seed)
+    comp = str.maketrans("ACGT", "TGCA")
+    prefixes, files = [], []
+    for s in range(n_samples):
+        mine = [h for h in range(haplotypes) if (h + s) % 3 != 0]
+        if len(mine) < 2:
+            mine = list(range(haplotypes))[:2]
+        reads = []
+        for h in mine:
+            hs = haps[h]
+            n = depth * len(hs) // read_len
+            for a in rng.integers(0, len(hs) - read_len, n):
+                r = hs[a:a + read_len]
+                reads.append(r.translate(comp)[::-1] if rng.random() < 0.5 else r)
+        fn = f"reads{s}.fa"
+        with open(os.path.join(workdir, fn), "w") as f:
+            for i, r in enumerate(reads):
+                f.write(f">s{s}r{i}\n{r}\n")
+        files.append(fn)
+        u, c = kmcdb.count_canonical_kmers(reads, k)
+        kmcdb.write_kmc_db(os.path.join(workdir, f"db{s}"), u, c.astype(np.uint64), k, version=0x200 if s % 2 == 0 else 0, lut_prefix_len=5,
+                           counter_size=2, n_bins=64, sig_len=9)
+        prefixes.append(f"db{s}")
+    open(os.path.join(workdir, "dbs.txt"), "w").write("".join(p + "\n" for p in prefixes))
+    open(os.path.join(workdir, "cov.txt"), "w").write("".join(f"{low}\t{up}\n" for _ in prefixes))
+    cmd = [bf, "build", "-c", "-k", str(k), "-i", "-d", "-o", "dbg", "-t", "4"]
+    for fn in files:
+        cmd += ["-r", fn]
+    subprocess.run(cmd, cwd=workdir, check=True, capture_output=True)
+    return prefixes
+
+
+def run_reference_colored(workdir, threads=1, binary=None, **kw):
+    """The unmodified PloidyFrost (or `binary`) on the coloured inputs of make_colored_inputs; returns its output directory."""
+    import subprocess
+    if not os.path.exists(os.path.join(workdir, "dbg.gfa")):
+        make_colored_inputs(workdir, **kw)
+    pf, _ = reference_binaries()
+    r = subprocess.run([binary or pf, "-g", "dbg.gfa", "-f", "dbg.bfg_colors", "-d", "dbs.txt", "-C", "cov.txt", "-t", str(threads), "-o", "P"],
+                       cwd=workdir, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return os.path.join(workdir, "PloidyFrost_output")

@@ -86,7 +86,9 @@ struct DeviceWarmup {
     }
     DeviceWarmup() {
         const string prefix = kmc_prefix_of_this_process();
-        if (!prefix.empty() && !option_of_this_process('g').empty()) worker = thread([this, prefix] { open_now(prefix); });
+        // coloured command lines (`-f`) name a LIST of databases with `-d`; ploidy_estimation_colored_gpu.cpp brings those up
+        if (!prefix.empty() && !option_of_this_process('g').empty() && option_of_this_process('f').empty())
+            worker = thread([this, prefix] { open_now(prefix); });
     }
     void ready(const string &prefix) {               // called by the estimation phase
         if (worker.joinable()) worker.join();

@@ -32,6 +32,8 @@ struct pf_ctx {
     void *msa_handle = nullptr;
     pf_msa_batch_t msa;
     bool has_msa = false;
+    std::vector<uint64_t> sk_site_off, sk_key_off, sk_keys;   // pf_site_kmers
+    std::vector<uint8_t> sk_status;
 };
 struct pf_kmc {
     pf_ctx *ctx = nullptr;
@@ -125,6 +127,42 @@ int pf_kmc_open(pf_ctx *ctx, const char *prefix, pf_kmc **out) {
     pforc_kmc_info(h, &info);
     db->k = info.kmer_length;
     *out = db;
+    return PF_OK;
+}
+
+int pf_kmc_info(const pf_kmc *db, pf_kmc_info_t *info) { return pforc_kmc_info(db->orc, info) == 0 ? PF_OK : PF_E_INVALID; }
+
+// the site k-mers themselves (the coloured caller asks the graph about them before any database is read, CCDBG.cpp:1127)
+int pf_site_kmers(pf_ctx *ctx, uint32_t k, const uint8_t *skip, pf_site_kmers_t *out) {
+    if (!ctx->has_msa) { g_error = "pf_site_kmers: no alignment on this context"; return PF_E_INVALID; }
+    const pf_msa_batch_t &m = ctx->msa;
+    const uint32_t nb = m.n_bubbles;
+    ctx->sk_site_off.assign(m.var_off, m.var_off + nb + 1);
+    ctx->sk_key_off.assign(m.cls_off, m.cls_off + nb + 1);
+    ctx->sk_status.assign(m.var_off[nb], PF_SITE_SKIPPED);
+    ctx->sk_keys.assign(m.cls_off[nb], 0);
+    for (uint32_t b = 0; b < nb; b++) {
+        const uint32_t nr = m.n_rows[b], L = m.aln_len[b];
+        if ((skip && skip[b]) || nr == 0 || m.status[b] != PF_BUBBLE_OK) continue;
+        std::vector<std::string> rows(nr);
+        for (uint32_t r = 0; r < nr; r++) rows[r].assign(m.rows + m.rows_off[b] + (size_t)r * L, L);
+        size_t n_indel = 0;
+        for (uint64_t v = m.var_off[b]; v < m.var_off[b + 1]; v++) {
+            const bool is_indel = m.var_kind[v] == 1;
+            std::vector<std::string> km;
+            const bool formed = site_kmers(rows, m.var_col[v], k, is_indel, n_indel, km);
+            if (is_indel) n_indel++;
+            if (!formed) { ctx->sk_status[v] = PF_SITE_UNDEFINED; continue; }
+            ctx->sk_status[v] = PF_SITE_OK;
+            for (uint32_t r = 0; r < nr; r++) {
+                uint64_t key = 0;
+                for (char ch : km[r]) key = key << 2 | (uint64_t)(ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3);
+                ctx->sk_keys[m.cls_off[b] + (v - m.var_off[b]) * nr + r] = key;
+            }
+        }
+    }
+    out->n_bubbles = nb; out->reserved = 0;
+    out->site_off = ctx->sk_site_off.data(); out->key_off = ctx->sk_key_off.data(); out->keys = ctx->sk_keys.data(); out->status = ctx->sk_status.data();
     return PF_OK;
 }
 

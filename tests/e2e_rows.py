@@ -299,3 +299,27 @@ def run_reference_colored(workdir, threads=1, binary=None, **kw):
                        cwd=workdir, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return os.path.join(workdir, "PloidyFrost_output")
+
+
+def colored_thread_dialect_view(d):
+    """The coloured `-t N` files as sorted multisets (rows without the schedule-dependent VarId: ..., colour, type, indelLen, VarId,
+    VarNum, CramerV, VarDis, '')."""
+    useq = unitig_seq(d)
+    view = {}
+    for a in ("bi", "tri", "tetra", "penta"):
+        rows = []
+        for ln in open(os.path.join(d, f"P_{a}cov.txt")):
+            p = ln.rstrip("\n").split("\t")
+            del p[-5]
+            rows.append("\t".join(p))
+        view[a + "cov"] = sorted(rows)
+        view[a + "fre"] = sorted(open(os.path.join(d, f"P_{a}fre.txt")).read().split("\n"))
+    view["allfre"] = sorted(open(os.path.join(d, "P_allele_frequency.txt")).read().split("\n"))
+    groups, ids = {}, []
+    for ln in open(os.path.join(d, "P_alignseq.txt")):
+        p = ln.rstrip("\n").split("\t")
+        if p[0] not in groups:
+            ids.append(int(p[0]))
+        groups.setdefault(p[0], []).append((p[1], useq[p[2]], useq[p[3]], p[4]))
+    view["alignseq"] = sorted(tuple(g) for g in groups.values())
+    return view, ids

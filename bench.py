@@ -408,6 +408,7 @@ def main():
     ap.add_argument("--no-staged-align", action="store_true",
                     help="e2e leg: send the branches a second time with pf_align instead of aligning the copy the lookup call staged (pf_align_staged)")
     ap.add_argument("--e2e-sweep", default="", help="also time the e2e leg with these host thread counts (T) or T x sub-batches per thread (TxC), e.g. 1,2,4x4")
+    ap.add_argument("--e2e-trace", action="store_true", help="diagnostics: blocking time of every call of a single-threaded, single-batch e2e pass")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="sub-batches per host thread and step in the e2e leg")
     ap.add_argument("--region-rank", type=int, default=None,
                     help="diagnostics: take the batch another rank would take (its region of the genome) on this GPU")
@@ -600,7 +601,15 @@ def main():
     h_wo = pinned(wo)
     workers_all = [(ctx, db)]
 
-    def run_chunk(wctx, wdb, ch, keep=False):
+    def run_chunk(wctx, wdb, ch, keep=False, trace=None):
+        t_tr = time.perf_counter()
+
+        def lap(name):           # --e2e-trace: blocking time of every call of the sequence (host clock)
+            nonlocal t_tr
+            if trace is not None:
+                now = time.perf_counter()
+                trace[name] = trace.get(name, 0.0) + (now - t_tr) * 1e3
+                t_tr = now
         if main_route is not None:   # no host-pointer form of the routed lookup: copy in, route/exchange/lookup, copy the cov records out
             with torch.cuda.stream(stream):
                 e_lb = ch["lb"][0].to(dev, non_blocking=True)
@@ -612,13 +621,17 @@ def main():
             cv = ch["cov"]
         else:   # lookup-A runs on the handle's own stream beside the alignment (pf_kmc_cov_async ... pf_kmc_wait)
             cv = wdb.cov_async(ch["lb"][1], ch["lo"][1], ch["cov"], mode=capi.LOOKUP_CANONICAL, low=args.low, up=args.up)
+        lap("pf_kmc_cov_async (enqueue)")
         if main_route is None and not args.no_staged_align:   # the branches are in the lookup batch already: aligned where they were staged
             m = wctx.align_staged(wdb, ch["n"], ch["bo"][1], ch["max_len"], ch["max_rows"], copy=keep)
         else:
             m = wctx.align(ch["ab"][1], ch["ao"][1], ch["bo"][1], copy=keep)   # copy=False: views of the pinned result arena (C-ABI ownership rule)
+        lap("pf_align")
         st = wdb.site_cov(args.low, args.up, ch["skip"], copy=keep) if do_sites else None
+        lap("pf_site_cov")
         if main_route is None:
             wdb.wait()
+        lap("pf_kmc_wait")
         nb = cv.nbytes + sum(v.nbytes for v in m.values() if isinstance(v, np.ndarray))
         if st is not None:
             nb += sum(v.nbytes for v in st.values())
@@ -674,6 +687,18 @@ def main():
                 e2e_times.append(dt)
         return 1e3 * sum(e2e_times) / len(e2e_times), sum(ch["h2d"] for ch in chunks), sum(d2h_acc), T_e2e, n_chunks, chunks
 
+    e2e_trace = None
+    if args.e2e_trace and main_route is None:      # one host thread, whole batch in one sequence of calls, every call timed
+        _, _, _, _, _, tr_chunks = e2e_leg(1)
+        e2e_trace = {}
+        for it in range(3):
+            torch.cuda.synchronize()
+            tr = {}
+            t0_ = time.perf_counter()
+            run_chunk(ctx, db, tr_chunks[0], trace=tr)
+            torch.cuda.synchronize()
+            tr["total"] = (time.perf_counter() - t0_) * 1e3
+            e2e_trace = tr
     e2e_sweep = {}
     for spec in [x for x in args.e2e_sweep.split(",") if x]:       # "T" or "TxC": host threads x sub-batches per thread
         T_s, _, C_s = spec.partition("x")
@@ -834,6 +859,7 @@ def main():
                         "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e,
                         "host_threads": T_e2e, "sub_batches_per_step": n_chunks,
                         "ms_per_step_by_host_threads": {str(k_): v for k_, v in e2e_sweep.items()} or None,
+                        "single_thread_call_ms": e2e_trace,
                         "calls": ("pf_kmc_cov_async | " + ("pf_align" if (args.no_staged_align or main_route is not None) else "pf_align_staged") + " | pf_site_cov | pf_kmc_wait per sub-batch; one pf_ctx + pf_kmc_share handle per host thread")},
                 "gpu_launches": int(launches),
                 "roofline": dominant, "roofline_lookup": roof_lookup, "roofline_align": roof_align,

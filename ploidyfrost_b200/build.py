@@ -30,14 +30,33 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", os.path.join(ROOT, "include"), "-o", LIB] + srcs
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    # one object per translation unit, compiled side by side (objects under build/, git-ignored), then one link
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    inc = os.path.join(ROOT, "include")
+    hdr_t = max(os.path.getmtime(os.path.join(d, f)) for d in (CSRC, inc) for f in os.listdir(d) if f.endswith((".cuh", ".h", ".hpp")))
+    jobs, objs = [], []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(objdir, s.replace(".cu", ".o"))
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            continue
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + ["-I", inc, "-c", src, "-o", obj]
+        jobs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    failed = False
+    for s, pr in jobs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            sys.stderr.write(out + err)
+            failed = True
+        elif verbose:
+            sys.stderr.write(err)
+    if failed:
+        raise RuntimeError("nvcc failed building libpfgpu.so")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libpfgpu.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc failed linking libpfgpu.so")
     return LIB
 
 

@@ -408,6 +408,7 @@ def main():
     ap.add_argument("--no-staged-align", action="store_true",
                     help="e2e leg: send the branches a second time with pf_align instead of aligning the copy the lookup call staged (pf_align_staged)")
     ap.add_argument("--e2e-sweep", default="", help="also time the e2e leg with these host thread counts (T) or T x sub-batches per thread (TxC), e.g. 1,2,4x4")
+    ap.add_argument("--e2e-profile", default="", help="diagnostics: write a CUPTI timeline (chrome trace) of two e2e steps to this path")
     ap.add_argument("--e2e-trace", action="store_true", help="diagnostics: blocking time of every call of a single-threaded, single-batch e2e pass")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="sub-batches per host thread and step in the e2e leg")
     ap.add_argument("--region-rank", type=int, default=None,
@@ -637,7 +638,7 @@ def main():
             nb += sum(v.nbytes for v in st.values())
         return cv, m, st, nb
 
-    def e2e_leg(T_req, C_req=None):
+    def e2e_leg(T_req, C_req=None, profile_path=None):
         """-> (ms per step, h2d bytes, d2h bytes, threads, sub-batches) of the e2e leg with T_req host threads, C_req sub-batches each"""
         T_e2e = 1 if main_route is not None else max(1, T_req)
         n_chunks = T_e2e * max(1, C_req or args.e2e_chunks) if (T_e2e > 1 or C_req) and main_route is None else 1
@@ -661,32 +662,51 @@ def main():
         workers = workers_all[:T_e2e]
         d2h_acc = [0] * T_e2e
 
-        def worker_step(t):
+        def worker_steps(t, n_steps):
             wctx, wdb = workers[t]
             tot = 0
-            for c in range(t, n_chunks, T_e2e):
-                tot += run_chunk(wctx, wdb, chunks[c])[3]
-            d2h_acc[t] = tot
+            for _ in range(n_steps):
+                for c in range(t, n_chunks, T_e2e):
+                    tot += run_chunk(wctx, wdb, chunks[c])[3]
+            d2h_acc[t] = tot // max(n_steps, 1)
 
-        e2e_times = []
-        for it in range(2 + args.steps):
-            barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
+        def run_steps(n_steps):
             if T_e2e == 1:
-                worker_step(0)
+                worker_steps(0, n_steps)
             else:
-                th = [threading.Thread(target=worker_step, args=(t,)) for t in range(T_e2e)]
+                th = [threading.Thread(target=worker_steps, args=(t, n_steps)) for t in range(T_e2e)]
                 for x_ in th:
                     x_.start()
                 for x_ in th:
                     x_.join()
             torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            if it >= 2:
-                e2e_times.append(dt)
-        return 1e3 * sum(e2e_times) / len(e2e_times), sum(ch["h2d"] for ch in chunks), sum(d2h_acc), T_e2e, n_chunks, chunks
 
+        # K steps inside ONE bracket (barrier + synchronize on both sides), as the device-timed region: every host thread pushes
+        # its share of every step -- copy-in, calls, copy-out -- back to back, the way a host that walks a graph hands over batch
+        # after batch (integration/: block b + 1 is collected and sent while block b is on the device).  The figure of a single
+        # step synchronised on its own (head: the first copy-in, tail: the last copy-out, both exposed) is kept beside it.
+        run_steps(2)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_steps(args.steps)
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+        iso = []
+        for it in range(max(2, min(args.steps, 5))):
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run_steps(1)
+            iso.append(1e3 * (time.perf_counter() - t0))
+        e2e_isolated[(T_e2e, n_chunks)] = sum(iso) / len(iso)
+        if profile_path:      # diagnostics: a CUPTI timeline (kernels + copies of every stream) of three more steps
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                run_steps(3)
+            prof.export_chrome_trace(profile_path)
+        return e2e_ms, sum(ch["h2d"] for ch in chunks), sum(d2h_acc), T_e2e, n_chunks, chunks
+
+    e2e_isolated = {}
     e2e_trace = None
     if args.e2e_trace and main_route is None:      # one host thread, whole batch in one sequence of calls, every call timed
         _, _, _, _, _, tr_chunks = e2e_leg(1)
@@ -703,7 +723,7 @@ def main():
     for spec in [x for x in args.e2e_sweep.split(",") if x]:       # "T" or "TxC": host threads x sub-batches per thread
         T_s, _, C_s = spec.partition("x")
         e2e_sweep[spec] = e2e_leg(int(T_s), int(C_s) if C_s else None)[0]
-    ms_e2e, h2d_bytes, d2h_bytes, T_e2e, n_chunks, chunks = e2e_leg(args.e2e_threads)
+    ms_e2e, h2d_bytes, d2h_bytes, T_e2e, n_chunks, chunks = e2e_leg(args.e2e_threads, profile_path=args.e2e_profile or None)
     # the results the parity block diffs: one more (untimed) pass of the first bubbles of the batch through the same calls, copied out
     n_keep = min(bb.n_bubbles, args.cpu_sample if world == 1 else min(args.cpu_sample, 32768))
     if n_chunks == 1 and n_keep == bb.n_bubbles:
@@ -860,6 +880,8 @@ def main():
                         "host_threads": T_e2e, "sub_batches_per_step": n_chunks,
                         "ms_per_step_by_host_threads": {str(k_): v for k_, v in e2e_sweep.items()} or None,
                         "single_thread_call_ms": e2e_trace,
+                        "timed": f"{args.steps} steps in one bracket (barrier + synchronize on both sides), host threads free-running",
+                        "ms_per_step_synchronised_alone": e2e_isolated.get((T_e2e, n_chunks)),
                         "calls": ("pf_kmc_cov_async | " + ("pf_align" if (args.no_staged_align or main_route is not None) else "pf_align_staged") + " | pf_site_cov | pf_kmc_wait per sub-batch; one pf_ctx + pf_kmc_share handle per host thread")},
                 "gpu_launches": int(launches),
                 "roofline": dominant, "roofline_lookup": roof_lookup, "roofline_align": roof_align,

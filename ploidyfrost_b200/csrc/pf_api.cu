@@ -1,4 +1,5 @@
 // pf_api.cu -- context lifetime, error channel and buffer helpers of libpfgpu.so.
+#include <cstdlib>
 #include "pf_common.cuh"
 #include <cuda.h>   // driver-API TYPES only (green contexts); the entry points are fetched at run time, libcuda is not linked
 #include <algorithm>
@@ -87,7 +88,15 @@ int pf_init(int device, pf_ctx **out) {
     cudaDeviceProp prop;
     PF_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
-    PF_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    // The context's own stream carries the short helper kernels between the big ones (plan, sort, scans, compaction) and the
+    // copies: it gets the highest priority, so that when several contexts share the GPU (one per host thread, pf_kmc_share) a
+    // helper does not queue behind the pending CTAs of another context's alignment / lookup kernels (those streams stay at the
+    // default, lowest priority).  Measured with the CUPTI timeline of bench.py --e2e-profile (profiles/r02_summary.md).
+    {
+        int least = 0, greatest = 0;
+        PF_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        PF_CUDA_TRY(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, getenv("PF_FLAT_PRIORITY") ? least : greatest));
+    }
     if (const char *e = getenv("PF_L2_FETCH_GRANULARITY")) {   // 32 / 64 / 128: a hint to the L2 (random-sector workloads)
         const int g = atoi(e);
         if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);

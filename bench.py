@@ -410,7 +410,7 @@ def main():
     ap.add_argument("--e2e-sweep", default="", help="also time the e2e leg with these host thread counts (T) or T x sub-batches per thread (TxC), e.g. 1,2,4x4")
     ap.add_argument("--e2e-profile", default="", help="diagnostics: write a CUPTI timeline (chrome trace) of two e2e steps to this path")
     ap.add_argument("--e2e-trace", action="store_true", help="diagnostics: blocking time of every call of a single-threaded, single-batch e2e pass")
-    ap.add_argument("--e2e-chunks", type=int, default=2, help="sub-batches per host thread and step in the e2e leg")
+    ap.add_argument("--e2e-chunks", type=int, default=1, help="sub-batches per host thread and step in the e2e leg")
     ap.add_argument("--region-rank", type=int, default=None,
                     help="diagnostics: take the batch another rank would take (its region of the genome) on this GPU")
     ap.add_argument("--no-peer-lookup", action="store_true",
@@ -895,6 +895,14 @@ def main():
         if not args.no_cpu_baseline and cov is not None:
             base, par = cpu_baseline_and_parity(args, cfg, bb, prefix, n_keep, cov, msa, sites, skip_np, timed=(world == 1))
             if base is not None:
+                # the whole reference PROGRAM against the same binary with its estimation phase bound to this library
+                # (integration/time_program.py on a real Bifrost graph): captured separately, cited here, not measured in this run
+                wp_path = os.path.join(ROOT, "profiles", "r02_whole_program.json")
+                if os.path.exists(wp_path):
+                    try:
+                        base["whole_program"] = json.load(open(wp_path))
+                    except ValueError:
+                        pass
                 line["cpu_baseline"] = base
             line["parity"] = par
             if par["mismatches"]:

@@ -33,12 +33,31 @@ def run(binary, cwd, threads, extra_env=None):
     env = dict(os.environ)
     env.update(extra_env or {})
     t0 = time.perf_counter()
-    r = subprocess.run([binary, "-g", "dbg.gfa", "-d", "db", "-t", str(threads), "-l", "2", "-u", "1000", "-o", "P"], cwd=cwd,
-                       capture_output=True, text=True, env=env)
+    # the reference's own phase timer has 1 s resolution (time(NULL)); its messages end with endl, so the arrival times of the
+    # phase's first and last line on the pipe give the phase's wall time to a millisecond
+    pr = subprocess.Popen([binary, "-g", "dbg.gfa", "-d", "db", "-t", str(threads), "-l", "2", "-u", "1000", "-o", "P"], cwd=cwd,
+                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+    lines, t_begin, t_end = [], None, None
+    for ln in pr.stdout:
+        now = time.perf_counter()
+        lines.append(ln)
+        if "Analyzing superbubbles to generate" in ln:
+            t_begin = now
+        elif "PloidyEstimation():" in ln and "Cpu time" in ln:
+            t_end = now
+    err = pr.stderr.read()
+    pr.wait()
+
+    class R:
+        pass
+    r = R()
+    r.returncode, r.stdout, r.stderr = pr.returncode, "".join(lines), err
     wall = time.perf_counter() - t0
     if r.returncode != 0:
         return {"wall_s": round(wall, 3), "rc": r.returncode, "tail": r.stdout[-600:] + r.stderr[-300:]}
     out = {"wall_s": round(wall, 3)}
+    if t_begin is not None and t_end is not None:
+        out["estimation_phase_s"] = round(t_end - t_begin, 4)
     m = re.search(r"PloidyEstimation\(\):\s+Cpu time : ([0-9.e+-]+)s", r.stdout)
     if m:
         out["estimation_cpu_s"] = float(m.group(1))
@@ -110,6 +129,13 @@ def main():
             a = e2e_rows.thread_dialect_view(os.path.join(d_refN, "PloidyFrost_output"))
             b = e2e_rows.thread_dialect_view(os.path.join(d_gpuN, "PloidyFrost_output"))
             res["tN_files_equal_as_multisets"] = bool(a[0] == b[0])      # [1] = the VarIds in file order: schedule-dependent in the reference
+            if a[0] != b[0]:
+                # is the reference's own -t N run reproducible?  (its worker threads race on the visited marks, CDBG.cpp:1929-2000)
+                d_refN2 = fresh("refN2")
+                run(pf, d_refN2, cores)
+                a2 = e2e_rows.thread_dialect_view(os.path.join(d_refN2, "PloidyFrost_output"))
+                res["reference_tN_equals_its_own_second_run"] = bool(a[0] == a2[0])
+                res["tN_differences"] = {k_: [len(a[0][k_]), len(b[0][k_]), len(a2[0][k_])] for k_ in a[0] if a[0][k_] != b[0][k_]}
         except Exception as e:   # noqa: BLE001
             res["tN_files_equal_as_multisets"] = f"not compared: {e}"
         if os.environ.get("PF_PROGRAM_CHECK") == "1":
@@ -123,6 +149,15 @@ def main():
             res["bubbles_called"] = len({ln.split("\t")[0] for ln in open(os.path.join(d_gpu1, "PloidyFrost_output", "P_alignseq.txt"))})
         except OSError:
             pass
+    rN, gN = res["runs"].get(f"reference -t {cores}", {}), res["runs"].get(f"gpu -t {cores}", {})
+    if "estimation_phase_s" in rN and "estimation_phase_s" in gN and gN.get("bubbles_walked"):
+        nb = gN["bubbles_walked"]
+        res["summary"] = {"workload": f"{genome / 1e6:g} Mbp, {n_hap} haplotypes, real Bifrost graph, {nb} superbubbles walked, {cores} host cores, -t {cores}",
+                          "reference_estimation_phase_s": rN["estimation_phase_s"], "gpu_estimation_phase_s": gN["estimation_phase_s"],
+                          "reference_bubbles_per_s": round(nb / rN["estimation_phase_s"]), "gpu_bubbles_per_s": round(nb / gN["estimation_phase_s"]),
+                          "estimation_phase_speedup": round(rN["estimation_phase_s"] / gN["estimation_phase_s"], 2),
+                          "reference_wall_s": rN["wall_s"], "gpu_wall_s": gN["wall_s"],
+                          "measured_by": "integration/time_program.py (wall clock between the phase's first and last console line)"}
     print(json.dumps(res))
     if out_json:
         json.dump(res, open(out_json, "w"), indent=1)

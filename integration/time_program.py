@@ -29,13 +29,15 @@ sys.path.insert(0, ROOT)
 from tests import e2e_rows  # noqa: E402
 
 
-def run(binary, cwd, threads, extra_env=None):
+def run(binary, cwd, threads, extra_env=None, colored=False):
     env = dict(os.environ)
     env.update(extra_env or {})
     t0 = time.perf_counter()
     # the reference's own phase timer has 1 s resolution (time(NULL)); its messages end with endl, so the arrival times of the
     # phase's first and last line on the pipe give the phase's wall time to a millisecond
-    pr = subprocess.Popen([binary, "-g", "dbg.gfa", "-d", "db", "-t", str(threads), "-l", "2", "-u", "1000", "-o", "P"], cwd=cwd,
+    cmd = ([binary, "-g", "dbg.gfa", "-f", "dbg.bfg_colors", "-d", "dbs.txt", "-C", "cov.txt", "-t", str(threads), "-o", "P"] if colored else
+           [binary, "-g", "dbg.gfa", "-d", "db", "-t", str(threads), "-l", "2", "-u", "1000", "-o", "P"])
+    pr = subprocess.Popen(cmd, cwd=cwd,
                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
     lines, t_begin, t_end = [], None, None
     for ln in pr.stdout:
@@ -64,6 +66,10 @@ def run(binary, cwd, threads, extra_env=None):
     m = re.search(r"PloidyEstimation\(\):\s+Real time : ([0-9.e+-]+)s", r.stdout)
     if m:
         out["estimation_real_s_1s_resolution"] = float(m.group(1))
+    gc = re.search(r"GPU path : (\d+) bubbles, (\d+) colours, (\d+) host threads, phase ([0-9.e+-]+)s = collecting ([0-9.e+-]+)s, waiting for the device ([0-9.e+-]+)s; device thread (.*)", r.stdout)
+    if gc:
+        out.update(bubbles_walked=int(gc.group(1)), colours=int(gc.group(2)), host_threads=int(gc.group(3)), phase_s=float(gc.group(4)),
+                   collect_s=float(gc.group(5)), device_wait_s=float(gc.group(6)), device_thread=gc.group(7))
     g = re.search(r"GPU path : (\d+) bubbles, (\d+) host threads, phase ([0-9.e+-]+)s = waited for device \+ database ([0-9.e+-]+)s, "
                   r"collecting ([0-9.e+-]+)s, waiting for the device ([0-9.e+-]+)s", r.stdout)
     if g:
@@ -77,7 +83,85 @@ def run(binary, cwd, threads, extra_env=None):
     return out
 
 
+def main_colored(genome, n_hap, n_samples, out_json):
+    """BASELINE configs[3] shape through the real programs: n_samples samples over haplotype subsets of one polyploid, `Bifrost build -c`
+    (one colour per sample), one KMC database per sample, `-C` thresholds; unmodified reference against the bound binary, `-t cores`."""
+    from ploidyfrost_b200.synth import workload as wl
+    pf, bf = e2e_rows.reference_binaries()
+    gpu = os.environ.get("PF_PROGRAM_BINARY") or os.path.join(ROOT, "oracle", "_ref", "PloidyFrost_gpu")
+    dev = os.environ.get("PF_PROGRAM_DEVICE", "cuda:0")
+    cores = os.cpu_count()
+    k = 25
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 60 * genome * n_samples else None
+    with tempfile.TemporaryDirectory(dir=base) as tmp:
+        t0 = time.perf_counter()
+        w = wl.Workload(20261017 + 3, genome, n_hap, p_snp=0.01, p_indel=0.001, n_threads=min(16, cores))
+        haps = [w.haplotype(i) for i in range(n_hap)]
+        w.close()
+        prefixes, n_kmers = [], 0
+        for s in range(n_samples):
+            mine = [h for h in range(n_hap) if (h + s) % 3 != 0]
+            if len(mine) < 2:
+                mine = list(range(n_hap))[:2]
+            with open(os.path.join(tmp, f"s{s}.fa"), "wb") as f:
+                for i in mine:
+                    f.write(b">s%dh%d\n" % (s, i))
+                    f.write(haps[i].tobytes())
+                    f.write(b"\n")
+            info = wl.write_db_torch(os.path.join(tmp, f"db{s}"), [haps[i] for i in mine], k, 12.6, 20261017 + s, device=dev, version=0x200,
+                                     lut_prefix_len=9, sig_len=9, n_bins=64)
+            n_kmers += info["N"]
+            prefixes.append(f"db{s}")
+        del haps
+        open(os.path.join(tmp, "dbs.txt"), "w").write("".join(p + "\n" for p in prefixes))
+        open(os.path.join(tmp, "cov.txt"), "w").write("".join("2\t1000\n" for _ in prefixes))
+        t_data = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        cmd = [bf, "build", "-c", "-k", str(k), "-i", "-d", "-o", "dbg", "-t", str(min(cores, 16))]
+        for s in range(n_samples):
+            cmd += ["-r", f"s{s}.fa"]
+        subprocess.run(cmd, cwd=tmp, check=True, capture_output=True)
+        t_graph = time.perf_counter() - t0
+        res = {"genome_bp": genome, "haplotypes": n_hap, "samples": n_samples, "k": k, "db_kmers_all_samples": n_kmers, "host_cores": cores,
+               "data_s": round(t_data, 1), "bifrost_build_s": round(t_graph, 1), "runs": {}}
+
+        def fresh(name):
+            d = os.path.join(tmp, name)
+            shutil.rmtree(d, ignore_errors=True)
+            os.mkdir(d)
+            for f in os.listdir(tmp):
+                if f.startswith("dbg.") or f.startswith("db") or f == "cov.txt":
+                    os.symlink(os.path.join(tmp, f), os.path.join(d, f))
+            return d
+
+        d_refN, d_gpuN = fresh("refN"), fresh("gpuN")
+        res["runs"][f"reference -t {cores}"] = run(pf, d_refN, cores, colored=True)
+        res["runs"][f"gpu -t {cores}"] = run(gpu, d_gpuN, cores, colored=True)
+        try:
+            a = e2e_rows.colored_thread_dialect_view(os.path.join(d_refN, "PloidyFrost_output"))
+            b = e2e_rows.colored_thread_dialect_view(os.path.join(d_gpuN, "PloidyFrost_output"))
+            res["tN_files_equal_as_multisets"] = bool(a[0] == b[0])
+            res["bubbles_called"] = len(b[1])
+        except Exception as e:   # noqa: BLE001
+            res["tN_files_equal_as_multisets"] = f"not compared: {e}"
+        rN, gN = res["runs"][f"reference -t {cores}"], res["runs"][f"gpu -t {cores}"]
+        if "estimation_phase_s" in rN and "estimation_phase_s" in gN and gN.get("bubbles_walked"):
+            nb = gN["bubbles_walked"]
+            res["summary"] = {"workload": f"coloured: {n_samples} samples over {n_hap} haplotypes of {genome / 1e6:g} Mbp, real `Bifrost build -c` graph, {nb} superbubbles walked, "
+                                          f"{cores} host cores, -t {cores}",
+                              "reference_estimation_phase_s": rN["estimation_phase_s"], "gpu_estimation_phase_s": gN["estimation_phase_s"],
+                              "reference_bubbles_per_s": round(nb / rN["estimation_phase_s"]), "gpu_bubbles_per_s": round(nb / gN["estimation_phase_s"]),
+                              "estimation_phase_speedup": round(rN["estimation_phase_s"] / gN["estimation_phase_s"], 2),
+                              "reference_wall_s": rN["wall_s"], "gpu_wall_s": gN["wall_s"],
+                              "measured_by": "integration/time_program.py --colored (wall clock between the phase's first and last console line)"}
+    print(json.dumps(res))
+    if out_json:
+        json.dump(res, open(out_json, "w"), indent=1)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--colored":     # --colored GENOME_BP HAPLOTYPES SAMPLES [out.json]
+        return main_colored(int(float(sys.argv[2])), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5] if len(sys.argv) > 5 else None)
     genome = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
     n_hap = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     out_json = sys.argv[3] if len(sys.argv) > 3 else None

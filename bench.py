@@ -40,6 +40,36 @@ SEED0 = 20261017               # seed = 20261017 + config index
 SUB_DIVERGENCE = 0.0527        # per-subgenome substitution rate from the root: 10 % between two subgenomes
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: keep this rank's host threads -- and through first touch its pinned staging memory -- on the NUMA node the
+    GPU hangs off (PCI bus id from NVML -> /sys/bus/pci/devices/<id>/numa_node -> that node's cpulist).  Returns a small report, or
+    the reason nothing was done (single-node hosts, containers without sysfs)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # NVML pads the domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return {"bound": False, "why": "the device reports no NUMA node"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"bound": False, "why": f"no allowed CPU on node {node}"}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "node": node, "cpus": len(cpus), "pci": bus}
+    except Exception as e:   # noqa: BLE001
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"}
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -408,6 +438,7 @@ def main():
     ap.add_argument("--no-staged-align", action="store_true",
                     help="e2e leg: send the branches a second time with pf_align instead of aligning the copy the lookup call staged (pf_align_staged)")
     ap.add_argument("--e2e-sweep", default="", help="also time the e2e leg with these host thread counts (T) or T x sub-batches per thread (TxC), e.g. 1,2,4x4")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not bind the rank to the NUMA node of its GPU (A/B runs)")
     ap.add_argument("--e2e-profile", default="", help="diagnostics: write a CUPTI timeline (chrome trace) of two e2e steps to this path")
     ap.add_argument("--e2e-trace", action="store_true", help="diagnostics: blocking time of every call of a single-threaded, single-batch e2e pass")
     ap.add_argument("--e2e-chunks", type=int, default=1, help="sub-batches per host thread and step in the e2e leg")
@@ -435,6 +466,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else {"bound": False, "why": "single process"}
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -811,7 +843,7 @@ def main():
 
     # ---- reduce over ranks (max time, summed work) ----
     sys.stderr.write(f"[rank {rank}] step {ms_step:.2f} ms (lookup {ms_lookup:.2f}, align {ms_align:.2f}, sites {ms_site:.2f}), "
-                     f"e2e {ms_e2e:.2f} ms; tiers {ctx.last_tier_counts} heavy-queued {heavy_q}; setup {t_setup:.1f}s "
+                     f"e2e {ms_e2e:.2f} ms (numa {numa}); tiers {ctx.last_tier_counts} heavy-queued {heavy_q}; setup {t_setup:.1f}s "
                      f"(bubbles {t_bubbles:.1f}s, open {t_open:.1f}s); batch {bb.stats()}\n")
     from ploidyfrost_b200 import shard
     (ms_step, ms_e2e, ms_lookup, ms_align, ms_site), (tot_bubbles, tot_win, tot_cells) = shard.reduce_step(
@@ -880,6 +912,7 @@ def main():
                         "host_threads": T_e2e, "sub_batches_per_step": n_chunks,
                         "ms_per_step_by_host_threads": {str(k_): v for k_, v in e2e_sweep.items()} or None,
                         "single_thread_call_ms": e2e_trace,
+                        "numa": numa,
                         "timed": f"{args.steps} steps in one bracket (barrier + synchronize on both sides), host threads free-running",
                         "ms_per_step_synchronised_alone": e2e_isolated.get((T_e2e, n_chunks)),
                         "calls": ("pf_kmc_cov_async | " + ("pf_align" if (args.no_staged_align or main_route is not None) else "pf_align_staged") + " | pf_site_cov | pf_kmc_wait per sub-batch; one pf_ctx + pf_kmc_share handle per host thread")},

@@ -13,7 +13,10 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -80,9 +83,80 @@ struct CallerFiles {   // what the reference appends to its streams (Appendix D 
     std::vector<unsigned char> called;   // appended per input bubble: 1 = it was aligned and got a VarId
 };
 
+// What SeqAlign::SequenceAlignment hands back for ONE bubble (SeqAlign.hpp:16): the result type of the host aligner a program may
+// give the caller for the bubbles that exceed a device limit (more than 64 co-optimal alignments / candidate MSAs, 64 rows, an
+// alignment beyond the work area; pf_msa_batch_t status != 0) -- inside the reference program that aligner is the reference's own
+// SeqAlign (integration/ploidy_estimation_gpu.cpp).  Without one such a bubble ends the batch with an error, as before.
+struct HostMsa {
+    std::vector<std::string> rows;                          // `str` after the call: aligned rows, or empty
+    std::vector<unsigned> snp_pos, indel_pos, indel_len;
+    std::vector<std::vector<unsigned short>> partition;     // per column
+};
+typedef std::function<void(std::vector<std::string> &str, HostMsa &out)> HostAligner;
+
+// The k-mer every row contributes at variable column c (CDBG.cpp:2338-2388 indel sites, :2433-2472 SNP sites), on the host: used for
+// the few bubbles that went through the host aligner (the device builds them from the aligned rows it holds, pf_site_cov).  false
+// where the reference itself would read outside a row.
+inline bool host_site_kmers(const std::vector<std::string> &rows, size_t c, size_t k, bool is_indel, size_t n_indel_before, std::vector<std::string> &out) {
+    const size_t n = rows.size(), L = rows[0].size();
+    out.assign(n, "");
+    if (is_indel) {
+        std::vector<size_t> cur(n, c);
+        std::vector<std::string> ext(n);
+        for (;;) {                                                   // extend to the right until the rows differ (:2338-2357)
+            std::set<char> chars;
+            for (size_t r = 0; r < n; r++) {
+                while (cur[r] < L && rows[r][cur[r]] == '-') cur[r]++;
+                if (cur[r] >= L) return false;
+                const char ch = rows[r][cur[r]++];
+                ext[r] += ch;
+                chars.insert(ch);
+            }
+            if (chars.size() > 1) break;
+        }
+        for (size_t r = 0; r < n; r++) {
+            const size_t e = ext[r].size();
+            if (e > k) return false;
+            if (n_indel_before == 0) {                               // left-pad from the aligned row itself (:2358-2365)
+                if (c + e < k) return false;
+                out[r] = rows[r].substr(c - k + e, k - e) + ext[r];
+            } else {                                                 // left-pad from the row with its gaps removed (:2366-2388)
+                std::string t;
+                for (size_t x = 0; x < c; x++) if (rows[r][x] != '-') t += rows[r][x];
+                if (t.size() < k - e) {
+                    std::string s = t + ext[r];
+                    for (size_t x = cur[r]; s.size() < k; x++) {
+                        if (x >= L) return false;
+                        if (rows[r][x] != '-') s += rows[r][x];
+                    }
+                    out[r] = s;
+                } else out[r] = t.substr(t.size() - (k - e)) + ext[r];
+            }
+        }
+        return true;
+    }
+    if (n_indel_before > 0) {                                        // SNP site after an indel site (:2433-2465)
+        for (size_t r = 0; r < n; r++) {
+            std::string t;
+            for (size_t x = 0; x <= c; x++) if (rows[r][x] != '-') t += rows[r][x];
+            if (t.size() < k) {
+                for (size_t x = c + 1; t.size() < k; x++) {
+                    if (x >= L) return false;
+                    if (rows[r][x] != '-') t += rows[r][x];
+                }
+                out[r] = t;
+            } else out[r] = t.substr(t.size() - k);
+        }
+        return true;
+    }
+    if (c + 1 < k) return false;
+    for (size_t r = 0; r < n; r++) out[r] = rows[r].substr(c - k + 1, k);   // the k-mer ending at the site (:2469-2472)
+    return true;
+}
+
 struct CallerStats {     // where the time of BubbleCaller::call went (seconds, summed over the calls)
     double lookup_s = 0, gate_s = 0, align_s = 0, site_s = 0, emit_s = 0;
-    size_t calls = 0, bubbles_in = 0, bubbles_aligned = 0;
+    size_t calls = 0, bubbles_in = 0, bubbles_aligned = 0, bubbles_host_aligned = 0;
 };
 
 class BubbleCaller {
@@ -100,6 +174,9 @@ class BubbleCaller {
     void set_thread_dialect(bool multithread) { mt_ = multithread; }
     // host threads that format the rows of a batch (contiguous ranges of its bubbles, joined in order: the text does not depend on it)
     void set_host_threads(unsigned n) { host_threads_ = n ? n : 1; }
+    // the aligner for bubbles beyond a device limit (see HostMsa); PF_CALLER_FORCE_HOST=<n> in the environment sends every n-th aligned
+    // bubble through it as well (tests)
+    void set_host_aligner(HostAligner f) { host_aligner_ = std::move(f); }
 
     // Calls one batch.  `var_id` is the reference's running variant counter (var_count_all; start it at 1 for the `-t 1` files)
     // and advances by one for every bubble whose alignment is not empty.  Returns false where the reference would have ended
@@ -219,15 +296,54 @@ class BubbleCaller {
         pf_site_batch_t sc;
         if (pf_site_cov(db_, lower_, upper_, skip_.data(), &sc) != PF_OK) return fail_batch(pf_last_error());
         lap(stats_.site_s);
-        for (size_t q = 0; q < n_kept; q++)
-            if (m.status[q] != PF_BUBBLE_OK)
-                return fail_batch("bubble " + std::to_string(k_src_[q]) + " of the batch does not fit the device limits (pf_msa_batch_t status " + std::to_string(m.status[q]) +
-                                  ": more than 64 co-optimal alignments / candidate MSAs, 64 rows, or an alignment beyond the work area)");
+        // ---- bubbles beyond a device limit: the host aligner, if the program gave one (HostMsa) ----
+        host_.clear();
+        host_of_.assign(n_kept, -1);
+        {
+            static const unsigned force = std::getenv("PF_CALLER_FORCE_HOST") ? (unsigned)std::atoi(std::getenv("PF_CALLER_FORCE_HOST")) : 0u;
+            for (size_t q = 0; q < n_kept; q++) {
+                const bool over = m.status[q] != PF_BUBBLE_OK;
+                if (!over && !(force && host_aligner_ && q % force == 0)) continue;
+                if (!host_aligner_ || m.status[q] == PF_BUBBLE_BAD_INPUT)
+                    return fail_batch("bubble " + std::to_string(k_src_[q]) + " of the batch does not fit the device limits (pf_msa_batch_t status " + std::to_string(m.status[q]) +
+                                      ": more than 64 co-optimal alignments / candidate MSAs, 64 rows, or an alignment beyond the work area) and no host aligner is set");
+                host_of_[q] = (int)host_.size();
+                host_.emplace_back();
+                if (!host_bubble(fb, q, sc, host_.back())) return fail_batch(err_);
+            }
+            stats_.bubbles_host_aligned += host_.size();
+            if (!host_.empty() && !host_site_lookups()) return fail_batch(err_);
+        }
+        // one view per kept bubble: the device's arrays, or the host aligner's
+        struct View {
+            uint32_t nr, L;
+            const char *rows;
+            size_t n_var, n_ilen;
+            const uint32_t *var_col, *ilen;
+            const uint8_t *var_kind, *site_status;
+            const uint16_t *cls;
+            const uint64_t *site_cov;
+        };
+        auto view_of = [&](size_t q) {
+            View v;
+            if (host_of_[q] >= 0) {
+                const HostBubble &h = host_[(size_t)host_of_[q]];
+                v.nr = h.nr; v.L = h.L; v.rows = h.rows.data(); v.n_var = h.var_col.size(); v.n_ilen = h.ilen.size();
+                v.var_col = h.var_col.data(); v.ilen = h.ilen.data(); v.var_kind = h.var_kind.data(); v.site_status = h.site_status.data();
+                v.cls = h.cls.data(); v.site_cov = h.site_cov.data();
+            } else {
+                v.nr = m.n_rows[q]; v.L = m.aln_len[q]; v.rows = m.rows + m.rows_off[q];
+                v.n_var = (size_t)(m.var_off[q + 1] - m.var_off[q]); v.n_ilen = (size_t)(m.ilen_off[q + 1] - m.ilen_off[q]);
+                v.var_col = m.var_col + m.var_off[q]; v.ilen = m.ilen + m.ilen_off[q]; v.var_kind = m.var_kind + m.var_off[q];
+                v.site_status = sc.status + sc.site_off[q]; v.cls = m.cls + m.cls_off[q]; v.site_cov = sc.cov + sc.cov_off[q];
+            }
+            return v;
+        };
         // ---- ids: the bubbles whose alignment is not empty take consecutive ids in batch order (:2051, :2273) ----
         std::vector<size_t> ids(n_kept, 0);
         size_t next_id = var_id, n_called = 0;
         for (size_t q = 0; q < n_kept; q++) {
-            if (m.n_rows[q] == 0) continue;                                        // str_vec came back empty
+            if (view_of(q).nr == 0) continue;                                      // str_vec came back empty
             ids[q] = next_id++;
             n_called++;
         }
@@ -240,10 +356,11 @@ class BubbleCaller {
                 const bool strict = fb.strict[bi] != 0;
                 const size_t ent_size = (size_t)fb.entrance_size[bi], ex_size = (size_t)fb.exit_size[bi];
                 const double *means = sorted_mean_.data() + k_first_[q];
-                const uint32_t nr = m.n_rows[q], L = m.aln_len[q];
+                const View vw = view_of(q);
+                const uint32_t nr = vw.nr, L = vw.L;
                 if (nr == 0) continue;
                 const size_t var_count = ids[q];
-                const char *rows = m.rows + m.rows_off[q];
+                const char *rows = vw.rows;
                 char head[96];
                 const int head_len = std::snprintf(head, sizeof head, "%zu\t%d\t%u\t%u\t", var_count, strict ? 1 : 0, fb.entrance_id[bi], fb.exit_id[bi]);
                 for (uint32_t r = 0; r < nr; r++) {
@@ -251,17 +368,16 @@ class BubbleCaller {
                     to.alignseq.append(rows + (size_t)r * L, L);
                     to.alignseq += "\n";
                 }
-                const uint64_t v0 = m.var_off[q], v1 = m.var_off[q + 1];
-                const size_t n_var = (size_t)(v1 - v0);
-                const uint16_t *cls = m.cls + m.cls_off[q];
-                const uint32_t *ilen = m.ilen + m.ilen_off[q];
-                const size_t n_ilen = (size_t)(m.ilen_off[q + 1] - m.ilen_off[q]);
+                const size_t n_var = vw.n_var;
+                const uint16_t *cls = vw.cls;
+                const uint32_t *ilen = vw.ilen;
+                const size_t n_ilen = vw.n_ilen;
                 size_t indel = 0;
                 for (int a = 0; a < 4; a++) grouped_fre[a].clear();
                 for (size_t i = 0; i < n_var; i++) {
-                    const bool is_indel = m.var_kind[v0 + i] == 1;
+                    const bool is_indel = vw.var_kind[i] == 1;
                     size_t var_distance;                                           // :2312-2330
-                    auto gap_to = [&](size_t a, size_t c) { return (size_t)(m.var_col[v0 + c] - m.var_col[v0 + a] - 1); };
+                    auto gap_to = [&](size_t a, size_t c) { return (size_t)(vw.var_col[c] - vw.var_col[a] - 1); };
                     if (i == 0) var_distance = n_var > 1 ? std::min(gap_to(0, 1), ent_size) : std::min(ent_size, ex_size);
                     else if (i == n_var - 1) var_distance = std::min(gap_to(i - 1, i), ex_size);
                     else var_distance = std::min(gap_to(i - 1, i), gap_to(i, i + 1));
@@ -274,7 +390,7 @@ class BubbleCaller {
                         for (uint32_t r = 0; r < nr; r++) tc[cls[i * nr + r] - 1] += means[r];   // :2105-2108
                         sum = k_sum_[q];
                     } else {
-                        const uint8_t st = sc.status[sc.site_off[q] + i];
+                        const uint8_t st = vw.site_status[i];
                         if (st == PF_SITE_DROPPED) continue;                       // :2415-2418
                         if (st == PF_SITE_MISSING) { why = "a site k-mer is not in the database: the reference exits here (CDBG.cpp:54)"; return false; }
                         if (st != PF_SITE_OK) {
@@ -282,7 +398,7 @@ class BubbleCaller {
                                           : "a site k-mer cannot be formed (the reference reads outside the aligned row here)";
                             return false;
                         }
-                        const uint64_t *cv = sc.cov + sc.cov_off[q] + i * nr;
+                        const uint64_t *cv = vw.site_cov + i * nr;
                         for (unsigned c = 0; c < maxnum; c++) { tc[c] = (double)cv[c]; sum += tc[c]; }
                     }
                     cov_info.clear();
@@ -325,7 +441,7 @@ class BubbleCaller {
             if (!ok[t]) return fail_batch(why[t]);
         // ---- commit: only a batch that went through completely changes the caller-visible state ----
         for (size_t q = 0; q < n_kept; q++)
-            if (m.n_rows[q]) out.called[called_base + k_src_[q]] = 1;
+            if (view_of(q).nr) out.called[called_base + k_src_[q]] = 1;
         out.bubbles_called += n_called;
         var_id = next_id;
         for (size_t t = 0; t < T; t++) {
@@ -338,6 +454,96 @@ class BubbleCaller {
     }
 
   private:
+    // a bubble that went through the host aligner, in the layout the rows are written from (one bubble of pf_msa_batch_t / pf_site_batch_t)
+    struct HostBubble {
+        uint32_t nr = 0, L = 0;
+        std::string rows;                       // nr x L
+        std::vector<uint32_t> var_col, ilen;
+        std::vector<uint8_t> var_kind, site_status;
+        std::vector<uint16_t> cls;              // [var][row]
+        std::vector<uint64_t> site_cov;         // [var][row], the first n_class entries are the class coverages
+        std::vector<size_t> kmer_first;         // per variable column: first entry in site_kmers_ / site_class_ (branching bubbles)
+        bool strict = false;
+    };
+    // SeqAlign::SequenceAlignment of kept bubble q on the host (the order of its branches is the alignment batch's)
+    bool host_bubble(const FlatBatch &fb, size_t q, const pf_site_batch_t &, HostBubble &h) {
+        std::vector<std::string> str;
+        for (uint32_t s = k_first_[q]; s < k_first_[q + 1]; s++) {
+            const size_t src = sorted_seq_[s];
+            str.emplace_back(fb.bases.data() + fb.seq_off[src], (size_t)(fb.seq_off[src + 1] - fb.seq_off[src]));
+        }
+        HostMsa r;
+        host_aligner_(str, r);
+        h.strict = fb.strict[k_src_[q]] != 0;
+        h.nr = (uint32_t)r.rows.size();
+        if (h.nr == 0) return true;
+        h.L = (uint32_t)r.rows[0].size();
+        for (const std::string &row : r.rows) {
+            if (row.size() != h.L) return fail("the host aligner returned rows of different lengths");
+            h.rows += row;
+        }
+        for (size_t c = 0; c < r.partition.size(); c++) {                          // the variable columns (:2070-2076)
+            if (r.partition[c].empty() || r.partition[c].back() == 0) continue;
+            if (r.partition[c].size() != h.nr) return fail("the host aligner returned a partition column of the wrong height");
+            h.var_col.push_back((uint32_t)c);
+            h.var_kind.push_back(std::find(r.indel_pos.begin(), r.indel_pos.end(), (unsigned)c) != r.indel_pos.end() ? 1 : 0);
+            for (unsigned short x : r.partition[c]) h.cls.push_back(x);
+        }
+        h.ilen.assign(r.indel_len.begin(), r.indel_len.end());
+        h.site_status.assign(h.var_col.size(), PF_SITE_SKIPPED);
+        h.site_cov.assign(h.var_col.size() * h.nr, 0);
+        h.kmer_first.assign(h.var_col.size() + 1, site_kmers_.size());
+        if (h.strict) return true;
+        // lookup phase B of a branching bubble: distinct k-mers per class in std::set order (:2393-2396)
+        if (k_ == 0) {
+            pf_kmc_info_t info;
+            if (pf_kmc_info(db_, &info) != PF_OK) return fail(pf_last_error());
+            k_ = info.kmer_length;
+        }
+        std::vector<std::string> rows(r.rows), km;
+        size_t n_indel = 0;
+        for (size_t i = 0; i < h.var_col.size(); i++) {
+            const bool is_indel = h.var_kind[i] == 1;
+            const bool formed = host_site_kmers(rows, h.var_col[i], k_, is_indel, n_indel, km);
+            if (is_indel) n_indel++;
+            h.kmer_first[i] = site_kmers_.size();
+            if (!formed) { h.site_status[i] = PF_SITE_UNDEFINED; continue; }
+            h.site_status[i] = PF_SITE_OK;
+            unsigned maxnum = 0;
+            for (uint32_t rr = 0; rr < h.nr; rr++) maxnum = std::max<unsigned>(maxnum, h.cls[i * h.nr + rr]);
+            std::vector<std::set<std::string>> sets(maxnum);
+            for (uint32_t rr = 0; rr < h.nr; rr++) sets[h.cls[i * h.nr + rr] - 1].insert(km[rr]);
+            for (unsigned c = 0; c < maxnum; c++)
+                for (const std::string &x : sets[c]) { site_kmers_ += x; site_class_.push_back(c); }
+        }
+        h.kmer_first[h.var_col.size()] = site_kmers_.size();
+        return true;
+    }
+    // one lookup call for the site k-mers of all host-aligned bubbles of the batch, then readCov(s, lower, upper)'s rule per site in the
+    // reference's iteration order: a missing k-mer ends the program (:52-56), a counter outside (lower, upper) drops the site (:2415-2418)
+    bool host_site_lookups() {
+        const size_t n = site_class_.size();
+        if (n) {
+            std::vector<uint64_t> off(n + 1);
+            for (size_t i = 0; i <= n; i++) off[i] = i * k_;
+            std::vector<pf_cov_t> cv(n);
+            if (pf_kmc_cov(db_, site_kmers_.data(), off.data(), (uint32_t)n, PF_LOOKUP_FWD_THEN_RC, 0, 0xFFFFFFFFu, cv.data()) != PF_OK) return fail(pf_last_error());
+            for (HostBubble &h : host_) {
+                if (h.strict) continue;
+                for (size_t i = 0; i < h.var_col.size(); i++) {
+                    if (h.site_status[i] != PF_SITE_OK) continue;
+                    for (size_t e = h.kmer_first[i] / k_; e < h.kmer_first[i + 1] / k_; e++) {
+                        if (cv[e].first_missing >= 0) { h.site_status[i] = PF_SITE_MISSING; break; }
+                        const uint64_t cnt = cv[e].sum;
+                        if (!(cnt > lower_ && cnt < upper_)) { h.site_status[i] = PF_SITE_DROPPED; break; }
+                        h.site_cov[i * h.nr + site_class_[e]] += cnt;
+                    }
+                }
+            }
+        }
+        site_kmers_.clear(); site_class_.clear();
+        return true;
+    }
     static void put_double(std::string &to, double v) {
         char buf[40];
         to.append(buf, (size_t)std::snprintf(buf, sizeof buf, "%g", v));
@@ -357,6 +563,12 @@ class BubbleCaller {
         }
     }
     CallerStats stats_;
+    HostAligner host_aligner_;
+    std::vector<HostBubble> host_;
+    std::vector<int> host_of_;
+    std::string site_kmers_;
+    std::vector<unsigned> site_class_;
+    unsigned k_ = 0;
     const std::vector<std::string> *explicit_keys_ = nullptr;
     std::vector<pf_cov_t> cov_;
     std::vector<uint32_t> k_src_, k_first_, sorted_seq_;

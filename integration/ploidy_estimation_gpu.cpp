@@ -39,6 +39,7 @@
 #include <vector>
 
 #include "CDBG.hpp"        // the reference's class (Bifrost graph, MyUnitig marks)
+#include "SeqAlign.hpp"    // the reference's own aligner: takes the bubbles that exceed a device limit
 #include "pf_caller.hpp"   // ours
 
 using namespace std;
@@ -293,6 +294,16 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
     pfdropin::BubbleCaller caller(ctx, db, match, mismatch, gap, (unsigned)lower, (unsigned)upper);
     caller.set_thread_dialect(thread_dialect);
     caller.set_host_threads(T);
+    // a bubble beyond the device limits (more than 64 co-optimal alignments / candidate MSAs, 64 rows) is aligned by the reference's
+    // own SeqAlign, as the reference would have done (CDBG.cpp:2036-2050); everything else about it still goes through the batch
+    {
+        double m_ = match, d_ = mismatch, g_ = gap;
+        caller.set_host_aligner([m_, d_, g_](std::vector<std::string> &str, pfdropin::HostMsa &out) mutable {
+            SeqAlign seqalign(m_, d_, g_);
+            seqalign.SequenceAlignment(str, out.snp_pos, out.indel_pos, out.partition, out.indel_len);
+            out.rows = str;
+        });
+    }
     pfdropin::CallerFiles files;
     size_t var_id = thread_dialect ? 0 : 1;
     size_t coreNum = 0, coreCov = 0, n_bubbles = 0;
@@ -380,7 +391,8 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
         const pfdropin::CallerStats &cs = caller.stats();
         cout << "CDBG::PloidyEstimation():  GPU path, device thread : entrance readCov " << t_entrance << "s, BubbleCaller::call " << t_call << "s (branch readCov "
              << cs.lookup_s << ", gate + order " << cs.gate_s << ", pf_align " << cs.align_s << ", pf_site_cov " << cs.site_s << ", rows " << cs.emit_s
-             << "; " << cs.bubbles_aligned << " of " << cs.bubbles_in << " bubbles aligned in " << cs.calls << " batches), coverage + files " << t_write << "s" << endl;
+             << "; " << cs.bubbles_aligned << " of " << cs.bubbles_in << " bubbles aligned in " << cs.calls << " batches, " << cs.bubbles_host_aligned
+             << " by the host aligner), coverage + files " << t_write << "s" << endl;
     }
     cout << "CDBG::PloidyEstimation(): Alleles in SuperBubbles  :\t"
          << "2 :" << files.alleles[0] << "\t" << "3 :" << files.alleles[1] << "\t" << "4 :" << files.alleles[2] << "\t" << "5 :" << files.alleles[3] << endl;

@@ -243,6 +243,14 @@ def test_bound_reference_binary_walk_and_host_logic(tmp_path, kw):
     def closing(text):
         return [ln for ln in text.split("\n") if "Alleles in SuperBubbles" in ln or "Average Coverage" in ln]
     assert closing(r.stdout) == closing(ref_stdout) and len(closing(r.stdout)) == 2
+    # bubbles beyond a device limit go through the host aligner (the reference's own SeqAlign in this binary) and the host-built site
+    # k-mers of include/pf_caller.hpp: force every other aligned bubble down that path -- same bytes
+    r2 = subprocess.run([hc] + cmd, cwd=run_dir, capture_output=True, text=True, env=dict(os.environ, PF_CALLER_FORCE_HOST="2"))
+    assert r2.returncode == 0, r2.stdout[-2000:] + r2.stderr[-2000:]
+    m = [ln for ln in r2.stdout.split("\n") if "by the host aligner" in ln]
+    assert m and " 0 by the host aligner" not in m[0]
+    for n in names:
+        assert filecmp.cmp(os.path.join(out, n), run_dir / "PloidyFrost_output" / n, shallow=False), n + " (host aligner path)"
     # -t 4: the reference's worker threads against the binding's single pass, as multisets (ids and order are schedule-dependent)
     cmd[5] = "4"
     subprocess.run([e2e_rows.reference_binaries()[0]] + cmd, cwd=ref_dir, check=True, capture_output=True)

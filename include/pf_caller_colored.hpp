@@ -67,6 +67,9 @@ class ColoredBubbleCaller {
     const CallerStats &stats() const { return stats_; }
     void set_thread_dialect(bool multithread) { mt_ = multithread; }
     void set_host_threads(unsigned n) { host_threads_ = n ? n : 1; }
+    // the aligner for bubbles beyond a device limit (HostMsa, pf_caller.hpp): inside the reference program the reference's own SeqAlign;
+    // PF_CALLER_FORCE_HOST=<n> sends every n-th aligned bubble through it as well (tests)
+    void set_host_aligner(HostAligner f) { host_aligner_ = std::move(f); }
     // sum of (size_t)core.first over the called bubbles and their number -- "Sites' Average Coverage" (:1441)
     size_t core_cov() const { return core_cov_; }
     size_t core_num() const { return core_num_; }
@@ -187,32 +190,105 @@ class ColoredBubbleCaller {
         pf_msa_batch_t m;
         if (pf_align(ctx_, M_, D_, G_, abases_.data(), aoff_.data(), boff_.data(), (uint32_t)n_kept, &m) != PF_OK) return fail_batch(pf_last_error());
         lap(stats_.align_s);
-        for (size_t q = 0; q < n_kept; q++)
-            if (m.status[q] != PF_BUBBLE_OK)
-                return fail_batch("bubble " + std::to_string(k_src_[q]) + " of the batch does not fit the device limits (pf_msa_batch_t status " + std::to_string(m.status[q]) + ")");
         pf_site_kmers_t sk;
         if (pf_site_kmers(ctx_, k_, skip_.data(), &sk) != PF_OK) return fail_batch(pf_last_error());
+        // ---- bubbles beyond a device limit: the host aligner, if the program gave one ----
+        host_.clear();
+        host_of_.assign(n_kept, -1);
+        {
+            static const unsigned force = std::getenv("PF_CALLER_FORCE_HOST") ? (unsigned)std::atoi(std::getenv("PF_CALLER_FORCE_HOST")) : 0u;
+            std::vector<std::string> str, km;
+            for (size_t q = 0; q < n_kept; q++) {
+                const bool over = m.status[q] != PF_BUBBLE_OK;
+                if (!over && !(force && host_aligner_ && q % force == 0)) continue;
+                if (!host_aligner_ || m.status[q] == PF_BUBBLE_BAD_INPUT)
+                    return fail_batch("bubble " + std::to_string(k_src_[q]) + " of the batch does not fit the device limits (pf_msa_batch_t status " + std::to_string(m.status[q]) +
+                                      ") and no host aligner is set");
+                host_of_[q] = (int)host_.size();
+                host_.emplace_back();
+                HostBubble &h = host_.back();
+                str.clear();
+                for (uint32_t s = k_first_[q]; s < k_first_[q + 1]; s++) str.emplace_back(seq_ptr(sorted_seq_[s]), seq_len(sorted_seq_[s]));
+                HostMsa r;
+                host_aligner_(str, r);
+                h.nr = (uint32_t)r.rows.size();
+                if (h.nr == 0) continue;
+                h.L = (uint32_t)r.rows[0].size();
+                for (const std::string &row : r.rows) h.rows += row;
+                for (size_t c = 0; c < r.partition.size(); c++) {
+                    if (r.partition[c].empty() || r.partition[c].back() == 0) continue;
+                    h.var_col.push_back((uint32_t)c);
+                    h.var_kind.push_back(std::find(r.indel_pos.begin(), r.indel_pos.end(), (unsigned)c) != r.indel_pos.end() ? 1 : 0);
+                    for (unsigned short x : r.partition[c]) h.cls.push_back(x);
+                }
+                h.ilen.assign(r.indel_len.begin(), r.indel_len.end());
+                h.site_status.assign(h.var_col.size(), PF_SITE_SKIPPED);
+                h.keys.assign(h.var_col.size() * h.nr, 0);
+                if (skip_[q]) continue;
+                size_t n_indel = 0;                                            // the site k-mers of a branching bubble, on the host
+                for (size_t i = 0; i < h.var_col.size(); i++) {
+                    const bool is_indel = h.var_kind[i] == 1;
+                    const bool formed = host_site_kmers(r.rows, h.var_col[i], k_, is_indel, n_indel, km);
+                    if (is_indel) n_indel++;
+                    h.site_status[i] = formed ? PF_SITE_OK : PF_SITE_UNDEFINED;
+                    if (!formed) continue;
+                    for (uint32_t rr = 0; rr < h.nr; rr++) {
+                        uint64_t key = 0;
+                        for (char ch : km[rr]) key = key << 2 | (uint64_t)(ch == 'A' || ch == 'a' ? 0 : ch == 'C' || ch == 'c' ? 1 : ch == 'G' || ch == 'g' ? 2 : 3);
+                        h.keys[i * h.nr + rr] = key;
+                    }
+                }
+            }
+            stats_.bubbles_host_aligned += host_.size();
+        }
+        // one view per kept bubble: the device's arrays, or the host aligner's
+        struct View {
+            uint32_t nr, L;
+            const char *rows;
+            size_t n_var, n_ilen;
+            const uint32_t *var_col, *ilen;
+            const uint8_t *var_kind, *site_status;
+            const uint16_t *cls;
+            const uint64_t *keys;
+        };
+        auto view_of = [&](size_t q) {
+            View v;
+            if (host_of_[q] >= 0) {
+                const HostBubble &h = host_[(size_t)host_of_[q]];
+                v.nr = h.nr; v.L = h.L; v.rows = h.rows.data(); v.n_var = h.var_col.size(); v.n_ilen = h.ilen.size();
+                v.var_col = h.var_col.data(); v.ilen = h.ilen.data(); v.var_kind = h.var_kind.data(); v.site_status = h.site_status.data();
+                v.cls = h.cls.data(); v.keys = h.keys.data();
+            } else {
+                v.nr = m.n_rows[q]; v.L = m.aln_len[q]; v.rows = m.rows + m.rows_off[q];
+                v.n_var = (size_t)(m.var_off[q + 1] - m.var_off[q]); v.n_ilen = (size_t)(m.ilen_off[q + 1] - m.ilen_off[q]);
+                v.var_col = m.var_col + m.var_off[q]; v.ilen = m.ilen + m.ilen_off[q]; v.var_kind = m.var_kind + m.var_off[q];
+                v.site_status = sk.status + sk.site_off[q]; v.cls = m.cls + m.cls_off[q]; v.keys = sk.keys + sk.key_off[q];
+            }
+            return v;
+        };
 
         // ---- lookup-B: distinct k-mers per (site, class) in std::set order, their colours from the graph, readCov per colour ----
-        // site_first_[v] .. site_first_[v+1]: entries of skey_ / sclass_ / smask_ of variable column v (batch-wide column index)
-        const uint64_t n_cols = m.var_off[n_kept];
+        // site_first_[col_first_[q] + i] ..: entries of skey_ / sclass_ / smask_ of variable column i of kept bubble q
+        col_first_.assign(n_kept + 1, 0);
+        for (size_t q = 0; q < n_kept; q++) col_first_[q + 1] = col_first_[q] + view_of(q).n_var;
+        const uint64_t n_cols = col_first_[n_kept];
         site_first_.assign(n_cols + 1, 0); skey_.clear(); sclass_.clear();
         {
             std::vector<std::pair<uint32_t, uint64_t>> tmp;
             for (size_t q = 0; q < n_kept; q++) {
-                const uint32_t nr = m.n_rows[q];
-                const uint64_t v0 = m.var_off[q], v1 = m.var_off[q + 1];
-                for (uint64_t v = v0; v < v1; v++) {
-                    if (!skip_[q] && nr && sk.status[v] == PF_SITE_OK) {
-                        const uint16_t *cls = m.cls + m.cls_off[q] + (v - v0) * nr;
-                        const uint64_t *keys = sk.keys + sk.key_off[q] + (v - v0) * nr;
+                const View vw = view_of(q);
+                const uint32_t nr = vw.nr;
+                for (size_t i = 0; i < vw.n_var; i++) {
+                    if (!skip_[q] && nr && vw.site_status[i] == PF_SITE_OK) {
+                        const uint16_t *cls = vw.cls + i * nr;
+                        const uint64_t *keys = vw.keys + i * nr;
                         tmp.clear();
                         for (uint32_t r = 0; r < nr; r++) tmp.push_back(std::make_pair((uint32_t)(cls[r] - 1), keys[r]));
                         std::sort(tmp.begin(), tmp.end());                           // class ascending, then k-mer ascending == set<string> order
                         tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
                         for (const auto &e : tmp) { sclass_.push_back(e.first); skey_.push_back(e.second); }
                     }
-                    site_first_[v + 1] = skey_.size();
+                    site_first_[col_first_[q] + i + 1] = skey_.size();
                 }
             }
         }
@@ -257,7 +333,7 @@ class ColoredBubbleCaller {
         std::vector<size_t> ids(n_kept, 0);
         size_t next_id = var_id, n_called = 0;
         for (size_t q = 0; q < n_kept; q++) {
-            if (m.n_rows[q] == 0) continue;
+            if (view_of(q).nr == 0) continue;
             ids[q] = next_id++;
             n_called++;
         }
@@ -273,7 +349,8 @@ class ColoredBubbleCaller {
             const size_t bi = k_src_[q];
             const bool strict = fb.strict[bi] != 0;
             const size_t ent_size = (size_t)fb.entrance_size[bi], ex_size = (size_t)fb.exit_size[bi];
-            const uint32_t nr = m.n_rows[q], L = m.aln_len[q];
+            const View vw = view_of(q);
+            const uint32_t nr = vw.nr, L = vw.L;
             if (nr == 0) continue;
             {   // core: the entrance's mean coverage summed over the colours up to the first one that fails (:656-666)
                 double core = 0;
@@ -281,7 +358,7 @@ class ColoredBubbleCaller {
                 core_cov += (size_t)core; core_num++;
             }
             const size_t var_count = ids[q];
-            const char *rows = m.rows + m.rows_off[q];
+            const char *rows = vw.rows;
             char head[96];
             const int head_len = std::snprintf(head, sizeof head, "%zu\t%d\t%u\t%u\t", var_count, strict ? 1 : 0, fb.entrance_id[bi], fb.exit_id[bi]);
             for (uint32_t r = 0; r < nr; r++) {
@@ -289,11 +366,11 @@ class ColoredBubbleCaller {
                 part.alignseq.append(rows + (size_t)r * L, L);
                 part.alignseq += "\n";
             }
-            const uint64_t v0 = m.var_off[q], v1 = m.var_off[q + 1];
-            const size_t n_var = (size_t)(v1 - v0);
-            const uint16_t *cls = m.cls + m.cls_off[q];
-            const uint32_t *ilen = m.ilen + m.ilen_off[q];
-            const size_t n_ilen = (size_t)(m.ilen_off[q + 1] - m.ilen_off[q]);
+            const uint64_t v0 = col_first_[q];
+            const size_t n_var = vw.n_var;
+            const uint16_t *cls = vw.cls;
+            const uint32_t *ilen = vw.ilen;
+            const size_t n_ilen = vw.n_ilen;
             size_t indel = 0;
             for (int a = 0; a < 4; a++) grouped_fre[a].clear();
             double strict_coef = 0;
@@ -308,9 +385,9 @@ class ColoredBubbleCaller {
                 strict_coef = max_cramer(cov_vec);
             }
             for (size_t i = 0; i < n_var; i++) {
-                const bool is_indel = m.var_kind[v0 + i] == 1;
+                const bool is_indel = vw.var_kind[i] == 1;
                 size_t var_distance;                                               // :805-824
-                auto gap_to = [&](size_t a, size_t c) { return (size_t)(m.var_col[v0 + c] - m.var_col[v0 + a] - 1); };
+                auto gap_to = [&](size_t a, size_t c) { return (size_t)(vw.var_col[c] - vw.var_col[a] - 1); };
                 if (i == 0) var_distance = n_var > 1 ? std::min(gap_to(0, 1), ent_size) : std::min(ent_size, ex_size);
                 else if (i == n_var - 1) var_distance = std::min(gap_to(i - 1, i), ex_size);
                 else var_distance = std::min(gap_to(i - 1, i), gap_to(i, i + 1));
@@ -320,7 +397,7 @@ class ColoredBubbleCaller {
                 const uint32_t il = is_indel ? (indel - 1 < n_ilen ? ilen[indel - 1] : 0u) : 0u;
                 double coef = strict_coef;
                 if (!strict) {
-                    const uint8_t st = sk.status[v0 + i];
+                    const uint8_t st = vw.site_status[i];
                     if (st != PF_SITE_OK) {
                         why = nr > 16 ? "a branching bubble with more than 16 aligned rows: beyond pf_site_kmers' per-site row limit"
                                       : "a site k-mer cannot be formed (the reference reads outside the aligned row here)";
@@ -380,7 +457,7 @@ class ColoredBubbleCaller {
         }
         // ---- commit ----
         for (size_t q = 0; q < n_kept; q++)
-            if (m.n_rows[q]) out.called[called_base + k_src_[q]] = 1;
+            if (view_of(q).nr) out.called[called_base + k_src_[q]] = 1;
         out.bubbles_called += n_called;
         var_id = next_id;
         core_cov_ += core_cov; core_num_ += core_num;
@@ -437,6 +514,18 @@ class ColoredBubbleCaller {
             key[i] = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c;
         }
     }
+    struct HostBubble {      // a bubble that went through the host aligner, in the layout the rows are written from
+        uint32_t nr = 0, L = 0;
+        std::string rows;
+        std::vector<uint32_t> var_col, ilen;
+        std::vector<uint8_t> var_kind, site_status;
+        std::vector<uint16_t> cls;
+        std::vector<uint64_t> keys;
+    };
+    HostAligner host_aligner_;
+    std::vector<HostBubble> host_;
+    std::vector<int> host_of_;
+    std::vector<uint64_t> col_first_;
     pf_ctx *ctx_;
     std::vector<pf_kmc *> dbs_;
     double M_, D_, G_;

@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "CCDBG.hpp"               // the reference's class (Bifrost coloured graph, MyUnitig marks)
+#include "SeqAlign.hpp"            // the reference's own aligner: takes the bubbles that exceed a device limit
 #include "pf_caller_colored.hpp"   // ours
 
 using namespace std;
@@ -269,6 +270,14 @@ void CCDBG::ploidyEstimation_ptr(const string &outpre, const vector<pair<int, in
         });
     caller.set_thread_dialect(thread_dialect);
     caller.set_host_threads(T);
+    {   // bubbles beyond the device limits: the reference's own SeqAlign (CCDBG.cpp:741-753), everything else still batched
+        double m_ = match, d_ = mismatch, g_ = gap;
+        caller.set_host_aligner([m_, d_, g_](std::vector<std::string> &str, pfdropin::HostMsa &out) mutable {
+            SeqAlign seqalign(m_, d_, g_);
+            seqalign.SequenceAlignment(str, out.snp_pos, out.indel_pos, out.partition, out.indel_len);
+            out.rows = str;
+        });
+    }
     pfdropin::CallerFiles files;
     size_t var_id = thread_dialect ? 0 : 1;
     size_t n_bubbles = 0;
@@ -332,7 +341,7 @@ void CCDBG::ploidyEstimation_ptr(const string &outpre, const vector<pair<int, in
         cout << "CCDBG::PloidyEstimation():  GPU path : " << n_bubbles << " bubbles, " << n_colors << " colours, " << T << " host threads, phase " << seconds_since(t_begin)
              << "s = collecting " << t_collect << "s, waiting for the device " << t_device_wait << "s; device thread " << t_call << "s (readCovUni " << cs.lookup_s
              << ", gate + order " << cs.gate_s << ", pf_align " << cs.align_s << ", site k-mers + colours + readCov " << cs.site_s << ", rows " << cs.emit_s << "; "
-             << cs.bubbles_aligned << " of " << cs.bubbles_in << " bubbles aligned in " << cs.calls << " batches)" << endl;
+             << cs.bubbles_aligned << " of " << cs.bubbles_in << " bubbles aligned in " << cs.calls << " batches, " << cs.bubbles_host_aligned << " by the host aligner)" << endl;
     }
     cout << "CCDBG::PloidyEstimation(): Alleles in SuperBubbles  :\t"
          << "2 :" << files.alleles[0] << "\t" << "3 :" << files.alleles[1] << "\t" << "4 :" << files.alleles[2] << "\t" << "5 :" << files.alleles[3] << endl;

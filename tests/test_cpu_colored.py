@@ -46,6 +46,15 @@ def test_colored_binding_t1_files_identical(colored_inputs, tmp_path):
     for n in names:
         assert filecmp.cmp(os.path.join(want, n), os.path.join(got, n), shallow=False), f"{n} differs from the unmodified reference's file"
     assert os.path.getsize(os.path.join(got, "P_bicov.txt")) > 3000
+    # bubbles beyond a device limit go through the host aligner (the reference's own SeqAlign in this binary) and host-built site
+    # k-mers: force every other aligned bubble down that path -- same bytes
+    hc2 = str(tmp_path / "hc2")
+    link_inputs(colored_inputs, hc2)
+    r2 = subprocess.run([HOSTCHECK] + ARGS + ["-t", "1"], cwd=hc2, capture_output=True, text=True, env=dict(os.environ, PF_CALLER_FORCE_HOST="2"))
+    assert r2.returncode == 0, r2.stdout[-2000:] + r2.stderr[-2000:]
+    assert "by the host aligner" in r2.stdout and " 0 by the host aligner" not in r2.stdout
+    for n in names:
+        assert filecmp.cmp(os.path.join(want, n), os.path.join(hc2, "PloidyFrost_output", n), shallow=False), f"{n} differs (host aligner path)"
     # the average entrance coverage line of the console (CCDBG.cpp:1441) is part of the contract too
     ref = subprocess.run([e2e_rows.reference_binaries()[0]] + ARGS + ["-t", "1"], cwd=colored_inputs, capture_output=True, text=True)
     line = [ln for ln in ref.stdout.splitlines() if "Average Coverage" in ln]

@@ -39,6 +39,12 @@ def test_colored_binary_t1_files_identical(tmp_path, kw):
     for n in names:
         assert filecmp.cmp(os.path.join(want, n), os.path.join(got, n), shallow=False), f"{n} differs from the unmodified reference's file"
     assert os.path.getsize(os.path.join(got, "P_bicov.txt")) > 5000
+    if kw["n_samples"] == 3:   # the host aligner path (bubbles beyond a device limit), forced for every other aligned bubble
+        r = subprocess.run([GPU_BIN] + ARGS + ["-t", "1"], cwd=gpu, capture_output=True, text=True, env=dict(os.environ, PF_CALLER_FORCE_HOST="2"))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "by the host aligner" in r.stdout and " 0 by the host aligner" not in r.stdout
+        for n in names:
+            assert filecmp.cmp(os.path.join(want, n), os.path.join(got, n), shallow=False), f"{n} differs (host aligner path)"
 
 
 def test_colored_binary_thread_dialect(tmp_path):

@@ -38,6 +38,15 @@ def test_patched_reference_binary_writes_identical_files(tmp_path, hap, genome, 
     for n in names:
         assert filecmp.cmp(os.path.join(out, n), got / n, shallow=False), f"{n} differs from the unmodified reference's file"
     assert os.path.getsize(got / "P_bicov.txt") > 10000
+    if hap == 4 and low == 2:
+        # bubbles beyond a device limit are aligned by the reference's own SeqAlign inside this binary and their site k-mers are
+        # built on the host (include/pf_caller.hpp, HostMsa): every third aligned bubble forced down that path -- same bytes
+        r = subprocess.run([GPU_BIN, "-g", "dbg.gfa", "-d", "db", "-t", "1", "-l", str(low), "-u", str(up), "-o", "P"], cwd=gpu_dir,
+                           capture_output=True, text=True, env=dict(os.environ, PF_CALLER_FORCE_HOST="3"))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "by the host aligner" in r.stdout and " 0 by the host aligner" not in r.stdout
+        for n in names:
+            assert filecmp.cmp(os.path.join(out, n), got / n, shallow=False), f"{n} differs (host aligner path)"
 
 
 def test_patched_reference_binary_thread_dialect(tmp_path):

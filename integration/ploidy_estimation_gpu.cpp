@@ -83,7 +83,33 @@ struct DeviceWarmup {
 
     void open_now(const string &prefix) {
         if (pf_init(0, &ctx) != PF_OK) { error = pf_last_error(); ctx = nullptr; return; }
-        if (pf_kmc_open(ctx, prefix.c_str(), &db) != PF_OK) { error = pf_last_error(); db = nullptr; }
+        if (pf_kmc_open(ctx, prefix.c_str(), &db) != PF_OK) { error = pf_last_error(); db = nullptr; return; }
+        warm_kernels();
+    }
+    // CUDA loads a kernel's code at its first launch and the library creates its streams and attributes at first use: a dummy batch with
+    // one two-branch bubble per size class goes through the three calls here, on the warm-up thread, so that none of it lands in
+    // the estimation phase.  Results are discarded (the made-up k-mers are simply not in the database).
+    void warm_kernels() {
+        static const int lens[] = {40, 90, 120, 180, 250, 300};
+        string bases;
+        vector<uint64_t> off{0};
+        vector<uint32_t> boff{0};
+        unsigned x = 12345;
+        for (int L : lens) {
+            string a;
+            for (int i = 0; i < L; i++) { x = x * 1664525u + 1013904223u; a += "ACGT"[(x >> 24) & 3]; }
+            string b = a;
+            b[L / 2] = b[L / 2] == 'A' ? 'C' : 'A';
+            bases += a; off.push_back(bases.size());
+            bases += b; off.push_back(bases.size());
+            boff.push_back((uint32_t)(off.size() - 1));
+        }
+        vector<pf_cov_t> cov(off.size() - 1);
+        pf_msa_batch_t m;
+        pf_site_batch_t sc;
+        pf_kmc_cov(db, bases.data(), off.data(), (uint32_t)cov.size(), PF_LOOKUP_FWD_THEN_RC, 0, 0xFFFFFFFFu, cov.data());
+        if (pf_align(ctx, 2.0, -1.0, -3.0, bases.data(), off.data(), boff.data(), (uint32_t)(boff.size() - 1), &m) == PF_OK)
+            pf_site_cov(db, 0, 0xFFFFFFFFu, nullptr, &sc);
     }
     DeviceWarmup() {
         const string prefix = kmc_prefix_of_this_process();

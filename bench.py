@@ -666,8 +666,8 @@ def main():
             wdb.wait()
         lap("pf_kmc_wait")
         nb = cv.nbytes + sum(v.nbytes for v in m.values() if isinstance(v, np.ndarray))
-        if st is not None:
-            nb += sum(v.nbytes for v in st.values())
+        if st is not None:   # site_off / cov_off are views of the alignment's var_off / cls_off (counted above): they do not cross the bus again
+            nb += sum(v.nbytes for k_, v in st.items() if k_ not in ("site_off", "cov_off"))
         return cv, m, st, nb
 
     def e2e_leg(T_req, C_req=None, profile_path=None):

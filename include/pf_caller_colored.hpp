@@ -339,13 +339,12 @@ class ColoredBubbleCaller {
         }
         // ---- rows ----
         const uint64_t all_colours = C == 64 ? ~0ull : ((1ull << C) - 1);
-        std::string why;
-        CallerFiles part;
+        // contiguous ranges of the kept bubbles, one host thread each, text joined in order (it does not depend on the thread count)
+        auto emit = [&](size_t q0, size_t q1, CallerFiles &part, std::string &why, size_t &core_cov, size_t &core_num) -> bool {
         std::string grouped_fre[4], cov_info, fre_info, tail;
         std::vector<std::vector<double>> cov_vec(C);
         std::vector<double> tc, res;
-        size_t core_cov = 0, core_num = 0;
-        for (size_t q = 0; q < n_kept; q++) {
+        for (size_t q = q0; q < q1; q++) {
             const size_t bi = k_src_[q];
             const bool strict = fb.strict[bi] != 0;
             const size_t ent_size = (size_t)fb.entrance_size[bi], ex_size = (size_t)fb.exit_size[bi];
@@ -401,7 +400,7 @@ class ColoredBubbleCaller {
                     if (st != PF_SITE_OK) {
                         why = nr > 16 ? "a branching bubble with more than 16 aligned rows: beyond pf_site_kmers' per-site row limit"
                                       : "a site k-mer cannot be formed (the reference reads outside the aligned row here)";
-                        return fail_batch(why);
+                        return false;
                     }
                     for (size_t c = 0; c < C; c++) cov_vec[c].assign(maxnum, 0.0);
                     uint64_t seen = 0;
@@ -455,15 +454,33 @@ class ColoredBubbleCaller {
             }
             if (mt_) { part.allele_frequency += grouped_fre[0]; part.allele_frequency += grouped_fre[1]; part.allele_frequency += grouped_fre[2]; }   // :873, :1391
         }
+        return true;
+        };
+        const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads_, n_kept / 64));
+        std::vector<CallerFiles> parts(T);
+        std::vector<std::string> whys(T);
+        std::vector<size_t> cc(T, 0), cn(T, 0);
+        std::vector<char> oks(T, 1);
+        if (T == 1) oks[0] = emit(0, n_kept, parts[0], whys[0], cc[0], cn[0]);
+        else {
+            std::vector<std::thread> workers;
+            for (size_t t = 0; t < T; t++)
+                workers.emplace_back([&, t] { oks[t] = emit(n_kept * t / T, n_kept * (t + 1) / T, parts[t], whys[t], cc[t], cn[t]); });
+            for (std::thread &w : workers) w.join();
+        }
+        for (size_t t = 0; t < T; t++)
+            if (!oks[t]) return fail_batch(whys[t]);
         // ---- commit ----
         for (size_t q = 0; q < n_kept; q++)
             if (view_of(q).nr) out.called[called_base + k_src_[q]] = 1;
         out.bubbles_called += n_called;
         var_id = next_id;
-        core_cov_ += core_cov; core_num_ += core_num;
-        out.alignseq += part.alignseq;
-        out.allele_frequency += part.allele_frequency;
-        for (int a = 0; a < 4; a++) { out.cov[a] += part.cov[a]; out.fre[a] += part.fre[a]; out.alleles[a] += part.alleles[a]; }
+        for (size_t t = 0; t < T; t++) {
+            core_cov_ += cc[t]; core_num_ += cn[t];
+            out.alignseq += parts[t].alignseq;
+            out.allele_frequency += parts[t].allele_frequency;
+            for (int a = 0; a < 4; a++) { out.cov[a] += parts[t].cov[a]; out.fre[a] += parts[t].fre[a]; out.alleles[a] += parts[t].alleles[a]; }
+        }
         lap(stats_.emit_s);
         return true;
     }
@@ -472,7 +489,10 @@ class ColoredBubbleCaller {
     static double cramer_v(const std::vector<double> &A, const std::vector<double> &Bv) {
         double n = 0, nA = 0, nB = 0, chi = 0;
         uint8_t count = 0;
-        std::vector<double> p(A.size(), 0);
+        double p_small[64];
+        std::vector<double> p_big;
+        double *p = p_small;
+        if (A.size() > 64) { p_big.assign(A.size(), 0); p = p_big.data(); }
         for (size_t i = 0; i < A.size(); i++) {
             nA += A[i]; nB += Bv[i];
             p[i] = A[i] + Bv[i];

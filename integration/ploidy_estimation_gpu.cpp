@@ -84,7 +84,7 @@ struct DeviceWarmup {
     void open_now(const string &prefix) {
         if (pf_init(0, &ctx) != PF_OK) { error = pf_last_error(); ctx = nullptr; return; }
         if (pf_kmc_open(ctx, prefix.c_str(), &db) != PF_OK) { error = pf_last_error(); db = nullptr; return; }
-        warm_kernels();
+        if (!getenv("PF_NO_WARM")) warm_kernels();
     }
     // CUDA loads a kernel's code at its first launch and the library creates its streams and attributes at first use: a dummy batch with
     // one two-branch bubble per size class goes through the three calls here, on the warm-up thread, so that none of it lands in
@@ -406,13 +406,15 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
     t_phase = chrono::steady_clock::now();
     if (pending.valid()) pending.get();
     t_device_wait += seconds_since(t_phase);
+    t_phase = chrono::steady_clock::now();
     g_device.release();
+    const double t_release = seconds_since(t_phase);
 
     const time_t end_time = time(NULL);
     cout << "CDBG::PloidyEstimation():  Cpu time : " << (double)(clock() - start_clock) / CLOCKS_PER_SEC << "s" << endl;
     cout << "CDBG::PloidyEstimation():  Real time : " << (double)difftime(end_time, start_time) << "s" << endl;
     cout << "CDBG::PloidyEstimation():  GPU path : " << n_bubbles << " bubbles, " << T << " host threads, phase " << seconds_since(t_begin)
-         << "s = waited for device + database " << t_open << "s, collecting " << t_collect << "s, waiting for the device " << t_device_wait << "s" << endl;
+         << "s = waited for device + database " << t_open << "s, collecting " << t_collect << "s, waiting for the device " << t_device_wait << "s" << ", releasing the device " << t_release << "s" << endl;
     {
         const pfdropin::CallerStats &cs = caller.stats();
         cout << "CDBG::PloidyEstimation():  GPU path, device thread : entrance readCov " << t_entrance << "s, BubbleCaller::call " << t_call << "s (branch readCov "

@@ -75,6 +75,9 @@ def run(binary, cwd, threads, extra_env=None, colored=False):
     if g:
         out.update(bubbles_walked=int(g.group(1)), host_threads=int(g.group(2)), phase_s=float(g.group(3)), open_wait_s=float(g.group(4)),
                    collect_s=float(g.group(5)), device_wait_s=float(g.group(6)))
+    g = re.search(r"releasing the device ([0-9.e+-]+)s", r.stdout)
+    if g:
+        out["release_s"] = float(g.group(1))
     # every section of the reference prints "<name>: Real time"; keep them all (1 s resolution) for the phase split
     m = re.search(r"GPU path, device thread : (.*)", r.stdout)
     if m:

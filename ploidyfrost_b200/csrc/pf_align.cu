@@ -1100,6 +1100,7 @@ struct pf_align_state {
     pf::PinnedBuf h_scalars, h_out[12];
     uint32_t last_retry_count = 0;
     uint32_t last_n = 0;              // bubbles of the last call; its compacted result is still in the buffers below
+    uint32_t host_n = 0;              // != 0: the pinned arena (h_out) holds the offsets of that same call (host-pointer forms)
     uint64_t last_tot[4] = {0, 0, 0, 0};   // rows bytes, variable columns, class entries, indel lengths
     uint32_t last_heavy_queued = 0;   // bubbles the first pass pushed on the heavy queue
     uint64_t last_cells = 0;
@@ -1623,6 +1624,7 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
     st->last_cells = h_tot[4];
     res.tot_rows = h_tot[0]; res.tot_var = h_tot[1]; res.tot_cls = h_tot[2]; res.tot_ilen = h_tot[3];
     st->last_n = n;
+    st->host_n = 0;
     for (int i = 0; i < 4; i++) st->last_tot[i] = h_tot[i];
     if ((rc = st->rows.reserve(res.tot_rows + 16))) return rc;
     if ((rc = st->var_col.reserve(res.tot_var * 4 + 16))) return rc;
@@ -1660,6 +1662,7 @@ static int align_fetch(pf_align_state *st, uint32_t n_bubbles, const DevResult &
         if (bytes[i]) PF_CUDA_TRY(cudaMemcpyAsync(st->h_out[i].p, src[i], bytes[i], cudaMemcpyDeviceToHost, s));
     }
     PF_CUDA_TRY(cudaStreamSynchronize(s));
+    st->host_n = n_bubbles;
     out->n_bubbles = n_bubbles;
     out->status = st->h_out[0].as<int32_t>(); out->n_rows = st->h_out[1].as<uint32_t>(); out->aln_len = st->h_out[2].as<uint32_t>();
     out->rows_off = st->h_out[3].as<uint64_t>(); out->rows = st->h_out[4].as<char>(); out->var_off = st->h_out[5].as<uint64_t>();
@@ -1791,6 +1794,15 @@ int pf_align_last_dev(pf_ctx *ctx, pf_msa_batch_t *out_dev, uint64_t totals[4]) 
     out_dev->cls_off = st->off[2].as<uint64_t>(); out_dev->cls = st->cls.as<uint16_t>();
     out_dev->ilen_off = st->off[3].as<uint64_t>(); out_dev->ilen = st->ilen.as<uint32_t>();
     for (int i = 0; i < 4; i++) totals[i] = st->last_tot[i];
+    return PF_OK;
+}
+
+// internal (pf_kmc.cu: pf_site_cov): var_off / cls_off of the last alignment as they sit in the context's pinned arena -- the site
+// batch's site_off / cov_off are the same numbers, so the host form of pf_site_cov does not copy them a second time
+int pf_align_last_host_offsets(pf_ctx *ctx, uint32_t n, const uint64_t **var_off, const uint64_t **cls_off) {
+    if (!ctx || !ctx->align || ctx->align->host_n != n || !n) return PF_E_INVALID;
+    *var_off = ctx->align->h_out[5].as<uint64_t>();
+    *cls_off = ctx->align->h_out[8].as<uint64_t>();
     return PF_OK;
 }
 

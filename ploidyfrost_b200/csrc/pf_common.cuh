@@ -44,6 +44,8 @@ struct PinnedBuf {
 struct pf_align_state;  // defined in pf_align.cu
 // device pointers + totals {row bytes, variable columns, class entries, indel lengths} of the context's last alignment result
 int pf_align_last_dev(pf_ctx *ctx, pf_msa_batch_t *out_dev, uint64_t totals[4]);
+// var_off / cls_off of that result in the context's pinned arena (host-pointer forms of pf_align only; PF_E_INVALID otherwise)
+int pf_align_last_host_offsets(pf_ctx *ctx, uint32_t n, const uint64_t **var_off, const uint64_t **cls_off);
 
 struct pf_kmc;
 // device copy of the sequences of the handle's last pf_kmc_cov / pf_kmc_cov_async call (zero-based offsets) + the event after which they are there

@@ -1547,16 +1547,20 @@ int pf_site_cov(pf_kmc *db, uint32_t low, uint32_t up, const uint8_t *skip, pf_s
     pf_site_batch_t d;
     if ((rc = pf_site_cov_dev(db, low, up, skip ? db->site_skip.p : nullptr, &d, st))) return rc;
     const uint64_t n1 = (uint64_t)n + 1, n_var = db->site_totals[0], n_cls = db->site_totals[1];
+    // site_off / cov_off ARE var_off / cls_off of the alignment: when that came through a host-pointer call they already sit in the
+    // context's pinned arena (valid until its next pf_align*), and 16 bytes per bubble need not cross the bus a second time
+    const uint64_t *h_var_off = nullptr, *h_cls_off = nullptr;
+    const bool have_off = pf_align_last_host_offsets(ctx, n, &h_var_off, &h_cls_off) == PF_OK;
     const void *src[5] = {d.site_off, d.status, d.n_class, d.cov_off, d.cov};
-    const uint64_t bytes[5] = {n1 * 8, n_var, n_var, n1 * 8, n_cls * 8};
+    const uint64_t bytes[5] = {have_off ? 0 : n1 * 8, n_var, n_var, have_off ? 0 : n1 * 8, n_cls * 8};
     for (int i = 0; i < 5; i++) {
         if ((rc = db->h_site[i].reserve(bytes[i] + 16))) return rc;
         if (bytes[i]) PF_CUDA_TRY(cudaMemcpyAsync(db->h_site[i].p, src[i], bytes[i], cudaMemcpyDeviceToHost, st));
     }
     PF_CUDA_TRY(cudaStreamSynchronize(st));
     out->n_bubbles = n;
-    out->site_off = db->h_site[0].as<uint64_t>(); out->status = db->h_site[1].as<uint8_t>(); out->n_class = db->h_site[2].as<uint8_t>();
-    out->cov_off = db->h_site[3].as<uint64_t>(); out->cov = db->h_site[4].as<uint64_t>();
+    out->site_off = have_off ? h_var_off : db->h_site[0].as<uint64_t>(); out->status = db->h_site[1].as<uint8_t>(); out->n_class = db->h_site[2].as<uint8_t>();
+    out->cov_off = have_off ? h_cls_off : db->h_site[3].as<uint64_t>(); out->cov = db->h_site[4].as<uint64_t>();
     return PF_OK;
 }
 

@@ -665,7 +665,9 @@ def main():
         if main_route is None:
             wdb.wait()
         lap("pf_kmc_wait")
-        nb = cv.nbytes + sum(v.nbytes for v in m.values() if isinstance(v, np.ndarray))
+        # what crossed the bus: every array of the result except the four offset arrays, which the library rebuilds on the host
+        # from the per-bubble counts it copies instead (2 x 4 bytes per bubble)
+        nb = cv.nbytes + sum(v.nbytes for k_, v in m.items() if isinstance(v, np.ndarray) and k_ not in ("rows_off", "var_off", "cls_off", "ilen_off")) + 8 * ch["n"]
         if st is not None:   # site_off / cov_off are views of the alignment's var_off / cls_off (counted above): they do not cross the bus again
             nb += sum(v.nbytes for k_, v in st.items() if k_ not in ("site_off", "cov_off"))
         return cv, m, st, nb

@@ -1034,11 +1034,14 @@ __global__ void reject_dash_kernel(const uint8_t *__restrict__ bases, const uint
 
 // per bubble: sizes of its four variable-length outputs (+ the scalar outputs)
 __global__ void result_size_kernel(const uint64_t *__restrict__ slot_ptr, uint32_t n, int32_t *status, uint32_t *n_rows,
-                                   uint32_t *aln_len, uint64_t *sz_rows, uint64_t *sz_var, uint64_t *sz_cls, uint64_t *sz_ilen) {
+                                   uint32_t *aln_len, uint64_t *sz_rows, uint64_t *sz_var, uint64_t *sz_cls, uint64_t *sz_ilen,
+                                   uint32_t *cnt_var, uint32_t *cnt_ilen) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > n) return;
     if (b == n) { sz_rows[b] = sz_var[b] = sz_cls[b] = sz_ilen[b] = 0; return; }
     const SlotHdr *h = (const SlotHdr *)(uintptr_t)slot_ptr[b];
+    cnt_var[b] = h->n_var;      // what travels to the host instead of the four offset arrays (align_fetch)
+    cnt_ilen[b] = h->n_ilen;
     status[b] = h->status;
     n_rows[b] = h->n_rows;
     aln_len[b] = h->alen;
@@ -1094,8 +1097,9 @@ __global__ void gather_kernel(const GatherArgs g) {
 struct pf_align_state {
     pf::DevBuf ws_warp[3], slots[3], slot_sizes, slot_off, slot_ptr, tier, counter, retry_list, cub_tmp;
     pf::DevBuf keys[2], ids[2];
-    pf::DevBuf status, n_rows, aln_len, sz[4], off[4];
+    pf::DevBuf status, n_rows, aln_len, sz[4], off[4], cnt[2];
     pf::DevBuf rows, var_col, var_kind, cls, ilen;
+    pf::PinnedBuf h_cnt[2];
     pf::DevBuf in_bases, in_seq_off, in_bubble_off;
     pf::PinnedBuf h_scalars, h_out[12];
     uint32_t last_retry_count = 0;
@@ -1607,12 +1611,15 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         if ((rc = st->sz[i].reserve((uint64_t)n1 * 8))) return rc;
         if ((rc = st->off[i].reserve((uint64_t)n1 * 8))) return rc;
     }
+    for (int i = 0; i < 2; i++)
+        if ((rc = st->cnt[i].reserve((uint64_t)n1 * 4))) return rc;
     reject_dash_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_bases, d_seq_off, d_bubble_off, n, st->slot_ptr.as<uint64_t>());
     ctx->launches++;
     result_size_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(st->slot_ptr.as<uint64_t>(), n, st->status.as<int32_t>(),
                                                         st->n_rows.as<uint32_t>(), st->aln_len.as<uint32_t>(),
                                                         st->sz[0].as<uint64_t>(), st->sz[1].as<uint64_t>(),
-                                                        st->sz[2].as<uint64_t>(), st->sz[3].as<uint64_t>());
+                                                        st->sz[2].as<uint64_t>(), st->sz[3].as<uint64_t>(),
+                                                        st->cnt[0].as<uint32_t>(), st->cnt[1].as<uint32_t>());
     ctx->launches++;
     uint64_t *h_tot = st->h_scalars.as<uint64_t>() + 16;
     for (int i = 0; i < 4; i++) {
@@ -1649,19 +1656,42 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
 }  // namespace
 
 
-// device -> pinned host: the compacted arrays of the last align_device call
+// device -> pinned host: the compacted arrays of the last align_device call.  The four offset arrays (8 bytes per bubble each) do not
+// cross the bus: the variable-column and indel-length COUNTS do (4 bytes each), and the offsets are the prefix sums of
+// n_rows * aln_len, n_var, n_var * n_rows and n_ilen, taken on the host.
 static int align_fetch(pf_align_state *st, uint32_t n_bubbles, const DevResult &res, cudaStream_t s, pf_msa_batch_t *out) {
     int rc;
     const uint64_t n1 = (uint64_t)n_bubbles + 1;
-    const void *src[12] = {st->status.p, st->n_rows.p, st->aln_len.p, st->off[0].p, st->rows.p, st->off[1].p,
-                           st->var_col.p, st->var_kind.p, st->off[2].p, st->cls.p, st->off[3].p, st->ilen.p};
+    const void *src[12] = {st->status.p, st->n_rows.p, st->aln_len.p, nullptr, st->rows.p, nullptr,
+                           st->var_col.p, st->var_kind.p, nullptr, st->cls.p, nullptr, st->ilen.p};
     const uint64_t bytes[12] = {(uint64_t)n_bubbles * 4, (uint64_t)n_bubbles * 4, (uint64_t)n_bubbles * 4, n1 * 8, res.tot_rows,
                                 n1 * 8, res.tot_var * 4, res.tot_var, n1 * 8, res.tot_cls * 2, n1 * 8, res.tot_ilen * 4};
     for (int i = 0; i < 12; i++) {
         if ((rc = st->h_out[i].reserve(bytes[i] + 16))) return rc;
-        if (bytes[i]) PF_CUDA_TRY(cudaMemcpyAsync(st->h_out[i].p, src[i], bytes[i], cudaMemcpyDeviceToHost, s));
+        if (bytes[i] && src[i]) PF_CUDA_TRY(cudaMemcpyAsync(st->h_out[i].p, src[i], bytes[i], cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < 2; i++) {
+        if ((rc = st->h_cnt[i].reserve((uint64_t)n_bubbles * 4 + 16))) return rc;
+        PF_CUDA_TRY(cudaMemcpyAsync(st->h_cnt[i].p, st->cnt[i].p, (uint64_t)n_bubbles * 4, cudaMemcpyDeviceToHost, s));
     }
     PF_CUDA_TRY(cudaStreamSynchronize(s));
+    {
+        const uint32_t *nr = st->h_out[1].as<uint32_t>(), *al = st->h_out[2].as<uint32_t>();
+        const uint32_t *nv = st->h_cnt[0].as<uint32_t>(), *ni = st->h_cnt[1].as<uint32_t>();
+        uint64_t *o_rows = st->h_out[3].as<uint64_t>(), *o_var = st->h_out[5].as<uint64_t>(), *o_cls = st->h_out[8].as<uint64_t>(),
+                 *o_ilen = st->h_out[10].as<uint64_t>();
+        uint64_t a = 0, b = 0, c = 0, d = 0;
+        for (uint32_t q = 0; q < n_bubbles; q++) {
+            o_rows[q] = a; o_var[q] = b; o_cls[q] = c; o_ilen[q] = d;
+            a += (uint64_t)nr[q] * al[q]; b += nv[q]; c += (uint64_t)nv[q] * nr[q]; d += ni[q];
+        }
+        o_rows[n_bubbles] = a; o_var[n_bubbles] = b; o_cls[n_bubbles] = c; o_ilen[n_bubbles] = d;
+        if (a != res.tot_rows || b != res.tot_var || c != res.tot_cls || d != res.tot_ilen) {
+            pf::set_error("pf_align: offsets rebuilt on the host disagree with the device totals (%llu/%llu rows, %llu/%llu columns)",
+                          (unsigned long long)a, (unsigned long long)res.tot_rows, (unsigned long long)b, (unsigned long long)res.tot_var);
+            return PF_E_CUDA;
+        }
+    }
     st->host_n = n_bubbles;
     out->n_bubbles = n_bubbles;
     out->status = st->h_out[0].as<int32_t>(); out->n_rows = st->h_out[1].as<uint32_t>(); out->aln_len = st->h_out[2].as<uint32_t>();

@@ -86,24 +86,30 @@ struct DeviceWarmup {
         if (pf_kmc_open(ctx, prefix.c_str(), &db) != PF_OK) { error = pf_last_error(); db = nullptr; return; }
         if (!getenv("PF_NO_WARM")) warm_kernels();
     }
-    // CUDA loads a kernel's code at its first launch and the library creates its streams and attributes at first use: a dummy batch with
-    // one two-branch bubble per size class goes through the three calls here, on the warm-up thread, so that none of it lands in
-    // the estimation phase.  Results are discarded (the made-up k-mers are simply not in the database).
+    // CUDA loads a kernel's code at its first launch, the library creates its streams and attributes at first use and grows its
+    // pinned staging / device work areas to the largest batch it has seen: a dummy batch -- one two-branch bubble per size class plus
+    // a block's worth of SNP-sized bubbles -- goes through the three calls here, on the warm-up thread, so that none of that lands in
+    // the estimation phase (pinning memory in particular can take a second on a host whose page cache is full).  Results are
+    // discarded (the made-up k-mers are simply not in the database).
     void warm_kernels() {
         static const int lens[] = {40, 90, 120, 180, 250, 300};
+        const int n_snp = 100000;
         string bases;
         vector<uint64_t> off{0};
         vector<uint32_t> boff{0};
         unsigned x = 12345;
-        for (int L : lens) {
-            string a;
-            for (int i = 0; i < L; i++) { x = x * 1664525u + 1013904223u; a += "ACGT"[(x >> 24) & 3]; }
-            string b = a;
-            b[L / 2] = b[L / 2] == 'A' ? 'C' : 'A';
-            bases += a; off.push_back(bases.size());
-            bases += b; off.push_back(bases.size());
+        bases.reserve((size_t)n_snp * 100 + 4096);
+        auto add_bubble = [&](int L) {
+            const size_t a0 = bases.size();
+            for (int i = 0; i < L; i++) { x = x * 1664525u + 1013904223u; bases += "ACGT"[(x >> 24) & 3]; }
+            off.push_back(bases.size());
+            bases.append(bases, a0, (size_t)L);
+            bases[a0 + L + L / 2] = bases[a0 + L / 2] == 'A' ? 'C' : 'A';
+            off.push_back(bases.size());
             boff.push_back((uint32_t)(off.size() - 1));
-        }
+        };
+        for (int L : lens) add_bubble(L);
+        for (int i = 0; i < n_snp; i++) add_bubble(49);
         vector<pf_cov_t> cov(off.size() - 1);
         pf_msa_batch_t m;
         pf_site_batch_t sc;

@@ -1662,20 +1662,21 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
 static int align_fetch(pf_align_state *st, uint32_t n_bubbles, const DevResult &res, cudaStream_t s, pf_msa_batch_t *out) {
     int rc;
     const uint64_t n1 = (uint64_t)n_bubbles + 1;
-    const void *src[12] = {st->status.p, st->n_rows.p, st->aln_len.p, nullptr, st->rows.p, nullptr,
-                           st->var_col.p, st->var_kind.p, nullptr, st->cls.p, nullptr, st->ilen.p};
+    static const bool copy_offsets = getenv("PF_COPY_OFFSETS") != nullptr;     // A/B switch: the offsets as the device computed them
+    const void *src[12] = {st->status.p, st->n_rows.p, st->aln_len.p, copy_offsets ? st->off[0].p : nullptr, st->rows.p, copy_offsets ? st->off[1].p : nullptr,
+                           st->var_col.p, st->var_kind.p, copy_offsets ? st->off[2].p : nullptr, st->cls.p, copy_offsets ? st->off[3].p : nullptr, st->ilen.p};
     const uint64_t bytes[12] = {(uint64_t)n_bubbles * 4, (uint64_t)n_bubbles * 4, (uint64_t)n_bubbles * 4, n1 * 8, res.tot_rows,
                                 n1 * 8, res.tot_var * 4, res.tot_var, n1 * 8, res.tot_cls * 2, n1 * 8, res.tot_ilen * 4};
     for (int i = 0; i < 12; i++) {
         if ((rc = st->h_out[i].reserve(bytes[i] + 16))) return rc;
         if (bytes[i] && src[i]) PF_CUDA_TRY(cudaMemcpyAsync(st->h_out[i].p, src[i], bytes[i], cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 2 && !copy_offsets; i++) {
         if ((rc = st->h_cnt[i].reserve((uint64_t)n_bubbles * 4 + 16))) return rc;
         PF_CUDA_TRY(cudaMemcpyAsync(st->h_cnt[i].p, st->cnt[i].p, (uint64_t)n_bubbles * 4, cudaMemcpyDeviceToHost, s));
     }
     PF_CUDA_TRY(cudaStreamSynchronize(s));
-    {
+    if (!copy_offsets) {
         const uint32_t *nr = st->h_out[1].as<uint32_t>(), *al = st->h_out[2].as<uint32_t>();
         const uint32_t *nv = st->h_cnt[0].as<uint32_t>(), *ni = st->h_cnt[1].as<uint32_t>();
         uint64_t *o_rows = st->h_out[3].as<uint64_t>(), *o_var = st->h_out[5].as<uint64_t>(), *o_cls = st->h_out[8].as<uint64_t>(),

@@ -1,6 +1,6 @@
 #!/bin/bash
-# round-2 GPU call v: whole programs FIRST on the fresh box (r02s / r02u measured them after minutes of benches and tests: the first
-# pinned allocation of the phase then waits for the page cache to be reclaimed and the phase reads 1.2 - 1.6 s instead of 0.35 s);
+# round-2 GPU call v: whole programs FIRST on the fresh box (r02s / r02u measured them after minutes of benches and tests on the same
+# box: the first lookup calls of the phase then take 0.5 - 1 s longer and the phase reads 1.2 - 1.6 s instead of 0.35 s; cause not identified);
 # then the GPU suite and the bench line of record with the offsets rebuilt on the host
 mkdir -p gpurun_out
 free -g > gpurun_out/r02v_free_before.txt

@@ -77,35 +77,6 @@ struct ColoredDevice {
             if (pf_kmc_open(ctx, name.c_str(), &db) != PF_OK) { error = pf_last_error(); return; }
             dbs.push_back(db);
         }
-        if (!dbs.empty() && !getenv("PF_NO_WARM")) warm_kernels();
-    }
-    // as in ploidy_estimation_gpu.cpp: a dummy batch on the warm-up thread loads the kernels, creates the streams and sizes the
-    // pinned staging / device work areas before the estimation phase starts; results are discarded
-    void warm_kernels() {
-        static const int lens[] = {40, 90, 120, 180, 250, 300};
-        const int n_snp = 50000;
-        string bases;
-        vector<uint64_t> off{0};
-        vector<uint32_t> boff{0};
-        unsigned x = 54321;
-        bases.reserve((size_t)n_snp * 100 + 4096);
-        auto add_bubble = [&](int L) {
-            const size_t a0 = bases.size();
-            for (int i = 0; i < L; i++) { x = x * 1664525u + 1013904223u; bases += "ACGT"[(x >> 24) & 3]; }
-            off.push_back(bases.size());
-            bases.append(bases, a0, (size_t)L);
-            bases[a0 + L + L / 2] = bases[a0 + L / 2] == 'A' ? 'C' : 'A';
-            off.push_back(bases.size());
-            boff.push_back((uint32_t)(off.size() - 1));
-        };
-        for (int L : lens) add_bubble(L);
-        for (int i = 0; i < n_snp; i++) add_bubble(49);
-        vector<pf_cov_t> cov(off.size() - 1);
-        pf_msa_batch_t m;
-        pf_site_kmers_t sk;
-        for (pf_kmc *db : dbs) pf_kmc_cov(db, bases.data(), off.data(), (uint32_t)cov.size(), PF_LOOKUP_FWD_THEN_RC, 0, 0xFFFFFFFFu, cov.data());
-        if (pf_align(ctx, 2.0, -1.0, -3.0, bases.data(), off.data(), boff.data(), (uint32_t)(boff.size() - 1), &m) == PF_OK)
-            pf_site_kmers(ctx, 25, nullptr, &sk);
     }
     ColoredDevice() {
         const string list_file = option_of_this_process('d');

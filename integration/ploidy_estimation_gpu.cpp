@@ -86,14 +86,14 @@ struct DeviceWarmup {
         if (pf_kmc_open(ctx, prefix.c_str(), &db) != PF_OK) { error = pf_last_error(); db = nullptr; return; }
         if (!getenv("PF_NO_WARM")) warm_kernels();
     }
-    // CUDA loads a kernel's code at its first launch, the library creates its streams and attributes at first use and grows its
-    // pinned staging / device work areas to the largest batch it has seen: a dummy batch -- one two-branch bubble per size class plus
-    // a block's worth of SNP-sized bubbles -- goes through the three calls here, on the warm-up thread, so that none of that lands in
-    // the estimation phase (pinning memory in particular can take a second on a host whose page cache is full).  Results are
-    // discarded (the made-up k-mers are simply not in the database).
+    // CUDA loads a kernel's code at its first launch and the library creates its streams and attributes at first use: a dummy batch --
+    // one two-branch bubble per size class plus a few thousand SNP-sized ones -- goes through the three calls here, on the warm-up
+    // thread, so that none of that lands in the estimation phase (0.43 -> 0.35 s on the 20 Mbp diploid, profiles/r02_summary.md section 8;
+    // a block-sized dummy batch bought nothing more, and in the coloured binding -- eight databases to open first -- it was still
+    // running when the phase began).  Results are discarded (the made-up k-mers are simply not in the database).
     void warm_kernels() {
         static const int lens[] = {40, 90, 120, 180, 250, 300};
-        const int n_snp = 100000;
+        const int n_snp = 4096;
         string bases;
         vector<uint64_t> off{0};
         vector<uint32_t> boff{0};

@@ -299,6 +299,7 @@ class BubbleCaller {
         // ---- bubbles beyond a device limit: the host aligner, if the program gave one (HostMsa) ----
         host_.clear();
         host_of_.assign(n_kept, -1);
+        site_kmers_.clear(); site_class_.clear();
         {
             static const unsigned force = std::getenv("PF_CALLER_FORCE_HOST") ? (unsigned)std::atoi(std::getenv("PF_CALLER_FORCE_HOST")) : 0u;
             for (size_t q = 0; q < n_kept; q++) {

@@ -340,7 +340,7 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
     size_t var_id = thread_dialect ? 0 : 1;
     size_t coreNum = 0, coreCov = 0, n_bubbles = 0;
     const size_t k = (size_t)cdbg.getK();
-    double t_collect = 0, t_device_wait = 0;
+    double t_collect = 0, t_device_wait = 0, t_iter = 0, t_resolve = 0;
 
     // the device side of one block; runs on its own thread while the next block is collected
     vector<pf_cov_t> ent_cov;
@@ -392,6 +392,7 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
             if (++nb_unitig_processed % 100000 == 0) cout << "CDBG::PloidyEstimation(): Processed " << nb_unitig_processed << " unitigs " << endl;
         }
         const size_t n = units.size();
+        t_iter += seconds_since(t_phase);
         const unsigned Tn = (unsigned)min<size_t>(T, max<size_t>(1, n / 256));
         if (Tn == 1) speculate(units, 0, n, k, outs[0]);
         else {
@@ -400,7 +401,9 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
             for (thread &w : th) w.join();
         }
         for (unsigned t = Tn; t < T; t++) outs[t].clear();
+        const auto t_res = chrono::steady_clock::now();
         resolve(outs, blocks[cur]);
+        t_resolve += seconds_since(t_res);
         t_collect += seconds_since(t_phase);
         t_phase = chrono::steady_clock::now();
         if (pending.valid()) pending.get();                 // the device is done with the previous block
@@ -420,7 +423,7 @@ void CDBG::ploidyEstimation_ptr(const string &outpre, const int &lower, const in
     cout << "CDBG::PloidyEstimation():  Cpu time : " << (double)(clock() - start_clock) / CLOCKS_PER_SEC << "s" << endl;
     cout << "CDBG::PloidyEstimation():  Real time : " << (double)difftime(end_time, start_time) << "s" << endl;
     cout << "CDBG::PloidyEstimation():  GPU path : " << n_bubbles << " bubbles, " << T << " host threads, phase " << seconds_since(t_begin)
-         << "s = waited for device + database " << t_open << "s, collecting " << t_collect << "s, waiting for the device " << t_device_wait << "s" << ", releasing the device " << t_release << "s" << endl;
+         << "s = waited for device + database " << t_open << "s, collecting " << t_collect << "s (unitig iteration " << t_iter << ", resolve " << t_resolve << "), waiting for the device " << t_device_wait << "s" << ", releasing the device " << t_release << "s" << endl;
     {
         const pfdropin::CallerStats &cs = caller.stats();
         cout << "CDBG::PloidyEstimation():  GPU path, device thread : entrance readCov " << t_entrance << "s, BubbleCaller::call " << t_call << "s (branch readCov "

@@ -71,7 +71,7 @@ def run(binary, cwd, threads, extra_env=None, colored=False):
         out.update(bubbles_walked=int(gc.group(1)), colours=int(gc.group(2)), host_threads=int(gc.group(3)), phase_s=float(gc.group(4)),
                    collect_s=float(gc.group(5)), device_wait_s=float(gc.group(6)), device_thread=gc.group(7))
     g = re.search(r"GPU path : (\d+) bubbles, (\d+) host threads, phase ([0-9.e+-]+)s = waited for device \+ database ([0-9.e+-]+)s, "
-                  r"collecting ([0-9.e+-]+)s, waiting for the device ([0-9.e+-]+)s", r.stdout)
+                  r"collecting ([0-9.e+-]+)s(?: \([^)]*\))?, waiting for the device ([0-9.e+-]+)s", r.stdout)
     if g:
         out.update(bubbles_walked=int(g.group(1)), host_threads=int(g.group(2)), phase_s=float(g.group(3)), open_wait_s=float(g.group(4)),
                    collect_s=float(g.group(5)), device_wait_s=float(g.group(6)))

@@ -26,7 +26,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from tests import e2e_rows  # noqa: E402
+from tests import refrun as e2e_rows  # noqa: E402  (reference binaries + multiset views; no checker is loaded here)
 
 
 def run(binary, cwd, threads, extra_env=None, colored=False):

@@ -303,7 +303,8 @@ class BubbleCaller {
         {
             static const unsigned force = std::getenv("PF_CALLER_FORCE_HOST") ? (unsigned)std::atoi(std::getenv("PF_CALLER_FORCE_HOST")) : 0u;
             for (size_t q = 0; q < n_kept; q++) {
-                const bool over = m.status[q] != PF_BUBBLE_OK;
+                // beyond a device limit: no alignment result, or a branching bubble with more rows than the per-site kernels take (16)
+                const bool over = m.status[q] != PF_BUBBLE_OK || (host_aligner_ && !skip_[q] && m.n_rows[q] > 16);
                 if (!over && !(force && host_aligner_ && q % force == 0)) continue;
                 if (!host_aligner_ || m.status[q] == PF_BUBBLE_BAD_INPUT)
                     return fail_batch("bubble " + std::to_string(k_src_[q]) + " of the batch does not fit the device limits (pf_msa_batch_t status " + std::to_string(m.status[q]) +

@@ -1453,7 +1453,7 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
     PF_CUDA_TRY(cudaMemcpyAsync(h_total, st->slot_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));
     PF_CUDA_TRY(cudaMemcpyAsync(h_bounds, d_bounds, (CLS_HUGE + 2) * 4, cudaMemcpyDeviceToHost, s));
     PF_CUDA_TRY(cudaMemsetAsync(st->counter.p, 0, 256, s));   // work queues [0..15], stat_cells at byte 128
-    PF_CUDA_TRY(cudaStreamSynchronize(s));
+    PF_CUDA_TRY(pf::stream_sync(s));
     if ((rc = st->slots[0].reserve(*h_total + 64))) return rc;
 
     // ---- heavy queue: a few one-warp CTAs that re-run exploding DFS bubbles beside the first pass ----
@@ -1566,7 +1566,7 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         uint32_t *h_cnt = (uint32_t *)(st->h_scalars.as<uint8_t>() + 64);
         PF_CUDA_TRY(cudaMemcpyAsync(h_cnt, d_retry_cnt, 4, cudaMemcpyDeviceToHost, s));
         if (pass == 0 && d_hq) PF_CUDA_TRY(cudaMemcpyAsync(h_cnt + 1, d_hq, 8, cudaMemcpyDeviceToHost, s));   // queue tail, tickets
-        PF_CUDA_TRY(cudaStreamSynchronize(s));
+        PF_CUDA_TRY(pf::stream_sync(s));
         const uint32_t nr = *h_cnt;
         st->last_class_count[tier] = nr;
         if (pass == 0) {
@@ -1592,7 +1592,7 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         ctx->launches++;
         if ((rc = exclusive_scan_u64(ctx, st, st->slot_sizes.as<uint64_t>(), st->slot_off.as<uint64_t>(), nr + 1, s))) return rc;
         PF_CUDA_TRY(cudaMemcpyAsync(h_total, st->slot_off.as<uint64_t>() + nr, 8, cudaMemcpyDeviceToHost, s));
-        PF_CUDA_TRY(cudaStreamSynchronize(s));
+        PF_CUDA_TRY(pf::stream_sync(s));
         if ((rc = st->slots[1 + pass].reserve(*h_total + 64))) return rc;
         if (pass == 0) rc = launch_warp_smem_tier(ctx, st, 1, heavy, sc, d_bases, d_seq_off, d_bubble_off, st->retry_list.as<uint32_t>(), nr, tier,
                                                   st->counter.as<uint32_t>() + tier, s);
@@ -1627,7 +1627,7 @@ int align_device(pf_ctx *ctx, const Scoring &sc, const uint8_t *d_bases, const u
         PF_CUDA_TRY(cudaMemcpyAsync(h_tot + i, st->off[i].as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));
     }
     PF_CUDA_TRY(cudaMemcpyAsync(h_tot + 4, st->counter.as<uint8_t>() + 128, 8, cudaMemcpyDeviceToHost, s));
-    PF_CUDA_TRY(cudaStreamSynchronize(s));
+    PF_CUDA_TRY(pf::stream_sync(s));
     st->last_cells = h_tot[4];
     res.tot_rows = h_tot[0]; res.tot_var = h_tot[1]; res.tot_cls = h_tot[2]; res.tot_ilen = h_tot[3];
     st->last_n = n;
@@ -1675,7 +1675,7 @@ static int align_fetch(pf_align_state *st, uint32_t n_bubbles, const DevResult &
         if ((rc = st->h_cnt[i].reserve((uint64_t)n_bubbles * 4 + 16))) return rc;
         PF_CUDA_TRY(cudaMemcpyAsync(st->h_cnt[i].p, st->cnt[i].p, (uint64_t)n_bubbles * 4, cudaMemcpyDeviceToHost, s));
     }
-    PF_CUDA_TRY(cudaStreamSynchronize(s));
+    PF_CUDA_TRY(pf::stream_sync(s));
     if (!copy_offsets) {
         const uint32_t *nr = st->h_out[1].as<uint32_t>(), *al = st->h_out[2].as<uint32_t>();
         const uint32_t *nv = st->h_cnt[0].as<uint32_t>(), *ni = st->h_cnt[1].as<uint32_t>();

@@ -17,6 +17,16 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+cudaError_t stream_sync(cudaStream_t s) {
+    static const bool blocking = getenv("PF_BLOCKING_SYNC") != nullptr;
+    if (!blocking) return cudaStreamSynchronize(s);
+    thread_local cudaEvent_t ev = nullptr;      // one per host thread (a pf_ctx is used by one thread at a time)
+    cudaError_t e;
+    if (!ev && (e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(ev, s)) != cudaSuccess) return e;
+    return cudaEventSynchronize(ev);
+}
+
 int DevBuf::reserve(size_t bytes) {
     if (bytes <= cap) return PF_OK;
     if (p) cudaFree(p);

@@ -13,6 +13,10 @@
 namespace pf {
 
 void set_error(const char *fmt, ...);
+// The host's wait for a stream.  Default: cudaStreamSynchronize (the runtime's spin wait, lowest latency).  PF_BLOCKING_SYNC=1 in the
+// environment: record a cudaEventBlockingSync event and sleep on it -- for hosts where every GPU's worker threads spinning at once
+// (N ranks x T threads) leaves no core for the threads that have work to enqueue.
+cudaError_t stream_sync(cudaStream_t s);
 
 #define PF_CUDA_TRY(expr)                                                                     \
     do {                                                                                      \

@@ -824,13 +824,13 @@ int kmc_stream_hash(pf_kmc *db, const std::vector<uint64_t> &lut, const std::vec
     if (V.lut64) {
         PF_TRY_CLEAN(cudaMalloc(&d_lut, lut.size() * 8));
         PF_TRY_CLEAN(cudaMemcpyAsync(d_lut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, st));
-        PF_TRY_CLEAN(cudaStreamSynchronize(st));
+        PF_TRY_CLEAN(pf::stream_sync(st));
     } else {
         std::vector<uint32_t> l32(lut.size());
         for (size_t i = 0; i < lut.size(); i++) l32[i] = (uint32_t)lut[i];
         PF_TRY_CLEAN(cudaMalloc(&d_lut, l32.size() * 4));
         PF_TRY_CLEAN(cudaMemcpyAsync(d_lut, l32.data(), l32.size() * 4, cudaMemcpyHostToDevice, st));
-        PF_TRY_CLEAN(cudaStreamSynchronize(st));
+        PF_TRY_CLEAN(pf::stream_sync(st));
     }
     V.lut = d_lut;
     if (V.is_kmc2) {
@@ -838,7 +838,7 @@ int kmc_stream_hash(pf_kmc *db, const std::vector<uint64_t> &lut, const std::vec
         PF_TRY_CLEAN(cudaMemcpyAsync(d_sigmap, sigmap.data(), sigmap.size() * 4, cudaMemcpyHostToDevice, st));
         PF_TRY_CLEAN(cudaMalloc(&d_norm, norm.size() * 4));
         PF_TRY_CLEAN(cudaMemcpyAsync(d_norm, norm.data(), norm.size() * 4, cudaMemcpyHostToDevice, st));
-        PF_TRY_CLEAN(cudaStreamSynchronize(st));
+        PF_TRY_CLEAN(pf::stream_sync(st));
         V.sigmap = (const uint32_t *)d_sigmap; V.norm = (const uint32_t *)d_norm;
     }
     for (int i = 0; i < 2; i++) {
@@ -894,7 +894,7 @@ int kmc_stream_hash(pf_kmc *db, const std::vector<uint64_t> &lut, const std::vec
         }
         PF_TRY_CLEAN(cudaGetLastError());
         PF_TRY_CLEAN(cudaMemcpyAsync(h_status, d_status, 16, cudaMemcpyDeviceToHost, st));
-        PF_TRY_CLEAN(cudaStreamSynchronize(st));
+        PF_TRY_CLEAN(pf::stream_sync(st));
         db->build_status = h_status[0];
         if (!(h_status[0] & (HB_UNSORTED | HB_WRONG_BIN | HB_OVERFLOW))) break;
         cudaFree(tab);
@@ -1072,14 +1072,14 @@ int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_par
     if (V.lut64) {
         PF_CUDA_TRY(cudaMalloc(&db->d_lut, lut.size() * 8));
         PF_CUDA_TRY(cudaMemcpyAsync(db->d_lut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, st));
-        PF_CUDA_TRY(cudaStreamSynchronize(st));
+        PF_CUDA_TRY(pf::stream_sync(st));
         bytes += lut.size() * 8;
     } else {
         std::vector<uint32_t> l32(lut.size());
         for (size_t i = 0; i < lut.size(); i++) l32[i] = (uint32_t)lut[i];
         PF_CUDA_TRY(cudaMalloc(&db->d_lut, l32.size() * 4));
         PF_CUDA_TRY(cudaMemcpyAsync(db->d_lut, l32.data(), l32.size() * 4, cudaMemcpyHostToDevice, st));
-        PF_CUDA_TRY(cudaStreamSynchronize(st));
+        PF_CUDA_TRY(pf::stream_sync(st));
         bytes += l32.size() * 4;
     }
     V.lut = db->d_lut;
@@ -1088,7 +1088,7 @@ int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_par
         PF_CUDA_TRY(cudaMemcpyAsync(db->d_sigmap, sigmap.data(), sigmap.size() * 4, cudaMemcpyHostToDevice, st));
         PF_CUDA_TRY(cudaMalloc(&db->d_norm, norm.size() * 4));
         PF_CUDA_TRY(cudaMemcpyAsync(db->d_norm, norm.data(), norm.size() * 4, cudaMemcpyHostToDevice, st));
-        PF_CUDA_TRY(cudaStreamSynchronize(st));
+        PF_CUDA_TRY(pf::stream_sync(st));
         bytes += (sigmap.size() + norm.size()) * 4;
         V.sigmap = (const uint32_t *)db->d_sigmap;
         V.norm = (const uint32_t *)db->d_norm;
@@ -1117,7 +1117,7 @@ int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_par
                     at += nb; left -= nb; slot ^= 1;
                 }
             }
-            cudaStreamSynchronize(st);
+            pf::stream_sync(st);
             for (int i = 0; i < 2; i++) { cudaEventDestroy(done[i]); stage[i].release(); }
             if (!io_ok || rcs) { cudaFree(d_raw); if (!io_ok) { pf::set_error("%s.kmc_suf: short read", prefix); return PF_E_IO; } return rcs; }
         }
@@ -1134,10 +1134,10 @@ int kmc_open_impl(pf_ctx *ctx, const char *prefix, uint32_t part, uint32_t n_par
                                                             (uint64_t *)db->d_rec, (uint64_t *)db->d_suf, (uint32_t *)db->d_cnt);
         ctx->launches++;
         PF_CUDA_TRY(cudaGetLastError());
-        PF_CUDA_TRY(cudaStreamSynchronize(st));
+        PF_CUDA_TRY(pf::stream_sync(st));
         PF_CUDA_TRY(cudaFree(d_raw));
     }
-    PF_CUDA_TRY(cudaStreamSynchronize(st));
+    PF_CUDA_TRY(pf::stream_sync(st));
     V.rec = (const uint64_t *)db->d_rec; V.suf = (const uint64_t *)db->d_suf; V.cnt = (const uint32_t *)db->d_cnt;
     db->device_bytes = bytes;
     db->local_kmers = N;
@@ -1194,7 +1194,7 @@ int pf_kmc_close(pf_kmc *db) {
     db->tile_seq.release();
     db->site_status.release(); db->site_ncls.release(); db->site_cov.release(); db->site_skip.release(); db->site_map.release();
     for (auto &b : db->h_site) b.release();
-    if (db->k_stream) { cudaStreamSynchronize(db->k_stream); if (!db->k_stream_borrowed) cudaStreamDestroy(db->k_stream); }
+    if (db->k_stream) { pf::stream_sync(db->k_stream); if (!db->k_stream_borrowed) cudaStreamDestroy(db->k_stream); }
     db->k_stage.release();
     if (db->k_staged_ev) cudaEventDestroy(db->k_staged_ev);
     for (auto &b : db->k_in) b.release();
@@ -1384,7 +1384,7 @@ int pf_kmc_route_dev(pf_kmc *db, const void *d_bases, uint64_t n_bases, const vo
     ctx->launches += 6;
     PF_CUDA_TRY(cudaGetLastError());
     PF_CUDA_TRY(cudaMemcpyAsync(R->h_bounds.p, R->bounds.p, (P + 1) * 8, cudaMemcpyDeviceToHost, st));
-    PF_CUDA_TRY(cudaStreamSynchronize(st));
+    PF_CUDA_TRY(pf::stream_sync(st));
     for (uint32_t o = 0; o <= P; o++) h_send_off[o] = R->h_bounds.as<uint64_t>()[o];
     return PF_OK;
 }
@@ -1557,7 +1557,7 @@ int pf_site_cov(pf_kmc *db, uint32_t low, uint32_t up, const uint8_t *skip, pf_s
         if ((rc = db->h_site[i].reserve(bytes[i] + 16))) return rc;
         if (bytes[i]) PF_CUDA_TRY(cudaMemcpyAsync(db->h_site[i].p, src[i], bytes[i], cudaMemcpyDeviceToHost, st));
     }
-    PF_CUDA_TRY(cudaStreamSynchronize(st));
+    PF_CUDA_TRY(pf::stream_sync(st));
     out->n_bubbles = n;
     out->site_off = have_off ? h_var_off : db->h_site[0].as<uint64_t>(); out->status = db->h_site[1].as<uint8_t>(); out->n_class = db->h_site[2].as<uint8_t>();
     out->cov_off = have_off ? h_cls_off : db->h_site[3].as<uint64_t>(); out->cov = db->h_site[4].as<uint64_t>();
@@ -1614,7 +1614,7 @@ int pf_site_kmers(pf_ctx *ctx, uint32_t k, const uint8_t *skip, pf_site_kmers_t 
     PF_CUDA_TRY(cudaMemcpyAsync(h_key_off, m.cls_off, n1 * 8, cudaMemcpyDeviceToHost, st));
     if (n_cls) PF_CUDA_TRY(cudaMemcpyAsync(h_keys, d_keys.p, n_cls * 8, cudaMemcpyDeviceToHost, st));
     if (n_var) PF_CUDA_TRY(cudaMemcpyAsync(h_status, d_status.p, n_var, cudaMemcpyDeviceToHost, st));
-    PF_CUDA_TRY(cudaStreamSynchronize(st));
+    PF_CUDA_TRY(pf::stream_sync(st));
     out->n_bubbles = n;
     out->site_off = h_site_off; out->key_off = h_key_off; out->keys = h_keys; out->status = h_status;
     return PF_OK;
@@ -1637,7 +1637,7 @@ static int kmc_host_call(pf_kmc *db, const char *bases, const uint64_t *seq_off,
         if (part_env >= 8 && pf_lookup_partition(ctx, (uint32_t)part_env, &ps) == PF_OK && ps) { db->k_stream = (cudaStream_t)ps; db->k_stream_borrowed = true; }
         else PF_CUDA_TRY(cudaStreamCreateWithFlags(&db->k_stream, cudaStreamNonBlocking));
     }
-    PF_CUDA_TRY(cudaStreamSynchronize(db->k_stream));   // an earlier asynchronous call still owns the staging buffers
+    PF_CUDA_TRY(pf::stream_sync(db->k_stream));   // an earlier asynchronous call still owns the staging buffers
     const uint64_t n_bases = seq_off[n_seq] - seq_off[0];
     int rc;
     if (cov && !counts && !found && seq_off[0] == 0) {
@@ -1666,7 +1666,7 @@ static int kmc_host_call(pf_kmc *db, const char *bases, const uint64_t *seq_off,
                                nullptr, nullptr, db->k_out[2].p, st);
         if (rc) return rc;
         PF_CUDA_TRY(cudaMemcpyAsync(cov, db->k_out[2].p, (uint64_t)n_seq * sizeof(pf_cov_t), cudaMemcpyDeviceToHost, st));
-        if (!async) PF_CUDA_TRY(cudaStreamSynchronize(st));
+        if (!async) PF_CUDA_TRY(pf::stream_sync(st));
         return PF_OK;
     }
     db->k_staged_seq = 0;
@@ -1692,7 +1692,7 @@ static int kmc_host_call(pf_kmc *db, const char *bases, const uint64_t *seq_off,
     if (counts && W) PF_CUDA_TRY(cudaMemcpyAsync(counts, db->k_out[0].p, W * 4, cudaMemcpyDeviceToHost, st));
     if (found && W) PF_CUDA_TRY(cudaMemcpyAsync(found, db->k_out[1].p, W, cudaMemcpyDeviceToHost, st));
     if (cov) PF_CUDA_TRY(cudaMemcpyAsync(cov, db->k_out[2].p, (uint64_t)n_seq * sizeof(pf_cov_t), cudaMemcpyDeviceToHost, st));
-    if (!async) PF_CUDA_TRY(cudaStreamSynchronize(st));
+    if (!async) PF_CUDA_TRY(pf::stream_sync(st));
     return PF_OK;
 }
 
@@ -1705,7 +1705,7 @@ int pf_kmc_cov_async(pf_kmc *db, const char *bases, const uint64_t *seq_off, uin
 int pf_kmc_wait(pf_kmc *db) {
     if (!db) return PF_E_INVALID;
     PF_CUDA_TRY(cudaSetDevice(db->ctx->device));
-    if (db->k_stream) PF_CUDA_TRY(cudaStreamSynchronize(db->k_stream));
+    if (db->k_stream) PF_CUDA_TRY(pf::stream_sync(db->k_stream));
     return PF_OK;
 }
 

@@ -261,3 +261,63 @@ def test_bound_reference_binary_walk_and_host_logic(tmp_path, kw):
     assert ids == list(range(len(ids)))
     for key in want:
         assert got[key] == want[key], key
+
+
+def test_host_site_kmers_match_the_pinned_restatement(tmp_path):
+    """include/pf_caller.hpp: host_site_kmers (the site k-mers of the few bubbles that go through the host aligner) against
+    oracle/caller.py::site_kmers -- the restatement of CDBG.cpp:2331-2473 that is pinned on the reference's own end-to-end files --
+    on random gapped alignments: SNP / indel sites, before / after an earlier indel site, k-mers that reach past either end."""
+    import random
+    from oracle import caller
+    src = r'''
+#include "pf_caller.hpp"
+#include <iostream>
+int main() {
+    size_t n_cases; std::cin >> n_cases;
+    for (size_t t = 0; t < n_cases; t++) {
+        size_t n, c, k, ni; int indel;
+        std::cin >> n >> c >> k >> indel >> ni;
+        std::vector<std::string> rows(n), out;
+        for (auto &r : rows) std::cin >> r;
+        if (!pfdropin::host_site_kmers(rows, c, k, indel != 0, ni, out)) { std::cout << "UNDEFINED\n"; continue; }
+        for (size_t r = 0; r < n; r++) std::cout << out[r] << (r + 1 < n ? " " : "\n");
+    }
+}
+'''
+    (tmp_path / "t.cpp").write_text(src)
+    exe = str(tmp_path / "t")
+    subprocess.run(["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"), str(tmp_path / "t.cpp"), "-o", exe,
+                    "-Wl,--unresolved-symbols=ignore-all", "-pthread"], check=True)
+    rng = random.Random(7)
+    cases, want = [], []
+    while len(cases) < 3000:
+        n, L, k = rng.randint(2, 5), rng.randint(30, 70), rng.choice([9, 15, 25])
+        base = [rng.choice("ACGT") for _ in range(L)]
+        rows = []
+        for _ in range(n):
+            r = list(base)
+            for _ in range(rng.randint(0, 3)):
+                r[rng.randrange(L)] = rng.choice("ACGT")
+            for _ in range(rng.randint(0, 2)):                   # a gap run
+                a = rng.randrange(L)
+                for x in range(a, min(L, a + rng.randint(1, 4))):
+                    r[x] = "-"
+            rows.append("".join(r))
+        c, is_indel, ni = rng.randrange(L), rng.random() < 0.5, rng.choice([0, 0, 1, 2])
+        try:
+            exp = caller.site_kmers(rows, c, k, is_indel, ni)
+            if any(len(x) != k for x in exp):
+                exp = None                                       # a slice that ran off the row: the reference would throw / misbehave
+        except (AssertionError, IndexError):
+            exp = None
+        cases.append(f"{n} {c} {k} {int(is_indel)} {ni} " + " ".join(rows))
+        want.append(exp)
+    out = subprocess.run([exe], input=f"{len(cases)}\n" + "\n".join(cases) + "\n", capture_output=True, text=True, check=True).stdout.splitlines()
+    assert len(out) == len(cases)
+    n_defined = 0
+    for line, exp, case in zip(out, want, cases):
+        if exp is None:
+            continue          # outside the reference's own domain: the header may report UNDEFINED or any string, no row is written from it
+        n_defined += 1
+        assert line.split(" ") == exp, case
+    assert n_defined > 1000
